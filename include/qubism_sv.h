@@ -1,0 +1,181 @@
+/* qubism_sv.h -- C ABI of the B200-native state-vector backend for qubism.
+ *
+ * This is the drop-in boundary for the one hot path of qubitrot/qubism: applying
+ * single-qubit / controlled / multi-qubit gate matrices to the 2^n Complex-Double
+ * amplitude vector, plus the measurement reduction and collapse.  The reference has no
+ * FFI of its own; the seam is the Haskell module API of
+ *     src/Qubism/StateVec.hs:14-25   and   src/Qubism/QGate.hs:14-31,
+ * and each entry point below names the reference definition it replaces.  The Haskell
+ * side binds these with `foreign import ccall` (INTEGRATION.md shows the stubs).
+ *
+ * Conventions
+ *   - qb_c64 is layout-compatible with Haskell `Storable (Complex Double)` / C99
+ *     `double _Complex`: (re, im).
+ *   - Qubit indices are REFERENCE indices: qubit 0 is the MOST significant bit of the
+ *     amplitude index (StateVec.hs:65-67); qubit i is bit n-1-i.
+ *   - 2x2 matrices are row-major [a, b, c, d] exactly as `(2><2) [a,b,c,d]`
+ *     (QGate.hs:91-118); 2^k x 2^k blocks are row-major with qs[0] the most significant
+ *     index bit (the order `kronecker a b` produces, QGate.hs:142-144).
+ *   - Matrices need NOT be unitary and states need NOT be normalised: the reference's
+ *     `unitary theta phi lambda` is not unitary in general.
+ *   - The device state is uniquely owned and mutated in place; the pure `(#>)` of the
+ *     reference (QGate.hs:78-80) is qb_state_clone + an in-place apply.
+ *   - Gate calls only ENQUEUE; the library fuses queued gates into few passes over HBM and
+ *     runs them at qb_flush or at the first call that observes the state.
+ *   - Every function returns QB_OK (0) or a negative qb_status; it never aborts.  The
+ *     message for the last failure on the calling thread is at qb_last_error().
+ *   - There is no CPU fallback: without a usable CUDA device qb_init fails with
+ *     QB_ERR_CUDA.
+ */
+#ifndef QUBISM_SV_H
+#define QUBISM_SV_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { double re, im; } qb_c64;
+typedef struct qb_ctx qb_ctx;     /* device, stream, scratch, (optional) NCCL communicator */
+typedef struct qb_state qb_state; /* n, device amplitudes (a shard when distributed), bit map,
+                                     op queue, deferred scalar */
+
+typedef enum {
+  QB_OK = 0,
+  QB_ERR_ARG = -1,      /* bad qubit index / size / null pointer (Haskell: `finite` error) */
+  QB_ERR_OOM = -2,      /* device or host allocation failed */
+  QB_ERR_CUDA = -3,     /* CUDA runtime failure, or no device */
+  QB_ERR_NCCL = -4,     /* NCCL failure / library not loadable */
+  QB_ERR_UNSUPPORTED = -5,
+  QB_ERR_STATE = -6     /* operands on different contexts / sizes (hmatrix shape error) */
+} qb_status;
+
+/* ---- context ------------------------------------------------------------------------- */
+/* One context per process and GPU.  device = CUDA ordinal. */
+int qb_init(int device, qb_ctx **out);
+/* Distributed context: one process per GPU, rank r of nranks (a power of two) owns the
+ * amplitudes whose top log2(nranks) physical index bits equal r.  `nccl_id`
+ * is the 128-byte ncclUniqueId produced by qb_dist_unique_id on rank 0 and broadcast by the
+ * caller (torch.distributed, MPI, a file ...). */
+int qb_dist_unique_id(void *id128);
+int qb_init_dist(int device, int rank, int nranks, const void *nccl_id, qb_ctx **out);
+int qb_shutdown(qb_ctx *ctx);
+int qb_ctx_rank(const qb_ctx *ctx);
+int qb_ctx_nranks(const qb_ctx *ctx);
+/* Barrier over all ranks of a distributed context (no-op on a single-GPU one). */
+int qb_barrier(qb_ctx *ctx);
+const char *qb_last_error(void);
+/* Library build identification ("qubism_sv <version> sm_100a ..."). */
+const char *qb_version(void);
+
+/* ---- state creation / lifetime ------------------------------------------------------- */
+/* mkStateVec / mkStateVec' (StateVec.hs:78-85): basis != 0 -> |0...0>;
+ * zero (StateVec.hs:52): basis == 0 -> all-zero vector. */
+int qb_state_create(qb_ctx *ctx, int nqubits, int basis, qb_state **out);
+/* LA.fromList (StateVec.hs:89, test generators StateVecSpec.hs:26-28): upload 2^n host
+ * amplitudes.  In a distributed context every rank passes its own shard
+ * (2^n / nranks amplitudes, the ones it owns). */
+int qb_state_from_host(qb_ctx *ctx, int nqubits, const qb_c64 *amps, qb_state **out);
+/* Value semantics of the pure (#>) (QGate.hs:78-80). */
+int qb_state_clone(qb_state *src, qb_state **out);
+/* ForeignPtr finalizer; callable from any thread. */
+void qb_state_free(qb_state *s);
+/* dimension (StateVec.hs:74-75). */
+int qb_state_nqubits(const qb_state *s);
+/* Number of amplitudes held by this rank (2^n on a single GPU). */
+uint64_t qb_state_local_len(const qb_state *s);
+/* Show / :dump / parity (StateVec.hs:60-68): copy amplitudes [first, first+count) of the
+ * LOGICAL index space to the host.  Forces a flush.  Distributed: a collective -- every
+ * rank calls it with the same range and receives the same data. */
+int qb_state_read(qb_state *s, uint64_t first, uint64_t count, qb_c64 *out);
+/* Copy this rank's raw shard (physical order) to the host: bench/e2e only. */
+int qb_state_read_local(qb_state *s, uint64_t first, uint64_t count, qb_c64 *out);
+
+/* ---- gates (enqueue) ------------------------------------------------------------------ */
+/* onJust q m #> v   (QGate.hs:148-154, 78-80) */
+int qb_apply_1q(qb_state *s, int q, const qb_c64 m[4]);
+/* onRange qlo qhi m #> v / onEvery m #> v   (QGate.hs:158-165) */
+int qb_apply_1q_range(qb_state *s, int qlo, int qhi, const qb_c64 m[4]);
+/* controlled c1 (controlled c2 (... (onJust t m))) #> v   (QGate.hs:125-132) */
+int qb_apply_ctrl_1q(qb_state *s, const int *ctrls, int nctrl, int t, const qb_c64 m[4]);
+/* cnot c t #> v   (QGate.hs:121-122) */
+int qb_apply_cnot(qb_state *s, int c, int t);
+/* kronecker / (<>) blocks (QGate.hs:58-59, 142-144): dense 2^k x 2^k block on qubits
+ * qs[0..k), optionally under nctrl controls.  k <= QB_MAX_KQ. */
+#define QB_MAX_KQ 5
+int qb_apply_kq(qb_state *s, const int *qs, int k, const qb_c64 *m, const int *ctrls, int nctrl);
+
+/* Batch submission: one FFI crossing for a whole op list. */
+typedef struct {
+  int32_t kind;      /* 0 = (controlled) 1q gate, 1 = cnot */
+  int32_t target;
+  int32_t nctrl;
+  int32_t ctrl[4];
+  int32_t _pad;
+  qb_c64 m[4];
+} qb_op;
+int qb_submit(qb_state *s, const qb_op *ops, int64_t nops);
+
+/* Plan and run every queued gate.  Returns after the work is ENQUEUED on the stream;
+ * use qb_sync to wait for completion. */
+int qb_flush(qb_state *s);
+int qb_sync(qb_ctx *ctx);
+
+/* ---- measurement ---------------------------------------------------------------------- */
+/* Raw reduction behind pOne (StateVec.hs:124-126): s0 / s1 = sum |z_k|^2 over the
+ * amplitudes whose qubit-q bit is 0 / 1.  The reference's decision value is sqrt(s1).
+ * Deterministic (fixed-order two-stage reduction); distributed: all-reduced. */
+int qb_sumsq(qb_state *s, int q, double *s0, double *s1);
+/* collapse q bit (StateVec.hs:104-114): zero the rejected half, divide the kept half by
+ * its 2-norm.  A zero-weight outcome yields an all-NaN state, as in the reference. */
+int qb_collapse(qb_state *s, int q, int bit);
+/* measureQubit q (StateVec.hs:118-129) with the uniform draw r supplied by the caller
+ * (the RNG stays in Haskell): *bit = 1 iff r < sqrt(s1); the state collapses to *bit.
+ * *pone receives sqrt(s1) (0 where the reference has NaN; both decide Zero). */
+int qb_measure_qubit(qb_state *s, int q, double r, int *bit, double *pone);
+/* measure (StateVec.hs:133-137): measureQubit 0..n-1 in order with draws rs[0..n). */
+int qb_measure_all(qb_state *s, const double *rs, int *bits);
+
+/* ---- vector space / Hilbert space (StateVec.hs:51-58, 91-100; Algebra.hs:17-36) ------- */
+int qb_scale(qb_state *s, qb_c64 z);                          /* z .: v                   */
+int qb_axpy(qb_state *y, qb_c64 z, qb_state *x);              /* y <- y +: (z .: x)       */
+int qb_neg(qb_state *s);                                      /* neg v                    */
+int qb_dotc(qb_state *a, qb_state *b, qb_c64 *out);           /* a <.> b, conj on a       */
+int qb_norm2(qb_state *s, double *out);                       /* LA.norm_2 (NOT squared)  */
+int qb_normalize(qb_state *s);                                /* normalize                */
+int qb_tensor(qb_state *a, qb_state *b, qb_state **out);      /* a `tensor` b             */
+
+/* ---- introspection (tests, bench, profiling) ------------------------------------------- */
+typedef struct {
+  uint64_t ops_submitted;   /* primitive ops received through the ABI                     */
+  uint64_t ops_folded;      /* removed by the host peephole (scalars, cancelling CX pairs,
+                               merged 1q products)                                       */
+  uint64_t ops_executed;    /* gates that reached a kernel                                */
+  uint64_t passes;          /* fused-pass kernel launches (one read+write of the shard)   */
+  uint64_t rounds;          /* register-residency rounds inside those passes              */
+  uint64_t simple_launches; /* launches of the unfused small-n / dense-k kernels          */
+  uint64_t reduce_launches; /* launches of reduction kernels                              */
+  uint64_t exchange_bytes;  /* bytes this rank sent in global<->local qubit swaps         */
+  uint64_t exchanges;       /* number of such swaps                                       */
+  double plan_ms;           /* host time spent planning                                   */
+} qb_stats;
+int qb_get_stats(const qb_ctx *ctx, qb_stats *out);
+int qb_reset_stats(qb_ctx *ctx);
+/* Raw CUDA stream of the context (cudaStream_t as void*), for event timing by callers. */
+void *qb_ctx_stream(qb_ctx *ctx);
+/* Tuning knobs: "tile_bits", "reg_bits", "low_bits", "max_rounds", "peephole",
+ * "fuse" (0 = one pass per op).  Returns QB_ERR_ARG for unknown names / bad values. */
+int qb_set_option(qb_ctx *ctx, const char *name, int64_t value);
+int64_t qb_get_option(const qb_ctx *ctx, const char *name);
+/* Host-only planner entry point (no device needed): plan `nops` ops for an n-qubit local
+ * shard and write a textual plan ("pass tile=.. round regs=.. gates=..") into buf.
+ * Returns the number of bytes the full plan needs (snprintf-style) or a negative status. */
+int64_t qb_plan_describe(int nlocal, const qb_op *ops, int64_t nops, const char *options,
+                         char *buf, int64_t buflen);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QUBISM_SV_H */

@@ -1,0 +1,809 @@
+// C-ABI layer of the qubism state-vector backend (include/qubism_sv.h): contexts, device
+// states, the deferred op queue, flush = plan + launch, measurement, vector-space ops.
+// No torch types, no CPU fallback: every compute entry point needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "qb_dist.h"
+#include "qb_internal.h"
+#include "qb_kernels.h"
+
+using namespace qb;
+
+// ------------------------------------------------------------------------- errors
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define QB_CUDA(expr)                                                                      \
+  do {                                                                                     \
+    cudaError_t e__ = (expr);                                                              \
+    if (e__ != cudaSuccess)                                                                \
+      return fail(e__ == cudaErrorMemoryAllocation ? QB_ERR_OOM : QB_ERR_CUDA, "%s: %s",  \
+                  #expr, cudaGetErrorString(e__));                                         \
+  } while (0)
+
+#define QB_TRY(expr)         \
+  do {                       \
+    int rc__ = (expr);       \
+    if (rc__ != QB_OK) return rc__; \
+  } while (0)
+
+// ------------------------------------------------------------------------- objects
+struct qb_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  int rank = 0, nranks = 1, pbits = 0;
+  double *red_partials = nullptr;  // device, 2 * max blocks
+  double *red_out = nullptr;       // device, 2 doubles (+2 spare)
+  double *red_host = nullptr;      // pinned, 4 doubles
+  int *kq_bits_dev = nullptr;      // 2 * QB_MAX_KQ ints
+  double2 *kq_mat_dev = nullptr;   // 4^QB_MAX_KQ
+  PlanOptions opt;
+  qb_stats stats{};
+  std::recursive_mutex mu;
+  DistState *dist = nullptr;
+};
+
+struct qb_state {
+  qb_ctx *ctx = nullptr;
+  int n = 0;           // total qubits
+  int L = 0;           // local bits (n - pbits)
+  double2 *amps = nullptr;
+  std::vector<int> perm;  // logical bit -> physical bit (bits >= L are rank bits)
+  OpQueue q;
+};
+
+namespace {
+
+struct Guard {
+  std::lock_guard<std::recursive_mutex> lk;
+  explicit Guard(qb_ctx *c) : lk(c->mu) { cudaSetDevice(c->device); }
+};
+
+int init_common(qb_ctx *c) {
+  QB_CUDA(cudaSetDevice(c->device));
+  cudaDeviceProp prop;
+  QB_CUDA(cudaGetDeviceProperties(&prop, c->device));
+  c->sm_count = prop.multiProcessorCount;
+  QB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  const int maxblocks = c->sm_count * 8 + 8;
+  QB_CUDA(cudaMalloc(&c->red_partials, sizeof(double) * 2 * maxblocks));
+  QB_CUDA(cudaMalloc(&c->red_out, sizeof(double) * 4));
+  QB_CUDA(cudaMallocHost(&c->red_host, sizeof(double) * 4));
+  QB_CUDA(cudaMalloc(&c->kq_bits_dev, sizeof(int) * 2 * QB_MAX_KQ));
+  QB_CUDA(cudaMalloc(&c->kq_mat_dev, sizeof(double2) << (2 * QB_MAX_KQ)));
+  for (const char *name : {"tile_bits", "reg_bits", "low_bits", "max_rounds", "peephole", "fuse", "max_pass_gates"}) {
+    std::string env = "QB_";
+    for (const char *p = name; *p; ++p) env.push_back((char)toupper(*p));
+    const char *v = getenv(env.c_str());
+    if (v && *v) set_opt(c->opt, name, strtoll(v, nullptr, 10));
+  }
+  return QB_OK;
+}
+
+int alloc_state(qb_ctx *ctx, int n, qb_state **out) {
+  if (!ctx || !out) return fail(QB_ERR_ARG, "null argument");
+  if (n < 1 || n > 62) return fail(QB_ERR_ARG, "nqubits %d out of range", n);
+  if (n < ctx->pbits) return fail(QB_ERR_ARG, "nqubits %d smaller than log2(nranks) = %d", n, ctx->pbits);
+  qb_state *s = new qb_state();
+  s->ctx = ctx;
+  s->n = n;
+  s->L = n - ctx->pbits;
+  s->perm.resize(n);
+  for (int i = 0; i < n; ++i) s->perm[i] = i;
+  s->q.reset(n, ctx->opt.peephole != 0);
+  const size_t bytes = sizeof(double2) << s->L;
+  cudaError_t e = cudaMalloc(&s->amps, bytes);
+  if (e != cudaSuccess) {
+    delete s;
+    return fail(e == cudaErrorMemoryAllocation ? QB_ERR_OOM : QB_ERR_CUDA, "cudaMalloc(%zu bytes): %s", bytes,
+                cudaGetErrorString(e));
+  }
+  *out = s;
+  return QB_OK;
+}
+
+inline int logical_bit(const qb_state *s, int q) { return s->n - 1 - q; }
+
+int check_qubit(const qb_state *s, int q) {
+  if (q < 0 || q >= s->n) return fail(QB_ERR_ARG, "qubit index %d out of range for %d qubits", q, s->n);
+  return QB_OK;
+}
+
+uint64_t phys_mask(const qb_state *s, uint64_t logical_mask) {
+  uint64_t m = 0;
+  for (uint64_t b = logical_mask; b; b &= b - 1) m |= 1ull << s->perm[__builtin_ctzll(b)];
+  return m;
+}
+
+// run one op with the unfused kernels
+int run_simple(qb_state *s, const HostOp &op) {
+  qb_ctx *c = s->ctx;
+  const uint64_t rank_bits = uint64_t(c->rank) << s->L;
+  const uint64_t cmask = phys_mask(s, op.ctrl);
+  if (op.kind == 2) {
+    int sorted[QB_MAX_KQ] = {0}, order[QB_MAX_KQ] = {0};
+    if (op.k < 1 || op.k > QB_MAX_KQ) return fail(QB_ERR_ARG, "bad k");
+    for (int j = 0; j < op.k; ++j) {
+      const int pb = s->perm[op.kq_bits[op.k - 1 - j]];  // matrix index bit j (LSB first)
+      if (pb >= s->L) return fail(QB_ERR_UNSUPPORTED, "dense k-qubit block on a global qubit");
+      order[j] = pb;
+      sorted[j] = pb;
+    }
+    std::sort(sorted, sorted + op.k);
+    int host[2 * QB_MAX_KQ];
+    memcpy(host, sorted, sizeof(sorted));
+    memcpy(host + QB_MAX_KQ, order, sizeof(order));
+    QB_CUDA(cudaMemcpyAsync(c->kq_bits_dev, host, sizeof(host), cudaMemcpyHostToDevice, c->stream));
+    QB_CUDA(cudaMemcpyAsync(c->kq_mat_dev, op.kq_m.data(), sizeof(double) * op.kq_m.size(), cudaMemcpyHostToDevice,
+                            c->stream));
+    QB_CUDA(launch_simple_kq(s->amps, s->L, op.k, c->kq_bits_dev, c->kq_bits_dev + QB_MAX_KQ, c->kq_mat_dev, cmask,
+                             rank_bits, c->sm_count, c->stream));
+    c->stats.simple_launches++;
+    c->stats.ops_executed++;
+    return QB_OK;
+  }
+  const int pt = s->perm[op.target];
+  if (op.type == G_DIAG) {
+    QB_CUDA(launch_simple_diag(s->amps, s->L, 1ull << pt, cmask, rank_bits, &op.m[0], &op.m[6], c->sm_count,
+                               c->stream));
+  } else {
+    if (pt >= s->L) return fail(QB_ERR_UNSUPPORTED, "internal: unfused gate on a global qubit");
+    if (s->L < 1) return fail(QB_ERR_UNSUPPORTED, "shard too small");
+    QB_CUDA(launch_simple_gate(s->amps, s->L, pt, cmask, rank_bits, op.type, op.m, c->sm_count, c->stream));
+  }
+  c->stats.simple_launches++;
+  c->stats.ops_executed++;
+  return QB_OK;
+}
+
+int run_gscale_simple(qb_state *s, const double g[2]) {
+  qb_ctx *c = s->ctx;
+  QB_CUDA(launch_simple_diag(s->amps, s->L, 0, 0, 0, g, g, c->sm_count, c->stream));
+  c->stats.simple_launches++;
+  return QB_OK;
+}
+
+// Make every op in `seg` (1q ops only, live) runnable locally: in a distributed context bring
+// the global targets of the not-yet-done ops into the shard with one multi-bit swap.
+int make_local(qb_state *s, const std::vector<const HostOp *> &pending) {
+  qb_ctx *c = s->ctx;
+  if (c->nranks == 1) return fail(QB_ERR_UNSUPPORTED, "internal: planner stuck on a single GPU");
+  return dist_make_local(c->dist, s->amps, s->n, s->L, s->perm, pending, c->stream, &c->stats);
+}
+
+int run_fused_segment(qb_state *s, std::vector<const HostOp *> seg, const double *gscale, bool *gscale_done) {
+  qb_ctx *c = s->ctx;
+  int T, R;
+  effective_tile(c->opt, s->L, T, R);
+  PlanOptions opt = c->opt;
+  opt.tile_bits = T;
+  opt.reg_bits = R;
+  if (!opt.fuse) opt.max_pass_gates = 1;
+  while (!seg.empty()) {
+    std::vector<PhysOp> pops(seg.size());
+    for (size_t i = 0; i < seg.size(); ++i) {
+      const HostOp &h = *seg[i];
+      pops[i].type = h.type;
+      pops[i].target = s->perm[h.target];
+      pops[i].ctrl = phys_mask(s, h.ctrl);
+      memcpy(pops[i].m, h.m, sizeof(h.m));
+    }
+    auto t0 = std::chrono::steady_clock::now();
+    PlanResult plan = plan_passes(pops, s->L, c->rank, opt, nullptr);
+    const bool all = plan.consumed == seg.size();
+    if (all && gscale && !*gscale_done && !plan.passes.empty()) {
+      DevPass *P = reinterpret_cast<DevPass *>(plan.passes.back().blob.data());
+      P->gscale[0] = gscale[0];
+      P->gscale[1] = gscale[1];
+      P->has_gscale = 1;
+      *gscale_done = true;
+    }
+    c->stats.plan_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    for (const PassPlan &p : plan.passes) {
+      QB_CUDA(launch_fused_pass(s->amps, p.blob.data(), (uint32_t)p.blob.size(), p.tile_bits, p.reg_bits, p.ntiles,
+                                c->sm_count, c->stream, nullptr));
+      c->stats.passes++;
+      c->stats.rounds += p.nrounds;
+      c->stats.ops_executed += p.ngates;
+    }
+    if (all) break;
+    std::vector<const HostOp *> rest;
+    for (size_t i = 0; i < seg.size(); ++i)
+      if (!plan.done[i]) rest.push_back(seg[i]);
+    if (plan.passes.empty() || true) {
+      // whatever is left starts with gates on global qubits: remap them into the shard
+      QB_TRY(make_local(s, rest));
+    }
+    seg.swap(rest);
+  }
+  return QB_OK;
+}
+
+int flush_locked(qb_state *s) {
+  qb_ctx *c = s->ctx;
+  OpQueue &q = s->q;
+  c->stats.ops_submitted += q.submitted;
+  c->stats.ops_folded += q.folded;
+  q.submitted = q.folded = 0;
+  if (q.empty()) {
+    q.clear();
+    return QB_OK;
+  }
+  const bool has_g = !(q.gscale[0] == 1.0 && q.gscale[1] == 0.0);
+  const double g[2] = {q.gscale[0], q.gscale[1]};
+  bool g_done = !has_g;
+  int T, R;
+  effective_tile(c->opt, s->L, T, R);
+  int rc = QB_OK;
+  if (T == 0) {
+    for (const auto &op : q.ops) {
+      if (op.dead) continue;
+      if (op.kind == 0 && op.type != G_DIAG && s->perm[op.target] >= s->L) {
+        std::vector<const HostOp *> pend;
+        for (const auto &o2 : q.ops)
+          if (!o2.dead && &o2 >= &op && o2.kind == 0) pend.push_back(&o2);
+        if ((rc = make_local(s, pend)) != QB_OK) break;
+      }
+      if ((rc = run_simple(s, op)) != QB_OK) break;
+    }
+  } else {
+    std::vector<const HostOp *> seg;
+    size_t last_live = 0;
+    for (size_t i = 0; i < q.ops.size(); ++i)
+      if (!q.ops[i].dead) last_live = i;
+    for (size_t i = 0; i < q.ops.size() && rc == QB_OK; ++i) {
+      const HostOp &op = q.ops[i];
+      if (op.dead) continue;
+      if (op.kind == 0) {
+        seg.push_back(&op);
+        continue;
+      }
+      if (!seg.empty()) {
+        rc = run_fused_segment(s, seg, nullptr, nullptr);
+        seg.clear();
+      }
+      if (rc == QB_OK) rc = run_simple(s, op);
+    }
+    (void)last_live;
+    if (rc == QB_OK && !seg.empty()) rc = run_fused_segment(s, seg, has_g ? g : nullptr, &g_done);
+  }
+  if (rc == QB_OK && !g_done) rc = run_gscale_simple(s, g);
+  q.clear();
+  return rc;
+}
+
+// reduce (S0, S1) split by a logical bit (lb < 0: total) into host doubles; all-reduced when distributed
+int sumsq_locked(qb_state *s, int lb, double *s0, double *s1) {
+  qb_ctx *c = s->ctx;
+  QB_TRY(flush_locked(s));
+  const int pb = lb < 0 ? -1 : s->perm[lb];
+  const int kbit = (pb >= 0 && pb < s->L) ? pb : -1;
+  QB_CUDA(launch_sumsq(s->amps, 1ull << s->L, kbit, c->red_partials, c->red_out, c->sm_count, c->stream));
+  c->stats.reduce_launches += 2;
+  QB_CUDA(cudaMemcpyAsync(c->red_host, c->red_out, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  QB_CUDA(cudaStreamSynchronize(c->stream));
+  double a0 = c->red_host[0], a1 = c->red_host[1];
+  if (pb >= s->L) {  // global bit: this rank's whole shard has one value of it
+    if ((c->rank >> (pb - s->L)) & 1) {
+      a1 = a0;
+      a0 = 0.0;
+    }
+  }
+  if (c->nranks > 1) {
+    double v[2] = {a0, a1};
+    int rc = dist_allreduce_sum(c->dist, v, 2, c->stream);
+    if (rc != QB_OK) return fail(rc, "allreduce failed");
+    a0 = v[0];
+    a1 = v[1];
+  }
+  if (s0) *s0 = a0;
+  if (s1) *s1 = a1;
+  return QB_OK;
+}
+
+int collapse_with(qb_state *s, int lb, int bit, double weight) {
+  double m[8] = {0};
+  if (weight == 0.0 || std::isnan(weight)) {
+    // the reference divides by norm_2 = 0: every amplitude becomes NaN (StateVec.hs:92,107)
+    m[0] = m[6] = NAN;
+  } else {
+    const double f = 1.0 / std::sqrt(weight);
+    m[bit ? 6 : 0] = f;
+  }
+  s->q.push_1q(lb, 0, m);
+  return QB_OK;
+}
+
+}  // namespace
+
+// ============================================================================ C ABI
+extern "C" {
+
+const char *qb_last_error(void) { return g_last_error.c_str(); }
+
+const char *qb_version(void) { return "qubism_sv 0.1 sm_100a fused-pass"; }
+
+int qb_init(int device, qb_ctx **out) {
+  if (!out) return fail(QB_ERR_ARG, "null out");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(QB_ERR_CUDA, "no CUDA device (%s); this backend has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  if (device < 0 || device >= ndev) return fail(QB_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
+  qb_ctx *c = new qb_ctx();
+  c->device = device;
+  int rc = init_common(c);
+  if (rc != QB_OK) {
+    delete c;
+    return rc;
+  }
+  *out = c;
+  return QB_OK;
+}
+
+int qb_dist_unique_id(void *id128) {
+  if (!id128) return fail(QB_ERR_ARG, "null id");
+  int rc = dist_unique_id(id128);
+  if (rc != QB_OK) return fail(rc, "ncclGetUniqueId failed: %s", dist_last_error());
+  return QB_OK;
+}
+
+int qb_init_dist(int device, int rank, int nranks, const void *nccl_id, qb_ctx **out) {
+  if (!out || !nccl_id) return fail(QB_ERR_ARG, "null argument");
+  if (nranks < 1 || (nranks & (nranks - 1)) || rank < 0 || rank >= nranks)
+    return fail(QB_ERR_ARG, "nranks must be a power of two and 0 <= rank < nranks");
+  QB_TRY(qb_init(device, out));
+  qb_ctx *c = *out;
+  if (nranks == 1) return QB_OK;
+  c->rank = rank;
+  c->nranks = nranks;
+  c->pbits = __builtin_ctz((unsigned)nranks);
+  int rc = dist_create(&c->dist, device, rank, nranks, nccl_id, c->stream);
+  if (rc != QB_OK) {
+    std::string msg = dist_last_error();
+    qb_shutdown(c);
+    *out = nullptr;
+    return fail(rc, "distributed init failed: %s", msg.c_str());
+  }
+  return QB_OK;
+}
+
+int qb_shutdown(qb_ctx *c) {
+  if (!c) return QB_OK;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->dist) dist_destroy(c->dist);
+  cudaFree(c->red_partials);
+  cudaFree(c->red_out);
+  cudaFreeHost(c->red_host);
+  cudaFree(c->kq_bits_dev);
+  cudaFree(c->kq_mat_dev);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return QB_OK;
+}
+
+int qb_ctx_rank(const qb_ctx *c) { return c ? c->rank : -1; }
+int qb_ctx_nranks(const qb_ctx *c) { return c ? c->nranks : -1; }
+
+int qb_barrier(qb_ctx *c) {
+  if (!c) return fail(QB_ERR_ARG, "null ctx");
+  Guard g(c);
+  QB_CUDA(cudaStreamSynchronize(c->stream));
+  if (c->nranks > 1) {
+    double v = 0.0;
+    int rc = dist_allreduce_sum(c->dist, &v, 1, c->stream);
+    if (rc != QB_OK) return fail(rc, "barrier failed: %s", dist_last_error());
+  }
+  return QB_OK;
+}
+
+int qb_state_create(qb_ctx *ctx, int nqubits, int basis, qb_state **out) {
+  if (!ctx) return fail(QB_ERR_ARG, "null ctx");
+  Guard g(ctx);
+  qb_state *s = nullptr;
+  QB_TRY(alloc_state(ctx, nqubits, &s));
+  cudaError_t e = cudaMemsetAsync(s->amps, 0, sizeof(double2) << s->L, ctx->stream);
+  if (e == cudaSuccess && basis && ctx->rank == 0) e = launch_set_amp(s->amps, 0, 1.0, 0.0, ctx->stream);
+  if (e != cudaSuccess) {
+    qb_state_free(s);
+    return fail(QB_ERR_CUDA, "state init: %s", cudaGetErrorString(e));
+  }
+  *out = s;
+  return QB_OK;
+}
+
+int qb_state_from_host(qb_ctx *ctx, int nqubits, const qb_c64 *amps, qb_state **out) {
+  if (!ctx || !amps) return fail(QB_ERR_ARG, "null argument");
+  Guard g(ctx);
+  qb_state *s = nullptr;
+  QB_TRY(alloc_state(ctx, nqubits, &s));
+  cudaError_t e = cudaMemcpyAsync(s->amps, amps, sizeof(double2) << s->L, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) {
+    qb_state_free(s);
+    return fail(QB_ERR_CUDA, "upload: %s", cudaGetErrorString(e));
+  }
+  *out = s;
+  return QB_OK;
+}
+
+int qb_state_clone(qb_state *src, qb_state **out) {
+  if (!src || !out) return fail(QB_ERR_ARG, "null argument");
+  Guard g(src->ctx);
+  QB_TRY(flush_locked(src));
+  qb_state *s = nullptr;
+  QB_TRY(alloc_state(src->ctx, src->n, &s));
+  s->perm = src->perm;
+  cudaError_t e =
+      cudaMemcpyAsync(s->amps, src->amps, sizeof(double2) << s->L, cudaMemcpyDeviceToDevice, src->ctx->stream);
+  if (e != cudaSuccess) {
+    qb_state_free(s);
+    return fail(QB_ERR_CUDA, "clone: %s", cudaGetErrorString(e));
+  }
+  *out = s;
+  return QB_OK;
+}
+
+void qb_state_free(qb_state *s) {
+  if (!s) return;
+  {
+    Guard g(s->ctx);
+    cudaStreamSynchronize(s->ctx->stream);
+    cudaFree(s->amps);
+  }
+  delete s;
+}
+
+int qb_state_nqubits(const qb_state *s) { return s ? s->n : QB_ERR_ARG; }
+uint64_t qb_state_local_len(const qb_state *s) { return s ? (1ull << s->L) : 0; }
+
+int qb_state_read_local(qb_state *s, uint64_t first, uint64_t count, qb_c64 *out) {
+  if (!s || !out) return fail(QB_ERR_ARG, "null argument");
+  Guard g(s->ctx);
+  QB_TRY(flush_locked(s));
+  if (first + count > (1ull << s->L)) return fail(QB_ERR_ARG, "range beyond the local shard");
+  QB_CUDA(cudaMemcpyAsync(out, s->amps + first, count * sizeof(double2), cudaMemcpyDeviceToHost, s->ctx->stream));
+  QB_CUDA(cudaStreamSynchronize(s->ctx->stream));
+  return QB_OK;
+}
+
+int qb_state_read(qb_state *s, uint64_t first, uint64_t count, qb_c64 *out) {
+  if (!s || (!out && count)) return fail(QB_ERR_ARG, "null argument");
+  if (first + count > (1ull << s->n)) return fail(QB_ERR_ARG, "range beyond 2^n");
+  qb_ctx *c = s->ctx;
+  Guard g(c);
+  QB_TRY(flush_locked(s));
+  if (c->nranks == 1) {
+    QB_CUDA(cudaMemcpyAsync(out, s->amps + first, count * sizeof(double2), cudaMemcpyDeviceToHost, c->stream));
+    QB_CUDA(cudaStreamSynchronize(c->stream));
+    return QB_OK;
+  }
+  int rc = dist_read_logical(c->dist, s->amps, s->n, s->L, s->perm, first, count, out, c->stream);
+  if (rc != QB_OK) return fail(rc, "distributed read failed: %s", dist_last_error());
+  return QB_OK;
+}
+
+// ---- gates
+int qb_apply_ctrl_1q(qb_state *s, const int *ctrls, int nctrl, int t, const qb_c64 m[4]) {
+  if (!s || !m || (nctrl > 0 && !ctrls)) return fail(QB_ERR_ARG, "null argument");
+  QB_TRY(check_qubit(s, t));
+  uint64_t cm = 0;
+  for (int i = 0; i < nctrl; ++i) {
+    QB_TRY(check_qubit(s, ctrls[i]));
+    if (ctrls[i] == t) return fail(QB_ERR_ARG, "control %d equals target", t);
+    cm |= 1ull << logical_bit(s, ctrls[i]);
+  }
+  std::lock_guard<std::recursive_mutex> lk(s->ctx->mu);
+  s->q.peephole = s->ctx->opt.peephole != 0;
+  s->q.push_1q(logical_bit(s, t), cm, reinterpret_cast<const double *>(m));
+  return QB_OK;
+}
+
+int qb_apply_1q(qb_state *s, int q, const qb_c64 m[4]) { return qb_apply_ctrl_1q(s, nullptr, 0, q, m); }
+
+int qb_apply_1q_range(qb_state *s, int qlo, int qhi, const qb_c64 m[4]) {
+  if (!s || !m) return fail(QB_ERR_ARG, "null argument");
+  QB_TRY(check_qubit(s, qlo));
+  QB_TRY(check_qubit(s, qhi));
+  // onRange f l m = mconcat [onJust i m | i <- [f..l]] (QGate.hs:164-165): the factors act
+  // on distinct qubits and commute; [f..l] is empty when f > l.
+  for (int q = qlo; q <= qhi; ++q) QB_TRY(qb_apply_1q(s, q, m));
+  return QB_OK;
+}
+
+int qb_apply_cnot(qb_state *s, int c, int t) {
+  static const qb_c64 X[4] = {{0, 0}, {1, 0}, {1, 0}, {0, 0}};
+  return qb_apply_ctrl_1q(s, &c, 1, t, X);
+}
+
+int qb_apply_kq(qb_state *s, const int *qs, int k, const qb_c64 *m, const int *ctrls, int nctrl) {
+  if (!s || !qs || !m || (nctrl > 0 && !ctrls)) return fail(QB_ERR_ARG, "null argument");
+  if (k < 1 || k > QB_MAX_KQ) return fail(QB_ERR_UNSUPPORTED, "dense blocks support 1 <= k <= %d", QB_MAX_KQ);
+  if (k == 1) return qb_apply_ctrl_1q(s, ctrls, nctrl, qs[0], m);
+  uint64_t seen = 0, cm = 0;
+  int bits[QB_MAX_KQ];
+  for (int i = 0; i < k; ++i) {
+    QB_TRY(check_qubit(s, qs[i]));
+    bits[i] = logical_bit(s, qs[i]);
+    if (seen & (1ull << bits[i])) return fail(QB_ERR_ARG, "repeated qubit %d", qs[i]);
+    seen |= 1ull << bits[i];
+  }
+  for (int i = 0; i < nctrl; ++i) {
+    QB_TRY(check_qubit(s, ctrls[i]));
+    const uint64_t b = 1ull << logical_bit(s, ctrls[i]);
+    if (seen & b) return fail(QB_ERR_ARG, "control %d is also a target", ctrls[i]);
+    cm |= b;
+  }
+  std::lock_guard<std::recursive_mutex> lk(s->ctx->mu);
+  s->q.push_kq(bits, k, reinterpret_cast<const double *>(m), cm);
+  return QB_OK;
+}
+
+int qb_submit(qb_state *s, const qb_op *ops, int64_t nops) {
+  if (!s || (!ops && nops)) return fail(QB_ERR_ARG, "null argument");
+  for (int64_t i = 0; i < nops; ++i) {
+    const qb_op &o = ops[i];
+    if (o.kind == 1) {
+      QB_TRY(qb_apply_cnot(s, o.ctrl[0], o.target));
+    } else if (o.kind == 0) {
+      if (o.nctrl < 0 || o.nctrl > 4) return fail(QB_ERR_ARG, "op %lld: nctrl out of range", (long long)i);
+      QB_TRY(qb_apply_ctrl_1q(s, o.ctrl, o.nctrl, o.target, o.m));
+    } else {
+      return fail(QB_ERR_ARG, "op %lld: unknown kind %d", (long long)i, o.kind);
+    }
+  }
+  return QB_OK;
+}
+
+int qb_flush(qb_state *s) {
+  if (!s) return fail(QB_ERR_ARG, "null state");
+  Guard g(s->ctx);
+  return flush_locked(s);
+}
+
+int qb_sync(qb_ctx *c) {
+  if (!c) return fail(QB_ERR_ARG, "null ctx");
+  Guard g(c);
+  QB_CUDA(cudaStreamSynchronize(c->stream));
+  return QB_OK;
+}
+
+// ---- measurement
+int qb_sumsq(qb_state *s, int q, double *s0, double *s1) {
+  if (!s) return fail(QB_ERR_ARG, "null state");
+  QB_TRY(check_qubit(s, q));
+  Guard g(s->ctx);
+  return sumsq_locked(s, logical_bit(s, q), s0, s1);
+}
+
+int qb_collapse(qb_state *s, int q, int bit) {
+  if (!s) return fail(QB_ERR_ARG, "null state");
+  QB_TRY(check_qubit(s, q));
+  if (bit != 0 && bit != 1) return fail(QB_ERR_ARG, "bit must be 0 or 1");
+  Guard g(s->ctx);
+  double s0, s1;
+  QB_TRY(sumsq_locked(s, logical_bit(s, q), &s0, &s1));
+  return collapse_with(s, logical_bit(s, q), bit, bit ? s1 : s0);
+}
+
+int qb_measure_qubit(qb_state *s, int q, double r, int *bit, double *pone) {
+  if (!s || !bit) return fail(QB_ERR_ARG, "null argument");
+  QB_TRY(check_qubit(s, q));
+  Guard g(s->ctx);
+  double s0, s1;
+  QB_TRY(sumsq_locked(s, logical_bit(s, q), &s0, &s1));
+  const double p = std::sqrt(s1);  // the reference's pOne (NaN there when s1 == 0; both pick Zero)
+  const int b = (r < p) ? 1 : 0;
+  *bit = b;
+  if (pone) *pone = p;
+  return collapse_with(s, logical_bit(s, q), b, b ? s1 : s0);
+}
+
+int qb_measure_all(qb_state *s, const double *rs, int *bits) {
+  if (!s || !rs || !bits) return fail(QB_ERR_ARG, "null argument");
+  for (int q = 0; q < s->n; ++q) QB_TRY(qb_measure_qubit(s, q, rs[q], &bits[q], nullptr));
+  return QB_OK;
+}
+
+// ---- vector space
+int qb_scale(qb_state *s, qb_c64 z) {
+  if (!s) return fail(QB_ERR_ARG, "null state");
+  std::lock_guard<std::recursive_mutex> lk(s->ctx->mu);
+  s->q.mul_gscale(z.re, z.im);
+  return QB_OK;
+}
+
+int qb_neg(qb_state *s) { return qb_scale(s, qb_c64{-1.0, 0.0}); }
+
+static int same_shape(qb_state *a, qb_state *b) {
+  if (!a || !b) return fail(QB_ERR_ARG, "null state");
+  if (a->ctx != b->ctx) return fail(QB_ERR_STATE, "states live on different contexts");
+  if (a->n != b->n) return fail(QB_ERR_STATE, "states have %d and %d qubits", a->n, b->n);
+  return QB_OK;
+}
+
+int qb_axpy(qb_state *y, qb_c64 z, qb_state *x) {
+  QB_TRY(same_shape(y, x));
+  qb_ctx *c = y->ctx;
+  Guard g(c);
+  QB_TRY(flush_locked(y));
+  QB_TRY(flush_locked(x));
+  if (y->perm != x->perm) return fail(QB_ERR_UNSUPPORTED, "operands have different qubit layouts");
+  const double zz[2] = {z.re, z.im};
+  QB_CUDA(launch_axpy(y->amps, x->amps, 1ull << y->L, zz, c->sm_count, c->stream));
+  return QB_OK;
+}
+
+int qb_dotc(qb_state *a, qb_state *b, qb_c64 *out) {
+  QB_TRY(same_shape(a, b));
+  if (!out) return fail(QB_ERR_ARG, "null out");
+  qb_ctx *c = a->ctx;
+  Guard g(c);
+  QB_TRY(flush_locked(a));
+  QB_TRY(flush_locked(b));
+  if (a->perm != b->perm) return fail(QB_ERR_UNSUPPORTED, "operands have different qubit layouts");
+  QB_CUDA(launch_dotc(a->amps, b->amps, 1ull << a->L, c->red_partials, c->red_out, c->sm_count, c->stream));
+  c->stats.reduce_launches += 2;
+  QB_CUDA(cudaMemcpyAsync(c->red_host, c->red_out, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  QB_CUDA(cudaStreamSynchronize(c->stream));
+  double v[2] = {c->red_host[0], c->red_host[1]};
+  if (c->nranks > 1) {
+    int rc = dist_allreduce_sum(c->dist, v, 2, c->stream);
+    if (rc != QB_OK) return fail(rc, "allreduce failed: %s", dist_last_error());
+  }
+  out->re = v[0];
+  out->im = v[1];
+  return QB_OK;
+}
+
+int qb_norm2(qb_state *s, double *out) {
+  if (!s || !out) return fail(QB_ERR_ARG, "null argument");
+  Guard g(s->ctx);
+  double s0 = 0, s1 = 0;
+  QB_TRY(sumsq_locked(s, -1, &s0, &s1));
+  *out = std::sqrt(s0 + s1);
+  return QB_OK;
+}
+
+int qb_normalize(qb_state *s) {
+  double nrm = 0;
+  QB_TRY(qb_norm2(s, &nrm));
+  return qb_scale(s, qb_c64{1.0 / nrm, 0.0});  // 0 -> inf -> 0 * inf = NaN, as LA.normalize
+}
+
+int qb_tensor(qb_state *a, qb_state *b, qb_state **out) {
+  if (!a || !b || !out) return fail(QB_ERR_ARG, "null argument");
+  if (a->ctx != b->ctx) return fail(QB_ERR_STATE, "states live on different contexts");
+  qb_ctx *c = a->ctx;
+  if (c->nranks > 1) return fail(QB_ERR_UNSUPPORTED, "tensor of distributed states");
+  Guard g(c);
+  QB_TRY(flush_locked(a));
+  QB_TRY(flush_locked(b));
+  qb_state *s = nullptr;
+  QB_TRY(alloc_state(c, a->n + b->n, &s));
+  cudaError_t e = launch_tensor(s->amps, a->amps, b->amps, a->n, b->n, c->sm_count, c->stream);
+  if (e != cudaSuccess) {
+    qb_state_free(s);
+    return fail(QB_ERR_CUDA, "tensor: %s", cudaGetErrorString(e));
+  }
+  *out = s;
+  return QB_OK;
+}
+
+// ---- introspection
+int qb_get_stats(const qb_ctx *c, qb_stats *out) {
+  if (!c || !out) return fail(QB_ERR_ARG, "null argument");
+  *out = c->stats;
+  return QB_OK;
+}
+
+int qb_reset_stats(qb_ctx *c) {
+  if (!c) return fail(QB_ERR_ARG, "null ctx");
+  c->stats = qb_stats{};
+  return QB_OK;
+}
+
+void *qb_ctx_stream(qb_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+int qb_set_option(qb_ctx *c, const char *name, int64_t value) {
+  if (!c || !name) return fail(QB_ERR_ARG, "null argument");
+  std::lock_guard<std::recursive_mutex> lk(c->mu);
+  if (!set_opt(c->opt, name, value)) return fail(QB_ERR_ARG, "bad option %s=%lld", name, (long long)value);
+  return QB_OK;
+}
+
+int64_t qb_get_option(const qb_ctx *c, const char *name) {
+  if (!c || !name) return QB_ERR_ARG;
+  return get_opt(c->opt, name);
+}
+
+int64_t qb_plan_describe(int nlocal, const qb_op *ops, int64_t nops, const char *options, char *buf,
+                         int64_t buflen) {
+  if (nlocal < 1 || nlocal > 62 || (!ops && nops)) return fail(QB_ERR_ARG, "bad argument");
+  PlanOptions opt;
+  if (options) {
+    std::string o(options);
+    size_t pos = 0;
+    while (pos < o.size()) {
+      size_t e = o.find(',', pos);
+      if (e == std::string::npos) e = o.size();
+      std::string kv = o.substr(pos, e - pos);
+      size_t eq = kv.find('=');
+      if (eq != std::string::npos && !set_opt(opt, kv.substr(0, eq), strtoll(kv.c_str() + eq + 1, nullptr, 10)))
+        return fail(QB_ERR_ARG, "bad option %s", kv.c_str());
+      pos = e + 1;
+    }
+  }
+  OpQueue q;
+  q.reset(nlocal, opt.peephole != 0);
+  for (int64_t i = 0; i < nops; ++i) {
+    const qb_op &o = ops[i];
+    uint64_t cm = 0;
+    if (o.target < 0 || o.target >= nlocal) return fail(QB_ERR_ARG, "op %lld: bad target", (long long)i);
+    const int nc = o.kind == 1 ? 1 : o.nctrl;
+    for (int k = 0; k < nc; ++k) {
+      if (o.ctrl[k] < 0 || o.ctrl[k] >= nlocal || o.ctrl[k] == o.target)
+        return fail(QB_ERR_ARG, "op %lld: bad control", (long long)i);
+      cm |= 1ull << (nlocal - 1 - o.ctrl[k]);
+    }
+    static const double X[8] = {0, 0, 1, 0, 1, 0, 0, 0};
+    q.push_1q(nlocal - 1 - o.target, cm, o.kind == 1 ? X : reinterpret_cast<const double *>(o.m));
+  }
+  int T, R;
+  effective_tile(opt, nlocal, T, R);
+  std::string text;
+  char head[160];
+  snprintf(head, sizeof head, "submitted=%llu folded=%llu gscale=(%.17g,%.17g)\n", (unsigned long long)q.submitted,
+           (unsigned long long)q.folded, q.gscale[0], q.gscale[1]);
+  text = head;
+  if (T == 0) {
+    text += "unfused (shard smaller than a tile)\n";
+  } else {
+    opt.tile_bits = T;
+    opt.reg_bits = R;
+    if (!opt.fuse) opt.max_pass_gates = 1;
+    std::vector<PhysOp> pops;
+    for (const auto &h : q.ops) {
+      if (h.dead) continue;
+      PhysOp p;
+      p.type = h.type;
+      p.target = h.target;
+      p.ctrl = h.ctrl;
+      memcpy(p.m, h.m, sizeof(h.m));
+      pops.push_back(p);
+    }
+    PlanResult r = plan_passes(pops, nlocal, 0, opt, q.gscale);
+    text += describe_plan(r);
+  }
+  if (buf && buflen > 0) {
+    const size_t ncopy = std::min<size_t>(text.size(), (size_t)buflen - 1);
+    memcpy(buf, text.data(), ncopy);
+    buf[ncopy] = 0;
+  }
+  return (int64_t)text.size() + 1;
+}
+
+}  // extern "C"

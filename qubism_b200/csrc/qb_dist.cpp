@@ -1,0 +1,336 @@
+// Multi-GPU layer, first cut: NCCL send/recv global<->local qubit swaps.
+//
+// A non-diagonal gate whose target is a GLOBAL physical bit (one of the rank bits) cannot run
+// inside a shard.  Instead of exchanging per gate, the k global bits that pending gates need
+// are swapped with the TOP k local bits in one step: every rank keeps the 2^-k of its shard
+// whose top-k local bits already equal its own value of those rank bits and trades each other
+// contiguous 2^(L-k) block with exactly one peer (all peers are equidistant through NVSwitch).
+// The logical->physical bit map is updated, so every later gate on those qubits is local.
+// Volume per rank: (1 - 2^-k) of the shard each way -- one half-shard for k = 1.
+#include "qb_dist.h"
+
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+namespace qb {
+
+static thread_local std::string g_dist_err;
+const char *dist_last_error() { return g_dist_err.c_str(); }
+
+namespace {
+
+struct NcclApi {
+  void *handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+NcclApi *nccl() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return api.handle ? &api : nullptr;
+  tried = true;
+  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char *nm : names) {
+    api.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (api.handle) break;
+  }
+  if (!api.handle) {
+    g_dist_err = std::string("cannot load libnccl.so.2: ") + dlerror();
+    return nullptr;
+  }
+#define QB_SYM(field, name)                                             \
+  api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.handle, name)); \
+  if (!api.field) {                                                     \
+    g_dist_err = std::string("missing NCCL symbol ") + name;            \
+    api.handle = nullptr;                                               \
+    return nullptr;                                                     \
+  }
+  QB_SYM(GetUniqueId, "ncclGetUniqueId")
+  QB_SYM(CommInitRank, "ncclCommInitRank")
+  QB_SYM(CommDestroy, "ncclCommDestroy")
+  QB_SYM(AllReduce, "ncclAllReduce")
+  QB_SYM(Send, "ncclSend")
+  QB_SYM(Recv, "ncclRecv")
+  QB_SYM(GroupStart, "ncclGroupStart")
+  QB_SYM(GroupEnd, "ncclGroupEnd")
+  QB_SYM(GetErrorString, "ncclGetErrorString")
+#undef QB_SYM
+  return &api;
+}
+
+}  // namespace
+
+struct DistState {
+  int device = 0, rank = 0, nranks = 1, pbits = 0;
+  ncclComm_t comm = nullptr;
+  double *scratch_dev = nullptr;   // 64 doubles
+  double2 *bounce[2] = {nullptr, nullptr};
+  size_t bounce_amps = 0;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_recv[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
+};
+
+#define QB_NCCL(expr)                                                              \
+  do {                                                                             \
+    ncclResult_t r__ = (expr);                                                     \
+    if (r__ != ncclSuccess) {                                                      \
+      g_dist_err = std::string(#expr) + ": " + nccl()->GetErrorString(r__);        \
+      return QB_ERR_NCCL;                                                          \
+    }                                                                              \
+  } while (0)
+
+#define QB_DCUDA(expr)                                                             \
+  do {                                                                             \
+    cudaError_t e__ = (expr);                                                      \
+    if (e__ != cudaSuccess) {                                                      \
+      g_dist_err = std::string(#expr) + ": " + cudaGetErrorString(e__);            \
+      return e__ == cudaErrorMemoryAllocation ? QB_ERR_OOM : QB_ERR_CUDA;          \
+    }                                                                              \
+  } while (0)
+
+int dist_unique_id(void *id128) {
+  NcclApi *a = nccl();
+  if (!a) return QB_ERR_NCCL;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  ncclUniqueId id;
+  QB_NCCL(a->GetUniqueId(&id));
+  memcpy(id128, &id, 128);
+  return QB_OK;
+}
+
+int dist_create(DistState **out, int device, int rank, int nranks, const void *id128, cudaStream_t stream) {
+  NcclApi *a = nccl();
+  if (!a) return QB_ERR_NCCL;
+  DistState *d = new DistState();
+  d->device = device;
+  d->rank = rank;
+  d->nranks = nranks;
+  d->pbits = __builtin_ctz((unsigned)nranks);
+  ncclUniqueId id;
+  memcpy(&id, id128, 128);
+  QB_DCUDA(cudaSetDevice(device));
+  QB_NCCL(a->CommInitRank(&d->comm, nranks, id, rank));
+  QB_DCUDA(cudaMalloc(&d->scratch_dev, 64 * sizeof(double)));
+  QB_DCUDA(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    QB_DCUDA(cudaEventCreateWithFlags(&d->ev_recv[i], cudaEventDisableTiming));
+    QB_DCUDA(cudaEventCreateWithFlags(&d->ev_copy[i], cudaEventDisableTiming));
+  }
+  (void)stream;
+  *out = d;
+  return QB_OK;
+}
+
+void dist_destroy(DistState *d) {
+  if (!d) return;
+  cudaSetDevice(d->device);
+  if (d->comm && nccl()) nccl()->CommDestroy(d->comm);
+  cudaFree(d->scratch_dev);
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(d->bounce[i]);
+    if (d->ev_recv[i]) cudaEventDestroy(d->ev_recv[i]);
+    if (d->ev_copy[i]) cudaEventDestroy(d->ev_copy[i]);
+  }
+  if (d->copy_stream) cudaStreamDestroy(d->copy_stream);
+  delete d;
+}
+
+int dist_allreduce_sum(DistState *d, double *vals, int n, cudaStream_t stream) {
+  if (n > 64) return QB_ERR_ARG;
+  NcclApi *a = nccl();
+  QB_DCUDA(cudaMemcpyAsync(d->scratch_dev, vals, n * sizeof(double), cudaMemcpyHostToDevice, stream));
+  QB_NCCL(a->AllReduce(d->scratch_dev, d->scratch_dev, n, ncclDouble, ncclSum, d->comm, stream));
+  QB_DCUDA(cudaMemcpyAsync(vals, d->scratch_dev, n * sizeof(double), cudaMemcpyDeviceToHost, stream));
+  QB_DCUDA(cudaStreamSynchronize(stream));
+  return QB_OK;
+}
+
+// ------------------------------------------------------------------ swap selection (host)
+std::vector<SwapPair> choose_swaps(int n, int L, const std::vector<int> &perm,
+                                   const std::vector<const HostOp *> &pending) {
+  // global physical bits that pending non-diagonal gates target, in order of first use
+  std::vector<int> need;
+  uint64_t seen = 0;
+  const size_t window = std::max<size_t>(64, size_t(4) * n);
+  for (size_t i = 0; i < pending.size() && i < window; ++i) {
+    const HostOp &h = *pending[i];
+    if (h.kind != 0 || h.type == G_DIAG) continue;
+    const int pb = perm[h.target];
+    if (pb >= L && !(seen & (1ull << pb))) {
+      seen |= 1ull << pb;
+      need.push_back(pb);
+    }
+  }
+  std::sort(need.begin(), need.end());
+  // they trade places with the top local bits (contiguous blocks => plain send/recv)
+  std::vector<SwapPair> out;
+  int lb = L - 1;
+  for (int g : need) {
+    out.push_back({g, lb});
+    --lb;
+  }
+  return out;
+}
+
+static int ensure_bounce(DistState *d, size_t amps) {
+  if (d->bounce_amps >= amps) return QB_OK;
+  for (int i = 0; i < 2; ++i) {
+    if (d->bounce[i]) cudaFree(d->bounce[i]);
+    d->bounce[i] = nullptr;
+  }
+  for (int i = 0; i < 2; ++i) QB_DCUDA(cudaMalloc(&d->bounce[i], amps * sizeof(double2)));
+  d->bounce_amps = amps;
+  return QB_OK;
+}
+
+int dist_make_local(DistState *d, double2 *amps, int n, int L, std::vector<int> &perm,
+                    const std::vector<const HostOp *> &pending, cudaStream_t stream, qb_stats *stats) {
+  NcclApi *a = nccl();
+  std::vector<SwapPair> sw = choose_swaps(n, L, perm, pending);
+  if (sw.empty()) {
+    g_dist_err = "planner stuck but no global target pending";
+    return QB_ERR_UNSUPPORTED;
+  }
+  const int k = (int)sw.size();
+  if (k > L) {
+    g_dist_err = "shard too small for the swap";
+    return QB_ERR_UNSUPPORTED;
+  }
+  // sw[i].lbit = L-1-i; block index (k bits, top local bits) <-> values of the swapped rank bits
+  const uint64_t block = 1ull << (L - k);
+  // my value of the swapped rank bits, expressed as a block index: rank bit sw[i].gbit <-> local bit sw[i].lbit
+  auto rank_to_block = [&](int rank) {
+    uint64_t b = 0;
+    for (int i = 0; i < k; ++i)
+      if ((rank >> (sw[i].gbit - L)) & 1) b |= 1ull << (sw[i].lbit - (L - k));
+    return b;
+  };
+  auto peer_for_block = [&](uint64_t blk) {
+    int r = d->rank;
+    for (int i = 0; i < k; ++i) {
+      const int rb = sw[i].gbit - L;
+      const int v = (blk >> (sw[i].lbit - (L - k))) & 1;
+      r = (r & ~(1 << rb)) | (v << rb);
+    }
+    return r;
+  };
+  const uint64_t mine = rank_to_block(d->rank);
+  // pieces of at most 2^24 amplitudes (256 MiB) through two bounce buffers
+  const uint64_t piece = std::min<uint64_t>(block, 1ull << 24);
+  int rc = ensure_bounce(d, piece);
+  if (rc != QB_OK) return rc;
+  int slot = 0;
+  bool used[2] = {false, false};
+  for (uint64_t blk = 0; blk < (1ull << k); ++blk) {
+    if (blk == mine) continue;
+    const int peer = peer_for_block(blk);
+    double2 *base = amps + blk * block;
+    for (uint64_t off = 0; off < block; off += piece) {
+      if (used[slot]) QB_DCUDA(cudaStreamWaitEvent(stream, d->ev_copy[slot], 0));  // bounce free again
+      QB_NCCL(a->GroupStart());
+      QB_NCCL(a->Send(base + off, piece * 2, ncclDouble, peer, d->comm, stream));
+      QB_NCCL(a->Recv(d->bounce[slot], piece * 2, ncclDouble, peer, d->comm, stream));
+      QB_NCCL(a->GroupEnd());
+      QB_DCUDA(cudaEventRecord(d->ev_recv[slot], stream));
+      QB_DCUDA(cudaStreamWaitEvent(d->copy_stream, d->ev_recv[slot], 0));
+      QB_DCUDA(cudaMemcpyAsync(base + off, d->bounce[slot], piece * sizeof(double2), cudaMemcpyDeviceToDevice,
+                               d->copy_stream));
+      QB_DCUDA(cudaEventRecord(d->ev_copy[slot], d->copy_stream));
+      used[slot] = true;
+      slot ^= 1;
+      if (stats) stats->exchange_bytes += piece * sizeof(double2);
+    }
+  }
+  for (int s = 0; s < 2; ++s)
+    if (used[s]) QB_DCUDA(cudaStreamWaitEvent(stream, d->ev_copy[s], 0));
+  if (stats) stats->exchanges++;
+  // update the logical -> physical map
+  for (int i = 0; i < k; ++i) {
+    int la = -1, lb = -1;
+    for (int q = 0; q < n; ++q) {
+      if (perm[q] == sw[i].gbit) la = q;
+      if (perm[q] == sw[i].lbit) lb = q;
+    }
+    std::swap(perm[la], perm[lb]);
+  }
+  return QB_OK;
+}
+
+int dist_read_logical(DistState *d, const double2 *amps, int n, int L, const std::vector<int> &perm, uint64_t first,
+                      uint64_t count, qb_c64 *out, cudaStream_t stream) {
+  NcclApi *a = nccl();
+  if (count == 0) return QB_OK;
+  if (count > (1ull << 22)) {
+    g_dist_err = "distributed qb_state_read is limited to 2^22 amplitudes per call";
+    return QB_ERR_UNSUPPORTED;
+  }
+  std::vector<qb_c64> host(count, qb_c64{0.0, 0.0});
+  QB_DCUDA(cudaStreamSynchronize(stream));
+  // gather the elements this rank owns, merging contiguous runs into single copies
+  uint64_t run_start = 0, run_len = 0, run_phys = 0;
+  auto flush_run = [&]() -> int {
+    if (run_len) QB_DCUDA(cudaMemcpyAsync(&host[run_start], amps + run_phys, run_len * sizeof(double2), cudaMemcpyDeviceToHost, stream));
+    run_len = 0;
+    return QB_OK;
+  };
+  for (uint64_t i = 0; i < count; ++i) {
+    const uint64_t logical = first + i;
+    uint64_t phys = 0;
+    for (int q = 0; q < n; ++q)
+      if ((logical >> q) & 1) phys |= 1ull << perm[q];
+    const int owner = (int)(phys >> L);
+    if (owner != d->rank) {
+      int rc = flush_run();
+      if (rc != QB_OK) return rc;
+      continue;
+    }
+    const uint64_t local = phys & ((1ull << L) - 1);
+    if (run_len && local == run_phys + run_len) {
+      ++run_len;
+    } else {
+      int rc = flush_run();
+      if (rc != QB_OK) return rc;
+      run_start = i;
+      run_phys = local;
+      run_len = 1;
+    }
+  }
+  {
+    int rc = flush_run();
+    if (rc != QB_OK) return rc;
+  }
+  QB_DCUDA(cudaStreamSynchronize(stream));
+  double *tmp = nullptr;
+  QB_DCUDA(cudaMalloc(&tmp, count * sizeof(double2)));
+  cudaError_t e = cudaMemcpyAsync(tmp, host.data(), count * sizeof(double2), cudaMemcpyHostToDevice, stream);
+  ncclResult_t r = ncclSuccess;
+  if (e == cudaSuccess) r = a->AllReduce(tmp, tmp, count * 2, ncclDouble, ncclSum, d->comm, stream);
+  if (e == cudaSuccess && r == ncclSuccess)
+    e = cudaMemcpyAsync(out, tmp, count * sizeof(double2), cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  cudaFree(tmp);
+  if (r != ncclSuccess) {
+    g_dist_err = std::string("ncclAllReduce: ") + a->GetErrorString(r);
+    return QB_ERR_NCCL;
+  }
+  if (e != cudaSuccess) {
+    g_dist_err = std::string("distributed read: ") + cudaGetErrorString(e);
+    return QB_ERR_CUDA;
+  }
+  return QB_OK;
+}
+
+}  // namespace qb

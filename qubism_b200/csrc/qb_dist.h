@@ -1,0 +1,40 @@
+// Multi-GPU layer: one process per GPU, rank r owns the amplitudes whose top log2(P)
+// physical index bits equal r.  NCCL is loaded lazily (dlopen) so that a
+// single-GPU process never needs it.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <vector>
+
+#include "qb_internal.h"
+
+namespace qb {
+
+struct DistState;
+
+const char *dist_last_error();
+int dist_unique_id(void *id128);
+int dist_create(DistState **out, int device, int rank, int nranks, const void *id128, cudaStream_t stream);
+void dist_destroy(DistState *d);
+
+// in-place sum over ranks of n host doubles (n <= 64); synchronises the stream
+int dist_allreduce_sum(DistState *d, double *vals, int n, cudaStream_t stream);
+
+// Which global physical bits must become local for the pending ops, as a list of
+// (global physical bit, local physical bit to evict) pairs.  Pure host logic (unit-tested).
+struct SwapPair {
+  int gbit, lbit;
+};
+std::vector<SwapPair> choose_swaps(int n, int L, const std::vector<int> &perm,
+                                   const std::vector<const HostOp *> &pending);
+
+// Exchange data so that the global targets of `pending` become local; updates perm.
+int dist_make_local(DistState *d, double2 *amps, int n, int L, std::vector<int> &perm,
+                    const std::vector<const HostOp *> &pending, cudaStream_t stream, qb_stats *stats);
+
+// Collective read of logical amplitudes [first, first + count) into `out` on every rank.
+int dist_read_logical(DistState *d, const double2 *amps, int n, int L, const std::vector<int> &perm, uint64_t first,
+                      uint64_t count, qb_c64 *out, cudaStream_t stream);
+
+}  // namespace qb

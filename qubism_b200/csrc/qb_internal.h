@@ -1,0 +1,182 @@
+// Internal structures shared by the host planner (qb_planner.cpp), the C-ABI layer
+// (qb_api.cpp) and the kernels (qb_kernels.cu).  Not installed; the public boundary is
+// include/qubism_sv.h.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/qubism_sv.h"
+
+namespace qb {
+
+// ------------------------------------------------------------------ compile-time limits
+constexpr int kMaxTileBits = 13;   // 2^13 amplitudes * 16 B = 128 KB of shared memory
+constexpr int kMaxRegBits = 5;     // 32 amplitudes (128 32-bit registers) per thread
+constexpr int kMaxRounds = 8;      // register-residency rounds per pass
+constexpr int kMaxRuns = 16;       // runs of non-tile bits in the tile-index deposit
+constexpr int kMaxPassGates = 96;  // gates per pass (bounds the shared-memory program copy)
+constexpr int kLaneFixedBits = 3;  // bits 0..2 (one 128-B line) stay on lanes in load/store rounds
+
+// ------------------------------------------------------------------ gate classes
+// Classification is by VALUE of the 2x2 the caller passed (SURVEY.md 7.2 "gate
+// classification"): it changes instruction count, never results beyond fp64 rounding.
+enum GateType : uint32_t {
+  G_GENERAL = 0,  // arbitrary complex 2x2                     8 DFMA-slot ops / amplitude
+  G_REAL = 1,     // real 2x2 (after pulling a common phase)   4
+  G_DIAG = 2,     // diag(d0, d1): target may be ANY bit       4
+  G_SWAP = 3,     // [[0,1],[1,0]]: pure permutation           0
+};
+
+// One gate as the fused-pass kernel sees it (per round: register/thread/external split).
+struct alignas(16) DevGate {
+  double m[8];     // row-major (re,im): a b c d.  G_REAL uses re parts; G_DIAG uses a and d.
+  uint32_t type;   // GateType
+  uint32_t treg;   // target register bit (GENERAL / REAL / SWAP)
+  uint32_t creg;   // controls that are register-index bits   (mask over the 2^R index)
+  uint32_t cthr;   // controls that are thread-id bits        (mask over threadIdx.x)
+  uint64_t cext;   // controls outside the tile               (mask over the full physical index)
+  uint32_t dreg;   // G_DIAG: target as register-index mask   (exactly one of dreg/dthr/dext set)
+  uint32_t dthr;   // G_DIAG: target as thread-id mask
+  uint64_t dext;   // G_DIAG: target as external mask
+};
+static_assert(sizeof(DevGate) == 112, "DevGate layout");
+
+struct DevRound {
+  uint32_t gate_begin, gate_end;
+  uint32_t nthr_bits;                 // T - R
+  uint32_t _pad;
+  uint8_t tid_pos[16];                // tile-local bit position carried by thread-id bit j
+  uint8_t reg_pos[8];                 // tile-local bit position carried by register bit j
+  uint32_t reg_sx[8];                 // swizzled shared-memory index contribution of register bit j
+  uint32_t _pad2[2];
+};
+static_assert(sizeof(DevRound) == 80, "DevRound layout");
+
+struct DevPass {
+  uint32_t nrounds, ngates, tile_bits, reg_bits;
+  uint32_t nruns, local_bits;
+  uint64_t rank_bits;                 // rank << local_bits: OR-ed into the tile base for predicates
+  uint32_t run_shift[kMaxRuns];       // deposit of the tile id into the non-tile bit runs
+  uint32_t run_len[kMaxRuns];
+  uint8_t tile_pos[16];               // physical bit position of tile-local bit i
+  double gscale[2];                   // deferred global scalar applied on the way out (1,0 = none)
+  uint32_t has_gscale, _pad[3];
+  DevRound rounds[kMaxRounds];
+  // followed in memory by ngates DevGate records
+};
+static_assert(sizeof(DevPass) % 16 == 0, "DevPass alignment");
+
+inline size_t pass_bytes(uint32_t ngates) { return sizeof(DevPass) + size_t(ngates) * sizeof(DevGate); }
+
+// shared-memory swizzle: XOR every higher 3-bit group of the tile-local index into the low
+// 3 bits (the 16-byte bank group of a 128-bit access).  Linear over XOR.
+inline uint32_t swz_host(uint32_t u) {
+  return u ^ ((u >> 3) & 7u) ^ ((u >> 6) & 7u) ^ ((u >> 9) & 7u) ^ ((u >> 12) & 7u);
+}
+
+// ------------------------------------------------------------------ host-side ops
+struct HostOp {
+  int kind = 0;             // 0 = (controlled) 1q, 2 = dense kq (barrier op)
+  uint32_t type = G_GENERAL;
+  int target = -1;          // LOGICAL bit position (n-1-q)
+  uint64_t ctrl = 0;        // mask over LOGICAL bit positions
+  double m[8] = {0};
+  // dense kq
+  int k = 0;
+  int kq_bits[QB_MAX_KQ] = {0};  // logical bit positions, kq_bits[0] = most significant index bit
+  std::vector<double> kq_m;
+  // peephole bookkeeping
+  bool dead = false;
+  int nprev = 0;
+  int prev_bit[6] = {0};    // for each qubit this op touches: the op that touched it before
+  int prev_idx[6] = {0};
+};
+
+struct PlanOptions {
+  int tile_bits = 12;
+  int reg_bits = 4;
+  int low_bits = 5;     // low physical bits always in the tile (contiguous run per chunk)
+  int max_rounds = 6;
+  int fuse = 1;         // 0: one pass per op
+  int peephole = 1;
+  int max_pass_gates = kMaxPassGates;
+};
+
+// (tile bits, register bits, min CTAs/SM) instantiations of k_fused_pass
+struct VariantSpec {
+  int T, R, minb;
+};
+constexpr VariantSpec kFusedVariants[] = {{10, 3, 4}, {10, 4, 4}, {11, 3, 3}, {11, 4, 4}, {11, 5, 6},
+                                          {12, 3, 2}, {12, 4, 2}, {12, 5, 3}, {13, 4, 1}, {13, 5, 1}};
+bool variant_supported(int T, int R);
+bool set_opt(PlanOptions &o, const std::string &name, int64_t v);
+int64_t get_opt(const PlanOptions &o, const std::string &name);
+// effective (T, R) for a shard with L local bits; T = 0 -> unfused kernels only
+void effective_tile(const PlanOptions &o, int L, int &T, int &R);
+
+// An op with PHYSICAL bit positions, as the planner consumes it.
+struct PhysOp {
+  uint32_t type;
+  int target;       // physical bit; may be >= local_bits (global) for G_DIAG only
+  uint64_t ctrl;    // physical mask (may include global bits)
+  double m[8];
+};
+
+struct PassPlan {
+  std::vector<uint8_t> blob;     // DevPass + gates
+  uint64_t ntiles = 0;
+  int tile_bits = 0, reg_bits = 0;
+  int nrounds = 0, ngates = 0;
+  uint64_t tile_mask = 0;        // physical bits in the tile
+  std::vector<int> op_index;     // indices (into the planner input) of the ops in this pass
+  std::vector<uint64_t> round_regmask;  // physical-bit mask of the register bits per round
+};
+
+struct PlanResult {
+  std::vector<PassPlan> passes;
+  size_t consumed = 0;           // number of input ops that were scheduled
+  std::vector<char> done;        // per input op: scheduled?
+};
+
+// Plan fused passes for `ops` on a shard with `local_bits` local qubits.  Ops that cannot run
+// locally (non-diagonal gate on a global bit) and everything that depends on them are left
+// unscheduled: result.consumed < ops.size(), result.done says which.
+// gscale (may be null) is folded into the last pass.
+PlanResult plan_passes(const std::vector<PhysOp> &ops, int local_bits, int rank, const PlanOptions &opt,
+                       const double *gscale);
+
+std::string describe_plan(const PlanResult &r);
+
+// The per-state op queue with its value-based peephole (host only, device independent):
+//   - scalar * I gates (the reference's u1 / z / s / t / rz) fold
+//     into the deferred global scalar;
+//   - an uncontrolled 1q gate directly following another on the same qubit is merged into it
+//     (2x2 product on the host);
+//   - a controlled-X directly following the identical controlled-X cancels (cx . cx = I).
+struct OpQueue {
+  int n = 0;
+  bool peephole = true;
+  std::vector<HostOp> ops;
+  std::vector<int> last_op;      // per logical bit: last live op touching it, or -1
+  double gscale[2] = {1.0, 0.0};
+  uint64_t submitted = 0, folded = 0;
+
+  void reset(int nqubits, bool peep);
+  void clear();
+  bool empty() const;            // nothing to execute (no live ops, gscale == 1)
+  void mul_gscale(double re, double im);
+  void push_1q(int target_bit, uint64_t ctrl_mask, const double m[8]);
+  void push_kq(const int *bits, int k, const double *m, uint64_t ctrl_mask);
+};
+
+// classification of a caller-supplied 2x2 (value-based)
+struct Classified {
+  uint32_t type;
+  double m[8];        // matrix to execute
+  double phase[2];    // common phase pulled out (multiply into the deferred scalar); (1,0) if none
+  bool is_scalar;     // m == phase * I
+};
+Classified classify_2x2(const double m[8], bool allow_phase_pull);
+
+}  // namespace qb

@@ -1,0 +1,575 @@
+// CUDA kernels of the qubism state-vector backend, written for sm_100a (B200).
+//
+// Hot path: k_fused_pass applies a whole *program* of
+// queued gates in ONE read + ONE write of the amplitude shard.  A CTA owns a tile of 2^T
+// amplitudes selected by T arbitrary physical index bits (the low bits always included so
+// every global access is a run of full 128-byte lines).  Each thread keeps 2^R amplitudes
+// in registers; a "round" fixes which R tile bits are register-resident, every gate whose
+// target is one of them is pure register arithmetic, and between rounds the tile is
+// transposed through XOR-swizzled shared memory (conflict-free 128-bit accesses).
+// Controls never constrain the tile: they are predicates on register index, thread id or
+// tile base.  Diagonal gates can sit on ANY bit.  The kernel is HBM-bound by design:
+// 32 B moved per amplitude per pass no matter how many gates the pass carries.
+//
+// Everything else here is plumbing around that kernel: unfused kernels for shards smaller
+// than a tile and for dense k-qubit blocks, deterministic two-stage reductions for
+// measurement (a13) and <.> (a15), element-wise vector-space kernels (a15/a16).
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+#include "qb_internal.h"
+#include "qb_kernels.h"
+
+namespace qb {
+
+__device__ __forceinline__ uint32_t swz(uint32_t u) {
+  return u ^ ((u >> 3) & 7u) ^ ((u >> 6) & 7u) ^ ((u >> 9) & 7u) ^ ((u >> 12) & 7u);
+}
+
+// ---------------------------------------------------------------- register-resident gates
+// Every gate body exists twice: CTRL = false is the common uncontrolled case (straight-line
+// DFMA code, nothing predicated); CTRL = true predicates each pair on the control masks.
+template <int R, int J, bool CTRL>
+__device__ __forceinline__ void gate_general(double (&re)[1 << R], double (&im)[1 << R], const DevGate &g,
+                                             bool ok_thr) {
+  const double2 A = *reinterpret_cast<const double2 *>(&g.m[0]), B = *reinterpret_cast<const double2 *>(&g.m[2]);
+  const double2 Cc = *reinterpret_cast<const double2 *>(&g.m[4]), D = *reinterpret_cast<const double2 *>(&g.m[6]);
+  const uint32_t creg = CTRL ? g.creg : 0u;
+#pragma unroll
+  for (int p = 0; p < (1 << (R - 1)); ++p) {
+    const int i0 = ((p >> J) << (J + 1)) | (p & ((1 << J) - 1));
+    const int i1 = i0 | (1 << J);
+    if (!CTRL || (ok_thr && ((uint32_t(i0) & creg) == creg))) {
+      const double x0r = re[i0], x0i = im[i0], x1r = re[i1], x1i = im[i1];
+      re[i0] = A.x * x0r - A.y * x0i + B.x * x1r - B.y * x1i;
+      im[i0] = A.x * x0i + A.y * x0r + B.x * x1i + B.y * x1r;
+      re[i1] = Cc.x * x0r - Cc.y * x0i + D.x * x1r - D.y * x1i;
+      im[i1] = Cc.x * x0i + Cc.y * x0r + D.x * x1i + D.y * x1r;
+    }
+  }
+}
+
+template <int R, int J, bool CTRL>
+__device__ __forceinline__ void gate_real(double (&re)[1 << R], double (&im)[1 << R], const DevGate &g,
+                                          bool ok_thr) {
+  const double a = g.m[0], b = g.m[2], c = g.m[4], d = g.m[6];
+  const uint32_t creg = CTRL ? g.creg : 0u;
+#pragma unroll
+  for (int p = 0; p < (1 << (R - 1)); ++p) {
+    const int i0 = ((p >> J) << (J + 1)) | (p & ((1 << J) - 1));
+    const int i1 = i0 | (1 << J);
+    if (!CTRL || (ok_thr && ((uint32_t(i0) & creg) == creg))) {
+      const double x0r = re[i0], x0i = im[i0], x1r = re[i1], x1i = im[i1];
+      re[i0] = a * x0r + b * x1r;
+      im[i0] = a * x0i + b * x1i;
+      re[i1] = c * x0r + d * x1r;
+      im[i1] = c * x0i + d * x1i;
+    }
+  }
+}
+
+template <int R, int J, bool CTRL>
+__device__ __forceinline__ void gate_swap(double (&re)[1 << R], double (&im)[1 << R], const DevGate &g,
+                                          bool ok_thr) {
+  const uint32_t creg = CTRL ? g.creg : 0u;
+#pragma unroll
+  for (int p = 0; p < (1 << (R - 1)); ++p) {
+    const int i0 = ((p >> J) << (J + 1)) | (p & ((1 << J) - 1));
+    const int i1 = i0 | (1 << J);
+    const bool ok = !CTRL || (ok_thr && ((uint32_t(i0) & creg) == creg));
+    const double x0r = re[i0], x0i = im[i0], x1r = re[i1], x1i = im[i1];
+    re[i0] = ok ? x1r : x0r;
+    im[i0] = ok ? x1i : x0i;
+    re[i1] = ok ? x0r : x1r;
+    im[i1] = ok ? x0i : x1i;
+  }
+}
+
+template <int R>
+__device__ __forceinline__ void gate_diag(double (&re)[1 << R], double (&im)[1 << R], const DevGate &g, bool ok_thr,
+                                          bool sel_thr) {
+  const double d0r = g.m[0], d0i = g.m[1], d1r = g.m[6], d1i = g.m[7];
+  const uint32_t creg = g.creg, dreg = g.dreg;
+#pragma unroll
+  for (int i = 0; i < (1 << R); ++i) {
+    const bool one = sel_thr || ((uint32_t(i) & dreg) != 0);
+    const double dr = one ? d1r : d0r, di = one ? d1i : d0i;
+    if (ok_thr && ((uint32_t(i) & creg) == creg)) {
+      const double xr = re[i], xi = im[i];
+      re[i] = dr * xr - di * xi;
+      im[i] = dr * xi + di * xr;
+    }
+  }
+}
+
+// one flat opcode = (type, controlled?, target register bit): a single jump per gate
+#define QB_CASES(TYPE, FN)                                                                      \
+  case (TYPE * 16 + 0): FN<R, 0, false>(re, im, g, true); break;                                \
+  case (TYPE * 16 + 1): FN<R, 1, false>(re, im, g, true); break;                                \
+  case (TYPE * 16 + 2): FN<R, 2, false>(re, im, g, true); break;                                \
+  case (TYPE * 16 + 3): if constexpr (R > 3) FN<R, 3, false>(re, im, g, true); break;           \
+  case (TYPE * 16 + 4): if constexpr (R > 4) FN<R, 4, false>(re, im, g, true); break;           \
+  case (TYPE * 16 + 8): FN<R, 0, true>(re, im, g, ok_thr); break;                               \
+  case (TYPE * 16 + 9): FN<R, 1, true>(re, im, g, ok_thr); break;                               \
+  case (TYPE * 16 + 10): FN<R, 2, true>(re, im, g, ok_thr); break;                              \
+  case (TYPE * 16 + 11): if constexpr (R > 3) FN<R, 3, true>(re, im, g, ok_thr); break;         \
+  case (TYPE * 16 + 12): if constexpr (R > 4) FN<R, 4, true>(re, im, g, ok_thr); break;
+
+template <int R>
+__device__ __forceinline__ void apply_gate(double (&re)[1 << R], double (&im)[1 << R], const DevGate &g, uint32_t tid,
+                                           uint64_t basefull) {
+  const bool ok_thr = ((tid & g.cthr) == g.cthr) && ((basefull & g.cext) == g.cext);
+  const bool ctrl = (g.creg | g.cthr) != 0 || g.cext != 0;
+  const uint32_t op = g.type * 16 + (ctrl ? 8u : 0u) + g.treg;
+  switch (op) {
+    QB_CASES(G_GENERAL, gate_general)
+    QB_CASES(G_REAL, gate_real)
+    QB_CASES(G_SWAP, gate_swap)
+    default:
+      if (g.type == G_DIAG) {
+        const bool sel_thr = ((tid & g.dthr) != 0) || ((basefull & g.dext) != 0);
+        gate_diag<R>(re, im, g, ok_thr, sel_thr);
+      }
+      break;
+  }
+}
+
+// ---------------------------------------------------------------- the fused pass
+template <int T, int R>
+__device__ __forceinline__ uint32_t thread_sidx(const DevRound &rd, uint32_t tid) {
+  uint32_t u = 0;
+#pragma unroll
+  for (int j = 0; j < T - R; ++j) u |= ((tid >> j) & 1u) << rd.tid_pos[j];
+  return swz(u);
+}
+
+template <int T, int R>
+__device__ __forceinline__ uint64_t thread_goff(const DevPass &P, const DevRound &rd, uint32_t tid) {
+  uint64_t o = 0;
+#pragma unroll
+  for (int j = 0; j < T - R; ++j) o |= uint64_t((tid >> j) & 1u) << P.tile_pos[rd.tid_pos[j]];
+  return o;
+}
+
+// The pass program (header + gates) travels as a __grid_constant__ kernel parameter: it lives
+// in the constant bank, is read through the uniform datapath (warp-uniform indices), costs no
+// shared memory, no upload, and no shared-memory round trip per gate.
+struct PassProgram {
+  DevPass hdr;
+  DevGate gates[kMaxPassGates];
+};
+static_assert(sizeof(PassProgram) <= 32000, "kernel parameter space");
+
+template <int T, int R, int MINB>
+__global__ void __launch_bounds__(1 << (T - R), MINB)
+    k_fused_pass(double2 *__restrict__ amps, unsigned long long ntiles, const __grid_constant__ PassProgram prog) {
+  constexpr int NR = 1 << R;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  double2 *tile = reinterpret_cast<double2 *>(smem_raw);
+  const DevPass &P = prog.hdr;
+  const DevGate *G = prog.gates;
+  const uint32_t tid = threadIdx.x;
+  const uint32_t nrounds = P.nrounds;
+  const uint64_t goff_ld = thread_goff<T, R>(P, P.rounds[0], tid);
+  const uint64_t goff_st = thread_goff<T, R>(P, P.rounds[nrounds - 1], tid);
+
+  for (unsigned long long tile_id = blockIdx.x; tile_id < ntiles; tile_id += gridDim.x) {
+    // deposit the tile id into the non-tile bit positions
+    uint64_t base = 0;
+    {
+      uint64_t t = tile_id;
+      const uint32_t nruns = P.nruns;
+      for (uint32_t k = 0; k < nruns; ++k) {
+        const uint32_t len = P.run_len[k];
+        base |= (t & ((1ull << len) - 1ull)) << P.run_shift[k];
+        t >>= len;
+      }
+    }
+    const uint64_t basefull = base | P.rank_bits;
+
+    double re[NR], im[NR];
+    {  // coalesced load: lanes walk the low tile bits, registers stride over the round-0 bits
+      const double2 *src = amps + base + goff_ld;
+      uint64_t st[R];
+#pragma unroll
+      for (int j = 0; j < R; ++j) st[j] = 1ull << P.tile_pos[P.rounds[0].reg_pos[j]];
+#pragma unroll
+      for (int i = 0; i < NR; ++i) {
+        uint64_t off = 0;
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+          if ((i >> j) & 1) off += st[j];
+        const double2 a = __ldcs(src + off);
+        re[i] = a.x;
+        im[i] = a.y;
+      }
+    }
+
+    for (uint32_t r = 0; r < nrounds; ++r) {
+      const DevRound &RD = P.rounds[r];
+      if (r > 0) {  // transpose through swizzled shared memory: new register-resident bits
+        const DevRound &PR = P.rounds[r - 1];
+        const uint32_t us = thread_sidx<T, R>(PR, tid);
+        uint32_t sx[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) sx[j] = PR.reg_sx[j];
+        __syncthreads();  // everyone finished reading the previous layout
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+          uint32_t x = us;
+#pragma unroll
+          for (int j = 0; j < R; ++j)
+            if ((i >> j) & 1) x ^= sx[j];
+          tile[x] = make_double2(re[i], im[i]);
+        }
+        __syncthreads();
+        const uint32_t ul = thread_sidx<T, R>(RD, tid);
+#pragma unroll
+        for (int j = 0; j < R; ++j) sx[j] = RD.reg_sx[j];
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+          uint32_t x = ul;
+#pragma unroll
+          for (int j = 0; j < R; ++j)
+            if ((i >> j) & 1) x ^= sx[j];
+          const double2 a = tile[x];
+          re[i] = a.x;
+          im[i] = a.y;
+        }
+      }
+      const uint32_t gend = RD.gate_end;
+      for (uint32_t gi = RD.gate_begin; gi < gend; ++gi) apply_gate<R>(re, im, G[gi], tid, basefull);
+    }
+
+    if (P.has_gscale) {  // deferred global scalar (folded u1-type phases, qb_scale)
+      const double sr = P.gscale[0], si = P.gscale[1];
+#pragma unroll
+      for (int i = 0; i < NR; ++i) {
+        const double xr = re[i], xi = im[i];
+        re[i] = sr * xr - si * xi;
+        im[i] = sr * xi + si * xr;
+      }
+    }
+    {  // coalesced store with the last round's layout
+      double2 *dst = amps + base + goff_st;
+      uint64_t st[R];
+#pragma unroll
+      for (int j = 0; j < R; ++j) st[j] = 1ull << P.tile_pos[P.rounds[nrounds - 1].reg_pos[j]];
+#pragma unroll
+      for (int i = 0; i < NR; ++i) {
+        uint64_t off = 0;
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+          if ((i >> j) & 1) off += st[j];
+        __stcs(dst + off, make_double2(re[i], im[i]));
+      }
+    }
+  }
+}
+
+struct FusedVariant {
+  int T, R, threads, minb;
+  const void *fn;
+};
+
+#define QB_VARIANT(T_, R_, MINB_) \
+  { T_, R_, 1 << (T_ - R_), MINB_, (const void *)&k_fused_pass<T_, R_, MINB_> }
+
+static const FusedVariant kVariants[] = {
+    QB_VARIANT(10, 3, 4), QB_VARIANT(10, 4, 4), QB_VARIANT(11, 3, 3), QB_VARIANT(11, 4, 4), QB_VARIANT(11, 5, 6),
+    QB_VARIANT(12, 3, 2), QB_VARIANT(12, 4, 2), QB_VARIANT(12, 5, 3), QB_VARIANT(13, 4, 1), QB_VARIANT(13, 5, 1),
+};
+
+static const FusedVariant *find_variant(int T, int R) {
+  for (const auto &v : kVariants)
+    if (v.T == T && v.R == R) return &v;
+  return nullptr;
+}
+
+bool fused_variant_supported(int tile_bits, int reg_bits) { return find_variant(tile_bits, reg_bits) != nullptr; }
+static_assert(sizeof(kVariants) / sizeof(kVariants[0]) == sizeof(kFusedVariants) / sizeof(kFusedVariants[0]), "variant tables out of sync");
+
+cudaError_t launch_fused_pass(double2 *amps, const uint8_t *blob, uint32_t blob_bytes, int tile_bits, int reg_bits,
+                              uint64_t ntiles, int sm_count, cudaStream_t stream, int *grid_out) {
+  const FusedVariant *v = find_variant(tile_bits, reg_bits);
+  if (!v) return cudaErrorInvalidValue;
+  if (blob_bytes > sizeof(PassProgram) || blob_bytes < sizeof(DevPass)) return cudaErrorInvalidValue;
+  static thread_local PassProgram prog;  // the launch copies it into the command buffer
+  memcpy(&prog, blob, blob_bytes);
+  const size_t smem = size_t(16) << tile_bits;
+  cudaError_t e = cudaFuncSetAttribute(v->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int occ = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v->fn, v->threads, smem);
+  if (e != cudaSuccess) return e;
+  if (occ < 1) return cudaErrorLaunchOutOfResources;
+  uint64_t grid = uint64_t(sm_count) * uint64_t(occ);
+  if (grid > ntiles) grid = ntiles;
+  if (grid_out) *grid_out = (int)grid;
+  unsigned long long nt = ntiles;
+  void *args[] = {(void *)&amps, (void *)&nt, (void *)&prog};
+  return cudaLaunchKernel(v->fn, dim3((unsigned)grid), dim3(v->threads), args, smem, stream);
+}
+
+// ---------------------------------------------------------------- unfused kernels
+// One gate, one sweep: shards smaller than a tile, and the `fuse = 0` reference schedule.
+__global__ void __launch_bounds__(256) k_simple_gate(double2 *__restrict__ amps, uint64_t npairs, int tbit,
+                                                     uint64_t cmask, uint64_t rank_bits, uint32_t type,
+                                                     double ar, double ai, double br, double bi, double cr,
+                                                     double ci, double dr, double di) {
+  const uint64_t stride = 1ull << tbit;
+  for (uint64_t p = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; p < npairs;
+       p += uint64_t(gridDim.x) * blockDim.x) {
+    const uint64_t i0 = ((p >> tbit) << (tbit + 1)) | (p & (stride - 1));
+    if (((i0 | rank_bits) & cmask) != cmask) continue;
+    const uint64_t i1 = i0 | stride;
+    const double2 x0 = amps[i0], x1 = amps[i1];
+    double2 y0, y1;
+    if (type == G_SWAP) {
+      y0 = x1;
+      y1 = x0;
+    } else {
+      y0.x = ar * x0.x - ai * x0.y + br * x1.x - bi * x1.y;
+      y0.y = ar * x0.y + ai * x0.x + br * x1.y + bi * x1.x;
+      y1.x = cr * x0.x - ci * x0.y + dr * x1.x - di * x1.y;
+      y1.y = cr * x0.y + ci * x0.x + dr * x1.y + di * x1.x;
+    }
+    amps[i0] = y0;
+    amps[i1] = y1;
+  }
+}
+
+// diagonal gate / controlled scalar with the target anywhere (local or rank bit)
+__global__ void __launch_bounds__(256) k_simple_diag(double2 *__restrict__ amps, uint64_t n, uint64_t tmask,
+                                                     uint64_t cmask, uint64_t rank_bits, double d0r, double d0i,
+                                                     double d1r, double d1i) {
+  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x) {
+    const uint64_t full = i | rank_bits;
+    if ((full & cmask) != cmask) continue;
+    const bool one = (full & tmask) != 0;
+    const double dr = one ? d1r : d0r, di = one ? d1i : d0i;
+    const double2 x = amps[i];
+    amps[i] = make_double2(dr * x.x - di * x.y, dr * x.y + di * x.x);
+  }
+}
+
+// dense 2^K x 2^K block on K arbitrary local bits (QGate.hs:58-59,142-144: kronecker / <> blocks)
+template <int K>
+__global__ void __launch_bounds__(128) k_simple_kq(double2 *__restrict__ amps, uint64_t ngroups, const int *__restrict__ bits_sorted,
+                                                   const int *__restrict__ bits_order, const double2 *__restrict__ mat,
+                                                   uint64_t cmask, uint64_t rank_bits) {
+  constexpr int D = 1 << K;
+  __shared__ double2 ms[D * D];
+  for (int i = threadIdx.x; i < D * D; i += blockDim.x) ms[i] = mat[i];
+  __syncthreads();
+  int sb[K], ob[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    sb[j] = bits_sorted[j];  // ascending physical positions
+    ob[j] = bits_order[j];   // position of matrix index bit j (bit 0 = least significant)
+  }
+  for (uint64_t gidx = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; gidx < ngroups;
+       gidx += uint64_t(gridDim.x) * blockDim.x) {
+    uint64_t base = gidx;
+#pragma unroll
+    for (int j = 0; j < K; ++j) base = ((base >> sb[j]) << (sb[j] + 1)) | (base & ((1ull << sb[j]) - 1));
+    if (((base | rank_bits) & cmask) != cmask) continue;
+    double2 x[D];
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+      uint64_t off = 0;
+#pragma unroll
+      for (int j = 0; j < K; ++j)
+        if ((a >> j) & 1) off |= 1ull << ob[j];
+      x[a] = amps[base | off];
+    }
+#pragma unroll 1
+    for (int row = 0; row < D; ++row) {
+      double yr = 0.0, yi = 0.0;
+#pragma unroll
+      for (int a = 0; a < D; ++a) {
+        const double2 mm = ms[row * D + a];
+        yr += mm.x * x[a].x - mm.y * x[a].y;
+        yi += mm.x * x[a].y + mm.y * x[a].x;
+      }
+      uint64_t off = 0;
+#pragma unroll
+      for (int j = 0; j < K; ++j)
+        if ((row >> j) & 1) off |= 1ull << ob[j];
+      amps[base | off] = make_double2(yr, yi);
+    }
+  }
+}
+
+static int grid_for(uint64_t work, int threads, int sm_count, int per_sm) {
+  uint64_t g = (work + threads - 1) / threads;
+  uint64_t cap = uint64_t(sm_count) * per_sm;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+cudaError_t launch_simple_gate(double2 *amps, int local_bits, int tbit, uint64_t cmask, uint64_t rank_bits,
+                               uint32_t type, const double m[8], int sm_count, cudaStream_t stream) {
+  const uint64_t npairs = 1ull << (local_bits - 1);
+  k_simple_gate<<<grid_for(npairs, 256, sm_count, 8), 256, 0, stream>>>(amps, npairs, tbit, cmask, rank_bits, type,
+                                                                       m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7]);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_simple_diag(double2 *amps, int local_bits, uint64_t tmask, uint64_t cmask, uint64_t rank_bits,
+                               const double d0[2], const double d1[2], int sm_count, cudaStream_t stream) {
+  const uint64_t n = 1ull << local_bits;
+  k_simple_diag<<<grid_for(n, 256, sm_count, 8), 256, 0, stream>>>(amps, n, tmask, cmask, rank_bits, d0[0], d0[1],
+                                                                  d1[0], d1[1]);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_simple_kq(double2 *amps, int local_bits, int k, const int *bits_sorted_dev,
+                             const int *bits_order_dev, const double2 *mat_dev, uint64_t cmask, uint64_t rank_bits,
+                             int sm_count, cudaStream_t stream) {
+  const uint64_t ngroups = 1ull << (local_bits - k);
+  const int g = grid_for(ngroups, 128, sm_count, 8);
+  switch (k) {
+    case 1: k_simple_kq<1><<<g, 128, 0, stream>>>(amps, ngroups, bits_sorted_dev, bits_order_dev, mat_dev, cmask, rank_bits); break;
+    case 2: k_simple_kq<2><<<g, 128, 0, stream>>>(amps, ngroups, bits_sorted_dev, bits_order_dev, mat_dev, cmask, rank_bits); break;
+    case 3: k_simple_kq<3><<<g, 128, 0, stream>>>(amps, ngroups, bits_sorted_dev, bits_order_dev, mat_dev, cmask, rank_bits); break;
+    case 4: k_simple_kq<4><<<g, 128, 0, stream>>>(amps, ngroups, bits_sorted_dev, bits_order_dev, mat_dev, cmask, rank_bits); break;
+    case 5: k_simple_kq<5><<<g, 128, 0, stream>>>(amps, ngroups, bits_sorted_dev, bits_order_dev, mat_dev, cmask, rank_bits); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- reductions (deterministic)
+// Stage 1: fixed grid, grid-stride in a fixed order, warp shuffles, one partial per block.
+// Stage 2: one block folds the partials in a fixed tree.  No floating-point atomics, so the
+// result is run-to-run identical for a given grid (SURVEY.md 7.2 "determinism").
+constexpr int kRedThreads = 256;
+
+template <int NV>
+__device__ __forceinline__ void block_reduce_store(double (&v)[NV], double *__restrict__ out) {
+  __shared__ double sh[NV][kRedThreads / 32];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_down_sync(0xffffffffu, v[k], o);
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) sh[k][w] = v[k];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      double s = 0.0;
+      for (int i = 0; i < kRedThreads / 32; ++i) s += sh[k][i];
+      out[k] = s;
+    }
+  }
+}
+
+// partials[block][2] = (S0, S1) by the value of physical bit `bit` (bit < 0: everything in S0)
+__global__ void __launch_bounds__(kRedThreads) k_sumsq_partial(const double2 *__restrict__ amps, uint64_t n, int bit,
+                                                              double *__restrict__ partials) {
+  double acc[2] = {0.0, 0.0};
+  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < n; i += stride) {
+    const double2 z = __ldcs(amps + i);
+    const double w = z.x * z.x + z.y * z.y;
+    if (bit >= 0 && ((i >> bit) & 1ull)) acc[1] += w; else acc[0] += w;
+  }
+  block_reduce_store<2>(acc, partials + 2 * blockIdx.x);
+}
+
+// a <.> b with the first argument conjugated (StateVec.hs:57-58).  The imaginary part is
+// formed from separately rounded products so that <a,b> == conj <b,a> holds EXACTLY
+// (test/Qubism/AlgebraTests.hs:43-47): no FMA contraction across the antisymmetric pair.
+__global__ void __launch_bounds__(kRedThreads) k_dotc_partial(const double2 *__restrict__ a, const double2 *__restrict__ b,
+                                                             uint64_t n, double *__restrict__ partials) {
+  double acc[2] = {0.0, 0.0};
+  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < n; i += stride) {
+    const double2 x = __ldcs(a + i), y = __ldcs(b + i);
+    acc[0] = __dadd_rn(acc[0], __dadd_rn(__dmul_rn(x.x, y.x), __dmul_rn(x.y, y.y)));
+    acc[1] = __dadd_rn(acc[1], __dsub_rn(__dmul_rn(x.x, y.y), __dmul_rn(x.y, y.x)));
+  }
+  block_reduce_store<2>(acc, partials + 2 * blockIdx.x);
+}
+
+__global__ void __launch_bounds__(kRedThreads) k_reduce_final(const double *__restrict__ partials, int nblocks,
+                                                             double *__restrict__ out) {
+  double acc[2] = {0.0, 0.0};
+  for (int i = threadIdx.x; i < nblocks; i += kRedThreads) {
+    acc[0] += partials[2 * i];
+    acc[1] += partials[2 * i + 1];
+  }
+  block_reduce_store<2>(acc, out);
+}
+
+int reduce_grid(uint64_t n, int sm_count) { return grid_for(n, kRedThreads * 4, sm_count, 8); }
+
+cudaError_t launch_sumsq(const double2 *amps, uint64_t n, int bit, double *partials_dev, double *out_dev, int sm_count,
+                         cudaStream_t stream) {
+  const int g = reduce_grid(n, sm_count);
+  k_sumsq_partial<<<g, kRedThreads, 0, stream>>>(amps, n, bit, partials_dev);
+  k_reduce_final<<<1, kRedThreads, 0, stream>>>(partials_dev, g, out_dev);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_dotc(const double2 *a, const double2 *b, uint64_t n, double *partials_dev, double *out_dev,
+                        int sm_count, cudaStream_t stream) {
+  const int g = reduce_grid(n, sm_count);
+  k_dotc_partial<<<g, kRedThreads, 0, stream>>>(a, b, n, partials_dev);
+  k_reduce_final<<<1, kRedThreads, 0, stream>>>(partials_dev, g, out_dev);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- element-wise kernels
+__global__ void __launch_bounds__(256) k_axpy(double2 *__restrict__ y, const double2 *__restrict__ x, uint64_t n,
+                                              double zr, double zi) {
+  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x) {
+    const double2 a = x[i];
+    double2 b = y[i];
+    b.x += zr * a.x - zi * a.y;
+    b.y += zr * a.y + zi * a.x;
+    y[i] = b;
+  }
+}
+
+// out[i * nb + j] = a[i] * b[j]  (StateVec.hs:98-100, flatten (outer a b), no conjugation)
+__global__ void __launch_bounds__(256) k_tensor(double2 *__restrict__ out, const double2 *__restrict__ a,
+                                                const double2 *__restrict__ b, uint64_t n, int bbits) {
+  const uint64_t bmask = (1ull << bbits) - 1;
+  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x) {
+    const double2 x = a[i >> bbits], y = b[i & bmask];
+    out[i] = make_double2(x.x * y.x - x.y * y.y, x.x * y.y + x.y * y.x);
+  }
+}
+
+__global__ void k_set_amp(double2 *amps, uint64_t idx, double re, double im) { amps[idx] = make_double2(re, im); }
+
+cudaError_t launch_axpy(double2 *y, const double2 *x, uint64_t n, const double z[2], int sm_count,
+                        cudaStream_t stream) {
+  k_axpy<<<grid_for(n, 256, sm_count, 8), 256, 0, stream>>>(y, x, n, z[0], z[1]);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_tensor(double2 *out, const double2 *a, const double2 *b, int abits, int bbits, int sm_count,
+                          cudaStream_t stream) {
+  const uint64_t n = 1ull << (abits + bbits);
+  k_tensor<<<grid_for(n, 256, sm_count, 8), 256, 0, stream>>>(out, a, b, n, bbits);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_set_amp(double2 *amps, uint64_t idx, double re, double im, cudaStream_t stream) {
+  k_set_amp<<<1, 1, 0, stream>>>(amps, idx, re, im);
+  return cudaGetLastError();
+}
+
+}  // namespace qb

@@ -1,0 +1,39 @@
+// Host-callable launchers for the kernels in qb_kernels.cu.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace qb {
+
+bool fused_variant_supported(int tile_bits, int reg_bits);
+
+// One fused pass: `blob` is the planner's HOST DevPass blob (header + gates); it is passed to
+// the kernel by value as a __grid_constant__ parameter.  Persistent grid = SMs x resident
+// CTAs/SM (capped at ntiles).
+cudaError_t launch_fused_pass(double2 *amps, const uint8_t *blob, uint32_t blob_bytes, int tile_bits, int reg_bits,
+                              uint64_t ntiles, int sm_count, cudaStream_t stream, int *grid_out);
+
+cudaError_t launch_simple_gate(double2 *amps, int local_bits, int tbit, uint64_t cmask, uint64_t rank_bits,
+                               uint32_t type, const double m[8], int sm_count, cudaStream_t stream);
+cudaError_t launch_simple_diag(double2 *amps, int local_bits, uint64_t tmask, uint64_t cmask, uint64_t rank_bits,
+                               const double d0[2], const double d1[2], int sm_count, cudaStream_t stream);
+cudaError_t launch_simple_kq(double2 *amps, int local_bits, int k, const int *bits_sorted_dev,
+                             const int *bits_order_dev, const double2 *mat_dev, uint64_t cmask, uint64_t rank_bits,
+                             int sm_count, cudaStream_t stream);
+
+int reduce_grid(uint64_t n, int sm_count);
+// out_dev[0..1] = (S0, S1) split by physical bit `bit` (bit < 0: total in S0).
+cudaError_t launch_sumsq(const double2 *amps, uint64_t n, int bit, double *partials_dev, double *out_dev, int sm_count,
+                         cudaStream_t stream);
+// out_dev[0..1] = (re, im) of sum conj(a_k) b_k.
+cudaError_t launch_dotc(const double2 *a, const double2 *b, uint64_t n, double *partials_dev, double *out_dev,
+                        int sm_count, cudaStream_t stream);
+
+cudaError_t launch_axpy(double2 *y, const double2 *x, uint64_t n, const double z[2], int sm_count,
+                        cudaStream_t stream);
+cudaError_t launch_tensor(double2 *out, const double2 *a, const double2 *b, int abits, int bbits, int sm_count,
+                          cudaStream_t stream);
+cudaError_t launch_set_amp(double2 *amps, uint64_t idx, double re, double im, cudaStream_t stream);
+
+}  // namespace qb

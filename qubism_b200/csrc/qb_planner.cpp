@@ -1,0 +1,558 @@
+// Host-side pass planner: turns a list of queued gates into fused-pass programs.
+//
+// The reference evaluator issues one `#>` per primitive op (QASM/Simulation.hs:94-122), each
+// a full sweep of the state.  Behind the C ABI the ops are queued and this planner groups
+// them so that one sweep of HBM carries as many of them as dependencies and the tile
+// geometry allow.  Pure host logic: unit-tested on the CPU through
+// qb_plan_describe and the numpy plan emulator in tests/.
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <sstream>
+
+#include "qb_internal.h"
+
+namespace qb {
+
+static inline int popc(uint64_t x) { return __builtin_popcountll(x); }
+
+// --------------------------------------------------------------------- options
+bool variant_supported(int T, int R) {
+  for (const auto &v : kFusedVariants)
+    if (v.T == T && v.R == R) return true;
+  return false;
+}
+
+bool set_opt(PlanOptions &o, const std::string &name, int64_t v) {
+  if (name == "tile_bits") {
+    if (v < 10 || v > kMaxTileBits) return false;
+    o.tile_bits = (int)v;
+  } else if (name == "reg_bits") {
+    if (v < 3 || v > kMaxRegBits) return false;
+    o.reg_bits = (int)v;
+  } else if (name == "low_bits") {
+    if (v < kLaneFixedBits || v > 10) return false;
+    o.low_bits = (int)v;
+  } else if (name == "max_rounds") {
+    if (v < 3 || v > kMaxRounds) return false;
+    o.max_rounds = (int)v;
+  } else if (name == "peephole") {
+    o.peephole = v ? 1 : 0;
+  } else if (name == "fuse") {
+    o.fuse = v ? 1 : 0;
+  } else if (name == "max_pass_gates") {
+    if (v < 1 || v > kMaxPassGates) return false;
+    o.max_pass_gates = (int)v;
+  } else {
+    return false;
+  }
+  return true;
+}
+
+int64_t get_opt(const PlanOptions &o, const std::string &name) {
+  if (name == "tile_bits") return o.tile_bits;
+  if (name == "reg_bits") return o.reg_bits;
+  if (name == "low_bits") return o.low_bits;
+  if (name == "max_rounds") return o.max_rounds;
+  if (name == "peephole") return o.peephole;
+  if (name == "fuse") return o.fuse;
+  if (name == "max_pass_gates") return o.max_pass_gates;
+  return -1;
+}
+
+// effective (T, R) for a shard with L local bits; T = 0 -> unfused kernels only
+void effective_tile(const PlanOptions &o, int L, int &T, int &R) {
+  T = std::min(o.tile_bits, L);
+  R = o.reg_bits;
+  if (T < 10) {
+    T = 0;
+    return;
+  }
+  if (variant_supported(T, R)) return;
+  for (int r : {4, 3, 5})
+    if (variant_supported(T, r)) {
+      R = r;
+      return;
+    }
+  T = 0;
+}
+
+// --------------------------------------------------------------------- classification
+Classified classify_2x2(const double m[8], bool allow_phase_pull) {
+  Classified c{};
+  std::memcpy(c.m, m, sizeof(c.m));
+  c.phase[0] = 1.0;
+  c.phase[1] = 0.0;
+  c.is_scalar = false;
+  c.type = G_GENERAL;
+  const bool b0 = (m[2] == 0.0 && m[3] == 0.0), c0 = (m[4] == 0.0 && m[5] == 0.0);
+  const bool a0 = (m[0] == 0.0 && m[1] == 0.0), d0 = (m[6] == 0.0 && m[7] == 0.0);
+  if (b0 && c0) {
+    c.type = G_DIAG;
+    c.is_scalar = (m[0] == m[6] && m[1] == m[7]);
+    return c;
+  }
+  if (a0 && d0 && m[2] == 1.0 && m[3] == 0.0 && m[4] == 1.0 && m[5] == 0.0) {
+    c.type = G_SWAP;
+    return c;
+  }
+  bool all_real = (m[1] == 0.0 && m[3] == 0.0 && m[5] == 0.0 && m[7] == 0.0);
+  if (all_real) {
+    c.type = G_REAL;
+    return c;
+  }
+  if (!allow_phase_pull) return c;
+  // m = s * r with r real?  s = phase of the largest entry; the residual imaginary parts must
+  // vanish to a few ulp (they are rounding noise of cis(phi)*cos(theta/2)-style products).
+  int big = 0;
+  double bigabs = 0.0;
+  for (int i = 0; i < 4; ++i) {
+    const double a = std::hypot(m[2 * i], m[2 * i + 1]);
+    if (a > bigabs) {
+      bigabs = a;
+      big = i;
+    }
+  }
+  if (!(bigabs > 0.0) || !std::isfinite(bigabs)) return c;
+  const double sr = m[2 * big] / bigabs, si = m[2 * big + 1] / bigabs;
+  const double tol = 4.0 * DBL_EPSILON * bigabs;
+  double r[4];
+  for (int i = 0; i < 4; ++i) {
+    const double xr = m[2 * i], xi = m[2 * i + 1];
+    const double yr = xr * sr + xi * si;   // x * conj(s)
+    const double yi = xi * sr - xr * si;
+    if (!(std::fabs(yi) <= tol)) return c;
+    r[i] = yr;
+  }
+  c.type = G_REAL;
+  for (int i = 0; i < 4; ++i) {
+    c.m[2 * i] = r[i];
+    c.m[2 * i + 1] = 0.0;
+  }
+  c.phase[0] = sr;
+  c.phase[1] = si;
+  return c;
+}
+
+// --------------------------------------------------------------------- op queue + peephole
+void OpQueue::reset(int nqubits, bool peep) {
+  n = nqubits;
+  peephole = peep;
+  clear();
+}
+
+void OpQueue::clear() {
+  ops.clear();
+  last_op.assign(n > 0 ? n : 0, -1);
+  gscale[0] = 1.0;
+  gscale[1] = 0.0;
+}
+
+bool OpQueue::empty() const {
+  if (!(gscale[0] == 1.0 && gscale[1] == 0.0)) return false;
+  for (const auto &o : ops)
+    if (!o.dead) return false;
+  return true;
+}
+
+void OpQueue::mul_gscale(double re, double im) {
+  const double r = gscale[0] * re - gscale[1] * im;
+  const double i = gscale[0] * im + gscale[1] * re;
+  gscale[0] = r;
+  gscale[1] = i;
+}
+
+static void link_op(OpQueue &q, HostOp &op, int idx, uint64_t qmask) {
+  op.nprev = 0;
+  for (uint64_t b = qmask; b; b &= b - 1) {
+    const int bit = __builtin_ctzll(b);
+    if (op.nprev < 6) {
+      op.prev_bit[op.nprev] = bit;
+      op.prev_idx[op.nprev] = q.last_op[bit];
+      ++op.nprev;
+    } else {
+      op.nprev = 7;  // too many qubits to unlink later: never cancelled
+    }
+    q.last_op[bit] = idx;
+  }
+}
+
+static void unlink_op(OpQueue &q, HostOp &op) {
+  op.dead = true;
+  for (int i = 0; i < op.nprev && i < 6; ++i) q.last_op[op.prev_bit[i]] = op.prev_idx[i];
+}
+
+static void mat2_mul(const double a[8], const double b[8], double out[8]) {  // out = a * b
+  auto cm = [](double xr, double xi, double yr, double yi, double &zr, double &zi) {
+    zr = xr * yr - xi * yi;
+    zi = xr * yi + xi * yr;
+  };
+  for (int r = 0; r < 2; ++r)
+    for (int c = 0; c < 2; ++c) {
+      double p0r, p0i, p1r, p1i;
+      cm(a[(2 * r) * 2], a[(2 * r) * 2 + 1], b[c * 2], b[c * 2 + 1], p0r, p0i);
+      cm(a[(2 * r + 1) * 2], a[(2 * r + 1) * 2 + 1], b[(2 + c) * 2], b[(2 + c) * 2 + 1], p1r, p1i);
+      out[(2 * r + c) * 2] = p0r + p1r;
+      out[(2 * r + c) * 2 + 1] = p0i + p1i;
+    }
+}
+
+void OpQueue::push_1q(int target_bit, uint64_t ctrl_mask, const double m[8]) {
+  ++submitted;
+  Classified c = classify_2x2(m, peephole && ctrl_mask == 0);
+  const uint64_t qmask = ctrl_mask | (1ull << target_bit);
+  if (peephole) {
+    if (ctrl_mask == 0) {
+      if (c.type == G_DIAG && c.is_scalar) {  // scalar * I: a global factor (reference u1 family)
+        mul_gscale(m[0], m[1]);
+        ++folded;
+        return;
+      }
+      if (!(c.phase[0] == 1.0 && c.phase[1] == 0.0)) mul_gscale(c.phase[0], c.phase[1]);
+      const int li = last_op[target_bit];
+      if (li >= 0 && !ops[li].dead && ops[li].kind == 0 && ops[li].ctrl == 0 && ops[li].target == target_bit &&
+          ops[li].nprev <= 6) {
+        double prod[8];
+        mat2_mul(c.m, ops[li].m, prod);
+        Classified pc = classify_2x2(prod, true);
+        ++folded;
+        if (pc.type == G_DIAG && pc.is_scalar) {
+          mul_gscale(prod[0], prod[1]);
+          unlink_op(*this, ops[li]);
+          ++folded;
+        } else {
+          if (!(pc.phase[0] == 1.0 && pc.phase[1] == 0.0)) mul_gscale(pc.phase[0], pc.phase[1]);
+          std::memcpy(ops[li].m, pc.m, sizeof(pc.m));
+          ops[li].type = pc.type;
+        }
+        return;
+      }
+    } else if (c.type == G_SWAP) {
+      const int li = last_op[target_bit];
+      if (li >= 0 && !ops[li].dead && ops[li].kind == 0 && ops[li].type == G_SWAP && ops[li].target == target_bit &&
+          ops[li].ctrl == ctrl_mask && ops[li].nprev <= 6) {
+        bool adjacent = true;
+        for (uint64_t b = ctrl_mask; b; b &= b - 1)
+          if (last_op[__builtin_ctzll(b)] != li) adjacent = false;
+        if (adjacent) {  // cx . cx = identity
+          unlink_op(*this, ops[li]);
+          folded += 2;
+          return;
+        }
+      }
+    }
+  }
+  HostOp op;
+  op.kind = 0;
+  op.type = c.type;
+  op.target = target_bit;
+  op.ctrl = ctrl_mask;
+  std::memcpy(op.m, c.m, sizeof(c.m));
+  const int idx = (int)ops.size();
+  link_op(*this, op, idx, qmask);
+  ops.push_back(std::move(op));
+}
+
+void OpQueue::push_kq(const int *bits, int k, const double *m, uint64_t ctrl_mask) {
+  ++submitted;
+  HostOp op;
+  op.kind = 2;
+  op.k = k;
+  op.ctrl = ctrl_mask;
+  uint64_t qmask = ctrl_mask;
+  for (int i = 0; i < k; ++i) {
+    op.kq_bits[i] = bits[i];
+    qmask |= 1ull << bits[i];
+  }
+  op.target = bits[0];
+  op.kq_m.assign(m, m + (size_t(2) << (2 * k)));
+  const int idx = (int)ops.size();
+  link_op(*this, op, idx, qmask);
+  op.nprev = 7;  // never merged / cancelled
+  ops.push_back(std::move(op));
+}
+
+// --------------------------------------------------------------------- one pass
+namespace {
+
+struct RoundTmp {
+  uint64_t regmask = 0;          // physical bits
+  std::vector<int> ops;          // op indices, program order
+};
+
+int tile_local_index(const std::vector<int> &tile_bits, int phys) {
+  for (size_t i = 0; i < tile_bits.size(); ++i)
+    if (tile_bits[i] == phys) return (int)i;
+  return -1;
+}
+
+}  // namespace
+
+static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &done, int L, int rank,
+                          const PlanOptions &opt, PassPlan &out) {
+  const int T = opt.tile_bits, R = opt.reg_bits;
+  const int C = std::min(std::max(opt.low_bits, kLaneFixedBits), T);
+  const int max_rounds = std::max(1, std::min(opt.max_rounds, kMaxRounds));
+  const int max_gates = std::max(1, std::min(opt.max_pass_gates, kMaxPassGates));
+  uint64_t tile_mask = (1ull << C) - 1;
+  int ntile = C;
+  uint64_t blocked = 0;
+  const uint64_t lowfixed = (1ull << kLaneFixedBits) - 1;
+  std::vector<RoundTmp> rounds;
+  int lastround[64];
+  std::fill(lastround, lastround + 64, 0);
+  std::vector<std::pair<int, int>> chosen;  // (op index, round)
+  const uint64_t allq = ~0ull;
+  (void)allq;
+
+  for (size_t i = 0; i < ops.size() && (int)chosen.size() < max_gates; ++i) {
+    if (done[i]) continue;
+    const PhysOp &op = ops[i];
+    const uint64_t tb = 1ull << op.target;
+    const uint64_t qmask = op.ctrl | tb;
+    if (qmask & blocked) {
+      blocked |= qmask;
+      continue;
+    }
+    int r0 = 0;
+    for (uint64_t q = qmask; q; q &= q - 1) r0 = std::max(r0, lastround[__builtin_ctzll(q)]);
+    int place = -1;
+    if (op.type == G_DIAG) {
+      place = r0;
+      if ((int)rounds.size() <= place) rounds.resize(place + 1);
+    } else {
+      if (op.target >= L) {  // needs a global<->local swap first
+        blocked |= qmask;
+        continue;
+      }
+      const bool in_tile = (tile_mask & tb) != 0;
+      if (!in_tile && ntile >= T) {
+        blocked |= qmask;
+        continue;
+      }
+      for (int r = r0; r < max_rounds; ++r) {
+        const bool edge = (r == 0) || (r == max_rounds - 1);  // load round / last possible store round
+        if (edge && (tb & lowfixed)) continue;
+        while ((int)rounds.size() <= r) rounds.emplace_back();
+        RoundTmp &rd = rounds[r];
+        if ((rd.regmask & tb) || popc(rd.regmask) < R) {
+          place = r;
+          break;
+        }
+      }
+      if (place < 0) {
+        // drop trailing empty rounds the search may have appended
+        while (!rounds.empty() && rounds.back().ops.empty() && rounds.back().regmask == 0 &&
+               (int)rounds.size() > 1)
+          rounds.pop_back();
+        blocked |= qmask;
+        continue;
+      }
+      rounds[place].regmask |= tb;
+      if (!in_tile) {
+        tile_mask |= tb;
+        ++ntile;
+      }
+    }
+    rounds[place].ops.push_back((int)i);
+    chosen.emplace_back((int)i, place);
+    for (uint64_t q = qmask; q; q &= q - 1) lastround[__builtin_ctzll(q)] = place;
+  }
+  if (chosen.empty()) return false;
+  while ((int)rounds.size() > 1 && rounds.back().ops.empty()) rounds.pop_back();
+  // the store round may not keep bits 0..2 in registers
+  if (rounds.back().regmask & lowfixed) rounds.emplace_back();
+  if (rounds[0].regmask & lowfixed) return false;  // cannot happen (edge rule), defensive
+
+  // fill the tile with the lowest unused local bits
+  for (int b = 0; b < L && ntile < T; ++b)
+    if (!(tile_mask & (1ull << b))) {
+      tile_mask |= 1ull << b;
+      ++ntile;
+    }
+  std::vector<int> tile_bits;
+  for (int b = 0; b < L; ++b)
+    if (tile_mask & (1ull << b)) tile_bits.push_back(b);
+
+  const int nrounds = (int)rounds.size();
+  // fill every round's register set to exactly R bits (highest free tile bits first)
+  for (int r = 0; r < nrounds; ++r) {
+    const bool edge = (r == 0) || (r == nrounds - 1);
+    for (int i = T - 1; i >= 0 && popc(rounds[r].regmask) < R; --i) {
+      const uint64_t b = 1ull << tile_bits[i];
+      if (rounds[r].regmask & b) continue;
+      if (edge && (b & lowfixed)) continue;
+      rounds[r].regmask |= b;
+    }
+  }
+
+  out = PassPlan();
+  out.tile_bits = T;
+  out.reg_bits = R;
+  out.nrounds = nrounds;
+  out.ngates = (int)chosen.size();
+  out.tile_mask = tile_mask;
+  out.ntiles = 1ull << (L - T);
+  out.blob.assign(pass_bytes((uint32_t)chosen.size()), 0);
+  DevPass *P = reinterpret_cast<DevPass *>(out.blob.data());
+  DevGate *G = reinterpret_cast<DevGate *>(out.blob.data() + sizeof(DevPass));
+  P->nrounds = nrounds;
+  P->ngates = (uint32_t)chosen.size();
+  P->tile_bits = T;
+  P->reg_bits = R;
+  P->local_bits = L;
+  P->rank_bits = uint64_t(rank) << L;
+  P->gscale[0] = 1.0;
+  P->gscale[1] = 0.0;
+  P->has_gscale = 0;
+  for (int i = 0; i < T; ++i) P->tile_pos[i] = (uint8_t)tile_bits[i];
+  {  // runs of non-tile local bits, ascending
+    uint32_t nruns = 0;
+    int b = 0;
+    while (b < L) {
+      if (tile_mask & (1ull << b)) {
+        ++b;
+        continue;
+      }
+      int e = b;
+      while (e < L && !(tile_mask & (1ull << e))) ++e;
+      P->run_shift[nruns] = b;
+      P->run_len[nruns] = e - b;
+      ++nruns;
+      b = e;
+    }
+    P->nruns = nruns;
+  }
+
+  uint32_t gcount = 0;
+  for (int r = 0; r < nrounds; ++r) {
+    DevRound &RD = P->rounds[r];
+    const bool edge = (r == 0) || (r == nrounds - 1);
+    RD.nthr_bits = T - R;
+    // register bits ascending
+    std::vector<int> regs, thr;
+    for (int i = 0; i < T; ++i) {
+      if (rounds[r].regmask & (1ull << tile_bits[i])) regs.push_back(i);
+      else thr.push_back(i);
+    }
+    // thread-id bit order: load/store rounds keep ascending order (lanes on the lowest bits =
+    // contiguous 128-byte lines).  Inner rounds put three positions with distinct residues
+    // mod 3 first so that each quarter-warp's 128-bit shared accesses hit 8 distinct bank
+    // groups under the XOR swizzle.
+    std::vector<int> order;
+    if (edge) {
+      order = thr;
+    } else {
+      std::vector<int> rest = thr;
+      int pick[3] = {-1, -1, -1};
+      for (int res_needed = 0; res_needed < 3; ++res_needed) {
+        // choose, for each residue, the lowest thread position with that residue
+        for (size_t k = 0; k < rest.size(); ++k)
+          if (rest[k] % 3 == res_needed) {
+            pick[res_needed] = rest[k];
+            rest.erase(rest.begin() + k);
+            break;
+          }
+      }
+      bool ok = pick[0] >= 0 && pick[1] >= 0 && pick[2] >= 0;
+      if (ok) {
+        std::sort(pick, pick + 3);
+        order.assign(pick, pick + 3);
+        order.insert(order.end(), rest.begin(), rest.end());
+      } else {
+        order = thr;
+      }
+    }
+    for (int j = 0; j < T - R; ++j) RD.tid_pos[j] = (uint8_t)order[j];
+    for (int j = 0; j < R; ++j) {
+      RD.reg_pos[j] = (uint8_t)regs[j];
+      RD.reg_sx[j] = swz_host(1u << regs[j]);
+    }
+    RD.gate_begin = gcount;
+    for (int oi : rounds[r].ops) {
+      const PhysOp &op = ops[oi];
+      DevGate &g = G[gcount++];
+      std::memcpy(g.m, op.m, sizeof(g.m));
+      g.type = op.type;
+      auto place_bit = [&](int phys, uint32_t &mreg, uint32_t &mthr, uint64_t &mext) {
+        const int tl = (phys < L) ? tile_local_index(tile_bits, phys) : -1;
+        if (tl < 0) {
+          mext |= 1ull << phys;
+          return;
+        }
+        for (int j = 0; j < R; ++j)
+          if (regs[j] == tl) {
+            mreg |= 1u << j;
+            return;
+          }
+        for (int j = 0; j < T - R; ++j)
+          if (order[j] == tl) {
+            mthr |= 1u << j;
+            return;
+          }
+      };
+      for (uint64_t q = op.ctrl; q; q &= q - 1) place_bit(__builtin_ctzll(q), g.creg, g.cthr, g.cext);
+      if (op.type == G_DIAG) {
+        place_bit(op.target, g.dreg, g.dthr, g.dext);
+      } else {
+        uint32_t treg_mask = 0, tthr = 0;
+        uint64_t text = 0;
+        place_bit(op.target, treg_mask, tthr, text);
+        g.treg = treg_mask ? (uint32_t)__builtin_ctz(treg_mask) : 0xffffffffu;  // must be a register bit
+      }
+      out.op_index.push_back(oi);
+    }
+    RD.gate_end = gcount;
+    out.round_regmask.push_back(rounds[r].regmask);
+  }
+  for (auto &pr : chosen) done[pr.first] = 1;
+  return true;
+}
+
+PlanResult plan_passes(const std::vector<PhysOp> &ops, int local_bits, int rank, const PlanOptions &opt,
+                       const double *gscale) {
+  PlanResult res;
+  std::vector<char> done(ops.size(), 0);
+  size_t ndone = 0;
+  while (ndone < ops.size()) {
+    PassPlan p;
+    if (!plan_one_pass(ops, done, local_bits, rank, opt, p)) break;
+    ndone += p.op_index.size();
+    res.passes.push_back(std::move(p));
+  }
+  res.consumed = ndone;
+  res.done = done;
+  if (gscale && !res.passes.empty() && !(gscale[0] == 1.0 && gscale[1] == 0.0)) {
+    DevPass *P = reinterpret_cast<DevPass *>(res.passes.back().blob.data());
+    P->gscale[0] = gscale[0];
+    P->gscale[1] = gscale[1];
+    P->has_gscale = 1;
+  }
+  return res;
+}
+
+std::string describe_plan(const PlanResult &r) {
+  std::ostringstream os;
+  os << "passes=" << r.passes.size() << " scheduled=" << r.consumed << "\n";
+  for (size_t i = 0; i < r.passes.size(); ++i) {
+    const PassPlan &p = r.passes[i];
+    const DevPass *P = reinterpret_cast<const DevPass *>(p.blob.data());
+    os << "pass " << i << " T=" << p.tile_bits << " R=" << p.reg_bits << " tiles=" << p.ntiles << " tile=[";
+    for (int b = 0; b < p.tile_bits; ++b) os << (b ? "," : "") << (int)P->tile_pos[b];
+    os << "] rounds=" << p.nrounds << " gates=" << p.ngates << " gscale=" << P->has_gscale << "\n";
+    for (int rd = 0; rd < p.nrounds; ++rd) {
+      const DevRound &RD = P->rounds[rd];
+      os << "  round " << rd << " regs=[";
+      for (int j = 0; j < p.reg_bits; ++j) os << (j ? "," : "") << (int)P->tile_pos[RD.reg_pos[j]];
+      os << "] tid=[";
+      for (int j = 0; j < p.tile_bits - p.reg_bits; ++j) os << (j ? "," : "") << (int)P->tile_pos[RD.tid_pos[j]];
+      os << "] ops=[";
+      for (uint32_t g = RD.gate_begin; g < RD.gate_end; ++g) os << (g > RD.gate_begin ? "," : "") << p.op_index[g];
+      os << "]\n";
+    }
+  }
+  return os.str();
+}
+
+}  // namespace qb

@@ -1,0 +1,240 @@
+// TEST INFRASTRUCTURE: a host emulator of k_fused_pass.
+//
+// Executes the planner's DevPass programs thread by thread exactly as the CUDA kernel is
+// specified to (tile deposit, register/thread/external bit split, XOR-swizzled shared-memory
+// transposes, gate predicates), so that planner and program-encoding bugs are caught on a
+// CPU-only box, and so that the shared-memory bank behaviour of every transpose can be
+// counted.  It is NOT part of libqubism_sv.so and nothing in qubism_b200 can reach it.
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../qubism_b200/csrc/qb_internal.h"
+
+using namespace qb;
+
+namespace {
+
+struct EmuStats {
+  int64_t passes = 0, rounds = 0, gates = 0, max_bank_conflict = 1;
+};
+
+void apply_gate_host(std::vector<double> &re, std::vector<double> &im, int R, const DevGate &g, uint32_t tid,
+                     uint64_t basefull) {
+  const bool ok_thr = ((tid & g.cthr) == g.cthr) && ((basefull & g.cext) == g.cext);
+  const int NR = 1 << R;
+  if (g.type == G_DIAG) {
+    const bool sel_thr = ((tid & g.dthr) != 0) || ((basefull & g.dext) != 0);
+    for (int i = 0; i < NR; ++i) {
+      const bool one = sel_thr || ((uint32_t(i) & g.dreg) != 0);
+      const double dr = one ? g.m[6] : g.m[0], di = one ? g.m[7] : g.m[1];
+      if (ok_thr && ((uint32_t(i) & g.creg) == g.creg)) {
+        const double xr = re[i], xi = im[i];
+        re[i] = dr * xr - di * xi;
+        im[i] = dr * xi + di * xr;
+      }
+    }
+    return;
+  }
+  const int J = (int)g.treg;
+  if (J < 0 || J >= R) {
+    std::fprintf(stderr, "emulator: gate target is not a register bit (treg=%u)\n", g.treg);
+    re[0] = NAN;
+    return;
+  }
+  for (int p = 0; p < NR / 2; ++p) {
+    const int i0 = ((p >> J) << (J + 1)) | (p & ((1 << J) - 1));
+    const int i1 = i0 | (1 << J);
+    if (!(ok_thr && ((uint32_t(i0) & g.creg) == g.creg))) continue;
+    const double x0r = re[i0], x0i = im[i0], x1r = re[i1], x1i = im[i1];
+    if (g.type == G_SWAP) {
+      re[i0] = x1r; im[i0] = x1i; re[i1] = x0r; im[i1] = x0i;
+    } else if (g.type == G_REAL) {
+      re[i0] = g.m[0] * x0r + g.m[2] * x1r;
+      im[i0] = g.m[0] * x0i + g.m[2] * x1i;
+      re[i1] = g.m[4] * x0r + g.m[6] * x1r;
+      im[i1] = g.m[4] * x0i + g.m[6] * x1i;
+    } else {
+      re[i0] = g.m[0] * x0r - g.m[1] * x0i + g.m[2] * x1r - g.m[3] * x1i;
+      im[i0] = g.m[0] * x0i + g.m[1] * x0r + g.m[2] * x1i + g.m[3] * x1r;
+      re[i1] = g.m[4] * x0r - g.m[5] * x0i + g.m[6] * x1r - g.m[7] * x1i;
+      im[i1] = g.m[4] * x0i + g.m[5] * x0r + g.m[6] * x1i + g.m[7] * x1r;
+    }
+  }
+}
+
+uint32_t thread_u(const DevRound &rd, int nthr_bits, uint32_t tid) {
+  uint32_t u = 0;
+  for (int j = 0; j < nthr_bits; ++j) u |= ((tid >> j) & 1u) << rd.tid_pos[j];
+  return u;
+}
+
+uint32_t reg_sx_of(const DevRound &rd, int R, int i) {
+  uint32_t x = 0;
+  for (int j = 0; j < R; ++j)
+    if ((i >> j) & 1) x ^= rd.reg_sx[j];
+  return x;
+}
+
+// worst bank-group multiplicity of one 128-bit shared access by a warp (quarter-warp phases)
+int conflict_degree(const DevRound &rd, int T, int R, int i) {
+  const int NT = 1 << (T - R);
+  int worst = 1;
+  for (int w = 0; w < NT; w += 8) {
+    int cnt[8] = {0};
+    for (int l = 0; l < 8 && w + l < NT; ++l) {
+      const uint32_t x = swz_host(thread_u(rd, T - R, w + l)) ^ reg_sx_of(rd, R, i);
+      worst = std::max(worst, ++cnt[x & 7]);
+    }
+  }
+  return worst;
+}
+
+void run_pass(const PassPlan &pp, int L, std::vector<double> &amps, EmuStats &st) {
+  const DevPass &P = *reinterpret_cast<const DevPass *>(pp.blob.data());
+  const DevGate *G = reinterpret_cast<const DevGate *>(pp.blob.data() + sizeof(DevPass));
+  const int T = P.tile_bits, R = P.reg_bits, NT = 1 << (T - R), NR = 1 << R;
+  std::vector<double> tile_re(size_t(1) << T), tile_im(size_t(1) << T);
+  std::vector<char> written(size_t(1) << T);
+  std::vector<std::vector<double>> re(NT, std::vector<double>(NR)), im(NT, std::vector<double>(NR));
+  for (uint32_t r = 1; r < P.nrounds; ++r)
+    for (int i = 0; i < NR; ++i) {
+      st.max_bank_conflict = std::max<int64_t>(st.max_bank_conflict, conflict_degree(P.rounds[r - 1], T, R, i));
+      st.max_bank_conflict = std::max<int64_t>(st.max_bank_conflict, conflict_degree(P.rounds[r], T, R, i));
+    }
+  auto goff = [&](const DevRound &rd, uint32_t tid, int i) {
+    uint64_t o = 0;
+    for (int j = 0; j < T - R; ++j) o |= uint64_t((tid >> j) & 1u) << P.tile_pos[rd.tid_pos[j]];
+    for (int j = 0; j < R; ++j)
+      if ((i >> j) & 1) o += 1ull << P.tile_pos[rd.reg_pos[j]];
+    return o;
+  };
+  for (uint64_t tile_id = 0; tile_id < pp.ntiles; ++tile_id) {
+    uint64_t base = 0, t = tile_id;
+    for (uint32_t k = 0; k < P.nruns; ++k) {
+      base |= (t & ((1ull << P.run_len[k]) - 1)) << P.run_shift[k];
+      t >>= P.run_len[k];
+    }
+    const uint64_t basefull = base | P.rank_bits;
+    for (int tid = 0; tid < NT; ++tid)
+      for (int i = 0; i < NR; ++i) {
+        const uint64_t a = base + goff(P.rounds[0], tid, i);
+        re[tid][i] = amps[2 * a];
+        im[tid][i] = amps[2 * a + 1];
+      }
+    for (uint32_t r = 0; r < P.nrounds; ++r) {
+      const DevRound &RD = P.rounds[r];
+      if (r > 0) {
+        const DevRound &PR = P.rounds[r - 1];
+        std::fill(written.begin(), written.end(), 0);
+        for (int tid = 0; tid < NT; ++tid)
+          for (int i = 0; i < NR; ++i) {
+            const uint32_t x = swz_host(thread_u(PR, T - R, tid)) ^ reg_sx_of(PR, R, i);
+            if (written[x]) std::fprintf(stderr, "emulator: shared-memory slot written twice\n");
+            written[x] = 1;
+            tile_re[x] = re[tid][i];
+            tile_im[x] = im[tid][i];
+          }
+        for (int tid = 0; tid < NT; ++tid)
+          for (int i = 0; i < NR; ++i) {
+            const uint32_t x = swz_host(thread_u(RD, T - R, tid)) ^ reg_sx_of(RD, R, i);
+            re[tid][i] = tile_re[x];
+            im[tid][i] = tile_im[x];
+          }
+      }
+      for (uint32_t gi = RD.gate_begin; gi < RD.gate_end; ++gi)
+        for (int tid = 0; tid < NT; ++tid) apply_gate_host(re[tid], im[tid], R, G[gi], tid, basefull);
+      st.gates += RD.gate_end - RD.gate_begin;
+    }
+    for (int tid = 0; tid < NT; ++tid)
+      for (int i = 0; i < NR; ++i) {
+        double xr = re[tid][i], xi = im[tid][i];
+        if (P.has_gscale) {
+          const double yr = P.gscale[0] * xr - P.gscale[1] * xi;
+          xi = P.gscale[0] * xi + P.gscale[1] * xr;
+          xr = yr;
+        }
+        const uint64_t a = base + goff(P.rounds[P.nrounds - 1], tid, i);
+        amps[2 * a] = xr;
+        amps[2 * a + 1] = xi;
+      }
+  }
+  st.passes++;
+  st.rounds += P.nrounds;
+  (void)L;
+}
+
+}  // namespace
+
+extern "C" {
+
+// Queue `ops` (reference qubit indices) for an nlocal-qubit single-rank state, plan, and
+// emulate the passes on `amps` (2 * 2^nlocal doubles, in place).  stats_out[0..3] = passes,
+// rounds, gates executed, worst shared-memory bank multiplicity.  Returns 0, or -1 on error.
+int qbe_run(int nlocal, const qb_op *ops, int64_t nops, const char *options, double *amps, int64_t *stats_out) {
+  PlanOptions opt;
+  if (options) {
+    std::string o(options);
+    size_t pos = 0;
+    while (pos < o.size()) {
+      size_t e = o.find(',', pos);
+      if (e == std::string::npos) e = o.size();
+      std::string kv = o.substr(pos, e - pos);
+      size_t eq = kv.find('=');
+      if (eq != std::string::npos && !set_opt(opt, kv.substr(0, eq), strtoll(kv.c_str() + eq + 1, nullptr, 10)))
+        return -1;
+      pos = e + 1;
+    }
+  }
+  OpQueue q;
+  q.reset(nlocal, opt.peephole != 0);
+  static const double X[8] = {0, 0, 1, 0, 1, 0, 0, 0};
+  for (int64_t i = 0; i < nops; ++i) {
+    const qb_op &o = ops[i];
+    uint64_t cm = 0;
+    const int nc = o.kind == 1 ? 1 : o.nctrl;
+    for (int k = 0; k < nc; ++k) cm |= 1ull << (nlocal - 1 - o.ctrl[k]);
+    q.push_1q(nlocal - 1 - o.target, cm, o.kind == 1 ? X : reinterpret_cast<const double *>(o.m));
+  }
+  int T, R;
+  effective_tile(opt, nlocal, T, R);
+  if (T == 0) return -2;  // the unfused kernels have no emulator (they are one-liners)
+  opt.tile_bits = T;
+  opt.reg_bits = R;
+  if (!opt.fuse) opt.max_pass_gates = 1;
+  std::vector<PhysOp> pops;
+  for (const auto &h : q.ops) {
+    if (h.dead) continue;
+    PhysOp p;
+    p.type = h.type;
+    p.target = h.target;
+    p.ctrl = h.ctrl;
+    std::memcpy(p.m, h.m, sizeof(h.m));
+    pops.push_back(p);
+  }
+  PlanResult plan = plan_passes(pops, nlocal, 0, opt, q.gscale);
+  if (plan.consumed != pops.size()) return -3;
+  std::vector<double> a(amps, amps + (size_t(2) << nlocal));
+  EmuStats st;
+  for (const auto &p : plan.passes) run_pass(p, nlocal, a, st);
+  if (plan.passes.empty() && !(q.gscale[0] == 1.0 && q.gscale[1] == 0.0)) {
+    for (size_t i = 0; i < (size_t(1) << nlocal); ++i) {
+      const double xr = a[2 * i], xi = a[2 * i + 1];
+      a[2 * i] = q.gscale[0] * xr - q.gscale[1] * xi;
+      a[2 * i + 1] = q.gscale[0] * xi + q.gscale[1] * xr;
+    }
+  }
+  std::memcpy(amps, a.data(), sizeof(double) * a.size());
+  if (stats_out) {
+    stats_out[0] = st.passes;
+    stats_out[1] = st.rounds;
+    stats_out[2] = st.gates;
+    stats_out[3] = st.max_bank_conflict;
+  }
+  return 0;
+}
+
+}  // extern "C"

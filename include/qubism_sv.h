@@ -92,6 +92,10 @@ uint64_t qb_state_local_len(const qb_state *s);
 int qb_state_read(qb_state *s, uint64_t first, uint64_t count, qb_c64 *out);
 /* Copy this rank's raw shard (physical order) to the host: bench/e2e only. */
 int qb_state_read_local(qb_state *s, uint64_t first, uint64_t count, qb_c64 *out);
+/* Overwrite amplitudes [first, first+count) of this rank's shard from a host buffer (pinned
+ * memory makes the copy asynchronous to the host); queued gates are dropped and the qubit
+ * layout returns to the identity map.  The upload counterpart of qb_state_read_local. */
+int qb_state_write_local(qb_state *s, uint64_t first, uint64_t count, const qb_c64 *amps);
 
 /* ---- gates (enqueue) ------------------------------------------------------------------ */
 /* onJust q m #> v   (QGate.hs:148-154, 78-80) */
@@ -160,13 +164,17 @@ typedef struct {
   uint64_t exchange_bytes;  /* bytes this rank sent in global<->local qubit swaps         */
   uint64_t exchanges;       /* number of such swaps                                       */
   double plan_ms;           /* host time spent planning                                   */
+  double fused_ms;          /* device time inside fused-pass kernels (CUDA events on the
+                               launching stream), accumulated while option "time_kernels"=1 */
+  uint64_t fused_timed;     /* number of fused launches that were timed                    */
 } qb_stats;
 int qb_get_stats(const qb_ctx *ctx, qb_stats *out);
 int qb_reset_stats(qb_ctx *ctx);
 /* Raw CUDA stream of the context (cudaStream_t as void*), for event timing by callers. */
 void *qb_ctx_stream(qb_ctx *ctx);
-/* Tuning knobs: "tile_bits", "reg_bits", "low_bits", "max_rounds", "peephole",
- * "fuse" (0 = one pass per op).  Returns QB_ERR_ARG for unknown names / bad values. */
+/* Tuning knobs: "tile_bits", "reg_bits", "low_bits", "max_rounds", "max_pass_gates",
+ * "peephole", "fuse" (0 = one pass per op), "time_kernels" (bracket every fused launch with
+ * CUDA events).  Returns QB_ERR_ARG for unknown names / bad values. */
 int qb_set_option(qb_ctx *ctx, const char *name, int64_t value);
 int64_t qb_get_option(const qb_ctx *ctx, const char *name);
 /* Host-only planner entry point (no device needed): plan `nops` ops for an n-qubit local

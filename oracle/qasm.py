@@ -537,7 +537,7 @@ class Evaluator:
             r = self.draw()
             bit, sv2 = self.be.measure_qubit(sv, k, r)
             self.ps.stVecs[reg.target] = sv2
-            self._emit("MEASURE", reg.target, k, r, bit)
+            self._emit("MEASURE", reg.target, k, r, bit, getattr(self.be, "last_pone", None))
             return bit
 
         if argq[0] == "ArgBit":
@@ -656,7 +656,7 @@ class DenseBackend:
         return (sv[0], _dense.apply(_dense.cnot(sv[0], c, t), sv[1]))
 
     def measure_qubit(self, sv, q, r):
-        bit, v, _ = _dense.measureQubit(sv[0], q, r, sv[1])
+        bit, v, self.last_pone = _dense.measureQubit(sv[0], q, r, sv[1])
         return bit, (sv[0], v)
 
     def collapse(self, sv, q, b):
@@ -694,7 +694,7 @@ class StructuredBackend:
 
     def measure_qubit(self, sv, q, r):
         from . import structured as S
-        bit, v, _ = S.measure_qubit(sv[0], q, r, sv[1])
+        bit, v, self.last_pone = S.measure_qubit(sv[0], q, r, sv[1])
         return bit, (sv[0], v)
 
     def collapse(self, sv, q, b):

@@ -36,7 +36,7 @@ class QbStats(C.Structure):
     _fields_ = [("ops_submitted", C.c_uint64), ("ops_folded", C.c_uint64), ("ops_executed", C.c_uint64),
                 ("passes", C.c_uint64), ("rounds", C.c_uint64), ("simple_launches", C.c_uint64),
                 ("reduce_launches", C.c_uint64), ("exchange_bytes", C.c_uint64), ("exchanges", C.c_uint64),
-                ("plan_ms", C.c_double)]
+                ("plan_ms", C.c_double), ("fused_ms", C.c_double), ("fused_timed", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -63,6 +63,7 @@ SIGNATURES = {
     "qb_state_local_len": (_U64, [_VP]),
     "qb_state_read": (_I, [_VP, _U64, _U64, _VP]),
     "qb_state_read_local": (_I, [_VP, _U64, _U64, _VP]),
+    "qb_state_write_local": (_I, [_VP, _U64, _U64, _VP]),
     "qb_apply_1q": (_I, [_VP, _I, _PC64]),
     "qb_apply_1q_range": (_I, [_VP, _I, _I, _PC64]),
     "qb_apply_ctrl_1q": (_I, [_VP, C.POINTER(_I), _I, _I, _PC64]),

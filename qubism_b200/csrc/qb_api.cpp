@@ -60,6 +60,8 @@ struct qb_ctx {
   double2 *kq_mat_dev = nullptr;   // 4^QB_MAX_KQ
   PlanOptions opt;
   qb_stats stats{};
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;  // pending (start, stop) pairs
+  std::vector<cudaEvent_t> event_pool;
   std::recursive_mutex mu;
   DistState *dist = nullptr;
 };
@@ -134,6 +136,32 @@ uint64_t phys_mask(const qb_state *s, uint64_t logical_mask) {
   uint64_t m = 0;
   for (uint64_t b = logical_mask; b; b &= b - 1) m |= 1ull << s->perm[__builtin_ctzll(b)];
   return m;
+}
+
+int get_event(qb_ctx *c, cudaEvent_t *out) {
+  if (!c->event_pool.empty()) {
+    *out = c->event_pool.back();
+    c->event_pool.pop_back();
+    return QB_OK;
+  }
+  QB_CUDA(cudaEventCreate(out));
+  return QB_OK;
+}
+
+// fold finished (start, stop) pairs into stats.fused_ms; waits for the stream
+int resolve_timed(qb_ctx *c) {
+  if (c->timed.empty()) return QB_OK;
+  QB_CUDA(cudaStreamSynchronize(c->stream));
+  for (auto &pr : c->timed) {
+    float ms = 0.f;
+    QB_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
+    c->stats.fused_ms += ms;
+    c->stats.fused_timed++;
+    c->event_pool.push_back(pr.first);
+    c->event_pool.push_back(pr.second);
+  }
+  c->timed.clear();
+  return QB_OK;
 }
 
 // run one op with the unfused kernels
@@ -221,8 +249,18 @@ int run_fused_segment(qb_state *s, std::vector<const HostOp *> seg, const double
     }
     c->stats.plan_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     for (const PassPlan &p : plan.passes) {
+      cudaEvent_t e0 = nullptr, e1 = nullptr;
+      if (c->opt.time_kernels) {
+        QB_TRY(get_event(c, &e0));
+        QB_TRY(get_event(c, &e1));
+        QB_CUDA(cudaEventRecord(e0, c->stream));
+      }
       QB_CUDA(launch_fused_pass(s->amps, p.blob.data(), (uint32_t)p.blob.size(), p.tile_bits, p.reg_bits, p.ntiles,
                                 c->sm_count, c->stream, nullptr));
+      if (e0) {
+        QB_CUDA(cudaEventRecord(e1, c->stream));
+        c->timed.emplace_back(e0, e1);
+      }
       c->stats.passes++;
       c->stats.rounds += p.nrounds;
       c->stats.ops_executed += p.ngates;
@@ -395,6 +433,11 @@ int qb_shutdown(qb_ctx *c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->dist) dist_destroy(c->dist);
+  for (auto &pr : c->timed) {
+    cudaEventDestroy(pr.first);
+    cudaEventDestroy(pr.second);
+  }
+  for (auto e : c->event_pool) cudaEventDestroy(e);
   cudaFree(c->red_partials);
   cudaFree(c->red_out);
   cudaFreeHost(c->red_host);
@@ -487,6 +530,16 @@ int qb_state_read_local(qb_state *s, uint64_t first, uint64_t count, qb_c64 *out
   if (first + count > (1ull << s->L)) return fail(QB_ERR_ARG, "range beyond the local shard");
   QB_CUDA(cudaMemcpyAsync(out, s->amps + first, count * sizeof(double2), cudaMemcpyDeviceToHost, s->ctx->stream));
   QB_CUDA(cudaStreamSynchronize(s->ctx->stream));
+  return QB_OK;
+}
+
+int qb_state_write_local(qb_state *s, uint64_t first, uint64_t count, const qb_c64 *amps) {
+  if (!s || !amps) return fail(QB_ERR_ARG, "null argument");
+  if (first + count > (1ull << s->L)) return fail(QB_ERR_ARG, "range beyond the local shard");
+  Guard g(s->ctx);
+  s->q.clear();
+  for (int i = 0; i < s->n; ++i) s->perm[i] = i;
+  QB_CUDA(cudaMemcpyAsync(s->amps + first, amps, count * sizeof(double2), cudaMemcpyHostToDevice, s->ctx->stream));
   return QB_OK;
 }
 
@@ -714,14 +767,19 @@ int qb_tensor(qb_state *a, qb_state *b, qb_state **out) {
 }
 
 // ---- introspection
-int qb_get_stats(const qb_ctx *c, qb_stats *out) {
-  if (!c || !out) return fail(QB_ERR_ARG, "null argument");
+int qb_get_stats(const qb_ctx *cc, qb_stats *out) {
+  if (!cc || !out) return fail(QB_ERR_ARG, "null argument");
+  qb_ctx *c = const_cast<qb_ctx *>(cc);
+  Guard g(c);
+  QB_TRY(resolve_timed(c));
   *out = c->stats;
   return QB_OK;
 }
 
 int qb_reset_stats(qb_ctx *c) {
   if (!c) return fail(QB_ERR_ARG, "null ctx");
+  Guard g(c);
+  QB_TRY(resolve_timed(c));
   c->stats = qb_stats{};
   return QB_OK;
 }

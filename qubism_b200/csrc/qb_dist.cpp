@@ -158,39 +158,13 @@ int dist_allreduce_sum(DistState *d, double *vals, int n, cudaStream_t stream) {
   return QB_OK;
 }
 
-// ------------------------------------------------------------------ swap selection (host)
-std::vector<SwapPair> choose_swaps(int n, int L, const std::vector<int> &perm,
-                                   const std::vector<const HostOp *> &pending) {
-  // global physical bits that pending non-diagonal gates target, in order of first use
-  std::vector<int> need;
-  uint64_t seen = 0;
-  const size_t window = std::max<size_t>(64, size_t(4) * n);
-  for (size_t i = 0; i < pending.size() && i < window; ++i) {
-    const HostOp &h = *pending[i];
-    if (h.kind != 0 || h.type == G_DIAG) continue;
-    const int pb = perm[h.target];
-    if (pb >= L && !(seen & (1ull << pb))) {
-      seen |= 1ull << pb;
-      need.push_back(pb);
-    }
-  }
-  std::sort(need.begin(), need.end());
-  // they trade places with the top local bits (contiguous blocks => plain send/recv)
-  std::vector<SwapPair> out;
-  int lb = L - 1;
-  for (int g : need) {
-    out.push_back({g, lb});
-    --lb;
-  }
-  return out;
-}
-
 static int ensure_bounce(DistState *d, size_t amps) {
   if (d->bounce_amps >= amps) return QB_OK;
   for (int i = 0; i < 2; ++i) {
     if (d->bounce[i]) cudaFree(d->bounce[i]);
     d->bounce[i] = nullptr;
   }
+  d->bounce_amps = 0;
   for (int i = 0; i < 2; ++i) QB_DCUDA(cudaMalloc(&d->bounce[i], amps * sizeof(double2)));
   d->bounce_amps = amps;
   return QB_OK;
@@ -209,63 +183,40 @@ int dist_make_local(DistState *d, double2 *amps, int n, int L, std::vector<int> 
     g_dist_err = "shard too small for the swap";
     return QB_ERR_UNSUPPORTED;
   }
-  // sw[i].lbit = L-1-i; block index (k bits, top local bits) <-> values of the swapped rank bits
   const uint64_t block = 1ull << (L - k);
-  // my value of the swapped rank bits, expressed as a block index: rank bit sw[i].gbit <-> local bit sw[i].lbit
-  auto rank_to_block = [&](int rank) {
-    uint64_t b = 0;
-    for (int i = 0; i < k; ++i)
-      if ((rank >> (sw[i].gbit - L)) & 1) b |= 1ull << (sw[i].lbit - (L - k));
-    return b;
-  };
-  auto peer_for_block = [&](uint64_t blk) {
-    int r = d->rank;
-    for (int i = 0; i < k; ++i) {
-      const int rb = sw[i].gbit - L;
-      const int v = (blk >> (sw[i].lbit - (L - k))) & 1;
-      r = (r & ~(1 << rb)) | (v << rb);
-    }
-    return r;
-  };
-  const uint64_t mine = rank_to_block(d->rank);
-  // pieces of at most 2^24 amplitudes (256 MiB) through two bounce buffers
-  const uint64_t piece = std::min<uint64_t>(block, 1ull << 24);
-  int rc = ensure_bounce(d, piece);
+  const std::vector<SwapStep> steps = swap_schedule(d->rank, L, sw);
+  const uint64_t nsteps = steps.size();
+  // Every peer at once (one NCCL group = an all-to-all over the 2^k - 1 partners, NVSwitch is
+  // non-blocking), in pieces of <= 2^22 amplitudes (64 MiB) per peer, double-buffered: while
+  // the copy-back of piece i drains on the copy stream, piece i+1 is already on the wire.
+  const uint64_t piece = std::min<uint64_t>(block, 1ull << 22);
+  int rc = ensure_bounce(d, piece * nsteps);
   if (rc != QB_OK) return rc;
   int slot = 0;
   bool used[2] = {false, false};
-  for (uint64_t blk = 0; blk < (1ull << k); ++blk) {
-    if (blk == mine) continue;
-    const int peer = peer_for_block(blk);
-    double2 *base = amps + blk * block;
-    for (uint64_t off = 0; off < block; off += piece) {
-      if (used[slot]) QB_DCUDA(cudaStreamWaitEvent(stream, d->ev_copy[slot], 0));  // bounce free again
-      QB_NCCL(a->GroupStart());
-      QB_NCCL(a->Send(base + off, piece * 2, ncclDouble, peer, d->comm, stream));
-      QB_NCCL(a->Recv(d->bounce[slot], piece * 2, ncclDouble, peer, d->comm, stream));
-      QB_NCCL(a->GroupEnd());
-      QB_DCUDA(cudaEventRecord(d->ev_recv[slot], stream));
-      QB_DCUDA(cudaStreamWaitEvent(d->copy_stream, d->ev_recv[slot], 0));
-      QB_DCUDA(cudaMemcpyAsync(base + off, d->bounce[slot], piece * sizeof(double2), cudaMemcpyDeviceToDevice,
-                               d->copy_stream));
-      QB_DCUDA(cudaEventRecord(d->ev_copy[slot], d->copy_stream));
-      used[slot] = true;
-      slot ^= 1;
-      if (stats) stats->exchange_bytes += piece * sizeof(double2);
+  for (uint64_t off = 0; off < block; off += piece) {
+    if (used[slot]) QB_DCUDA(cudaStreamWaitEvent(stream, d->ev_copy[slot], 0));  // bounce free again
+    QB_NCCL(a->GroupStart());
+    for (uint64_t i = 0; i < nsteps; ++i) {
+      double2 *src = amps + steps[i].block * block + off;
+      QB_NCCL(a->Send(src, piece * 2, ncclDouble, steps[i].peer, d->comm, stream));
+      QB_NCCL(a->Recv(d->bounce[slot] + i * piece, piece * 2, ncclDouble, steps[i].peer, d->comm, stream));
     }
+    QB_NCCL(a->GroupEnd());
+    QB_DCUDA(cudaEventRecord(d->ev_recv[slot], stream));
+    QB_DCUDA(cudaStreamWaitEvent(d->copy_stream, d->ev_recv[slot], 0));
+    for (uint64_t i = 0; i < nsteps; ++i)
+      QB_DCUDA(cudaMemcpyAsync(amps + steps[i].block * block + off, d->bounce[slot] + i * piece,
+                               piece * sizeof(double2), cudaMemcpyDeviceToDevice, d->copy_stream));
+    QB_DCUDA(cudaEventRecord(d->ev_copy[slot], d->copy_stream));
+    used[slot] = true;
+    slot ^= 1;
+    if (stats) stats->exchange_bytes += nsteps * piece * sizeof(double2);
   }
   for (int s = 0; s < 2; ++s)
     if (used[s]) QB_DCUDA(cudaStreamWaitEvent(stream, d->ev_copy[s], 0));
   if (stats) stats->exchanges++;
-  // update the logical -> physical map
-  for (int i = 0; i < k; ++i) {
-    int la = -1, lb = -1;
-    for (int q = 0; q < n; ++q) {
-      if (perm[q] == sw[i].gbit) la = q;
-      if (perm[q] == sw[i].lbit) lb = q;
-    }
-    std::swap(perm[la], perm[lb]);
-  }
+  apply_swaps_to_perm(perm, sw);
   return QB_OK;
 }
 

@@ -21,14 +21,6 @@ void dist_destroy(DistState *d);
 // in-place sum over ranks of n host doubles (n <= 64); synchronises the stream
 int dist_allreduce_sum(DistState *d, double *vals, int n, cudaStream_t stream);
 
-// Which global physical bits must become local for the pending ops, as a list of
-// (global physical bit, local physical bit to evict) pairs.  Pure host logic (unit-tested).
-struct SwapPair {
-  int gbit, lbit;
-};
-std::vector<SwapPair> choose_swaps(int n, int L, const std::vector<int> &perm,
-                                   const std::vector<const HostOp *> &pending);
-
 // Exchange data so that the global targets of `pending` become local; updates perm.
 int dist_make_local(DistState *d, double2 *amps, int n, int L, std::vector<int> &perm,
                     const std::vector<const HostOp *> &pending, cudaStream_t stream, qb_stats *stats);

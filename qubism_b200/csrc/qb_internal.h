@@ -101,6 +101,7 @@ struct PlanOptions {
   int fuse = 1;         // 0: one pass per op
   int peephole = 1;
   int max_pass_gates = kMaxPassGates;
+  int time_kernels = 0;
 };
 
 // (tile bits, register bits, min CTAs/SM) instantiations of k_fused_pass
@@ -169,6 +170,24 @@ struct OpQueue {
   void push_1q(int target_bit, uint64_t ctrl_mask, const double m[8]);
   void push_kq(const int *bits, int k, const double *m, uint64_t ctrl_mask);
 };
+
+// ------------------------------------------------------------------ multi-GPU host logic
+// Global<->local qubit swap.  The k global physical bits that pending gates
+// target trade places with the TOP k local bits, so each rank exchanges whole contiguous
+// blocks of 2^(L-k) amplitudes, one block per peer.
+struct SwapPair {
+  int gbit, lbit;
+};
+struct SwapStep {
+  uint64_t block;   // index of the 2^(L-k) block inside the shard
+  int peer;         // rank that receives it and sends back its block of the same index
+};
+// which global bits must become local for `pending` (op pointers in program order)
+std::vector<SwapPair> choose_swaps(int n, int L, const std::vector<int> &perm,
+                                   const std::vector<const HostOp *> &pending);
+// the pairwise exchanges rank `rank` performs (its own block stays in place)
+std::vector<SwapStep> swap_schedule(int rank, int L, const std::vector<SwapPair> &pairs);
+void apply_swaps_to_perm(std::vector<int> &perm, const std::vector<SwapPair> &pairs);
 
 // classification of a caller-supplied 2x2 (value-based)
 struct Classified {

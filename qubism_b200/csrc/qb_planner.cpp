@@ -44,6 +44,8 @@ bool set_opt(PlanOptions &o, const std::string &name, int64_t v) {
   } else if (name == "max_pass_gates") {
     if (v < 1 || v > kMaxPassGates) return false;
     o.max_pass_gates = (int)v;
+  } else if (name == "time_kernels") {
+    o.time_kernels = v ? 1 : 0;
   } else {
     return false;
   }
@@ -58,6 +60,7 @@ int64_t get_opt(const PlanOptions &o, const std::string &name) {
   if (name == "peephole") return o.peephole;
   if (name == "fuse") return o.fuse;
   if (name == "max_pass_gates") return o.max_pass_gates;
+  if (name == "time_kernels") return o.time_kernels;
   return -1;
 }
 
@@ -271,6 +274,65 @@ void OpQueue::push_kq(const int *bits, int k, const double *m, uint64_t ctrl_mas
   link_op(*this, op, idx, qmask);
   op.nprev = 7;  // never merged / cancelled
   ops.push_back(std::move(op));
+}
+
+// --------------------------------------------------------------------- multi-GPU swap logic
+std::vector<SwapPair> choose_swaps(int n, int L, const std::vector<int> &perm,
+                                   const std::vector<const HostOp *> &pending) {
+  // global physical bits that pending non-diagonal gates target, within a lookahead window
+  std::vector<int> need;
+  uint64_t seen = 0;
+  const size_t window = std::max<size_t>(64, size_t(4) * n);
+  for (size_t i = 0; i < pending.size() && i < window; ++i) {
+    const HostOp &h = *pending[i];
+    if (h.kind != 0 || h.type == G_DIAG) continue;
+    const int pb = perm[h.target];
+    if (pb >= L && !(seen & (1ull << pb))) {
+      seen |= 1ull << pb;
+      need.push_back(pb);
+    }
+  }
+  std::sort(need.begin(), need.end());
+  std::vector<SwapPair> out;
+  int lb = L - 1;
+  for (int g : need) {
+    out.push_back({g, lb});
+    --lb;
+  }
+  return out;
+}
+
+std::vector<SwapStep> swap_schedule(int rank, int L, const std::vector<SwapPair> &pairs) {
+  const int k = (int)pairs.size();
+  // block index bit (lbit - (L-k)) <-> rank bit (gbit - L)
+  uint64_t mine = 0;
+  for (int i = 0; i < k; ++i)
+    if ((rank >> (pairs[i].gbit - L)) & 1) mine |= 1ull << (pairs[i].lbit - (L - k));
+  std::vector<SwapStep> out;
+  // XOR order: at step s every rank is paired with the rank whose swapped bits differ by s,
+  // so the steps of all ranks match up (no rank waits for a busy peer)
+  for (uint64_t s = 1; s < (1ull << k); ++s) {
+    const uint64_t blk = mine ^ s;
+    int r = rank;
+    for (int i = 0; i < k; ++i) {
+      const int rb = pairs[i].gbit - L;
+      const int v = (int)((blk >> (pairs[i].lbit - (L - k))) & 1);
+      r = (r & ~(1 << rb)) | (v << rb);
+    }
+    out.push_back({blk, r});
+  }
+  return out;
+}
+
+void apply_swaps_to_perm(std::vector<int> &perm, const std::vector<SwapPair> &pairs) {
+  for (const SwapPair &sp : pairs) {
+    int la = -1, lb = -1;
+    for (size_t q = 0; q < perm.size(); ++q) {
+      if (perm[q] == sp.gbit) la = (int)q;
+      if (perm[q] == sp.lbit) lb = (int)q;
+    }
+    if (la >= 0 && lb >= 0) std::swap(perm[la], perm[lb]);
+  }
 }
 
 // --------------------------------------------------------------------- one pass

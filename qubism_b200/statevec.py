@@ -130,6 +130,17 @@ class StateVec:
         capi.check(self.ctx.L.qb_state_read_local(self._h, first, count, out.ctypes.data_as(C.c_void_p)))
         return out
 
+    def write_local(self, amps, first: int = 0):
+        """Upload a host buffer into this rank's shard (qb_state_write_local).  ``amps`` may be a
+        numpy complex128 array or a raw (pointer, count) pair, e.g. pinned memory."""
+        if isinstance(amps, tuple):
+            ptr, count = amps
+        else:
+            a = np.ascontiguousarray(amps, dtype=np.complex128)
+            ptr, count = a.ctypes.data, a.size
+        capi.check(self.ctx.L.qb_state_write_local(self._h, first, count, C.c_void_p(ptr)))
+        return self
+
     def show(self) -> str:
         """``Show (StateVec n)`` (StateVec.hs:60-68)."""
         n, v = self.n, self.to_host()
@@ -174,7 +185,8 @@ class StateVec:
         return self
 
     def run_ops(self, ops):
-        """Apply an op stream (oracle.structured.run_ops format) one ABI call per op, the way
+        """Apply an op stream (("U", q, m) | ("CX", c, t) | ("CU", ctrls, t, m) | ("KQ", qs, M[, ctrls]) |
+        ("COLLAPSE", q, b) | ("MEASURE", q, r)) one ABI call per op, the way
         the interpreter drives the boundary.  Returns the list of (q, bit, pOne) measured."""
         rec = []
         for op in ops:

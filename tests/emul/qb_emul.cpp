@@ -237,4 +237,110 @@ int qbe_run(int nlocal, const qb_op *ops, int64_t nops, const char *options, dou
   return 0;
 }
 
+// Distributed flush of ONE rank, emulated on the host.  `amps` is this rank's shard (2 * 2^L
+// doubles).  Whenever the planner is stuck on gates that target global qubits, the same
+// choose_swaps / swap_schedule code the NCCL path uses decides the exchange, and `xchg` moves
+// the data: xchg(peer, send, recv, ndoubles) must exchange the buffers with `peer`
+// (tests implement it with torch.distributed send/recv over gloo).  perm_inout[n] is the
+// logical->physical bit map.  Returns the number of swaps, or a negative error.
+typedef int (*qbe_xchg_fn)(int peer, const double *send, double *recv, int64_t ndoubles);
+
+int qbe_run_rank(int n, int nranks, int rank, const qb_op *ops, int64_t nops, const char *options, double *amps,
+                 int *perm_inout, qbe_xchg_fn xchg, int64_t *stats_out) {
+  PlanOptions opt;
+  if (options) {
+    std::string o(options);
+    size_t pos = 0;
+    while (pos < o.size()) {
+      size_t e = o.find(',', pos);
+      if (e == std::string::npos) e = o.size();
+      std::string kv = o.substr(pos, e - pos);
+      size_t eq = kv.find('=');
+      if (eq != std::string::npos && !set_opt(opt, kv.substr(0, eq), strtoll(kv.c_str() + eq + 1, nullptr, 10)))
+        return -1;
+      pos = e + 1;
+    }
+  }
+  int pbits = 0;
+  while ((1 << pbits) < nranks) ++pbits;
+  const int L = n - pbits;
+  OpQueue q;
+  q.reset(n, opt.peephole != 0);
+  static const double X[8] = {0, 0, 1, 0, 1, 0, 0, 0};
+  for (int64_t i = 0; i < nops; ++i) {
+    const qb_op &o = ops[i];
+    uint64_t cm = 0;
+    const int nc = o.kind == 1 ? 1 : o.nctrl;
+    for (int k = 0; k < nc; ++k) cm |= 1ull << (n - 1 - o.ctrl[k]);
+    q.push_1q(n - 1 - o.target, cm, o.kind == 1 ? X : reinterpret_cast<const double *>(o.m));
+  }
+  int T, R;
+  effective_tile(opt, L, T, R);
+  if (T == 0) return -2;
+  opt.tile_bits = T;
+  opt.reg_bits = R;
+  std::vector<int> perm(perm_inout, perm_inout + n);
+  std::vector<const HostOp *> seg;
+  for (const auto &h : q.ops)
+    if (!h.dead) seg.push_back(&h);
+  std::vector<double> a(amps, amps + (size_t(2) << L));
+  EmuStats st;
+  int nswaps = 0;
+  bool gdone = (q.gscale[0] == 1.0 && q.gscale[1] == 0.0);
+  while (!seg.empty()) {
+    std::vector<PhysOp> pops(seg.size());
+    for (size_t i = 0; i < seg.size(); ++i) {
+      const HostOp &h = *seg[i];
+      pops[i].type = h.type;
+      pops[i].target = perm[h.target];
+      uint64_t cm = 0;
+      for (uint64_t b = h.ctrl; b; b &= b - 1) cm |= 1ull << perm[__builtin_ctzll(b)];
+      pops[i].ctrl = cm;
+      std::memcpy(pops[i].m, h.m, sizeof(h.m));
+    }
+    PlanResult plan = plan_passes(pops, L, rank, opt, nullptr);
+    const bool all = plan.consumed == seg.size();
+    if (all && !gdone && !plan.passes.empty()) {
+      DevPass *P = reinterpret_cast<DevPass *>(plan.passes.back().blob.data());
+      P->gscale[0] = q.gscale[0];
+      P->gscale[1] = q.gscale[1];
+      P->has_gscale = 1;
+      gdone = true;
+    }
+    for (const auto &p : plan.passes) run_pass(p, L, a, st);
+    if (all) break;
+    std::vector<const HostOp *> rest;
+    for (size_t i = 0; i < seg.size(); ++i)
+      if (!plan.done[i]) rest.push_back(seg[i]);
+    std::vector<SwapPair> sw = choose_swaps(n, L, perm, rest);
+    if (sw.empty()) return -4;
+    const int k = (int)sw.size();
+    const uint64_t block = 1ull << (L - k);
+    std::vector<double> recv(2 * block);
+    for (const SwapStep &stp : swap_schedule(rank, L, sw)) {
+      double *base = a.data() + 2 * stp.block * block;
+      if (xchg(stp.peer, base, recv.data(), (int64_t)(2 * block)) != 0) return -5;
+      std::memcpy(base, recv.data(), sizeof(double) * 2 * block);
+    }
+    apply_swaps_to_perm(perm, sw);
+    ++nswaps;
+    seg.swap(rest);
+  }
+  if (!gdone)
+    for (size_t i = 0; i < (size_t(1) << L); ++i) {
+      const double xr = a[2 * i], xi = a[2 * i + 1];
+      a[2 * i] = q.gscale[0] * xr - q.gscale[1] * xi;
+      a[2 * i + 1] = q.gscale[0] * xi + q.gscale[1] * xr;
+    }
+  std::memcpy(amps, a.data(), sizeof(double) * a.size());
+  for (int i = 0; i < n; ++i) perm_inout[i] = perm[i];
+  if (stats_out) {
+    stats_out[0] = st.passes;
+    stats_out[1] = st.rounds;
+    stats_out[2] = st.gates;
+    stats_out[3] = st.max_bank_conflict;
+  }
+  return nswaps;
+}
+
 }  // extern "C"

@@ -1,0 +1,368 @@
+"""GPU parity tests: every call goes through the C ABI (libqubism_sv.so) and is compared with
+the CPU oracle on the same seeded inputs.  Tolerance: 1e-12 absolute on amplitudes and on the
+measurement reductions (BASELINE.json north_star); integer results (bits) must be identical.
+"A state containing NaN" is one equivalence class (SURVEY.md Appendix A iv)."""
+import itertools
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+import qubism_b200 as Q
+from oracle import dense as D, qasm, structured as S
+from qubism_b200 import capi
+from qubism_b200.circuits import adder_ops, proper_unitary_layers, qft_ops, random_layers
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden.json")))
+
+
+def close(a, b, tol=TOL):
+    a, b = np.asarray(a), np.asarray(b)
+    if np.isnan(a).any() or np.isnan(b).any():
+        return bool(np.isnan(a).any() and np.isnan(b).any())
+    return bool(np.abs(a - b).max() <= tol)
+
+
+def cvec(v):
+    a = np.asarray(v, dtype=float)
+    return a[:, 0] + 1j * a[:, 1]
+
+
+# ------------------------------------------------------------------ P sweeps
+@pytest.mark.parametrize("n", list(range(1, 13)))
+def test_single_gates_every_qubit_vs_literal_dense(ctx, n):
+    """Random reference-distribution states x random (non-unitary) `unitary theta phi lambda`
+    on every qubit, every (c, t) CNOT, collapse / sumsq on every qubit and both bits."""
+    rng = np.random.default_rng(1000 + n)
+    v = S.gen_state(n, rng)
+    dense_ok = n <= 9
+    for q in range(n):
+        m = D.unitary(*rng.uniform(0, 4 * np.pi, 3))
+        ref = D.apply(D.onJust(n, q, m), v) if dense_ok else S.apply_1q(n, q, m, v)
+        assert close(Q.StateVec.from_host(v).apply_1q(q, m).to_host(), ref)
+        s0, s1 = Q.StateVec.from_host(v).sumsq(q)
+        r0, r1 = S.sumsq(n, q, v)
+        assert abs(s0 - r0) < TOL and abs(s1 - r1) < TOL
+        for b in (0, 1):
+            ref = D.collapse(n, q, b, v) if dense_ok else S.collapse(n, q, b, v)
+            assert close(Q.collapse(q, b, Q.StateVec.from_host(v)).to_host(), ref)
+    pairs = [(c, t) for c in range(n) for t in range(n) if c != t]
+    if n > 8:
+        pairs = [pairs[i] for i in rng.choice(len(pairs), 24, replace=False)]
+    for c, t in pairs:
+        ref = D.apply(D.cnot(n, c, t), v) if dense_ok else S.apply_cnot(n, c, t, v)
+        assert close(Q.StateVec.from_host(v).apply_cnot(c, t).to_host(), ref, 0.0)  # a permutation: exact
+        m = D.unitary(*rng.uniform(0, 4 * np.pi, 3))
+        ref = D.apply(D.controlled(n, c, D.onJust(n, t, m)), v) if dense_ok else S.apply_1q(n, t, m, v, ctrls=(c,))
+        assert close(Q.StateVec.from_host(v).apply_ctrl_1q([c], t, m).to_host(), ref)
+
+
+def test_zero_weight_collapse_is_all_nan(ctx):
+    for n in (2, 11, 13):
+        z = Q.mkStateVec(n)  # |0...0>: no qubit is ever One
+        out = Q.collapse(0, 1, z).to_host()
+        assert np.isnan(out).all()
+        bit, p = z.measure_qubit_(n - 1, 0.0)  # pOne = 0 (NaN in the reference): Zero either way
+        assert bit == 0 and p == 0.0
+        ref = D.mkStateVec(n) if n <= 11 else S.mk_state(n)
+        assert close(z.to_host(), ref)
+
+
+def test_golden_gate_vectors(ctx):
+    for case in GOLD["gate_vectors"]:
+        n, op, vin, vout = case["n"], case["op"], cvec(case["in"]), cvec(case["out"])
+        sv = Q.StateVec.from_host(vin)
+        if op[0] == "U":
+            sv.apply_1q(op[1], D.unitary(*op[2]["angles"]))
+        elif op[0] == "CU":
+            sv.apply_ctrl_1q(op[1], op[2], D.unitary(*op[3]["angles"]))
+        elif op[0] == "CX":
+            sv.apply_cnot(op[1], op[2])
+        else:
+            sv.collapse_(op[1], op[2])
+        assert close(sv.to_host(), vout), op
+
+
+# ------------------------------------------------------------------ the fused-pass kernel
+VARIANTS = [(12, 4), (12, 5), (12, 3), (11, 4), (11, 3), (11, 5), (10, 3), (10, 4), (13, 4), (13, 5)]
+
+
+def extras(n):
+    return [("CU", [0, n - 1], 3, D.unitary(.3, .2, .1)), ("U", n - 1, np.diag([1, 1j])),
+            ("CU", [2], n - 2, np.diag([1, np.exp(.3j)])), ("U", 0, D.unitary(0, 0, .7)), ("CX", 1, 0), ("CX", 1, 0),
+            ("U", 5, D.hadamard()), ("U", 5, D.hadamard()), ("CU", [n - 1, n - 2, 4], 0, D.unitary(1, 2, 3)),
+            ("CU", [1], n - 1, D.pauliX()), ("U", 2, D.pauliY()), ("U", n - 3, np.array([[0, 2], [0.5, 0]])),
+            ("CU", [n - 1], n - 2, np.diag([0.5, 2j])), ("CU", [0], 1, np.diag([1, -1]))]
+
+
+@pytest.mark.parametrize("T,R", VARIANTS)
+@pytest.mark.parametrize("n", [10, 12, 14, 17])
+def test_fused_passes_all_variants(default_opts, n, T, R):
+    ctx = default_opts
+    ctx.set_option("tile_bits", T)
+    ctx.set_option("reg_bits", R)
+    rng = np.random.default_rng(n * 100 + T * 10 + R)
+    v = S.gen_state(n, rng)
+    ops = random_layers(n, 3, seed=n, lam0=True) + extras(n) + random_layers(n, 1, seed=5, lam0=False)
+    ref = S.run_ops(n, ops, v)
+    sv = Q.StateVec.from_host(v)
+    ctx.reset_stats()
+    sv.run_ops(ops)
+    assert close(sv.to_host(), ref)
+    st = ctx.stats()
+    assert st["passes"] >= 1 and st["simple_launches"] == 0, "the fused kernel must be the one that ran"
+
+
+@pytest.mark.parametrize("opts", [dict(peephole=0), dict(fuse=0), dict(max_rounds=3), dict(low_bits=3),
+                                  dict(low_bits=7), dict(max_pass_gates=7)])
+def test_fused_passes_planner_knobs(default_opts, opts):
+    ctx = default_opts
+    for k, val in opts.items():
+        ctx.set_option(k, val)
+    n = 15
+    rng = np.random.default_rng(42)
+    v = S.gen_state(n, rng)
+    ops = random_layers(n, 2, seed=9, lam0=False) + extras(n) + qft_ops(n)
+    sv = Q.StateVec.from_host(v)
+    sv.submit([o for o in ops])  # batch path (qb_submit)
+    assert close(sv.to_host(), S.run_ops(n, ops, v), 1e-11 if opts.get("peephole") == 0 else TOL)
+
+
+def test_submit_equals_per_gate_calls(ctx):
+    n = 13
+    v = S.gen_state(n, np.random.default_rng(3))
+    ops = random_layers(n, 2, seed=1) + [("CU", [0, 5], 7, D.unitary(1, 1, 1))]
+    a = Q.StateVec.from_host(v)
+    a.submit(ops)
+    b = Q.StateVec.from_host(v)
+    b.run_ops(ops)
+    assert np.array_equal(a.to_host(), b.to_host())  # same queue, same plan, same bits
+
+
+def test_reference_circuits_vs_structured_oracle(ctx):
+    # C2-style: QFT in reference semantics; the widened adder; true-SU(2) layers (GENERAL class)
+    for n, ops in ((16, qft_ops(16)), (12, adder_ops(5)), (14, proper_unitary_layers(14, 3)), (20, qft_ops(20))):
+        v = S.gen_state(n, np.random.default_rng(n))
+        sv = Q.StateVec.from_host(v)
+        sv.submit(ops)
+        assert close(sv.to_host(), S.run_ops(n, ops, v))
+
+
+def test_dense_kq_blocks(ctx):
+    rng = np.random.default_rng(8)
+    for n in (6, 13):
+        v = S.gen_state(n, rng)
+        for k in (2, 3, 4, 5):
+            qs = [int(x) for x in rng.choice(n, k, replace=False)]
+            M = rng.normal(size=(1 << k, 1 << k)) + 1j * rng.normal(size=(1 << k, 1 << k))
+            free = [q for q in range(n) if q not in qs]
+            for ctrls in ((), (free[0],)):
+                got = Q.StateVec.from_host(v).apply_1q(free[-1], D.hadamard()).apply_kq(qs, M, ctrls).to_host()
+                ref = S.apply_kq(n, qs, M, S.apply_1q(n, free[-1], D.hadamard(), v), ctrls)
+                assert close(got, ref, 1e-11)
+    # kronecker a b acts with a on the FIRST qubits (QGate.hs:142-144)
+    a, b = D.unitary(1, 2, 3), D.unitary(.4, .5, .6)
+    v = S.gen_state(2, rng)
+    assert close(Q.StateVec.from_host(v).apply_kq([0, 1], D.kronecker(a, b)).to_host(), D.apply(D.kronecker(a, b), v))
+
+
+# ------------------------------------------------------------------ measurement
+def test_measure_qubit_and_measure_all(ctx):
+    rng = np.random.default_rng(21)
+    for n in (1, 3, 10, 14):
+        v = S.gen_state(n, rng)
+        for r in (2.0, -1.0, 0.3, 0.7):
+            for q in {0, n // 2, n - 1}:
+                sv = Q.StateVec.from_host(v)
+                bit, p = sv.measure_qubit_(q, r)
+                rb, rv, rp = S.measure_qubit(n, q, r, v)
+                assert bit == rb and abs(p - rp) < TOL and close(sv.to_host(), rv)
+        rs = list(rng.uniform(0, 1, n))
+        sv = Q.StateVec.from_host(v)
+        bits = Q.measure(sv, rs)
+        w, ref_bits = v, []
+        for q in range(n):
+            b, w, _ = S.measure_qubit(n, q, rs[q], w)
+            ref_bits.append(b)
+        assert bits == ref_bits and close(sv.to_host(), w)
+
+
+def test_quickcheck_measurement_is_idempotent(ctx):
+    # test/Qubism/StateVecSpec.hs:35-62 (n = 1) and wider
+    rng = np.random.default_rng(22)
+    for n in (1, 1, 1, 4, 12):
+        v = S.gen_state(n, rng)
+        rs = list(rng.uniform(0, 1, n))
+        one = Q.StateVec.from_host(v)
+        b1 = one.measure_(rs)
+        two = Q.StateVec.from_host(v)
+        two.measure_(rs)
+        b2 = two.measure_(rs)
+        assert b1 == b2 and one == two
+
+
+def test_sumsq_is_deterministic(ctx):
+    v = S.gen_state(16, np.random.default_rng(2))
+    sv = Q.StateVec.from_host(v)
+    assert len({sv.sumsq(5) for _ in range(5)}) == 1
+
+
+# ------------------------------------------------------------------ vector / Hilbert space laws
+@pytest.mark.parametrize("n", [1, 3, 13])
+def test_quickcheck_vector_and_hilbert_space_laws(ctx, n):
+    # test/Qubism/AlgebraTests.hs:25-47 through the C ABI
+    rng = np.random.default_rng(30 + n)
+    zero = Q.zero(n)
+    for _ in range(6):
+        ha, hb, hw = (S.gen_state(n, rng) for _ in range(3))
+        a, b, w = (Q.StateVec.from_host(x) for x in (ha, hb, hw))
+        z = complex(*rng.uniform(-1, 1, 2))
+        assert (a + b) + w == a + (b + w) and a + b == b + a
+        assert zero + a == a and (-a) + a == zero
+        assert z * (a + b) == z * a + z * b
+        assert abs(w.inner(z * a + b) - (z * w.inner(a) + w.inner(b))) < 1e-5
+        assert a.inner(b) == b.inner(a).conjugate()  # EXACT, as AlgebraTests.hs:43-47 demands
+        assert abs(a.inner(b) - D.inner(ha, hb)) < TOL
+        assert abs(a.norm() - D.norm(ha)) < TOL and abs(a.norm2() - np.linalg.norm(ha)) < TOL
+        assert close((a - b).to_host(), ha - hb) and close((z * a).to_host(), z * ha)
+        assert close(Q.normalize(2.5 * a).to_host(), D.normalize(2.5 * ha))
+    assert np.isnan(Q.normalize(zero).to_host()).all()  # 0 / 0, as LA.normalize
+
+
+def test_tensor_clone_and_show(ctx):
+    rng = np.random.default_rng(40)
+    for na, nb in ((1, 2), (3, 9), (6, 7)):
+        a, b = S.gen_state(na, rng), S.gen_state(nb, rng)
+        t = Q.tensor(Q.StateVec.from_host(a), Q.StateVec.from_host(b))
+        assert Q.dimension(t) == na + nb and close(t.to_host(), D.tensor(a, b))
+    v = S.gen_state(3, rng)
+    sv = Q.StateVec.from_host(v)
+    out = Q.apply(Q.onJust(3, 1, Q.hadamard()), sv)  # pure (#>): the argument stays valid
+    assert close(sv.to_host(), v) and close(out.to_host(), D.apply(D.onJust(3, 1, D.hadamard()), v))
+    assert sv.show() == D.show(3, v)
+
+
+# ------------------------------------------------------------------ DSL + interpreter over the ABI
+def test_dsl_teleportation_example(ctx):
+    # examples/Teleportation.hs:20-29 with the reference's function names
+    rng = np.random.default_rng(50)
+    alice = S.gen_state(1, rng)
+    for r0, r1 in itertools.product([2.0, -1.0], repeat=2):
+        pair = Q.apply(Q.cnot(2, 0, 1) @ Q.onJust(2, 0, Q.hadamard()), Q.mkStateVec(2))
+        total = Q.tensor(Q.StateVec.from_host(alice), pair)
+        Q.gate(Q.cnot(3, 0, 1), total)
+        Q.gate(Q.onJust(3, 0, Q.hadamard()), total)
+        c0 = Q.measureQubit(0, total, r0)
+        c1 = Q.measureQubit(1, total, r1)
+        Q.gate(Q.ifBit(c0, Q.onJust(3, 2, Q.pauliZ())), total)
+        Q.gate(Q.ifBit(c1, Q.onJust(3, 2, Q.pauliX())), total)
+        v = total.to_host()
+        idx = (c0 << 2) | (c1 << 1)
+        assert abs(abs(np.vdot(v[idx:idx + 2], alice)) - 1) < TOL
+
+
+def test_symbolic_gates_through_the_abi(ctx):
+    n = 4
+    v = S.gen_state(n, np.random.default_rng(51))
+    g = Q.controlled(3, Q.controlled(0, Q.onJust(n, 1, Q.unitary(.3, .2, .1)))) @ Q.onEvery(n, Q.hadamard())
+    lin = (0.5 - 2j) * g + Q.kronecker(Q.onRange(2, 0, 1, Q.pauliY()), Q.cnot(2, 1, 0)) - Q.ident(n)
+    own = Q.controlled(1, Q.onJust(n, 1, Q.pauliX()))  # literal M.P + I - P, not a controlled gate
+    for gate in (g, lin, own):
+        assert close(Q.apply(gate, Q.StateVec.from_host(v)).to_host(), gate.dense() @ v, 1e-11)
+
+
+class GpuBackend:
+    """The evaluator seam (oracle.qasm.Evaluator) over the C ABI, with value semantics."""
+
+    def mk(self, n):
+        return Q.mkStateVec(n)
+
+    def tensor(self, a, b):
+        return Q.tensor(a, b)
+
+    def dimension(self, sv):
+        return Q.dimension(sv)
+
+    def apply_1q(self, sv, q, m):
+        return sv.clone().apply_1q(q, m)
+
+    def apply_range(self, sv, f, l, m):
+        return sv.clone().apply_1q_range(f, l, m)
+
+    def apply_cnot(self, sv, c, t):
+        return sv.clone().apply_cnot(c, t)
+
+    def measure_qubit(self, sv, q, r):
+        out = sv.clone()
+        bit, self.last_pone = out.measure_qubit_(q, r)
+        return bit, out
+
+    def collapse(self, sv, q, b):
+        return Q.collapse(q, b, sv)
+
+
+@pytest.mark.parametrize("name", ["teleportation", "fourier4", "invqft4", "adder2"])
+def test_golden_qasm_programs_through_the_abi(ctx, name):
+    """BASELINE config 0: the example programs run by the restated interpreter with the GPU
+    backend behind the L2 seam; amplitudes, classical registers and pOne must match the
+    literal-dense golden fixtures for every forced-outcome path."""
+    entry = GOLD[name]
+    for run in entry["runs"]:
+        if run["degenerate"]:
+            continue
+        trace = []
+        ps = qasm.run_qasm(entry["source"], backend=GpuBackend(), draws=run["draws"], trace=trace)
+        assert ps.cregs == run["cregs"]
+        for k, v in run["states"].items():
+            assert close(ps.stVecs[k].to_host(), cvec(v)), (name, run["draws"], k)
+        gold_p = [t[5] for t in run["trace"] if t[0] == "MEASURE"]
+        got_p = [t[5] for t in trace if t[0] == "MEASURE"]
+        for a, b in zip(got_p, gold_p):
+            assert (b is None or math.isnan(b) and a == 0.0) or abs(a - b) < TOL
+
+
+# ------------------------------------------------------------------ error behaviour
+def test_errors_are_status_codes_not_aborts(ctx):
+    sv = Q.mkStateVec(3)
+    for bad in (lambda: sv.apply_1q(3, np.eye(2)), lambda: sv.apply_cnot(1, 1), lambda: sv.apply_cnot(0, 7),
+                lambda: sv.collapse_(0, 2), lambda: sv.sumsq(-1), lambda: sv.apply_kq([0, 0], np.eye(4)),
+                lambda: sv.to_host(4, 8), lambda: Q.mkStateVec(0)):
+        with pytest.raises(capi.QbError) as e:
+            bad()
+        assert e.value.code == capi.QB_ERR_ARG
+    with pytest.raises(capi.QbError) as e:
+        sv.inner(Q.mkStateVec(4))
+    assert e.value.code == capi.QB_ERR_STATE  # hmatrix would throw on the shape mismatch
+    assert close(sv.to_host(), D.mkStateVec(3))  # the failed calls left the state alone
+
+
+# ------------------------------------------------------------------ full-size properties
+def _inverse(ops):
+    inv = []
+    for op in reversed(ops):
+        inv.append(("U", op[1], np.linalg.inv(op[2])) if op[0] == "U" else op)
+    return inv
+
+
+@pytest.mark.parametrize("n", [26, 30])
+def test_full_size_round_trip_and_norm(ctx, n):
+    """Size-independent properties at BASELINE's sizes: C^-1 C |0> = |0>, the squared norm is
+    preserved by a norm-preserving circuit, S0 + S1 equals it for every probed qubit."""
+    ops = qft_ops(n) + random_layers(n, 4, seed=1000)
+    sv = Q.mkStateVec(n)
+    sv.submit(ops)
+    tot = sv.norm2() ** 2
+    assert abs(tot - 1.0) < 1e-11
+    for q in (0, n // 2, n - 1):
+        s0, s1 = sv.sumsq(q)
+        assert abs(s0 + s1 - tot) < 1e-12 and 0 < s1 < 1
+    window = sv.to_host(12345, 4096)
+    assert np.abs(window).max() < 1e-2  # spread out, nothing left of the basis state
+    sv.submit(_inverse(ops))
+    head = sv.to_host(0, 4096)
+    assert abs(head[0] - 1.0) < 1e-11 and np.abs(head[1:]).max() < 1e-12
+    assert abs(sv.norm2() - 1.0) < 1e-11

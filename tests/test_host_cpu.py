@@ -1,0 +1,166 @@
+"""CPU tests of the product's host side: the C-ABI library loads and exports every symbol the
+header declares, fails loudly without a GPU, and the planner's fused-pass programs -- run by
+the test-only kernel emulator in tests/emul -- reproduce the oracle.  No compute call reaches
+a GPU here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import qubism_b200 as Q
+from oracle import dense as D, structured as S
+from qubism_b200 import capi
+from qubism_b200.circuits import adder_ops, proper_unitary_layers, qft_ops, random_layers
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "qubism_sv.h")).read()
+    declared = set(re.findall(r"\b(qb_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"qb_ctx", "qb_state"}
+    assert len(declared) >= 40
+    lib = capi.lib()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in qubism_sv.h but not exported"
+        assert name in capi.SIGNATURES, f"{name} has no ctypes signature"
+    assert b"sm_100a" in lib.qb_version()
+
+
+def test_struct_layouts_match_header():
+    assert C.sizeof(capi.QbC64) == 16
+    assert C.sizeof(capi.QbOp) == 4 * 8 + 64
+    assert C.sizeof(capi.QbStats) == 9 * 8 + 8 + 16
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present; the loud-failure path is for CPU-only hosts")
+    h = C.c_void_p()
+    rc = capi.lib().qb_init(0, C.byref(h))
+    assert rc == capi.QB_ERR_CUDA and not h
+    assert b"no CPU fallback" in capi.lib().qb_last_error()
+    with pytest.raises(capi.QbError):
+        Q.mkStateVec(3, ctx=None)
+
+
+def test_product_does_not_import_oracle():
+    for fn in os.listdir(os.path.join(ROOT, "qubism_b200")):
+        if fn.endswith(".py"):
+            src = open(os.path.join(ROOT, "qubism_b200", fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle|import_module\(.oracle", src, re.M), fn
+            assert "oracle" not in src, fn
+    for fn in os.listdir(os.path.join(ROOT, "qubism_b200", "csrc")):
+        assert "oracle" not in open(os.path.join(ROOT, "qubism_b200", "csrc", fn)).read(), fn
+
+
+# ------------------------------------------------------------------ planner + emulator parity
+OPTION_SETS = ["", "reg_bits=5", "reg_bits=3", "tile_bits=11,reg_bits=4", "tile_bits=10,reg_bits=3", "peephole=0",
+               "fuse=0", "max_rounds=3", "low_bits=3", "low_bits=7", "max_pass_gates=5",
+               "tile_bits=13,reg_bits=5,low_bits=7", "tile_bits=13,reg_bits=4"]
+
+
+def extras(n):
+    return [("CU", [0, n - 1], 3, D.unitary(.3, .2, .1)), ("U", n - 1, np.diag([1, 1j])),
+            ("CU", [2], n - 2, np.diag([1, np.exp(.3j)])), ("U", 0, D.unitary(0, 0, .7)), ("CX", 1, 0), ("CX", 1, 0),
+            ("U", 5, D.hadamard()), ("U", 5, D.hadamard()), ("CU", [n - 1, n - 2, 4], 0, D.unitary(1, 2, 3)),
+            ("CU", [1], n - 1, D.pauliX()), ("U", 2, D.pauliY()), ("U", n - 3, np.array([[0, 2], [0.5, 0]]))]
+
+
+@pytest.mark.parametrize("opts", OPTION_SETS)
+@pytest.mark.parametrize("n", [12, 13, 14])
+def test_emulated_passes_match_oracle(emul, n, opts):
+    if "tile_bits=13" in opts and n < 13:
+        pytest.skip("tile larger than the state")
+    rng = np.random.default_rng(n * 131 + len(opts))
+    v = S.gen_state(n, rng)
+    ops = random_layers(n, 3, seed=n, lam0=("peephole=0" not in opts)) + extras(n)
+    ref = S.run_ops(n, ops, v)
+    out, st = emul(n, ops, v, opts)
+    assert np.abs(out - ref).max() < 1e-13
+    assert st["bank"] == 1, "a shared-memory transpose is not bank-conflict free"
+    if "fuse=0" not in opts and "max_pass_gates" not in opts:
+        assert st["passes"] <= 6
+
+
+def test_emulated_reference_semantics_qft_and_adder(emul):
+    for n, ops in ((12, qft_ops(12)), (12, adder_ops(5)), (13, proper_unitary_layers(13, 2))):
+        rng = np.random.default_rng(n)
+        v = S.gen_state(n, rng)
+        ref = S.run_ops(n, ops, v)
+        for opts in ("", "peephole=0,max_pass_gates=40"):
+            out, st = emul(n, ops, v, opts)
+            assert np.abs(out - ref).max() < 1e-12, opts
+
+
+def test_peephole_counts_and_plan_text():
+    n = 16
+    txt = capi.plan_describe(n, qft_ops(n))
+    head = dict(kv.split("=") for kv in txt.splitlines()[0].split()[:2])
+    # reference semantics: every u1 is a scalar, the two cx of each cu1 become adjacent and cancel
+    assert int(head["submitted"]) == n + 5 * n * (n - 1) // 2 + 2
+    assert int(head["folded"]) == int(head["submitted"]) - n  # only one merged gate per qubit stays
+    passes = int(re.search(r"passes=(\d+)", txt).group(1))
+    assert passes <= 3
+    txt0 = capi.plan_describe(n, qft_ops(n), "peephole=0")
+    assert "folded=0" in txt0
+    assert int(re.search(r"scheduled=(\d+)", txt0).group(1)) == int(head["submitted"])
+    # every pass keeps bits 0..2 out of the registers of its first and last round
+    for line in txt.splitlines():
+        m = re.match(r"\s+round (\d+) regs=\[([\d,]+)\]", line)
+        if m and m.group(1) == "0":
+            assert not {0, 1, 2} & set(map(int, m.group(2).split(",")))
+
+
+def test_classification_by_value():
+    # scalar -> folded; phase * real -> REAL class with the phase in the deferred scalar
+    n = 12
+    t = capi.plan_describe(n, [("U", 0, np.exp(0.3j) * np.eye(2))])
+    assert "folded=1" in t and "passes=" not in t.split("\n")[1] or "passes=0" in t
+    t = capi.plan_describe(n, [("U", 0, D.unitary(0.3, 0.7, 0.0))])
+    g = re.search(r"gscale=\(([-\d.e]+),([-\d.e]+)\)", t)
+    assert abs(complex(float(g.group(1)), float(g.group(2))) - np.exp(0.7j)) < 1e-15
+
+
+# ------------------------------------------------------------------ symbolic gate algebra (host)
+def test_symbolic_qgate_algebra_matches_dense_oracle():
+    n = 3
+    g = Q.cnot(n, 0, 1) @ Q.onJust(n, 0, Q.hadamard())
+    assert np.abs(g.dense() - D.mul(D.cnot(n, 0, 1), D.onJust(n, 0, D.hadamard()))).max() < 1e-15
+    g2 = Q.controlled(0, Q.onJust(n, 0, Q.pauliX()))  # gate touches its own control: literal formula
+    assert np.abs(g2.dense() - D.controlled(n, 0, D.onJust(n, 0, D.pauliX()))).max() < 1e-15
+    u = (0.3, 0.2, 0.1)
+    g3 = Q.controlled(2, Q.controlled(0, Q.onJust(n, 1, Q.unitary(*u))))
+    assert np.abs(g3.dense() - D.controlled(n, 2, D.controlled(n, 0, D.onJust(n, 1, D.unitary(*u))))).max() < 1e-15
+    g4 = Q.kronecker(Q.hadamard(), Q.onEvery(2, Q.pauliY()))
+    assert np.abs(g4.dense() - D.kronecker(D.hadamard(), D.onEvery(2, D.pauliY()))).max() < 1e-15
+    g5 = Q.onRange(3, 1, 2, Q.unitary(1, 2, 3))
+    assert np.abs(g5.dense() - D.onRange(3, 1, 2, D.unitary(1, 2, 3))).max() < 1e-15
+    lin = (2 + 1j) * g + (-g3)
+    assert np.abs(lin.dense() - ((2 + 1j) * g.dense() - g3.dense())).max() < 1e-15
+    assert np.abs(Q.ifBit(0, g).dense() - np.eye(8)).max() == 0 and Q.ifBit(1, g) is g
+    with pytest.raises(IndexError):
+        Q.onJust(3, 3, Q.hadamard())
+
+
+def test_generators_match_reference_counts():
+    # QFT-n is n + 5 n (n-1)/2 ops (+2 x); one random layer is n U + floor(n/2) CX
+    assert len(qft_ops(24)) == 24 + 5 * 24 * 23 // 2 + 2 == 1406
+    assert len(qft_ops(30)) == 2207
+    assert len(random_layers(30, 20)) == 900
+    ops = qft_ops(4)  # same stream as the interpreter emits for the golden fourier4 program
+    import json
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "golden.json")))["fourier4"]["runs"][0]["trace"]
+    stream = [t for t in gold if t[0] in ("U", "CX")]
+    assert len(stream) == len(ops)
+    for a, b in zip(stream, ops):
+        assert a[0] == b[0]
+        if a[0] == "U":
+            assert a[2] == b[1]
+            m = np.array(a[3]["m"])
+            assert np.abs((m[:, 0] + 1j * m[:, 1]).reshape(2, 2) - b[2]).max() < 1e-15
+        else:
+            assert (a[2], a[3]) == (b[1], b[2])

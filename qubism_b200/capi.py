@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqubism_sv.so")
+LIB_PATH = os.environ.get("QB_LIB") or os.path.join(_HERE, "libqubism_sv.so")
 
 QB_OK = 0
 QB_ERR_ARG, QB_ERR_OOM, QB_ERR_CUDA, QB_ERR_NCCL, QB_ERR_UNSUPPORTED, QB_ERR_STATE = -1, -2, -3, -4, -5, -6

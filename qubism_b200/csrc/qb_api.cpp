@@ -94,7 +94,7 @@ int init_common(qb_ctx *c) {
   QB_CUDA(cudaMallocHost(&c->red_host, sizeof(double) * 4));
   QB_CUDA(cudaMalloc(&c->kq_bits_dev, sizeof(int) * 2 * QB_MAX_KQ));
   QB_CUDA(cudaMalloc(&c->kq_mat_dev, sizeof(double2) << (2 * QB_MAX_KQ)));
-  for (const char *name : {"tile_bits", "reg_bits", "low_bits", "max_rounds", "peephole", "fuse", "max_pass_gates"}) {
+  for (const char *name : {"tile_bits", "reg_bits", "low_bits", "max_rounds", "peephole", "fuse", "max_pass_gates", "l2_prefetch", "stagger_ns"}) {
     std::string env = "QB_";
     for (const char *p = name; *p; ++p) env.push_back((char)toupper(*p));
     const char *v = getenv(env.c_str());
@@ -668,8 +668,10 @@ int qb_measure_qubit(qb_state *s, int q, double r, int *bit, double *pone) {
   Guard g(s->ctx);
   double s0, s1;
   QB_TRY(sumsq_locked(s, logical_bit(s, q), &s0, &s1));
-  const double p = std::sqrt(s1);  // the reference's pOne (NaN there when s1 == 0; both pick Zero)
-  const int b = (r < p) ? 1 : 0;
+  // the reference's pOne = sqrt(s1); when s1 == 0 it is NaN there (0/0 in collapse) and
+  // `r < NaN` is False for EVERY r, so the outcome is Zero even for an out-of-range draw
+  const double p = std::sqrt(s1);
+  const int b = (s1 > 0.0 && r < p) ? 1 : 0;
   *bit = b;
   if (pone) *pone = p;
   return collapse_with(s, logical_bit(s, q), b, b ? s1 : s0);

@@ -45,7 +45,7 @@ static_assert(sizeof(DevGate) == 112, "DevGate layout");
 struct DevRound {
   uint32_t gate_begin, gate_end;
   uint32_t nthr_bits;                 // T - R
-  uint32_t _pad;
+  uint32_t warp_local;                // the transpose INTO this round stays inside each warp
   uint8_t tid_pos[16];                // tile-local bit position carried by thread-id bit j
   uint8_t reg_pos[8];                 // tile-local bit position carried by register bit j
   uint32_t reg_sx[8];                 // swizzled shared-memory index contribution of register bit j
@@ -61,7 +61,10 @@ struct DevPass {
   uint32_t run_len[kMaxRuns];
   uint8_t tile_pos[16];               // physical bit position of tile-local bit i
   double gscale[2];                   // deferred global scalar applied on the way out (1,0 = none)
-  uint32_t has_gscale, _pad[3];
+  uint32_t has_gscale;
+  uint32_t l2_prefetch;               // prefetch the CTA's next tile into L2 while this one computes
+  uint32_t stagger_ns;                // start-up delay per co-resident CTA index (phase de-sync)
+  uint32_t sm_count;
   DevRound rounds[kMaxRounds];
   // followed in memory by ngates DevGate records
 };
@@ -102,6 +105,8 @@ struct PlanOptions {
   int peephole = 1;
   int max_pass_gates = kMaxPassGates;
   int time_kernels = 0;
+  int l2_prefetch = 1;
+  int stagger_ns = 0;
 };
 
 // (tile bits, register bits, min CTAs/SM) instantiations of k_fused_pass
@@ -109,7 +114,7 @@ struct VariantSpec {
   int T, R, minb;
 };
 constexpr VariantSpec kFusedVariants[] = {{10, 3, 4}, {10, 4, 4}, {11, 3, 3}, {11, 4, 4}, {11, 5, 6},
-                                          {12, 3, 2}, {12, 4, 2}, {12, 5, 3}, {13, 4, 1}, {13, 5, 1}};
+                                          {12, 3, 2}, {12, 4, 3}, {12, 5, 3}, {13, 4, 1}, {13, 5, 1}};
 bool variant_supported(int T, int R);
 bool set_opt(PlanOptions &o, const std::string &name, int64_t v);
 int64_t get_opt(const PlanOptions &o, const std::string &name);

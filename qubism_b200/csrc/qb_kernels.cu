@@ -18,6 +18,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "qb_internal.h"
@@ -32,108 +33,195 @@ __device__ __forceinline__ uint32_t swz(uint32_t u) {
 // ---------------------------------------------------------------- register-resident gates
 // Every gate body exists twice: CTRL = false is the common uncontrolled case (straight-line
 // DFMA code, nothing predicated); CTRL = true predicates each pair on the control masks.
-template <int R, int J, bool CTRL>
+// ---- the flip mask ------------------------------------------------------------------------
+// An X / CX whose controls are NOT register bits never moves data: it toggles bit J of the
+// per-thread mask `f`, meaning "the amplitude in register i belongs to logical register index
+// i ^ f".  Gates that follow on bit J use the matrix with rows and columns exchanged (one
+// select per entry, per thread); controls on register bits test (i ^ f); and at the end of the
+// round f folds into the transpose / store ADDRESS as a single XOR (the index maps are linear
+// over XOR).  This turns the ~150 ALU instructions of a register-level conditional swap into 3.
+//
+// Gate bodies come in three flavours (FL): 0 = uncontrolled, no flip possible on this bit
+// (planner guarantees it): straight-line DFMA code on uniform-register operands;
+// 1 = uncontrolled, flip-aware; 2 = controlled (always flip-aware).
+//
+// The arithmetic is ordered so that the LAST fused multiply-add of every component reads the
+// old value of the register it overwrites: new values never need a second live register, and
+// the switch arms leave every amplitude in the register it came in (no shuffle MOVs between
+// gates -- they were 55% of all executed instructions in the first version, ncu r01).
+template <int R, int J, int FL>
 __device__ __forceinline__ void gate_general(double (&re)[1 << R], double (&im)[1 << R], const DevGate &g,
-                                             bool ok_thr) {
-  const double2 A = *reinterpret_cast<const double2 *>(&g.m[0]), B = *reinterpret_cast<const double2 *>(&g.m[2]);
-  const double2 Cc = *reinterpret_cast<const double2 *>(&g.m[4]), D = *reinterpret_cast<const double2 *>(&g.m[6]);
-  const uint32_t creg = CTRL ? g.creg : 0u;
+                                             bool ok_thr, uint32_t f) {
+  double Ar = g.m[0], Ai = g.m[1], Br = g.m[2], Bi = g.m[3];
+  double Cr = g.m[4], Ci = g.m[5], Dr = g.m[6], Di = g.m[7];
+  if (FL != 0 && ((f >> J) & 1u)) {  // logical pair order is reversed in this thread
+    double t;
+    t = Ar; Ar = Dr; Dr = t;
+    t = Ai; Ai = Di; Di = t;
+    t = Br; Br = Cr; Cr = t;
+    t = Bi; Bi = Ci; Ci = t;
+  }
+  const uint32_t creg = (FL == 2) ? g.creg : 0u;
 #pragma unroll
   for (int p = 0; p < (1 << (R - 1)); ++p) {
     const int i0 = ((p >> J) << (J + 1)) | (p & ((1 << J) - 1));
     const int i1 = i0 | (1 << J);
-    if (!CTRL || (ok_thr && ((uint32_t(i0) & creg) == creg))) {
-      const double x0r = re[i0], x0i = im[i0], x1r = re[i1], x1i = im[i1];
-      re[i0] = A.x * x0r - A.y * x0i + B.x * x1r - B.y * x1i;
-      im[i0] = A.x * x0i + A.y * x0r + B.x * x1i + B.y * x1r;
-      re[i1] = Cc.x * x0r - Cc.y * x0i + D.x * x1r - D.y * x1i;
-      im[i1] = Cc.x * x0i + Cc.y * x0r + D.x * x1i + D.y * x1r;
+    if (FL != 2 || (ok_thr && (((uint32_t(i0) ^ f) & creg) == creg))) {
+      // partial sums that need the OLD x0 / x1
+      double P = -Ai * im[i0];
+      double Q = Ai * re[i0];
+      double Tr = Cr * re[i0];
+      double Ti = Cr * im[i0];
+      P = fma(Br, re[i1], P);
+      Q = fma(Br, im[i1], Q);
+      Tr = fma(-Ci, im[i0], Tr);
+      Ti = fma(Ci, re[i0], Ti);
+      P = fma(-Bi, im[i1], P);
+      Q = fma(Bi, re[i1], Q);
+      Tr = fma(-Di, im[i1], Tr);
+      Ti = fma(Di, re[i1], Ti);
+      // in-place finishers
+      re[i0] = fma(Ar, re[i0], P);
+      im[i0] = fma(Ar, im[i0], Q);
+      re[i1] = fma(Dr, re[i1], Tr);
+      im[i1] = fma(Dr, im[i1], Ti);
     }
   }
 }
 
-template <int R, int J, bool CTRL>
+template <int R, int J, int FL>
 __device__ __forceinline__ void gate_real(double (&re)[1 << R], double (&im)[1 << R], const DevGate &g,
-                                          bool ok_thr) {
-  const double a = g.m[0], b = g.m[2], c = g.m[4], d = g.m[6];
-  const uint32_t creg = CTRL ? g.creg : 0u;
+                                          bool ok_thr, uint32_t f) {
+  double a = g.m[0], b = g.m[2], c = g.m[4], d = g.m[6];
+  if (FL != 0 && ((f >> J) & 1u)) {
+    double t;
+    t = a; a = d; d = t;
+    t = b; b = c; c = t;
+  }
+  const uint32_t creg = (FL == 2) ? g.creg : 0u;
 #pragma unroll
   for (int p = 0; p < (1 << (R - 1)); ++p) {
     const int i0 = ((p >> J) << (J + 1)) | (p & ((1 << J) - 1));
     const int i1 = i0 | (1 << J);
-    if (!CTRL || (ok_thr && ((uint32_t(i0) & creg) == creg))) {
-      const double x0r = re[i0], x0i = im[i0], x1r = re[i1], x1i = im[i1];
-      re[i0] = a * x0r + b * x1r;
-      im[i0] = a * x0i + b * x1i;
-      re[i1] = c * x0r + d * x1r;
-      im[i1] = c * x0i + d * x1i;
+    if (FL != 2 || (ok_thr && (((uint32_t(i0) ^ f) & creg) == creg))) {
+      const double Tr = c * re[i0];
+      const double Ti = c * im[i0];
+      const double Pr = b * re[i1];
+      const double Pi = b * im[i1];
+      re[i0] = fma(a, re[i0], Pr);
+      im[i0] = fma(a, im[i0], Pi);
+      re[i1] = fma(d, re[i1], Tr);
+      im[i1] = fma(d, im[i1], Ti);
     }
   }
 }
 
-template <int R, int J, bool CTRL>
+// Conditional swap IN PLACE with the masked-XOR trick (t = (a ^ b) & m; a ^= t; b ^= t), in
+// inline PTX so that the optimiser cannot turn it back into selects.  A C++ select
+// (a = ok ? b : a ...) makes the compiler rename registers inside the arm, and the resulting
+// permutation was repaired with ~64 MOVs around EVERY switch arm of the kernel.
+__device__ __forceinline__ void cswap_inplace(double &a, double &b, unsigned long long m) {
+  asm volatile(
+      "{ .reg .b64 t;\n"
+      "  xor.b64 t, %0, %1;\n"
+      "  and.b64 t, t, %2;\n"
+      "  xor.b64 %0, %0, t;\n"
+      "  xor.b64 %1, %1, t;\n"
+      "}"
+      : "+d"(a), "+d"(b)
+      : "l"(m));
+}
+
+// X / CX with a control on a REGISTER bit: data really moves (only this flavour exists; the
+// others are flip-mask toggles handled in apply_gate)
+template <int R, int J, int FL>
 __device__ __forceinline__ void gate_swap(double (&re)[1 << R], double (&im)[1 << R], const DevGate &g,
-                                          bool ok_thr) {
-  const uint32_t creg = CTRL ? g.creg : 0u;
+                                          bool ok_thr, uint32_t f) {
+  const uint32_t creg = g.creg;
 #pragma unroll
   for (int p = 0; p < (1 << (R - 1)); ++p) {
     const int i0 = ((p >> J) << (J + 1)) | (p & ((1 << J) - 1));
     const int i1 = i0 | (1 << J);
-    const bool ok = !CTRL || (ok_thr && ((uint32_t(i0) & creg) == creg));
-    const double x0r = re[i0], x0i = im[i0], x1r = re[i1], x1i = im[i1];
-    re[i0] = ok ? x1r : x0r;
-    im[i0] = ok ? x1i : x0i;
-    re[i1] = ok ? x0r : x1r;
-    im[i1] = ok ? x0i : x1i;
+    const bool ok = ok_thr && (((uint32_t(i0) ^ f) & creg) == creg);
+    const unsigned long long m = ok ? ~0ull : 0ull;
+    cswap_inplace(re[i0], re[i1], m);
+    cswap_inplace(im[i0], im[i1], m);
   }
 }
 
-template <int R>
-__device__ __forceinline__ void gate_diag(double (&re)[1 << R], double (&im)[1 << R], const DevGate &g, bool ok_thr,
-                                          bool sel_thr) {
-  const double d0r = g.m[0], d0i = g.m[1], d1r = g.m[6], d1i = g.m[7];
-  const uint32_t creg = g.creg, dreg = g.dreg;
+// diagonal gate whose target is register bit J
+template <int R, int J, int FL>
+__device__ __forceinline__ void gate_diag_reg(double (&re)[1 << R], double (&im)[1 << R], const DevGate &g,
+                                              bool ok_thr, uint32_t f) {
+  double d0r = g.m[0], d0i = g.m[1], d1r = g.m[6], d1i = g.m[7];
+  if (FL != 0 && ((f >> J) & 1u)) {
+    double t;
+    t = d0r; d0r = d1r; d1r = t;
+    t = d0i; d0i = d1i; d1i = t;
+  }
+  const uint32_t creg = (FL == 2) ? g.creg : 0u;
 #pragma unroll
   for (int i = 0; i < (1 << R); ++i) {
-    const bool one = sel_thr || ((uint32_t(i) & dreg) != 0);
-    const double dr = one ? d1r : d0r, di = one ? d1i : d0i;
-    if (ok_thr && ((uint32_t(i) & creg) == creg)) {
-      const double xr = re[i], xi = im[i];
-      re[i] = dr * xr - di * xi;
-      im[i] = dr * xi + di * xr;
+    const double dr = ((i >> J) & 1) ? d1r : d0r, di = ((i >> J) & 1) ? d1i : d0i;
+    if (FL != 2 || (ok_thr && (((uint32_t(i) ^ f) & creg) == creg))) {
+      const double t = -di * im[i];
+      im[i] = fma(dr, im[i], di * re[i]);
+      re[i] = fma(dr, re[i], t);
     }
   }
 }
 
-// one flat opcode = (type, controlled?, target register bit): a single jump per gate
-#define QB_CASES(TYPE, FN)                                                                      \
-  case (TYPE * 16 + 0): FN<R, 0, false>(re, im, g, true); break;                                \
-  case (TYPE * 16 + 1): FN<R, 1, false>(re, im, g, true); break;                                \
-  case (TYPE * 16 + 2): FN<R, 2, false>(re, im, g, true); break;                                \
-  case (TYPE * 16 + 3): if constexpr (R > 3) FN<R, 3, false>(re, im, g, true); break;           \
-  case (TYPE * 16 + 4): if constexpr (R > 4) FN<R, 4, false>(re, im, g, true); break;           \
-  case (TYPE * 16 + 8): FN<R, 0, true>(re, im, g, ok_thr); break;                               \
-  case (TYPE * 16 + 9): FN<R, 1, true>(re, im, g, ok_thr); break;                               \
-  case (TYPE * 16 + 10): FN<R, 2, true>(re, im, g, ok_thr); break;                              \
-  case (TYPE * 16 + 11): if constexpr (R > 3) FN<R, 3, true>(re, im, g, ok_thr); break;         \
-  case (TYPE * 16 + 12): if constexpr (R > 4) FN<R, 4, true>(re, im, g, ok_thr); break;
+// diagonal gate whose target is a thread-id bit or lies outside the tile: one factor per thread
+template <int R>
+__device__ __forceinline__ void gate_diag_thr(double (&re)[1 << R], double (&im)[1 << R], const DevGate &g,
+                                              bool ok_thr, bool one, uint32_t f) {
+  const double dr = one ? g.m[6] : g.m[0], di = one ? g.m[7] : g.m[1];
+  const uint32_t creg = g.creg;
+#pragma unroll
+  for (int i = 0; i < (1 << R); ++i) {
+    if (ok_thr && (((uint32_t(i) ^ f) & creg) == creg)) {
+      const double t = -di * im[i];
+      im[i] = fma(dr, im[i], di * re[i]);
+      re[i] = fma(dr, re[i], t);
+    }
+  }
+}
+
+// one flat opcode = (type, flavour, target register bit): a single jump per gate
+#define QB_CASES_FL(TYPE, FN, FL)                                                               \
+  case (TYPE * 32 + FL * 8 + 0): FN<R, 0, FL>(re, im, g, ok_thr, f); break;                     \
+  case (TYPE * 32 + FL * 8 + 1): FN<R, 1, FL>(re, im, g, ok_thr, f); break;                     \
+  case (TYPE * 32 + FL * 8 + 2): FN<R, 2, FL>(re, im, g, ok_thr, f); break;                     \
+  case (TYPE * 32 + FL * 8 + 3): if constexpr (R > 3) FN<R, 3, FL>(re, im, g, ok_thr, f); break; \
+  case (TYPE * 32 + FL * 8 + 4): if constexpr (R > 4) FN<R, 4, FL>(re, im, g, ok_thr, f); break;
+#define QB_CASES(TYPE, FN) QB_CASES_FL(TYPE, FN, 0) QB_CASES_FL(TYPE, FN, 1) QB_CASES_FL(TYPE, FN, 2)
 
 template <int R>
 __device__ __forceinline__ void apply_gate(double (&re)[1 << R], double (&im)[1 << R], const DevGate &g, uint32_t tid,
-                                           uint64_t basefull) {
+                                           uint64_t basefull, uint32_t &f) {
   const bool ok_thr = ((tid & g.cthr) == g.cthr) && ((basefull & g.cext) == g.cext);
+  const uint32_t J = g.treg & 0xffu;
+  if (g.type == G_SWAP && g.creg == 0) {  // flip-mask toggle: no data movement
+    f ^= ok_thr ? (1u << J) : 0u;
+    return;
+  }
   const bool ctrl = (g.creg | g.cthr) != 0 || g.cext != 0;
-  const uint32_t op = g.type * 16 + (ctrl ? 8u : 0u) + g.treg;
+  // flavour: 2 = controlled, 1 = uncontrolled but a flip may be pending on bit J, 0 = plain.
+  // G_DIAG carries J = its register bit, or 7 when the target is a thread / external bit.
+  const uint32_t fl = ctrl ? 2u : ((g.treg >> 8) & 1u);
+  const uint32_t op = g.type * 32 + fl * 8 + J;
   switch (op) {
     QB_CASES(G_GENERAL, gate_general)
     QB_CASES(G_REAL, gate_real)
-    QB_CASES(G_SWAP, gate_swap)
-    default:
-      if (g.type == G_DIAG) {
-        const bool sel_thr = ((tid & g.dthr) != 0) || ((basefull & g.dext) != 0);
-        gate_diag<R>(re, im, g, ok_thr, sel_thr);
-      }
-      break;
+    QB_CASES_FL(G_SWAP, gate_swap, 2)
+    QB_CASES(G_DIAG, gate_diag_reg)
+    case (G_DIAG * 32 + 0 * 8 + 7):
+    case (G_DIAG * 32 + 1 * 8 + 7):
+    case (G_DIAG * 32 + 2 * 8 + 7): {
+      const bool one = ((tid & g.dthr) != 0) || ((basefull & g.dext) != 0);
+      gate_diag_thr<R>(re, im, g, ok_thr, one, f);
+    } break;
+    default: break;
   }
 }
 
@@ -176,6 +264,12 @@ __global__ void __launch_bounds__(1 << (T - R), MINB)
   const uint64_t goff_ld = thread_goff<T, R>(P, P.rounds[0], tid);
   const uint64_t goff_st = thread_goff<T, R>(P, P.rounds[nrounds - 1], tid);
 
+  // Co-resident CTAs do identical work and would march in lockstep (all loading, then all
+  // computing), leaving HBM idle half of the time: start them a fraction of a tile period apart.
+  if (P.stagger_ns) {
+    const uint32_t slot = blockIdx.x / P.sm_count;
+    for (uint32_t k = 0; k < slot; ++k) __nanosleep(P.stagger_ns);
+  }
   for (unsigned long long tile_id = blockIdx.x; tile_id < ntiles; tile_id += gridDim.x) {
     // deposit the tile id into the non-tile bit positions
     uint64_t base = 0;
@@ -206,17 +300,48 @@ __global__ void __launch_bounds__(1 << (T - R), MINB)
         re[i] = a.x;
         im[i] = a.y;
       }
+      // While this tile is in registers, pull the CTA's NEXT tile from HBM into L2 (one request
+      // per 128-byte line): its loads then hit L2 instead of waiting on DRAM, which overlaps
+      // the memory phase of tile k+1 with the gate / transpose phases of tile k.
+      const unsigned long long next_id = tile_id + gridDim.x;
+      if (P.l2_prefetch && next_id < ntiles && (tid & 7u) == 0u) {
+        uint64_t nbase = 0;
+        uint64_t t = next_id;
+        const uint32_t nruns = P.nruns;
+        for (uint32_t k = 0; k < nruns; ++k) {
+          const uint32_t len = P.run_len[k];
+          nbase |= (t & ((1ull << len) - 1ull)) << P.run_shift[k];
+          t >>= len;
+        }
+        const double2 *nsrc = amps + nbase + goff_ld;
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+          uint64_t off = 0;
+#pragma unroll
+          for (int j = 0; j < R; ++j)
+            if ((i >> j) & 1) off += st[j];
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(nsrc + off));
+        }
+      }
     }
 
+    uint32_t f = 0;  // flip mask: register i holds logical register index i ^ f
     for (uint32_t r = 0; r < nrounds; ++r) {
       const DevRound &RD = P.rounds[r];
       if (r > 0) {  // transpose through swizzled shared memory: new register-resident bits
         const DevRound &PR = P.rounds[r - 1];
-        const uint32_t us = thread_sidx<T, R>(PR, tid);
+        uint32_t us = thread_sidx<T, R>(PR, tid);
         uint32_t sx[R];
 #pragma unroll
-        for (int j = 0; j < R; ++j) sx[j] = PR.reg_sx[j];
-        __syncthreads();  // everyone finished reading the previous layout
+        for (int j = 0; j < R; ++j) {
+          sx[j] = PR.reg_sx[j];
+          us ^= ((f >> j) & 1u) ? sx[j] : 0u;  // fold the flip mask into the address
+        }
+        f = 0;
+        // A warp-local transpose only touches this warp's own slots: the barriers shrink to
+        // __syncwarp() and the warps of the CTA stay decoupled.
+        const bool local = RD.warp_local != 0;
+        if (local) __syncwarp(); else __syncthreads();  // everyone finished reading the previous layout
 #pragma unroll
         for (int i = 0; i < NR; ++i) {
           uint32_t x = us;
@@ -225,7 +350,7 @@ __global__ void __launch_bounds__(1 << (T - R), MINB)
             if ((i >> j) & 1) x ^= sx[j];
           tile[x] = make_double2(re[i], im[i]);
         }
-        __syncthreads();
+        if (local) __syncwarp(); else __syncthreads();
         const uint32_t ul = thread_sidx<T, R>(RD, tid);
 #pragma unroll
         for (int j = 0; j < R; ++j) sx[j] = RD.reg_sx[j];
@@ -241,7 +366,7 @@ __global__ void __launch_bounds__(1 << (T - R), MINB)
         }
       }
       const uint32_t gend = RD.gate_end;
-      for (uint32_t gi = RD.gate_begin; gi < gend; ++gi) apply_gate<R>(re, im, G[gi], tid, basefull);
+      for (uint32_t gi = RD.gate_begin; gi < gend; ++gi) apply_gate<R>(re, im, G[gi], tid, basefull, f);
     }
 
     if (P.has_gscale) {  // deferred global scalar (folded u1-type phases, qb_scale)
@@ -253,18 +378,23 @@ __global__ void __launch_bounds__(1 << (T - R), MINB)
         im[i] = sr * xi + si * xr;
       }
     }
-    {  // coalesced store with the last round's layout
-      double2 *dst = amps + base + goff_st;
+    {  // coalesced store with the last round's layout (register strides are distinct bits, so
+       // the pending flip mask is one XOR on the element index)
       uint64_t st[R];
+      uint64_t fx = 0;
 #pragma unroll
-      for (int j = 0; j < R; ++j) st[j] = 1ull << P.tile_pos[P.rounds[nrounds - 1].reg_pos[j]];
+      for (int j = 0; j < R; ++j) {
+        st[j] = 1ull << P.tile_pos[P.rounds[nrounds - 1].reg_pos[j]];
+        fx |= ((f >> j) & 1u) ? st[j] : 0ull;
+      }
+      const uint64_t at = (base + goff_st) ^ fx;
 #pragma unroll
       for (int i = 0; i < NR; ++i) {
         uint64_t off = 0;
 #pragma unroll
         for (int j = 0; j < R; ++j)
-          if ((i >> j) & 1) off += st[j];
-        __stcs(dst + off, make_double2(re[i], im[i]));
+          if ((i >> j) & 1) off |= st[j];
+        __stcs(amps + (at ^ off), make_double2(re[i], im[i]));
       }
     }
   }
@@ -280,10 +410,21 @@ struct FusedVariant {
 
 static const FusedVariant kVariants[] = {
     QB_VARIANT(10, 3, 4), QB_VARIANT(10, 4, 4), QB_VARIANT(11, 3, 3), QB_VARIANT(11, 4, 4), QB_VARIANT(11, 5, 6),
-    QB_VARIANT(12, 3, 2), QB_VARIANT(12, 4, 2), QB_VARIANT(12, 5, 3), QB_VARIANT(13, 4, 1), QB_VARIANT(13, 5, 1),
+    QB_VARIANT(12, 3, 2), QB_VARIANT(12, 4, 3), QB_VARIANT(12, 5, 3), QB_VARIANT(13, 4, 1), QB_VARIANT(13, 5, 1),
+};
+// experimental: same (T, R) with a different register budget (selected with QB_ALT_VARIANTS=1)
+static const FusedVariant kAltVariants[] = {
+    QB_VARIANT(11, 4, 5),
+    QB_VARIANT(11, 4, 6), QB_VARIANT(12, 4, 2),
 };
 
 static const FusedVariant *find_variant(int T, int R) {
+  static const char *alt = getenv("QB_ALT_VARIANTS");
+  if (alt && *alt) {
+    const int want = atoi(alt);
+    for (const auto &v : kAltVariants)
+      if (v.T == T && v.R == R && v.minb == want) return &v;
+  }
   for (const auto &v : kVariants)
     if (v.T == T && v.R == R) return &v;
   return nullptr;

@@ -46,6 +46,11 @@ bool set_opt(PlanOptions &o, const std::string &name, int64_t v) {
     o.max_pass_gates = (int)v;
   } else if (name == "time_kernels") {
     o.time_kernels = v ? 1 : 0;
+  } else if (name == "l2_prefetch") {
+    o.l2_prefetch = v ? 1 : 0;
+  } else if (name == "stagger_ns") {
+    if (v < 0 || v > 100000) return false;
+    o.stagger_ns = (int)v;
   } else {
     return false;
   }
@@ -61,6 +66,8 @@ int64_t get_opt(const PlanOptions &o, const std::string &name) {
   if (name == "fuse") return o.fuse;
   if (name == "max_pass_gates") return o.max_pass_gates;
   if (name == "time_kernels") return o.time_kernels;
+  if (name == "l2_prefetch") return o.l2_prefetch;
+  if (name == "stagger_ns") return o.stagger_ns;
   return -1;
 }
 
@@ -438,16 +445,99 @@ static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &don
     if (tile_mask & (1ull << b)) tile_bits.push_back(b);
 
   const int nrounds = (int)rounds.size();
-  // fill every round's register set to exactly R bits (highest free tile bits first)
-  for (int r = 0; r < nrounds; ++r) {
-    const bool edge = (r == 0) || (r == nrounds - 1);
-    for (int i = T - 1; i >= 0 && popc(rounds[r].regmask) < R; --i) {
-      const uint64_t b = 1ull << tile_bits[i];
-      if (rounds[r].regmask & b) continue;
-      if (edge && (b & lowfixed)) continue;
-      rounds[r].regmask |= b;
+  // ---- layout of every round: which tile bits sit in registers / lanes / warp-id bits.
+  // A transpose between two rounds whose warp-id bits carry the SAME tile bits is warp-local:
+  // each warp reads back exactly the shared-memory slots it wrote, so __syncwarp() replaces the
+  // two CTA barriers and the warps of a CTA stay decoupled.  The warp bits are therefore kept
+  // as long as no gate needs them in registers, and re-chosen Belady-style (the bits whose next
+  // use as a register bit is furthest away) when one does.  Tile-local bits 0..2 are never warp
+  // bits: they are the lanes that make global accesses whole 128-byte lines.
+  const int nw = std::max(0, T - R - 5);
+  auto tl_of = [&](int phys) { return tile_local_index(tile_bits, phys); };
+  std::vector<uint32_t> req(nrounds, 0);  // tile-local masks
+  for (int r = 0; r < nrounds; ++r)
+    for (int i = 0; i < T; ++i)
+      if (rounds[r].regmask & (1ull << tile_bits[i])) req[r] |= 1u << i;
+  std::vector<std::vector<int>> warp_bits(nrounds), lane_bits(nrounds), reg_bits_v(nrounds), qw_lanes(nrounds);
+  {
+    // quarter-warp lanes: three tile-local bits with distinct residues mod 3, outside `busy`
+    auto pick_qw = [&](uint32_t busy, int out[3]) {
+      for (int res = 0; res < 3; ++res) {
+        out[res] = -1;
+        for (int i = res; i < T; i += 3)
+          if (!(busy & (1u << i))) {
+            out[res] = i;
+            break;
+          }
+      }
+      return out[0] >= 0 && out[1] >= 0 && out[2] >= 0;
+    };
+    std::vector<int> W;  // current warp bits (tile-local), ascending
+    for (int r = 0; r < nrounds; ++r) {
+      const bool edge = (r == 0) || (r == nrounds - 1);
+      uint32_t wmask = 0;
+      for (int w : W) wmask |= 1u << w;
+      bool keep = (int)W.size() == nw && !(wmask & req[r]);
+      int qw[3];
+      if (keep && !pick_qw(req[r] | wmask, qw)) keep = false;  // keeping W would cost bank conflicts
+      if (!keep) {
+        wmask = 0;
+        const bool have_qw = pick_qw(req[r], qw);
+        uint32_t busy = req[r];
+        if (have_qw) busy |= (1u << qw[0]) | (1u << qw[1]) | (1u << qw[2]);
+        // candidates: free bits >= 3, furthest next use as a register first (Belady)
+        std::vector<std::pair<int, int>> cand;
+        for (int i = kLaneFixedBits; i < T; ++i) {
+          if (busy & (1u << i)) continue;
+          int next = 1000;
+          for (int r2 = r + 1; r2 < nrounds; ++r2)
+            if (req[r2] & (1u << i)) {
+              next = r2;
+              break;
+            }
+          cand.emplace_back(-next, -i);
+        }
+        std::sort(cand.begin(), cand.end());
+        W.clear();
+        for (size_t k = 0; k < cand.size() && (int)W.size() < nw; ++k) W.push_back(-cand[k].second);
+        std::sort(W.begin(), W.end());
+        for (int w : W) wmask |= 1u << w;
+        if (!have_qw) pick_qw(req[r] | wmask, qw);  // best effort
+      }
+      warp_bits[r] = W;
+      uint32_t qmask = 0;
+      for (int k = 0; k < 3; ++k)
+        if (qw[k] >= 0) {
+          qmask |= 1u << qw[k];
+          qw_lanes[r].push_back(qw[k]);
+        }
+      if (qw_lanes[r].size() != 3) {
+        qw_lanes[r].clear();
+        qmask = 0;
+      }
+      std::sort(qw_lanes[r].begin(), qw_lanes[r].end());
+      // fill the register set to exactly R bits: highest free bits (not warp bits, not the
+      // quarter-warp lanes, and never bits 0..2 in a load / store round)
+      uint32_t regm = req[r];
+      for (int pass2 = 0; pass2 < 2; ++pass2)
+        for (int i = T - 1; i >= 0 && popc(regm) < R; --i) {
+          if ((regm | wmask) & (1u << i)) continue;
+          if (edge && i < kLaneFixedBits) continue;
+          if (pass2 == 0 && (qmask & (1u << i))) continue;
+          regm |= 1u << i;
+        }
+      rounds[r].regmask = 0;
+      for (int i = 0; i < T; ++i) {
+        if (regm & (1u << i)) {
+          reg_bits_v[r].push_back(i);
+          rounds[r].regmask |= 1ull << tile_bits[i];
+        } else if (!(wmask & (1u << i))) {
+          lane_bits[r].push_back(i);
+        }
+      }
     }
   }
+  (void)tl_of;
 
   out = PassPlan();
   out.tile_bits = T;
@@ -468,6 +558,9 @@ static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &don
   P->gscale[0] = 1.0;
   P->gscale[1] = 0.0;
   P->has_gscale = 0;
+  P->l2_prefetch = opt.l2_prefetch ? 1u : 0u;
+  P->stagger_ns = (uint32_t)opt.stagger_ns;
+  P->sm_count = 148;
   for (int i = 0; i < T; ++i) P->tile_pos[i] = (uint8_t)tile_bits[i];
   {  // runs of non-tile local bits, ascending
     uint32_t nruns = 0;
@@ -492,46 +585,32 @@ static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &don
     DevRound &RD = P->rounds[r];
     const bool edge = (r == 0) || (r == nrounds - 1);
     RD.nthr_bits = T - R;
-    // register bits ascending
-    std::vector<int> regs, thr;
-    for (int i = 0; i < T; ++i) {
-      if (rounds[r].regmask & (1ull << tile_bits[i])) regs.push_back(i);
-      else thr.push_back(i);
-    }
-    // thread-id bit order: load/store rounds keep ascending order (lanes on the lowest bits =
-    // contiguous 128-byte lines).  Inner rounds put three positions with distinct residues
-    // mod 3 first so that each quarter-warp's 128-bit shared accesses hit 8 distinct bank
-    // groups under the XOR swizzle.
+    const std::vector<int> &regs = reg_bits_v[r];
+    // thread-id bit order: lanes first, warp-id bits last.  Load/store rounds keep the lanes
+    // ascending (bits 0..2 first = whole 128-byte lines per quarter-warp).  Inner rounds put
+    // three lane positions with distinct residues mod 3 first so that each quarter-warp's
+    // 128-bit shared accesses hit 8 distinct bank groups under the XOR swizzle.
     std::vector<int> order;
-    if (edge) {
-      order = thr;
-    } else {
-      std::vector<int> rest = thr;
-      int pick[3] = {-1, -1, -1};
-      for (int res_needed = 0; res_needed < 3; ++res_needed) {
-        // choose, for each residue, the lowest thread position with that residue
-        for (size_t k = 0; k < rest.size(); ++k)
-          if (rest[k] % 3 == res_needed) {
-            pick[res_needed] = rest[k];
-            rest.erase(rest.begin() + k);
-            break;
-          }
+    {
+      std::vector<int> rest = lane_bits[r];
+      bool qw_ok = !edge && qw_lanes[r].size() == 3;
+      for (int q : qw_lanes[r])
+        if (std::find(rest.begin(), rest.end(), q) == rest.end()) qw_ok = false;  // became a register
+      if (qw_ok) {
+        for (int q : qw_lanes[r]) rest.erase(std::find(rest.begin(), rest.end(), q));
+        order = qw_lanes[r];
       }
-      bool ok = pick[0] >= 0 && pick[1] >= 0 && pick[2] >= 0;
-      if (ok) {
-        std::sort(pick, pick + 3);
-        order.assign(pick, pick + 3);
-        order.insert(order.end(), rest.begin(), rest.end());
-      } else {
-        order = thr;
-      }
+      order.insert(order.end(), rest.begin(), rest.end());
+      order.insert(order.end(), warp_bits[r].begin(), warp_bits[r].end());
     }
+    RD.warp_local = (r > 0 && warp_bits[r] == warp_bits[r - 1]) ? 1u : 0u;
     for (int j = 0; j < T - R; ++j) RD.tid_pos[j] = (uint8_t)order[j];
     for (int j = 0; j < R; ++j) {
       RD.reg_pos[j] = (uint8_t)regs[j];
       RD.reg_sx[j] = swz_host(1u << regs[j]);
     }
     RD.gate_begin = gcount;
+    uint32_t flip_possible = 0;  // register bits an earlier X / CX of this round may have flipped
     for (int oi : rounds[r].ops) {
       const PhysOp &op = ops[oi];
       DevGate &g = G[gcount++];
@@ -557,11 +636,18 @@ static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &don
       for (uint64_t q = op.ctrl; q; q &= q - 1) place_bit(__builtin_ctzll(q), g.creg, g.cthr, g.cext);
       if (op.type == G_DIAG) {
         place_bit(op.target, g.dreg, g.dthr, g.dext);
+        g.treg = g.dreg ? (uint32_t)__builtin_ctz(g.dreg) : 7u;  // 7: target is not a register bit
       } else {
         uint32_t treg_mask = 0, tthr = 0;
         uint64_t text = 0;
         place_bit(op.target, treg_mask, tthr, text);
-        g.treg = treg_mask ? (uint32_t)__builtin_ctz(treg_mask) : 0xffffffffu;  // must be a register bit
+        g.treg = treg_mask ? (uint32_t)__builtin_ctz(treg_mask) : 0xffu;  // must be a register bit
+      }
+      // bit 8 of treg: a flip may be pending on the target register bit (flavour 1 in the kernel)
+      if (op.type == G_SWAP && g.creg == 0 && g.treg < 8) {
+        flip_possible |= 1u << g.treg;
+      } else if (g.treg < 8 && (flip_possible & (1u << g.treg))) {
+        g.treg |= 1u << 8;
       }
       out.op_index.push_back(oi);
     }
@@ -607,7 +693,7 @@ std::string describe_plan(const PlanResult &r) {
       const DevRound &RD = P->rounds[rd];
       os << "  round " << rd << " regs=[";
       for (int j = 0; j < p.reg_bits; ++j) os << (j ? "," : "") << (int)P->tile_pos[RD.reg_pos[j]];
-      os << "] tid=[";
+      os << "] local=" << RD.warp_local << " tid=[";
       for (int j = 0; j < p.tile_bits - p.reg_bits; ++j) os << (j ? "," : "") << (int)P->tile_pos[RD.tid_pos[j]];
       os << "] ops=[";
       for (uint32_t g = RD.gate_begin; g < RD.gate_end; ++g) os << (g > RD.gate_begin ? "," : "") << p.op_index[g];

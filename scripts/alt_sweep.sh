@@ -1,0 +1,26 @@
+#!/bin/bash
+for cfg in "0 12 0" "0 12 1500" "0 12 3000" "0 12 5000" "3 12 0" "3 12 1500" "3 12 3000" "3 12 5000" "0 11 2000" "0 11 4000"; do
+  set -- $cfg
+  echo "== alt=$1 T=$2 stagger_ns=$3"
+  QB_ALT_VARIANTS=$1 QB_TILE_BITS=$2 QB_STAGGER_NS=$3 python - <<PY
+import sys, time, json
+sys.path.insert(0, '.')
+import qubism_b200 as Q
+from qubism_b200 import capi
+from qubism_b200.circuits import random_layers, qft_ops
+from qubism_b200.qgate import unitary_matrix
+n=30
+ctx=Q.Context.default(); sv=Q.mkStateVec(n)
+G=unitary_matrix(.3,.2,.1)
+def t(build, reps=3):
+    build(); sv.flush(); ctx.sync(); ctx.reset_stats()
+    t0=time.perf_counter()
+    for _ in range(reps): build(); sv.flush()
+    ctx.sync(); return (time.perf_counter()-t0)/reps*1e3
+print("1 gate pass ms", round(t(lambda: sv.apply_1q(0,G)),3), " bit0 (3 rounds) ms", round(t(lambda: sv.apply_1q(n-1,G)),3))
+ops=capi.pack_ops(qft_ops(n)+random_layers(n,20,seed=1000))
+ms=t(lambda: sv.submit(ops), reps=2)
+st=ctx.stats()
+print("circuit ms", round(ms,1), "passes", st["passes"]//2, "ms/pass", round(ms/(st["passes"]//2),2))
+PY
+done

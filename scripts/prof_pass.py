@@ -12,6 +12,7 @@ n, T, R, wl = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), sys.argv[4]
 reps = int(sys.argv[5]) if len(sys.argv) > 5 else 3
 ctx = Q.Context.default()
 ctx.set_option("tile_bits", T); ctx.set_option("reg_bits", R)
+if wl in ("real52", "gen13"): ctx.set_option("peephole", 0)
 for kv in os.environ.get("QB_OPTS", "").split(","):
     if "=" in kv:
         k, v = kv.split("="); ctx.set_option(k, int(v))
@@ -26,6 +27,11 @@ def build():
         sv.apply_1q(0, G)
     elif wl == "one0":
         sv.apply_1q(n - 1, G)
+    elif wl == "real52":
+        for _ in range(13):
+            for q in range(4): sv.apply_1q(q, U)
+    elif wl == "gen13":
+        for _ in range(13): sv.apply_1q(0, G)
     elif wl == "rand":
         sv.submit(random_layers(n, 2, seed=1000))
 build(); sv.flush(); ctx.sync()

@@ -45,11 +45,11 @@ def emul():
 
     def run(n, ops, v, options=""):
         a = np.ascontiguousarray(v, dtype=np.complex128).copy()
-        st = (C.c_int64 * 4)()
+        st = (C.c_int64 * 6)()
         arr = capi.pack_ops(ops)
         rc = E.qbe_run(n, arr, len(arr), options.encode(), a.ctypes.data_as(C.c_void_p), st)
         assert rc == 0, f"emulator rc={rc}"
-        return a, dict(passes=st[0], rounds=st[1], gates=st[2], bank=st[3])
+        return a, dict(passes=st[0], rounds=st[1], gates=st[2], bank=st[3], transposes=st[4], local=st[5])
 
     run.lib = E
     return run

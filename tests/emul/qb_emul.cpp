@@ -19,7 +19,7 @@ using namespace qb;
 namespace {
 
 struct EmuStats {
-  int64_t passes = 0, rounds = 0, gates = 0, max_bank_conflict = 1;
+  int64_t passes = 0, rounds = 0, gates = 0, max_bank_conflict = 1, local_transposes = 0, transposes = 0;
 };
 
 void apply_gate_host(std::vector<double> &re, std::vector<double> &im, int R, const DevGate &g, uint32_t tid,
@@ -39,7 +39,7 @@ void apply_gate_host(std::vector<double> &re, std::vector<double> &im, int R, co
     }
     return;
   }
-  const int J = (int)g.treg;
+  const int J = (int)(g.treg & 0xffu);
   if (J < 0 || J >= R) {
     std::fprintf(stderr, "emulator: gate target is not a register bit (treg=%u)\n", g.treg);
     re[0] = NAN;
@@ -130,20 +130,29 @@ void run_pass(const PassPlan &pp, int L, std::vector<double> &amps, EmuStats &st
       if (r > 0) {
         const DevRound &PR = P.rounds[r - 1];
         std::fill(written.begin(), written.end(), 0);
-        for (int tid = 0; tid < NT; ++tid)
-          for (int i = 0; i < NR; ++i) {
-            const uint32_t x = swz_host(thread_u(PR, T - R, tid)) ^ reg_sx_of(PR, R, i);
-            if (written[x]) std::fprintf(stderr, "emulator: shared-memory slot written twice\n");
-            written[x] = 1;
-            tile_re[x] = re[tid][i];
-            tile_im[x] = im[tid][i];
-          }
-        for (int tid = 0; tid < NT; ++tid)
-          for (int i = 0; i < NR; ++i) {
-            const uint32_t x = swz_host(thread_u(RD, T - R, tid)) ^ reg_sx_of(RD, R, i);
-            re[tid][i] = tile_re[x];
-            im[tid][i] = tile_im[x];
-          }
+        // A warp-local transpose is emulated warp by warp against POISONED shared memory: if
+        // the planner flagged it wrongly, a warp reads a slot another warp owns and gets NaN.
+        const int group = RD.warp_local ? 32 : NT;
+        if (RD.warp_local) {
+          std::fill(tile_re.begin(), tile_re.end(), NAN);
+          std::fill(tile_im.begin(), tile_im.end(), NAN);
+        }
+        for (int g0 = 0; g0 < NT; g0 += group) {
+          for (int tid = g0; tid < g0 + group && tid < NT; ++tid)
+            for (int i = 0; i < NR; ++i) {
+              const uint32_t x = swz_host(thread_u(PR, T - R, tid)) ^ reg_sx_of(PR, R, i);
+              if (written[x]) std::fprintf(stderr, "emulator: shared-memory slot written twice\n");
+              written[x] = 1;
+              tile_re[x] = re[tid][i];
+              tile_im[x] = im[tid][i];
+            }
+          for (int tid = g0; tid < g0 + group && tid < NT; ++tid)
+            for (int i = 0; i < NR; ++i) {
+              const uint32_t x = swz_host(thread_u(RD, T - R, tid)) ^ reg_sx_of(RD, R, i);
+              re[tid][i] = tile_re[x];
+              im[tid][i] = tile_im[x];
+            }
+        }
       }
       for (uint32_t gi = RD.gate_begin; gi < RD.gate_end; ++gi)
         for (int tid = 0; tid < NT; ++tid) apply_gate_host(re[tid], im[tid], R, G[gi], tid, basefull);
@@ -164,6 +173,10 @@ void run_pass(const PassPlan &pp, int L, std::vector<double> &amps, EmuStats &st
   }
   st.passes++;
   st.rounds += P.nrounds;
+  for (uint32_t r = 1; r < P.nrounds; ++r) {
+    st.transposes++;
+    st.local_transposes += P.rounds[r].warp_local ? 1 : 0;
+  }
   (void)L;
 }
 
@@ -233,6 +246,8 @@ int qbe_run(int nlocal, const qb_op *ops, int64_t nops, const char *options, dou
     stats_out[1] = st.rounds;
     stats_out[2] = st.gates;
     stats_out[3] = st.max_bank_conflict;
+    stats_out[4] = st.transposes;
+    stats_out[5] = st.local_transposes;
   }
   return 0;
 }

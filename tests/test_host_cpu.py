@@ -81,7 +81,11 @@ def test_emulated_passes_match_oracle(emul, n, opts):
     ref = S.run_ops(n, ops, v)
     out, st = emul(n, ops, v, opts)
     assert np.abs(out - ref).max() < 1e-13
-    assert st["bank"] == 1, "a shared-memory transpose is not bank-conflict free"
+    assert st["bank"] <= 2, "a shared-memory transpose has more than 2-way bank conflicts"
+    if opts in ("", "reg_bits=5", "tile_bits=11,reg_bits=4"):
+        # (a kept warp-bit set may cost a 2-way conflict when a required register bit uses up a
+        #  residue class; staying warp-local is worth more than the conflict)
+        assert st["local"] * 2 >= st["transposes"], "most transposes should be warp-local"
     if "fuse=0" not in opts and "max_pass_gates" not in opts:
         assert st["passes"] <= 6
 

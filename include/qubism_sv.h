@@ -146,6 +146,9 @@ int qb_measure_all(qb_state *s, const double *rs, int *bits);
 int qb_scale(qb_state *s, qb_c64 z);                          /* z .: v                   */
 int qb_axpy(qb_state *y, qb_c64 z, qb_state *x);              /* y <- y +: (z .: x)       */
 int qb_neg(qb_state *s);                                      /* neg v                    */
+/* the same two with the scalar as (re, im) doubles: Haskell's FFI cannot pass structs by value */
+int qb_scale_ri(qb_state *s, double re, double im);
+int qb_axpy_ri(qb_state *y, double re, double im, qb_state *x);
 int qb_dotc(qb_state *a, qb_state *b, qb_c64 *out);           /* a <.> b, conj on a       */
 int qb_norm2(qb_state *s, double *out);                       /* LA.norm_2 (NOT squared)  */
 int qb_normalize(qb_state *s);                                /* normalize                */

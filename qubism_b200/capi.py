@@ -79,6 +79,8 @@ SIGNATURES = {
     "qb_scale": (_I, [_VP, QbC64]),
     "qb_axpy": (_I, [_VP, QbC64, _VP]),
     "qb_neg": (_I, [_VP]),
+    "qb_scale_ri": (_I, [_VP, _D, _D]),
+    "qb_axpy_ri": (_I, [_VP, _D, _D, _VP]),
     "qb_dotc": (_I, [_VP, _VP, _PC64]),
     "qb_norm2": (_I, [_VP, C.POINTER(_D)]),
     "qb_normalize": (_I, [_VP]),

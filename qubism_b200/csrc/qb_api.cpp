@@ -94,7 +94,7 @@ int init_common(qb_ctx *c) {
   QB_CUDA(cudaMallocHost(&c->red_host, sizeof(double) * 4));
   QB_CUDA(cudaMalloc(&c->kq_bits_dev, sizeof(int) * 2 * QB_MAX_KQ));
   QB_CUDA(cudaMalloc(&c->kq_mat_dev, sizeof(double2) << (2 * QB_MAX_KQ)));
-  for (const char *name : {"tile_bits", "reg_bits", "low_bits", "max_rounds", "peephole", "fuse", "max_pass_gates", "l2_prefetch", "stagger_ns"}) {
+  for (const char *name : {"tile_bits", "reg_bits", "low_bits", "max_rounds", "peephole", "fuse", "max_pass_gates", "l2_prefetch", "stagger_ns", "avoid_regswap"}) {
     std::string env = "QB_";
     for (const char *p = name; *p; ++p) env.push_back((char)toupper(*p));
     const char *v = getenv(env.c_str());
@@ -692,6 +692,7 @@ int qb_scale(qb_state *s, qb_c64 z) {
 }
 
 int qb_neg(qb_state *s) { return qb_scale(s, qb_c64{-1.0, 0.0}); }
+int qb_scale_ri(qb_state *s, double re, double im) { return qb_scale(s, qb_c64{re, im}); }
 
 static int same_shape(qb_state *a, qb_state *b) {
   if (!a || !b) return fail(QB_ERR_ARG, "null state");
@@ -711,6 +712,8 @@ int qb_axpy(qb_state *y, qb_c64 z, qb_state *x) {
   QB_CUDA(launch_axpy(y->amps, x->amps, 1ull << y->L, zz, c->sm_count, c->stream));
   return QB_OK;
 }
+
+int qb_axpy_ri(qb_state *y, double re, double im, qb_state *x) { return qb_axpy(y, qb_c64{re, im}, x); }
 
 int qb_dotc(qb_state *a, qb_state *b, qb_c64 *out) {
   QB_TRY(same_shape(a, b));

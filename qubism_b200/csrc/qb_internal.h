@@ -39,6 +39,20 @@ struct alignas(16) DevGate {
   uint32_t dreg;   // G_DIAG: target as register-index mask   (exactly one of dreg/dthr/dext set)
   uint32_t dthr;   // G_DIAG: target as thread-id mask
   uint64_t dext;   // G_DIAG: target as external mask
+  uint32_t op;     // dense kernel opcode (dev_opcode below): one jump-table dispatch per gate
+  uint32_t _pad;
+};
+
+// Dense opcode space of k_fused_pass's gate switch.  FL = flavour: 0 uncontrolled / no flip
+// possible, 1 uncontrolled / flip-aware, 2 controlled (flip-aware).  J = target register bit.
+enum : uint32_t {
+  OP_GENERAL = 0,    // + FL * 5 + J          (15)
+  OP_REAL = 15,      // + FL * 5 + J          (15)
+  OP_DIAG_REG = 30,  // + FL * 5 + J          (15)
+  OP_SWAP_REG = 45,  // + J: X / CX with a control on a register bit (data moves)   (5)
+  OP_TOGGLE = 50,    // X / CX without register-bit controls: flip-mask toggle
+  OP_DIAG_THR = 51,  // diagonal gate whose target is a thread bit or outside the tile
+  OP_COUNT = 52,
 };
 static_assert(sizeof(DevGate) == 112, "DevGate layout");
 
@@ -107,6 +121,7 @@ struct PlanOptions {
   int time_kernels = 0;
   int l2_prefetch = 1;
   int stagger_ns = 0;
+  int avoid_regswap = 0;  // planner: refuse rounds where a CX control would be a register bit
 };
 
 // (tile bits, register bits, min CTAs/SM) instantiations of k_fused_pass

@@ -187,39 +187,37 @@ __device__ __forceinline__ void gate_diag_thr(double (&re)[1 << R], double (&im)
   }
 }
 
-// one flat opcode = (type, flavour, target register bit): a single jump per gate
-#define QB_CASES_FL(TYPE, FN, FL)                                                               \
-  case (TYPE * 32 + FL * 8 + 0): FN<R, 0, FL>(re, im, g, ok_thr, f); break;                     \
-  case (TYPE * 32 + FL * 8 + 1): FN<R, 1, FL>(re, im, g, ok_thr, f); break;                     \
-  case (TYPE * 32 + FL * 8 + 2): FN<R, 2, FL>(re, im, g, ok_thr, f); break;                     \
-  case (TYPE * 32 + FL * 8 + 3): if constexpr (R > 3) FN<R, 3, FL>(re, im, g, ok_thr, f); break; \
-  case (TYPE * 32 + FL * 8 + 4): if constexpr (R > 4) FN<R, 4, FL>(re, im, g, ok_thr, f); break;
-#define QB_CASES(TYPE, FN) QB_CASES_FL(TYPE, FN, 0) QB_CASES_FL(TYPE, FN, 1) QB_CASES_FL(TYPE, FN, 2)
+// One dense opcode per gate (planner-assigned, qb_internal.h): a single jump-table dispatch.
+// The control predicate (thread-id / external masks) is only evaluated in the arms that need it.
+#define QB_ARM(BASE, FN, FL, JJ)                                                        \
+  case (BASE + FL * 5 + JJ):                                                            \
+    if constexpr (JJ < R) FN<R, JJ, FL>(re, im, g, (FL == 2) ? ok_thr(g, tid, basefull) : true, f); \
+    break;
+#define QB_ARMS_FL(BASE, FN, FL) QB_ARM(BASE, FN, FL, 0) QB_ARM(BASE, FN, FL, 1) QB_ARM(BASE, FN, FL, 2) QB_ARM(BASE, FN, FL, 3) QB_ARM(BASE, FN, FL, 4)
+#define QB_ARMS(BASE, FN) QB_ARMS_FL(BASE, FN, 0) QB_ARMS_FL(BASE, FN, 1) QB_ARMS_FL(BASE, FN, 2)
+
+__device__ __forceinline__ bool ok_thr(const DevGate &g, uint32_t tid, uint64_t basefull) {
+  return ((tid & g.cthr) == g.cthr) && ((basefull & g.cext) == g.cext);
+}
 
 template <int R>
 __device__ __forceinline__ void apply_gate(double (&re)[1 << R], double (&im)[1 << R], const DevGate &g, uint32_t tid,
                                            uint64_t basefull, uint32_t &f) {
-  const bool ok_thr = ((tid & g.cthr) == g.cthr) && ((basefull & g.cext) == g.cext);
-  const uint32_t J = g.treg & 0xffu;
-  if (g.type == G_SWAP && g.creg == 0) {  // flip-mask toggle: no data movement
-    f ^= ok_thr ? (1u << J) : 0u;
-    return;
-  }
-  const bool ctrl = (g.creg | g.cthr) != 0 || g.cext != 0;
-  // flavour: 2 = controlled, 1 = uncontrolled but a flip may be pending on bit J, 0 = plain.
-  // G_DIAG carries J = its register bit, or 7 when the target is a thread / external bit.
-  const uint32_t fl = ctrl ? 2u : ((g.treg >> 8) & 1u);
-  const uint32_t op = g.type * 32 + fl * 8 + J;
-  switch (op) {
-    QB_CASES(G_GENERAL, gate_general)
-    QB_CASES(G_REAL, gate_real)
-    QB_CASES_FL(G_SWAP, gate_swap, 2)
-    QB_CASES(G_DIAG, gate_diag_reg)
-    case (G_DIAG * 32 + 0 * 8 + 7):
-    case (G_DIAG * 32 + 1 * 8 + 7):
-    case (G_DIAG * 32 + 2 * 8 + 7): {
+  switch (g.op) {
+    QB_ARMS(OP_GENERAL, gate_general)
+    QB_ARMS(OP_REAL, gate_real)
+    QB_ARMS(OP_DIAG_REG, gate_diag_reg)
+    case OP_SWAP_REG + 0: gate_swap<R, 0, 2>(re, im, g, ok_thr(g, tid, basefull), f); break;
+    case OP_SWAP_REG + 1: gate_swap<R, 1, 2>(re, im, g, ok_thr(g, tid, basefull), f); break;
+    case OP_SWAP_REG + 2: gate_swap<R, 2, 2>(re, im, g, ok_thr(g, tid, basefull), f); break;
+    case OP_SWAP_REG + 3: if constexpr (R > 3) gate_swap<R, 3, 2>(re, im, g, ok_thr(g, tid, basefull), f); break;
+    case OP_SWAP_REG + 4: if constexpr (R > 4) gate_swap<R, 4, 2>(re, im, g, ok_thr(g, tid, basefull), f); break;
+    case OP_TOGGLE:  // flip-mask toggle: no data movement
+      f ^= ok_thr(g, tid, basefull) ? (1u << (g.treg & 0xffu)) : 0u;
+      break;
+    case OP_DIAG_THR: {
       const bool one = ((tid & g.dthr) != 0) || ((basefull & g.dext) != 0);
-      gate_diag_thr<R>(re, im, g, ok_thr, one, f);
+      gate_diag_thr<R>(re, im, g, ok_thr(g, tid, basefull), one, f);
     } break;
     default: break;
   }

@@ -48,6 +48,8 @@ bool set_opt(PlanOptions &o, const std::string &name, int64_t v) {
     o.time_kernels = v ? 1 : 0;
   } else if (name == "l2_prefetch") {
     o.l2_prefetch = v ? 1 : 0;
+  } else if (name == "avoid_regswap") {
+    o.avoid_regswap = v ? 1 : 0;
   } else if (name == "stagger_ns") {
     if (v < 0 || v > 100000) return false;
     o.stagger_ns = (int)v;
@@ -68,6 +70,7 @@ int64_t get_opt(const PlanOptions &o, const std::string &name) {
   if (name == "time_kernels") return o.time_kernels;
   if (name == "l2_prefetch") return o.l2_prefetch;
   if (name == "stagger_ns") return o.stagger_ns;
+  if (name == "avoid_regswap") return o.avoid_regswap;
   return -1;
 }
 
@@ -347,6 +350,7 @@ namespace {
 
 struct RoundTmp {
   uint64_t regmask = 0;          // physical bits
+  uint64_t swap_ctrl = 0;        // control bits of the X / CX gates placed in this round
   std::vector<int> ops;          // op indices, program order
 };
 
@@ -400,14 +404,23 @@ static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &don
         blocked |= qmask;
         continue;
       }
-      for (int r = r0; r < max_rounds; ++r) {
-        const bool edge = (r == 0) || (r == max_rounds - 1);  // load round / last possible store round
-        if (edge && (tb & lowfixed)) continue;
-        while ((int)rounds.size() <= r) rounds.emplace_back();
-        RoundTmp &rd = rounds[r];
-        if ((rd.regmask & tb) || popc(rd.regmask) < R) {
-          place = r;
-          break;
+      // Two attempts: first refuse rounds where an X / CX would end up with a control on a
+      // REGISTER bit (that flavour moves data, ~150 instructions per thread, instead of toggling
+      // the flip mask); if no round qualifies, accept such a round.
+      for (int attempt = opt.avoid_regswap ? 0 : 1; attempt < 2 && place < 0; ++attempt) {
+        for (int r = r0; r < max_rounds; ++r) {
+          const bool edge = (r == 0) || (r == max_rounds - 1);  // load round / last possible store round
+          if (edge && (tb & lowfixed)) continue;
+          while ((int)rounds.size() <= r) rounds.emplace_back();
+          RoundTmp &rd = rounds[r];
+          if (attempt == 0) {
+            if (op.type == G_SWAP && (rd.regmask & op.ctrl)) continue;           // my control is a register bit here
+            if (!(rd.regmask & tb) && (rd.swap_ctrl & tb)) continue;             // I would turn a placed CX's control into one
+          }
+          if ((rd.regmask & tb) || popc(rd.regmask) < R) {
+            place = r;
+            break;
+          }
         }
       }
       if (place < 0) {
@@ -419,6 +432,7 @@ static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &don
         continue;
       }
       rounds[place].regmask |= tb;
+      if (op.type == G_SWAP) rounds[place].swap_ctrl |= op.ctrl;
       if (!in_tile) {
         tile_mask |= tb;
         ++ntile;
@@ -649,6 +663,14 @@ static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &don
       } else if (g.treg < 8 && (flip_possible & (1u << g.treg))) {
         g.treg |= 1u << 8;
       }
+      {  // dense opcode for the kernel's jump table
+        const bool ctrl = (g.creg | g.cthr) != 0 || g.cext != 0;
+        const uint32_t J = g.treg & 0xffu;
+        const uint32_t fl = ctrl ? 2u : ((g.treg >> 8) & 1u);
+        if (g.type == G_SWAP) g.op = (g.creg == 0) ? OP_TOGGLE : OP_SWAP_REG + J;
+        else if (g.type == G_DIAG) g.op = (J < 8 && g.dreg) ? OP_DIAG_REG + fl * 5 + J : OP_DIAG_THR;
+        else g.op = (g.type == G_GENERAL ? OP_GENERAL : OP_REAL) + fl * 5 + J;
+      }
       out.op_index.push_back(oi);
     }
     RD.gate_end = gcount;
@@ -688,7 +710,23 @@ std::string describe_plan(const PlanResult &r) {
     const DevPass *P = reinterpret_cast<const DevPass *>(p.blob.data());
     os << "pass " << i << " T=" << p.tile_bits << " R=" << p.reg_bits << " tiles=" << p.ntiles << " tile=[";
     for (int b = 0; b < p.tile_bits; ++b) os << (b ? "," : "") << (int)P->tile_pos[b];
-    os << "] rounds=" << p.nrounds << " gates=" << p.ngates << " gscale=" << P->has_gscale << "\n";
+    os << "] rounds=" << p.nrounds << " gates=" << p.ngates << " gscale=" << P->has_gscale;
+    {
+      const DevGate *G = reinterpret_cast<const DevGate *>(p.blob.data() + sizeof(DevPass));
+      int kinds[8] = {0};
+      for (int g = 0; g < p.ngates; ++g) {
+        const DevGate &d = G[g];
+        const bool ctrl = (d.creg | d.cthr) != 0 || d.cext != 0;
+        if (d.type == G_SWAP && d.creg == 0) kinds[0]++;           // flip toggle
+        else if (d.type == G_SWAP) kinds[1]++;                     // register-controlled swap (data moves)
+        else if (ctrl) kinds[2]++;                                 // controlled non-swap
+        else if ((d.treg >> 8) & 1) kinds[3]++;                    // uncontrolled, flip-aware
+        else kinds[4]++;                                           // plain
+      }
+      os << " kinds[toggle,regswap,ctrl,flipaware,plain]=" << kinds[0] << "," << kinds[1] << "," << kinds[2] << ","
+         << kinds[3] << "," << kinds[4];
+    }
+    os << "\n";
     for (int rd = 0; rd < p.nrounds; ++rd) {
       const DevRound &RD = P->rounds[rd];
       os << "  round " << rd << " regs=[";

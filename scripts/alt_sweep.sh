@@ -1,13 +1,13 @@
 #!/bin/bash
-for cfg in "0 12 0" "0 12 1500" "0 12 3000" "0 12 5000" "3 12 0" "3 12 1500" "3 12 3000" "3 12 5000" "0 11 2000" "0 11 4000"; do
+for cfg in "0 12 0" "0 12 1" "2 12 0" "0 11 0" "0 11 1"; do
   set -- $cfg
-  echo "== alt=$1 T=$2 stagger_ns=$3"
-  QB_ALT_VARIANTS=$1 QB_TILE_BITS=$2 QB_STAGGER_NS=$3 python - <<PY
+  echo "== alt=$1 T=$2 avoid_regswap=$3"
+  QB_ALT_VARIANTS=$1 QB_TILE_BITS=$2 QB_AVOID_REGSWAP=$3 python - <<PY
 import sys, time, json
 sys.path.insert(0, '.')
 import qubism_b200 as Q
 from qubism_b200 import capi
-from qubism_b200.circuits import random_layers, qft_ops
+from qubism_b200.circuits import random_layers, qft_ops, proper_unitary_layers
 from qubism_b200.qgate import unitary_matrix
 n=30
 ctx=Q.Context.default(); sv=Q.mkStateVec(n)
@@ -21,6 +21,9 @@ print("1 gate pass ms", round(t(lambda: sv.apply_1q(0,G)),3), " bit0 (3 rounds) 
 ops=capi.pack_ops(qft_ops(n)+random_layers(n,20,seed=1000))
 ms=t(lambda: sv.submit(ops), reps=2)
 st=ctx.stats()
-print("circuit ms", round(ms,1), "passes", st["passes"]//2, "ms/pass", round(ms/(st["passes"]//2),2))
+print("circuit ms", round(ms,1), "passes", st["passes"]//2, "rounds", st["rounds"]//2, "ms/pass", round(ms/(st["passes"]//2),2))
+opsg=capi.pack_ops(proper_unitary_layers(n,20))
+ms=t(lambda: sv.submit(opsg), reps=1)
+print("general-class circuit ms", round(ms,1))
 PY
 done

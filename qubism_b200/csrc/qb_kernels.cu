@@ -253,12 +253,17 @@ template <int T, int R, int MINB>
 __global__ void __launch_bounds__(1 << (T - R), MINB)
     k_fused_pass(double2 *__restrict__ amps, unsigned long long ntiles, const __grid_constant__ PassProgram prog) {
   constexpr int NR = 1 << R;
+  constexpr int NT = 1 << (T - R);
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  double2 *tile = reinterpret_cast<double2 *>(smem_raw);
+  // after the tile: for every round, each thread's swizzled shared-memory index (computed once
+  // per kernel; the persistent tile loop then needs one 16-bit load per transpose side)
+  uint16_t *sidx_tab = reinterpret_cast<uint16_t *>(smem_raw + (size_t(16) << T));
   const DevPass &P = prog.hdr;
   const DevGate *G = prog.gates;
   const uint32_t tid = threadIdx.x;
   const uint32_t nrounds = P.nrounds;
+  for (uint32_t r = 0; r < nrounds; ++r) sidx_tab[r * NT + tid] = (uint16_t)thread_sidx<T, R>(P.rounds[r], tid);
+  // (each thread only ever reads its own entries: no barrier needed)
   const uint64_t goff_ld = thread_goff<T, R>(P, P.rounds[0], tid);
   const uint64_t goff_st = thread_goff<T, R>(P, P.rounds[nrounds - 1], tid);
 
@@ -328,11 +333,12 @@ __global__ void __launch_bounds__(1 << (T - R), MINB)
       const DevRound &RD = P.rounds[r];
       if (r > 0) {  // transpose through swizzled shared memory: new register-resident bits
         const DevRound &PR = P.rounds[r - 1];
-        uint32_t us = thread_sidx<T, R>(PR, tid);
+        // byte offsets throughout: address = tile + (thread part ^ register part)
+        uint32_t us = uint32_t(sidx_tab[(r - 1) * NT + tid]) << 4;
         uint32_t sx[R];
 #pragma unroll
         for (int j = 0; j < R; ++j) {
-          sx[j] = PR.reg_sx[j];
+          sx[j] = PR.reg_sx[j] << 4;
           us ^= ((f >> j) & 1u) ? sx[j] : 0u;  // fold the flip mask into the address
         }
         f = 0;
@@ -342,23 +348,23 @@ __global__ void __launch_bounds__(1 << (T - R), MINB)
         if (local) __syncwarp(); else __syncthreads();  // everyone finished reading the previous layout
 #pragma unroll
         for (int i = 0; i < NR; ++i) {
-          uint32_t x = us;
+          uint32_t c = 0;  // uniform: folds at compile time into one XOR operand per register
 #pragma unroll
           for (int j = 0; j < R; ++j)
-            if ((i >> j) & 1) x ^= sx[j];
-          tile[x] = make_double2(re[i], im[i]);
+            if ((i >> j) & 1) c ^= sx[j];
+          *reinterpret_cast<double2 *>(smem_raw + (us ^ c)) = make_double2(re[i], im[i]);
         }
         if (local) __syncwarp(); else __syncthreads();
-        const uint32_t ul = thread_sidx<T, R>(RD, tid);
+        const uint32_t ul = uint32_t(sidx_tab[r * NT + tid]) << 4;
 #pragma unroll
-        for (int j = 0; j < R; ++j) sx[j] = RD.reg_sx[j];
+        for (int j = 0; j < R; ++j) sx[j] = RD.reg_sx[j] << 4;
 #pragma unroll
         for (int i = 0; i < NR; ++i) {
-          uint32_t x = ul;
+          uint32_t c = 0;
 #pragma unroll
           for (int j = 0; j < R; ++j)
-            if ((i >> j) & 1) x ^= sx[j];
-          const double2 a = tile[x];
+            if ((i >> j) & 1) c ^= sx[j];
+          const double2 a = *reinterpret_cast<const double2 *>(smem_raw + (ul ^ c));
           re[i] = a.x;
           im[i] = a.y;
         }
@@ -438,7 +444,7 @@ cudaError_t launch_fused_pass(double2 *amps, const uint8_t *blob, uint32_t blob_
   if (blob_bytes > sizeof(PassProgram) || blob_bytes < sizeof(DevPass)) return cudaErrorInvalidValue;
   static thread_local PassProgram prog;  // the launch copies it into the command buffer
   memcpy(&prog, blob, blob_bytes);
-  const size_t smem = size_t(16) << tile_bits;
+  const size_t smem = (size_t(16) << tile_bits) + size_t(kMaxRounds) * v->threads * sizeof(uint16_t);
   cudaError_t e = cudaFuncSetAttribute(v->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int occ = 0;

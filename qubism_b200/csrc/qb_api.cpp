@@ -72,6 +72,7 @@ struct qb_state {
   int L = 0;           // local bits (n - pbits)
   double2 *amps = nullptr;
   std::vector<int> perm;  // logical bit -> physical bit (bits >= L are rank bits)
+  std::vector<double2 *> peers;  // distributed: every rank's shard through CUDA IPC (empty: NCCL swaps)
   OpQueue q;
 };
 
@@ -120,6 +121,14 @@ int alloc_state(qb_ctx *ctx, int n, qb_state **out) {
     delete s;
     return fail(e == cudaErrorMemoryAllocation ? QB_ERR_OOM : QB_ERR_CUDA, "cudaMalloc(%zu bytes): %s", bytes,
                 cudaGetErrorString(e));
+  }
+  if (ctx->nranks > 1) {  // collective: map every peer's shard for the NVLink swap kernel
+    int rc = dist_register(ctx->dist, s->amps, s->peers, ctx->stream);
+    if (rc != QB_OK) {
+      cudaFree(s->amps);
+      delete s;
+      return fail(rc, "peer registration failed: %s", dist_last_error());
+    }
   }
   *out = s;
   return QB_OK;
@@ -217,7 +226,9 @@ int run_gscale_simple(qb_state *s, const double g[2]) {
 int make_local(qb_state *s, const std::vector<const HostOp *> &pending) {
   qb_ctx *c = s->ctx;
   if (c->nranks == 1) return fail(QB_ERR_UNSUPPORTED, "internal: planner stuck on a single GPU");
-  return dist_make_local(c->dist, s->amps, s->n, s->L, s->perm, pending, c->stream, &c->stats);
+  int rc = dist_make_local(c->dist, s->amps, s->peers, s->n, s->L, s->perm, pending, c->sm_count, c->stream, &c->stats);
+  if (rc != QB_OK) return fail(rc, "global<->local swap failed: %s", dist_last_error());
+  return QB_OK;
 }
 
 int run_fused_segment(qb_state *s, std::vector<const HostOp *> seg, const double *gscale, bool *gscale_done) {
@@ -515,6 +526,7 @@ void qb_state_free(qb_state *s) {
   {
     Guard g(s->ctx);
     cudaStreamSynchronize(s->ctx->stream);
+    if (s->ctx->nranks > 1 && !s->peers.empty()) dist_unregister(s->ctx->dist, s->peers, s->ctx->stream);  // collective
     cudaFree(s->amps);
   }
   delete s;

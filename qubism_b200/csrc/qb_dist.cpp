@@ -8,12 +8,14 @@
 // The logical->physical bit map is updated, so every later gate on those qubits is local.
 // Volume per rank: (1 - 2^-k) of the shard each way -- one half-shard for k = 1.
 #include "qb_dist.h"
+#include "qb_kernels.h"
 
 #include <dlfcn.h>
 #include <nccl.h>
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -30,6 +32,7 @@ struct NcclApi {
   ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
@@ -62,6 +65,7 @@ NcclApi *nccl() {
   QB_SYM(CommInitRank, "ncclCommInitRank")
   QB_SYM(CommDestroy, "ncclCommDestroy")
   QB_SYM(AllReduce, "ncclAllReduce")
+  QB_SYM(AllGather, "ncclAllGather")
   QB_SYM(Send, "ncclSend")
   QB_SYM(Recv, "ncclRecv")
   QB_SYM(GroupStart, "ncclGroupStart")
@@ -77,6 +81,8 @@ struct DistState {
   int device = 0, rank = 0, nranks = 1, pbits = 0;
   ncclComm_t comm = nullptr;
   double *scratch_dev = nullptr;   // 64 doubles
+  unsigned char *ipc_dev = nullptr;  // nranks IPC handles
+  bool ipc_ok = true;                // cleared for good after the first failed import
   double2 *bounce[2] = {nullptr, nullptr};
   size_t bounce_amps = 0;
   cudaStream_t copy_stream = nullptr;
@@ -124,6 +130,9 @@ int dist_create(DistState **out, int device, int rank, int nranks, const void *i
   QB_DCUDA(cudaSetDevice(device));
   QB_NCCL(a->CommInitRank(&d->comm, nranks, id, rank));
   QB_DCUDA(cudaMalloc(&d->scratch_dev, 64 * sizeof(double)));
+  QB_DCUDA(cudaMalloc(&d->ipc_dev, size_t(nranks) * sizeof(cudaIpcMemHandle_t)));
+  if (const char *e = getenv("QB_PEER_EXCHANGE"))
+    if (*e == '0') d->ipc_ok = false;
   QB_DCUDA(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
   for (int i = 0; i < 2; ++i) {
     QB_DCUDA(cudaEventCreateWithFlags(&d->ev_recv[i], cudaEventDisableTiming));
@@ -139,6 +148,7 @@ void dist_destroy(DistState *d) {
   cudaSetDevice(d->device);
   if (d->comm && nccl()) nccl()->CommDestroy(d->comm);
   cudaFree(d->scratch_dev);
+  cudaFree(d->ipc_dev);
   for (int i = 0; i < 2; ++i) {
     cudaFree(d->bounce[i]);
     if (d->ev_recv[i]) cudaEventDestroy(d->ev_recv[i]);
@@ -158,6 +168,77 @@ int dist_allreduce_sum(DistState *d, double *vals, int n, cudaStream_t stream) {
   return QB_OK;
 }
 
+// stream-ordered barrier over all ranks: every rank's earlier work on its stream is complete
+// before anything enqueued after it starts on any rank
+static int stream_barrier(DistState *d, cudaStream_t stream) {
+  NcclApi *a = nccl();
+  QB_NCCL(a->AllReduce(d->scratch_dev + 32, d->scratch_dev + 32, 1, ncclDouble, ncclSum, d->comm, stream));
+  return QB_OK;
+}
+
+int dist_register(DistState *d, double2 *ptr, std::vector<double2 *> &peers, cudaStream_t stream) {
+  NcclApi *a = nccl();
+  peers.clear();
+  // every rank takes part in the handle exchange even if IPC is switched off, so that the
+  // collective call sequence stays identical on all ranks
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof mine);
+  bool ok = d->ipc_ok;
+  if (ok && cudaIpcGetMemHandle(&mine, ptr) != cudaSuccess) {
+    cudaGetLastError();
+    ok = false;
+    memset(&mine, 0, sizeof mine);
+  }
+  std::vector<cudaIpcMemHandle_t> all(d->nranks);
+  QB_DCUDA(cudaMemcpyAsync(d->ipc_dev + size_t(d->rank) * sizeof mine, &mine, sizeof mine, cudaMemcpyHostToDevice,
+                           stream));
+  QB_NCCL(a->AllGather(d->ipc_dev + size_t(d->rank) * sizeof mine, d->ipc_dev, sizeof mine, ncclChar, d->comm, stream));
+  QB_DCUDA(cudaMemcpyAsync(all.data(), d->ipc_dev, all.size() * sizeof mine, cudaMemcpyDeviceToHost, stream));
+  QB_DCUDA(cudaStreamSynchronize(stream));
+  cudaIpcMemHandle_t zero;
+  memset(&zero, 0, sizeof zero);
+  for (int r = 0; r < d->nranks; ++r)
+    if (memcmp(&all[r], &zero, sizeof zero) == 0) ok = false;  // some rank could not export
+  std::vector<double2 *> out(d->nranks, nullptr);
+  if (ok) {
+    for (int r = 0; r < d->nranks && ok; ++r) {
+      if (r == d->rank) {
+        out[r] = ptr;
+        continue;
+      }
+      void *p = nullptr;
+      if (cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        ok = false;
+      } else {
+        out[r] = static_cast<double2 *>(p);
+      }
+    }
+  }
+  // agree on the outcome: one failed import anywhere switches every rank to the NCCL path
+  double flag = ok ? 0.0 : 1.0;
+  int rc = dist_allreduce_sum(d, &flag, 1, stream);
+  if (rc != QB_OK) return rc;
+  if (flag != 0.0) {
+    for (int r = 0; r < d->nranks; ++r)
+      if (r != d->rank && out[r]) cudaIpcCloseMemHandle(out[r]);
+    d->ipc_ok = false;
+    return QB_OK;
+  }
+  peers.swap(out);
+  return QB_OK;
+}
+
+int dist_unregister(DistState *d, std::vector<double2 *> &peers, cudaStream_t stream) {
+  QB_DCUDA(cudaStreamSynchronize(stream));
+  for (int r = 0; r < (int)peers.size(); ++r)
+    if (r != d->rank && peers[r]) cudaIpcCloseMemHandle(peers[r]);
+  peers.clear();
+  // nobody frees an exported shard while a peer may still have it mapped
+  double z = 0.0;
+  return dist_allreduce_sum(d, &z, 1, stream);
+}
+
 static int ensure_bounce(DistState *d, size_t amps) {
   if (d->bounce_amps >= amps) return QB_OK;
   for (int i = 0; i < 2; ++i) {
@@ -170,10 +251,12 @@ static int ensure_bounce(DistState *d, size_t amps) {
   return QB_OK;
 }
 
-int dist_make_local(DistState *d, double2 *amps, int n, int L, std::vector<int> &perm,
-                    const std::vector<const HostOp *> &pending, cudaStream_t stream, qb_stats *stats) {
+int dist_make_local(DistState *d, double2 *amps, const std::vector<double2 *> &peers, int n, int L,
+                    std::vector<int> &perm, const std::vector<const HostOp *> &pending, int sm_count,
+                    cudaStream_t stream, qb_stats *stats) {
   NcclApi *a = nccl();
-  std::vector<SwapPair> sw = choose_swaps(n, L, perm, pending);
+  const bool peer_path = (int)peers.size() == d->nranks;
+  std::vector<SwapPair> sw = choose_swaps(n, L, perm, pending, peer_path);
   if (sw.empty()) {
     g_dist_err = "planner stuck but no global target pending";
     return QB_ERR_UNSUPPORTED;
@@ -186,9 +269,30 @@ int dist_make_local(DistState *d, double2 *amps, int n, int L, std::vector<int> 
   const uint64_t block = 1ull << (L - k);
   const std::vector<SwapStep> steps = swap_schedule(d->rank, L, sw);
   const uint64_t nsteps = steps.size();
-  // Every peer at once (one NCCL group = an all-to-all over the 2^k - 1 partners, NVSwitch is
-  // non-blocking), in pieces of <= 2^22 amplitudes (64 MiB) per peer, double-buffered: while
-  // the copy-back of piece i drains on the copy stream, piece i+1 is already on the wire.
+  if (peer_path) {
+    // NVLink-native path: barrier, one in-place swap kernel per partner (the lower rank of a pair
+    // takes the first half of the index range, the higher rank the second), barrier.
+    uint64_t swapped = 0;
+    for (const SwapPair &sp : sw) swapped |= 1ull << sp.lbit;
+    int rc = stream_barrier(d, stream);
+    if (rc != QB_OK) return rc;
+    for (const SwapStep &st : steps) {
+      const uint64_t half = block / 2;
+      const uint64_t tb = (d->rank < st.peer) ? 0 : half, te = (d->rank < st.peer) ? half : block;
+      QB_DCUDA(launch_peer_swap(amps, peers[st.peer], tb, te, L, swapped, place_sel(st.my_sel, sw),
+                                place_sel(st.peer_sel, sw), sm_count, stream));
+      if (stats) stats->exchange_bytes += (te - tb) * sizeof(double2) * 2;  // read + written remotely
+    }
+    rc = stream_barrier(d, stream);
+    if (rc != QB_OK) return rc;
+    if (stats) stats->exchanges++;
+    apply_swaps_to_perm(perm, sw);
+    return QB_OK;
+  }
+  // NCCL path: every peer at once (one group = an all-to-all over the 2^k - 1 partners), in
+  // pieces of <= 2^22 amplitudes (64 MiB) per peer, double-buffered: while the copy-back of
+  // piece i drains on the copy stream, piece i+1 is already on the wire.
+  const uint64_t lowest = (uint64_t)(L - k);  // the swapped bits are the top k local bits here
   const uint64_t piece = std::min<uint64_t>(block, 1ull << 22);
   int rc = ensure_bounce(d, piece * nsteps);
   if (rc != QB_OK) return rc;
@@ -198,7 +302,7 @@ int dist_make_local(DistState *d, double2 *amps, int n, int L, std::vector<int> 
     if (used[slot]) QB_DCUDA(cudaStreamWaitEvent(stream, d->ev_copy[slot], 0));  // bounce free again
     QB_NCCL(a->GroupStart());
     for (uint64_t i = 0; i < nsteps; ++i) {
-      double2 *src = amps + steps[i].block * block + off;
+      double2 *src = amps + (place_sel(steps[i].my_sel, sw) >> lowest) * block + off;
       QB_NCCL(a->Send(src, piece * 2, ncclDouble, steps[i].peer, d->comm, stream));
       QB_NCCL(a->Recv(d->bounce[slot] + i * piece, piece * 2, ncclDouble, steps[i].peer, d->comm, stream));
     }
@@ -206,15 +310,16 @@ int dist_make_local(DistState *d, double2 *amps, int n, int L, std::vector<int> 
     QB_DCUDA(cudaEventRecord(d->ev_recv[slot], stream));
     QB_DCUDA(cudaStreamWaitEvent(d->copy_stream, d->ev_recv[slot], 0));
     for (uint64_t i = 0; i < nsteps; ++i)
-      QB_DCUDA(cudaMemcpyAsync(amps + steps[i].block * block + off, d->bounce[slot] + i * piece,
-                               piece * sizeof(double2), cudaMemcpyDeviceToDevice, d->copy_stream));
+      QB_DCUDA(cudaMemcpyAsync(amps + (place_sel(steps[i].my_sel, sw) >> lowest) * block + off,
+                               d->bounce[slot] + i * piece, piece * sizeof(double2), cudaMemcpyDeviceToDevice,
+                               d->copy_stream));
     QB_DCUDA(cudaEventRecord(d->ev_copy[slot], d->copy_stream));
     used[slot] = true;
     slot ^= 1;
     if (stats) stats->exchange_bytes += nsteps * piece * sizeof(double2);
   }
-  for (int s = 0; s < 2; ++s)
-    if (used[s]) QB_DCUDA(cudaStreamWaitEvent(stream, d->ev_copy[s], 0));
+  for (int s2 = 0; s2 < 2; ++s2)
+    if (used[s2]) QB_DCUDA(cudaStreamWaitEvent(stream, d->ev_copy[s2], 0));
   if (stats) stats->exchanges++;
   apply_swaps_to_perm(perm, sw);
   return QB_OK;

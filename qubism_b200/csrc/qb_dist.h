@@ -21,9 +21,20 @@ void dist_destroy(DistState *d);
 // in-place sum over ranks of n host doubles (n <= 64); synchronises the stream
 int dist_allreduce_sum(DistState *d, double *vals, int n, cudaStream_t stream);
 
+// Collective: export `ptr` (a cudaMalloc'ed shard) over CUDA IPC and map every peer's shard.
+// peers[r] is rank r's shard as seen from this process (peers[rank] == ptr); empty if IPC is
+// unavailable, in which case swaps fall back to NCCL send/recv.
+int dist_register(DistState *d, double2 *ptr, std::vector<double2 *> &peers, cudaStream_t stream);
+// Collective: unmap the peers' shards (call before freeing the exported buffer).
+int dist_unregister(DistState *d, std::vector<double2 *> &peers, cudaStream_t stream);
+
 // Exchange data so that the global targets of `pending` become local; updates perm.
-int dist_make_local(DistState *d, double2 *amps, int n, int L, std::vector<int> &perm,
-                    const std::vector<const HostOp *> &pending, cudaStream_t stream, qb_stats *stats);
+// With peer mappings: one in-place swap kernel per partner over NVLink peer memory, evicting
+// the local bits that are needed furthest in the future.  Without: NCCL send/recv of the top
+// local bits through bounce buffers.
+int dist_make_local(DistState *d, double2 *amps, const std::vector<double2 *> &peers, int n, int L,
+                    std::vector<int> &perm, const std::vector<const HostOp *> &pending, int sm_count,
+                    cudaStream_t stream, qb_stats *stats);
 
 // Collective read of logical amplitudes [first, first + count) into `out` on every rank.
 int dist_read_logical(DistState *d, const double2 *amps, int n, int L, const std::vector<int> &perm, uint64_t first,

@@ -193,21 +193,28 @@ struct OpQueue {
 
 // ------------------------------------------------------------------ multi-GPU host logic
 // Global<->local qubit swap.  The k global physical bits that pending gates
-// target trade places with the TOP k local bits, so each rank exchanges whole contiguous
-// blocks of 2^(L-k) amplitudes, one block per peer.
+// target trade places with k local bits in ONE all-to-all step: rank r keeps the elements whose
+// swapped local bits already equal its own value of the swapped rank bits, and trades every
+// other group of 2^(L-k) elements with exactly one peer.
 struct SwapPair {
-  int gbit, lbit;
+  int gbit, lbit;   // physical bit positions (gbit >= L > lbit)
 };
 struct SwapStep {
-  uint64_t block;   // index of the 2^(L-k) block inside the shard
-  int peer;         // rank that receives it and sends back its block of the same index
+  int peer;            // the rank I trade with
+  uint32_t my_sel;     // value of the k swapped local bits selecting MY elements that go to `peer`
+  uint32_t peer_sel;   // ... and the peer's elements that come to me (bit i <-> pairs[i])
 };
-// which global bits must become local for `pending` (op pointers in program order)
+// Which global bits must become local for `pending` (op pointers in program order), and which
+// local bits they evict.  any_local = false: the TOP k local bits (contiguous blocks: what a
+// plain send/recv needs).  any_local = true: Belady -- the local bits (>= 5, so that warps still
+// see 512 contiguous bytes) whose qubits are needed furthest in the future (peer-memory kernel).
 std::vector<SwapPair> choose_swaps(int n, int L, const std::vector<int> &perm,
-                                   const std::vector<const HostOp *> &pending);
-// the pairwise exchanges rank `rank` performs (its own block stays in place)
+                                   const std::vector<const HostOp *> &pending, bool any_local);
+// the pairwise exchanges rank `rank` performs, XOR-ordered so all ranks' steps match up
 std::vector<SwapStep> swap_schedule(int rank, int L, const std::vector<SwapPair> &pairs);
 void apply_swaps_to_perm(std::vector<int> &perm, const std::vector<SwapPair> &pairs);
+// scatter the k-bit selector into the local-bit positions of `pairs`
+uint64_t place_sel(uint32_t sel, const std::vector<SwapPair> &pairs);
 
 // classification of a caller-supplied 2x2 (value-based)
 struct Classified {

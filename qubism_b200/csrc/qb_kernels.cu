@@ -26,6 +26,8 @@
 
 namespace qb {
 
+static int grid_for(uint64_t work, int threads, int sm_count, int per_sm);
+
 __device__ __forceinline__ uint32_t swz(uint32_t u) {
   return u ^ ((u >> 3) & 7u) ^ ((u >> 6) & 7u) ^ ((u >> 9) & 7u) ^ ((u >> 12) & 7u);
 }
@@ -587,6 +589,79 @@ cudaError_t launch_simple_kq(double2 *amps, int local_bits, int k, const int *bi
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------- global<->local qubit swap
+// In-place pairwise exchange over NVLink peer memory (no NCCL in the data path,
+// no bounce buffer): thread t reads its own element and the partner GPU's element through the
+// IPC-mapped peer pointer, and writes each where the other was.  The two ranks of a pair split
+// the index range in halves, so both GPUs' SMs work and both link directions carry the same
+// load: per rank (1 - 2^-k) of the shard crosses NVLink each way for a k-bit swap.
+struct SwapGeom {
+  uint32_t nruns;
+  uint32_t run_shift[kMaxRuns];  // deposit of the free index into the non-swapped local bits
+  uint32_t run_len[kMaxRuns];
+  uint64_t my_place, peer_place; // the swapped local bits: my elements that leave / the peer's that arrive
+};
+
+__global__ void __launch_bounds__(256) k_peer_swap(double2 *__restrict__ mine, double2 *__restrict__ peer,
+                                                   unsigned long long t_begin, unsigned long long t_end,
+                                                   const __grid_constant__ SwapGeom geo) {
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long t0 = t_begin + blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; t0 < t_end;
+       t0 += 4 * stride) {
+    uint64_t im[4], ip[4];
+    double2 a[4], b[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const unsigned long long t = t0 + u * stride;
+      uint64_t idx = 0, rest = t;
+      for (uint32_t k = 0; k < geo.nruns; ++k) {
+        idx |= (rest & ((1ull << geo.run_len[k]) - 1ull)) << geo.run_shift[k];
+        rest >>= geo.run_len[k];
+      }
+      im[u] = idx | geo.my_place;
+      ip[u] = idx | geo.peer_place;
+      if (t < t_end) {
+        a[u] = mine[im[u]];
+        b[u] = peer[ip[u]];  // NVLink read
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (t0 + u * stride < t_end) {
+        mine[im[u]] = b[u];
+        peer[ip[u]] = a[u];  // NVLink write
+      }
+    }
+  }
+}
+
+cudaError_t launch_peer_swap(double2 *mine, double2 *peer, uint64_t t_begin, uint64_t t_end, int local_bits,
+                             uint64_t swapped_mask, uint64_t my_place, uint64_t peer_place, int sm_count,
+                             cudaStream_t stream) {
+  SwapGeom geo{};
+  int b = 0;
+  while (b < local_bits) {
+    if (swapped_mask & (1ull << b)) {
+      ++b;
+      continue;
+    }
+    int e = b;
+    while (e < local_bits && !(swapped_mask & (1ull << e))) ++e;
+    if (geo.nruns >= kMaxRuns) return cudaErrorInvalidValue;
+    geo.run_shift[geo.nruns] = b;
+    geo.run_len[geo.nruns] = e - b;
+    ++geo.nruns;
+    b = e;
+  }
+  geo.my_place = my_place;
+  geo.peer_place = peer_place;
+  if (t_end <= t_begin) return cudaSuccess;
+  unsigned long long tb = t_begin, te = t_end;
+  const int grid = grid_for((te - tb + 3) / 4, 256, sm_count, 8);
+  void *args[] = {(void *)&mine, (void *)&peer, (void *)&tb, (void *)&te, (void *)&geo};
+  return cudaLaunchKernel((const void *)&k_peer_swap, dim3(grid), dim3(256), args, 0, stream);
 }
 
 // ---------------------------------------------------------------- reductions (deterministic)

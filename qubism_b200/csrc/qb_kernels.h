@@ -22,6 +22,12 @@ cudaError_t launch_simple_kq(double2 *amps, int local_bits, int k, const int *bi
                              const int *bits_order_dev, const double2 *mat_dev, uint64_t cmask, uint64_t rank_bits,
                              int sm_count, cudaStream_t stream);
 
+// In-place exchange with one peer GPU over IPC-mapped memory: free indices [t_begin, t_end) of the
+// 2^(L-k) elements whose swapped local bits (swapped_mask) equal my_place / peer_place.
+cudaError_t launch_peer_swap(double2 *mine, double2 *peer, uint64_t t_begin, uint64_t t_end, int local_bits,
+                             uint64_t swapped_mask, uint64_t my_place, uint64_t peer_place, int sm_count,
+                             cudaStream_t stream);
+
 int reduce_grid(uint64_t n, int sm_count);
 // out_dev[0..1] = (S0, S1) split by physical bit `bit` (bit < 0: total in S0).
 cudaError_t launch_sumsq(const double2 *amps, uint64_t n, int bit, double *partials_dev, double *out_dev, int sm_count,

@@ -9,6 +9,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstring>
+#include <functional>
 #include <sstream>
 
 #include "qb_internal.h"
@@ -288,7 +289,7 @@ void OpQueue::push_kq(const int *bits, int k, const double *m, uint64_t ctrl_mas
 
 // --------------------------------------------------------------------- multi-GPU swap logic
 std::vector<SwapPair> choose_swaps(int n, int L, const std::vector<int> &perm,
-                                   const std::vector<const HostOp *> &pending) {
+                                   const std::vector<const HostOp *> &pending, bool any_local) {
   // global physical bits that pending non-diagonal gates target, within a lookahead window
   std::vector<int> need;
   uint64_t seen = 0;
@@ -303,35 +304,63 @@ std::vector<SwapPair> choose_swaps(int n, int L, const std::vector<int> &perm,
     }
   }
   std::sort(need.begin(), need.end());
-  std::vector<SwapPair> out;
-  int lb = L - 1;
-  for (int g : need) {
-    out.push_back({g, lb});
-    --lb;
+  const int k = (int)need.size();
+  std::vector<int> evict;
+  if (!any_local || L - 5 < k) {
+    for (int i = 0; i < k; ++i) evict.push_back(L - 1 - i);
+  } else {
+    // next use (as a non-diagonal target) of the qubit sitting on each local physical bit
+    std::vector<int> logical_of(n, -1);
+    for (int q = 0; q < n; ++q) logical_of[perm[q]] = q;
+    std::vector<std::pair<long, int>> cand;  // (-next_use, -bit): furthest first, high bits first
+    for (int b = 5; b < L; ++b) {
+      long next = 1L << 40;
+      for (size_t i = 0; i < pending.size(); ++i) {
+        const HostOp &h = *pending[i];
+        if (h.kind == 0 && h.type != G_DIAG && h.target == logical_of[b]) {
+          next = (long)i;
+          break;
+        }
+        if (h.kind == 2)
+          for (int j = 0; j < h.k; ++j)
+            if (h.kq_bits[j] == logical_of[b]) next = std::min(next, (long)i);
+      }
+      cand.emplace_back(-next, -b);
+    }
+    std::sort(cand.begin(), cand.end());
+    for (int i = 0; i < k; ++i) evict.push_back(-cand[i].second);
+    std::sort(evict.begin(), evict.end(), std::greater<int>());
   }
+  std::vector<SwapPair> out;
+  for (int i = 0; i < k; ++i) out.push_back({need[i], evict[i]});
   return out;
 }
 
 std::vector<SwapStep> swap_schedule(int rank, int L, const std::vector<SwapPair> &pairs) {
   const int k = (int)pairs.size();
-  // block index bit (lbit - (L-k)) <-> rank bit (gbit - L)
-  uint64_t mine = 0;
+  uint32_t mine = 0;  // my value of the swapped rank bits, as a k-bit selector
   for (int i = 0; i < k; ++i)
-    if ((rank >> (pairs[i].gbit - L)) & 1) mine |= 1ull << (pairs[i].lbit - (L - k));
+    if ((rank >> (pairs[i].gbit - L)) & 1) mine |= 1u << i;
   std::vector<SwapStep> out;
   // XOR order: at step s every rank is paired with the rank whose swapped bits differ by s,
   // so the steps of all ranks match up (no rank waits for a busy peer)
-  for (uint64_t s = 1; s < (1ull << k); ++s) {
-    const uint64_t blk = mine ^ s;
+  for (uint32_t s = 1; s < (1u << k); ++s) {
+    const uint32_t sel = mine ^ s;  // the peer's value of the swapped rank bits
     int r = rank;
     for (int i = 0; i < k; ++i) {
       const int rb = pairs[i].gbit - L;
-      const int v = (int)((blk >> (pairs[i].lbit - (L - k))) & 1);
-      r = (r & ~(1 << rb)) | (v << rb);
+      r = (r & ~(1 << rb)) | (int)(((sel >> i) & 1u) << rb);
     }
-    out.push_back({blk, r});
+    out.push_back({r, sel, mine});
   }
   return out;
+}
+
+uint64_t place_sel(uint32_t sel, const std::vector<SwapPair> &pairs) {
+  uint64_t m = 0;
+  for (size_t i = 0; i < pairs.size(); ++i)
+    if ((sel >> i) & 1u) m |= 1ull << pairs[i].lbit;
+  return m;
 }
 
 void apply_swaps_to_perm(std::vector<int> &perm, const std::vector<SwapPair> &pairs) {

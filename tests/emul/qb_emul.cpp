@@ -261,7 +261,7 @@ int qbe_run(int nlocal, const qb_op *ops, int64_t nops, const char *options, dou
 typedef int (*qbe_xchg_fn)(int peer, const double *send, double *recv, int64_t ndoubles);
 
 int qbe_run_rank(int n, int nranks, int rank, const qb_op *ops, int64_t nops, const char *options, double *amps,
-                 int *perm_inout, qbe_xchg_fn xchg, int64_t *stats_out) {
+                 int *perm_inout, qbe_xchg_fn xchg, int64_t *stats_out, int any_local) {
   PlanOptions opt;
   if (options) {
     std::string o(options);
@@ -327,15 +327,38 @@ int qbe_run_rank(int n, int nranks, int rank, const qb_op *ops, int64_t nops, co
     std::vector<const HostOp *> rest;
     for (size_t i = 0; i < seg.size(); ++i)
       if (!plan.done[i]) rest.push_back(seg[i]);
-    std::vector<SwapPair> sw = choose_swaps(n, L, perm, rest);
+    std::vector<SwapPair> sw = choose_swaps(n, L, perm, rest, any_local != 0);
     if (sw.empty()) return -4;
     const int k = (int)sw.size();
     const uint64_t block = 1ull << (L - k);
-    std::vector<double> recv(2 * block);
+    uint64_t swapped = 0;
+    for (const SwapPair &sp : sw) swapped |= 1ull << sp.lbit;
+    std::vector<double> send(2 * block), recv(2 * block);
+    auto deposit = [&](uint64_t t) {  // free index -> local index with the swapped bits clear
+      uint64_t idx = 0;
+      int src = 0;
+      for (int b2 = 0; b2 < L; ++b2)
+        if (!(swapped & (1ull << b2))) {
+          idx |= ((t >> src) & 1ull) << b2;
+          ++src;
+        }
+      return idx;
+    };
     for (const SwapStep &stp : swap_schedule(rank, L, sw)) {
-      double *base = a.data() + 2 * stp.block * block;
-      if (xchg(stp.peer, base, recv.data(), (int64_t)(2 * block)) != 0) return -5;
-      std::memcpy(base, recv.data(), sizeof(double) * 2 * block);
+      // my elements whose swapped local bits equal the peer's rank-bit value leave; the peer's
+      // elements whose swapped bits equal MINE arrive and take exactly those places
+      const uint64_t mine_at = place_sel(stp.my_sel, sw);
+      for (uint64_t t = 0; t < block; ++t) {
+        const uint64_t i = deposit(t) | mine_at;
+        send[2 * t] = a[2 * i];
+        send[2 * t + 1] = a[2 * i + 1];
+      }
+      if (xchg(stp.peer, send.data(), recv.data(), (int64_t)(2 * block)) != 0) return -5;
+      for (uint64_t t = 0; t < block; ++t) {
+        const uint64_t i = deposit(t) | mine_at;
+        a[2 * i] = recv[2 * t];
+        a[2 * i + 1] = recv[2 * t + 1];
+      }
     }
     apply_swaps_to_perm(perm, sw);
     ++nswaps;

@@ -24,7 +24,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, n, seed, out_dir):
+def _worker(rank, world, port, n, seed, out_dir, any_local):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -39,7 +39,7 @@ def _worker(rank, world, port, n, seed, out_dir):
     E = C.CDLL(os.path.join(ROOT, "tests", "emul", "libqb_emul.so"))
     XCHG = C.CFUNCTYPE(C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int64)
     E.qbe_run_rank.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(capi.QbOp), C.c_int64, C.c_char_p, C.c_void_p,
-                               C.POINTER(C.c_int), XCHG, C.POINTER(C.c_int64)]
+                               C.POINTER(C.c_int), XCHG, C.POINTER(C.c_int64), C.c_int]
     nbytes = [0]
 
     def xchg(peer, send, recv, nd):
@@ -64,7 +64,7 @@ def _worker(rank, world, port, n, seed, out_dir):
     arr = capi.pack_ops(ops)
     st = (C.c_int64 * 4)()
     cb = XCHG(xchg)
-    nsw = E.qbe_run_rank(n, world, rank, arr, len(arr), b"", shard.ctypes.data_as(C.c_void_p), perm, cb, st)
+    nsw = E.qbe_run_rank(n, world, rank, arr, len(arr), b"", shard.ctypes.data_as(C.c_void_p), perm, cb, st, any_local)
     assert nsw >= 1, f"expected at least one global<->local swap, rc={nsw}"
     # every rank must have made the same layout decisions
     perms = [None] * world
@@ -87,11 +87,14 @@ def _worker(rank, world, port, n, seed, out_dir):
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("any_local", [0, 1], ids=["top_bits_nccl_style", "belady_peer_style"])
 @pytest.mark.parametrize("world,n", [(2, 13), (4, 13)])
-def test_sharded_exchange_over_gloo(tmp_path, emul, world, n):
+def test_sharded_exchange_over_gloo(tmp_path, emul, world, n, any_local):
+    """any_local = 0: the top local bits are evicted (contiguous blocks, what the NCCL send/recv
+    fallback moves); 1: the bits needed furthest in the future (what the peer-memory kernel moves)."""
     import torch.multiprocessing as mp
     port = _free_port()
-    mp.spawn(_worker, args=(world, port, n, 77 + world, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, n, 77 + world, str(tmp_path), any_local), nprocs=world, join=True)
     err, nsw, nbytes, L = open(tmp_path / "result.txt").read().split()
     assert float(err) < 1e-13
     # volume per swap of k bits is (1 - 2^-k) of the shard each way (SURVEY.md 8d)

@@ -60,7 +60,7 @@ class ClockSampler:
 
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,timestamp")
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
@@ -78,7 +78,11 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark(self):
+        """The timed region starts now: only samples taken from here on count."""
+        self.t0 = time.time()
 
     def stop(self):
         if not self.proc:
@@ -90,7 +94,10 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, power, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        t0 = getattr(self, "t0", 0.0)
+        for stamp, ln in self.lines:
+            if stamp < t0:
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -215,23 +222,31 @@ def run_ours(args):
         sv.submit(packed)
         sv.flush()
 
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()  # nvidia-smi takes a moment to start: launch it before the warm-up
     for _ in range(args.warmup):
         step()
     barrier()
     ctx.reset_stats()
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    clocks.mark()
     e0.record(stream)
     for _ in range(args.steps):
         step()
     e1.record(stream)
     barrier()
     elapsed = e0.elapsed_time(e1) / 1e3
-    clk = clocks.stop() if rank == 0 else None
     st = ctx.stats()
+    if world == 1 and elapsed < 1.5:
+        # nvidia-smi samples every 100 ms: keep the same load running (outside the timed region,
+        # after the counters were read) until it has seen at least 1.5 s of it
+        t_more = time.time()
+        while time.time() - t_more < 1.5 - elapsed:
+            step()
+        ctx.sync()
+    clk = clocks.stop() if rank == 0 else None
     if dist is not None:
         t = torch.tensor([elapsed], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

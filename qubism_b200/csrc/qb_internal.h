@@ -113,7 +113,8 @@ struct HostOp {
 struct PlanOptions {
   int tile_bits = 12;
   int reg_bits = 4;
-  int low_bits = 5;     // low physical bits always in the tile (contiguous run per chunk)
+  int low_bits = 3;     // low physical bits always in the tile: 3 = one 128-byte line per chunk
+                        // (measured: no bandwidth loss vs 512-byte chunks, two more free tile bits)
   int max_rounds = 6;
   int fuse = 1;         // 0: one pass per op
   int peephole = 1;
@@ -122,6 +123,8 @@ struct PlanOptions {
   int l2_prefetch = 1;
   int stagger_ns = 0;
   int avoid_regswap = 0;  // planner: refuse rounds where a CX control would be a register bit
+  int hot_bits = 0;       // planner: max distinct TARGET bits per pass (0 = tile_bits).  With
+                          // hot_bits <= tile_bits - warp bits every transpose can stay warp-local.
 };
 
 // (tile bits, register bits, min CTAs/SM) instantiations of k_fused_pass

@@ -49,6 +49,9 @@ bool set_opt(PlanOptions &o, const std::string &name, int64_t v) {
     o.time_kernels = v ? 1 : 0;
   } else if (name == "l2_prefetch") {
     o.l2_prefetch = v ? 1 : 0;
+  } else if (name == "hot_bits") {
+    if (v < 0 || v > kMaxTileBits) return false;
+    o.hot_bits = (int)v;
   } else if (name == "avoid_regswap") {
     o.avoid_regswap = v ? 1 : 0;
   } else if (name == "stagger_ns") {
@@ -72,6 +75,7 @@ int64_t get_opt(const PlanOptions &o, const std::string &name) {
   if (name == "l2_prefetch") return o.l2_prefetch;
   if (name == "stagger_ns") return o.stagger_ns;
   if (name == "avoid_regswap") return o.avoid_regswap;
+  if (name == "hot_bits") return o.hot_bits;
   return -1;
 }
 
@@ -399,6 +403,8 @@ static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &don
   const int max_gates = std::max(1, std::min(opt.max_pass_gates, kMaxPassGates));
   uint64_t tile_mask = (1ull << C) - 1;
   int ntile = C;
+  uint64_t hot_mask = 0;  // bits that carry a non-diagonal gate in this pass
+  const int max_hot = (opt.hot_bits > 0 && opt.hot_bits < T) ? opt.hot_bits : 0;
   uint64_t blocked = 0;
   const uint64_t lowfixed = (1ull << kLaneFixedBits) - 1;
   std::vector<RoundTmp> rounds;
@@ -433,6 +439,10 @@ static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &don
         blocked |= qmask;
         continue;
       }
+      if (max_hot > 0 && !(hot_mask & tb) && popc(hot_mask) >= max_hot) {  // too many distinct targets
+        blocked |= qmask;
+        continue;
+      }
       // Two attempts: first refuse rounds where an X / CX would end up with a control on a
       // REGISTER bit (that flavour moves data, ~150 instructions per thread, instead of toggling
       // the flip mask); if no round qualifies, accept such a round.
@@ -461,6 +471,7 @@ static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &don
         continue;
       }
       rounds[place].regmask |= tb;
+      hot_mask |= tb;
       if (op.type == G_SWAP) rounds[place].swap_ctrl |= op.ctrl;
       if (!in_tile) {
         tile_mask |= tb;

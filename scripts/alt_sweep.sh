@@ -1,29 +1,6 @@
 #!/bin/bash
-for cfg in "0 12 0" "0 12 1" "2 12 0" "0 11 0" "0 11 1"; do
+for cfg in "12 4 3" "12 5 3" "13 5 3" "13 4 3" "11 4 3" "12 5 4"; do
   set -- $cfg
-  echo "== alt=$1 T=$2 avoid_regswap=$3"
-  QB_ALT_VARIANTS=$1 QB_TILE_BITS=$2 QB_AVOID_REGSWAP=$3 python - <<PY
-import sys, time, json
-sys.path.insert(0, '.')
-import qubism_b200 as Q
-from qubism_b200 import capi
-from qubism_b200.circuits import random_layers, qft_ops, proper_unitary_layers
-from qubism_b200.qgate import unitary_matrix
-n=30
-ctx=Q.Context.default(); sv=Q.mkStateVec(n)
-G=unitary_matrix(.3,.2,.1)
-def t(build, reps=3):
-    build(); sv.flush(); ctx.sync(); ctx.reset_stats()
-    t0=time.perf_counter()
-    for _ in range(reps): build(); sv.flush()
-    ctx.sync(); return (time.perf_counter()-t0)/reps*1e3
-print("1 gate pass ms", round(t(lambda: sv.apply_1q(0,G)),3), " bit0 (3 rounds) ms", round(t(lambda: sv.apply_1q(n-1,G)),3))
-ops=capi.pack_ops(qft_ops(n)+random_layers(n,20,seed=1000))
-ms=t(lambda: sv.submit(ops), reps=2)
-st=ctx.stats()
-print("circuit ms", round(ms,1), "passes", st["passes"]//2, "rounds", st["rounds"]//2, "ms/pass", round(ms/(st["passes"]//2),2))
-opsg=capi.pack_ops(proper_unitary_layers(n,20))
-ms=t(lambda: sv.submit(opsg), reps=1)
-print("general-class circuit ms", round(ms,1))
-PY
+  echo "== T=$1 R=$2 low_bits=$3"
+  QB_TILE_BITS=$1 QB_REG_BITS=$2 QB_LOW_BITS=$3 python scripts/quick_bench.py 2>&1 | grep -E "circuit"
 done

@@ -95,7 +95,7 @@ int init_common(qb_ctx *c) {
   QB_CUDA(cudaMallocHost(&c->red_host, sizeof(double) * 4));
   QB_CUDA(cudaMalloc(&c->kq_bits_dev, sizeof(int) * 2 * QB_MAX_KQ));
   QB_CUDA(cudaMalloc(&c->kq_mat_dev, sizeof(double2) << (2 * QB_MAX_KQ)));
-  for (const char *name : {"tile_bits", "reg_bits", "low_bits", "max_rounds", "peephole", "fuse", "max_pass_gates", "l2_prefetch", "stagger_ns", "avoid_regswap", "hot_bits"}) {
+  for (const char *name : {"tile_bits", "reg_bits", "low_bits", "max_rounds", "peephole", "fuse", "max_pass_gates", "l2_prefetch", "stagger_ns", "avoid_regswap", "hot_bits", "rot", "lite", "groups", "dbg_skip", "lane_fixed"}) {
     std::string env = "QB_";
     for (const char *p = name; *p; ++p) env.push_back((char)toupper(*p));
     const char *v = getenv(env.c_str());
@@ -114,7 +114,7 @@ int alloc_state(qb_ctx *ctx, int n, qb_state **out) {
   s->L = n - ctx->pbits;
   s->perm.resize(n);
   for (int i = 0; i < n; ++i) s->perm[i] = i;
-  s->q.reset(n, ctx->opt.peephole != 0);
+  s->q.reset(n, ctx->opt.peephole != 0, ctx->opt.rot != 0);
   const size_t bytes = sizeof(double2) << s->L;
   cudaError_t e = cudaMalloc(&s->amps, bytes);
   if (e != cudaSuccess) {
@@ -583,6 +583,7 @@ int qb_apply_ctrl_1q(qb_state *s, const int *ctrls, int nctrl, int t, const qb_c
   }
   std::lock_guard<std::recursive_mutex> lk(s->ctx->mu);
   s->q.peephole = s->ctx->opt.peephole != 0;
+  s->q.use_rot = s->ctx->opt.rot != 0;
   s->q.push_1q(logical_bit(s, t), cm, reinterpret_cast<const double *>(m));
   return QB_OK;
 }
@@ -833,7 +834,7 @@ int64_t qb_plan_describe(int nlocal, const qb_op *ops, int64_t nops, const char 
     }
   }
   OpQueue q;
-  q.reset(nlocal, opt.peephole != 0);
+  q.reset(nlocal, opt.peephole != 0, opt.rot != 0);
   for (int64_t i = 0; i < nops; ++i) {
     const qb_op &o = ops[i];
     uint64_t cm = 0;

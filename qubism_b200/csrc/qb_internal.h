@@ -26,11 +26,14 @@ enum GateType : uint32_t {
   G_REAL = 1,     // real 2x2 (after pulling a common phase)   4
   G_DIAG = 2,     // diag(d0, d1): target may be ANY bit       4
   G_SWAP = 3,     // [[0,1],[1,0]]: pure permutation           0
+  G_ROT = 4,      // rotation [[c,-s],[s,c]], c >= 0 (a scale / sign is pulled into the deferred
+                  // scalar): three in-place shears            3
 };
 
 // One gate as the fused-pass kernel sees it (per round: register/thread/external split).
 struct alignas(16) DevGate {
   double m[8];     // row-major (re,im): a b c d.  G_REAL uses re parts; G_DIAG uses a and d.
+                   // G_ROT: m[0] = t = -tan(theta/2), m[1] = s = sin(theta) (the shear coefficients)
   uint32_t type;   // GateType
   uint32_t treg;   // target register bit (GENERAL / REAL / SWAP)
   uint32_t creg;   // controls that are register-index bits   (mask over the 2^R index)
@@ -43,18 +46,42 @@ struct alignas(16) DevGate {
   uint32_t _pad;
 };
 
-// Dense opcode space of k_fused_pass's gate switch.  FL = flavour: 0 uncontrolled / no flip
-// possible, 1 uncontrolled / flip-aware, 2 controlled (flip-aware).  J = target register bit.
-enum : uint32_t {
-  OP_GENERAL = 0,    // + FL * 5 + J          (15)
-  OP_REAL = 15,      // + FL * 5 + J          (15)
-  OP_DIAG_REG = 30,  // + FL * 5 + J          (15)
-  OP_SWAP_REG = 45,  // + J: X / CX with a control on a register bit (data moves)   (5)
-  OP_TOGGLE = 50,    // X / CX without register-bit controls: flip-mask toggle
-  OP_DIAG_THR = 51,  // diagonal gate whose target is a thread bit or outside the tile
-  OP_COUNT = 52,
-};
+// Opcode space of k_fused_pass's gate switch, DENSE for a kernel with R register bits (one jump
+// table, no decision tree).  FL = flavour: 0 uncontrolled / no flip possible, 1 uncontrolled /
+// flip-aware, 2 controlled (flip-aware).  J = target register bit (< R).
+#ifdef __CUDACC__
+#define QB_HD __host__ __device__
+#else
+#define QB_HD
+#endif
+enum GateClass : uint32_t { C_GENERAL = 0, C_REAL = 1, C_ROT = 2, C_DIAG_REG = 3, C_COUNT = 4 };
+QB_HD constexpr uint32_t op_arith(int R, uint32_t cls, uint32_t fl, uint32_t J) { return (cls * 3u + fl) * uint32_t(R) + J; }
+QB_HD constexpr uint32_t op_swap_reg(int R, uint32_t J) { return C_COUNT * 3u * uint32_t(R) + J; }  // X / CX with a register-bit control
+QB_HD constexpr uint32_t op_toggle(int R) { return (C_COUNT * 3u + 1u) * uint32_t(R); }            // X / CX: flip-mask toggle
+QB_HD constexpr uint32_t op_diag_thr(int R) { return op_toggle(R) + 1u; }  // diagonal gate, target on a thread bit / outside the tile
+QB_HD constexpr uint32_t op_count(int R) { return op_toggle(R) + 2u; }
 static_assert(sizeof(DevGate) == 112, "DevGate layout");
+
+// LITE passes (uncontrolled rotations and X / CX only) are not interpreted gate by gate: the
+// planner packs each round into STEPS of mutually independent work -- one rotation slot per
+// register bit, then up to four flip-mask toggles, then at most one register-controlled X --
+// which the kernel runs as straight-line code behind a few uniform skip-branches.  No opcode
+// fetch, no dispatch tree, no jump table: per step ONE header read, per gate two constants.
+constexpr int kStepToggles = 4;
+struct alignas(16) DevStep {
+  double rot[kMaxRegBits][2];  // (t, s) of the rotation on register bit J
+  uint32_t rot_mask;           // bit J: slot J holds a rotation
+  uint32_t rot_flip;           // bit J: a flip may be pending on register bit J (sign-aware flavour)
+  uint32_t ntog;               // toggles applied after the rotations
+  uint32_t swap_j;             // >= 8: none; else X / CX with register-bit control(s) on target register bit swap_j
+  struct Tog {
+    uint32_t cthr, bit;
+    uint64_t cext;
+  } tog[kStepToggles];
+  uint32_t swap_creg, swap_cthr;
+  uint64_t swap_cext;
+};
+static_assert(sizeof(DevStep) == 176, "DevStep layout");
 
 struct DevRound {
   uint32_t gate_begin, gate_end;
@@ -63,7 +90,7 @@ struct DevRound {
   uint8_t tid_pos[16];                // tile-local bit position carried by thread-id bit j
   uint8_t reg_pos[8];                 // tile-local bit position carried by register bit j
   uint32_t reg_sx[8];                 // swizzled shared-memory index contribution of register bit j
-  uint32_t _pad2[2];
+  uint32_t step_begin, step_end;      // lite passes: this round's DevSteps
 };
 static_assert(sizeof(DevRound) == 80, "DevRound layout");
 
@@ -77,10 +104,15 @@ struct DevPass {
   double gscale[2];                   // deferred global scalar applied on the way out (1,0 = none)
   uint32_t has_gscale;
   uint32_t l2_prefetch;               // prefetch the CTA's next tile into L2 while this one computes
-  uint32_t stagger_ns;                // start-up delay per co-resident CTA index (phase de-sync)
+  uint32_t stagger_ns;                // PROFILING ONLY (results are wrong): bit 0 skip global loads, bit 1 skip
+                                      // global stores, bit 2 skip the shared-memory transposes, bit 3 skip gates
   uint32_t sm_count;
+  uint32_t lite;                      // only uncontrolled rotations and X / CX: rounds index DevSteps, not DevGates
+  uint32_t nsteps;
+  uint32_t zero;                      // always 0 (a run-time zero the kernel uses to touch a register)
+  uint32_t groups;                    // thread groups per CTA (phase tokens), 1 = plain CTAs
   DevRound rounds[kMaxRounds];
-  // followed in memory by ngates DevGate records
+  // followed in memory by ngates DevGate records (lite: by nsteps DevStep records)
 };
 static_assert(sizeof(DevPass) % 16 == 0, "DevPass alignment");
 
@@ -121,8 +153,12 @@ struct PlanOptions {
   int max_pass_gates = kMaxPassGates;
   int time_kernels = 0;
   int l2_prefetch = 1;
-  int stagger_ns = 0;
+  int stagger_ns = 0;     // profiling switches, see DevPass::stagger_ns (named "dbg_skip" in set_option)
   int avoid_regswap = 0;  // planner: refuse rounds where a CX control would be a register bit
+  int rot = 1;            // rotations [[c,-s],[s,c]] run as three in-place shears (G_ROT) instead of G_REAL
+  int lane_fixed = 3;     // low tile bits that stay on lanes in the load / store rounds (1..3)
+  int groups = 1;         // 3: one CTA per SM with three tile groups that pass phase tokens (k_fused_pass)
+  int lite = 1;           // passes of rotations and X / CX only use the lean kernel instantiation
   int hot_bits = 0;       // planner: max distinct TARGET bits per pass (0 = tile_bits).  With
                           // hot_bits <= tile_bits - warp bits every transpose can stay warp-local.
 };
@@ -148,7 +184,8 @@ struct PhysOp {
 };
 
 struct PassPlan {
-  std::vector<uint8_t> blob;     // DevPass + gates
+  std::vector<uint8_t> blob;     // what the kernel receives: DevPass + gates (lite: DevPass + steps)
+  std::vector<DevGate> gates;    // the gate records in execution order (also kept for lite passes)
   uint64_t ntiles = 0;
   int tile_bits = 0, reg_bits = 0;
   int nrounds = 0, ngates = 0;
@@ -181,12 +218,13 @@ std::string describe_plan(const PlanResult &r);
 struct OpQueue {
   int n = 0;
   bool peephole = true;
+  bool use_rot = true;
   std::vector<HostOp> ops;
   std::vector<int> last_op;      // per logical bit: last live op touching it, or -1
   double gscale[2] = {1.0, 0.0};
   uint64_t submitted = 0, folded = 0;
 
-  void reset(int nqubits, bool peep);
+  void reset(int nqubits, bool peep, bool rot = true);
   void clear();
   bool empty() const;            // nothing to execute (no live ops, gscale == 1)
   void mul_gscale(double re, double im);
@@ -226,6 +264,6 @@ struct Classified {
   double phase[2];    // common phase pulled out (multiply into the deferred scalar); (1,0) if none
   bool is_scalar;     // m == phase * I
 };
-Classified classify_2x2(const double m[8], bool allow_phase_pull);
+Classified classify_2x2(const double m[8], bool allow_phase_pull, bool allow_scale = true);
 
 }  // namespace qb

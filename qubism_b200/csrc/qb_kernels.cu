@@ -16,6 +16,8 @@
 // measurement (a13) and <.> (a15), element-wise vector-space kernels (a15/a16).
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -189,14 +191,72 @@ __device__ __forceinline__ void gate_diag_thr(double (&re)[1 << R], double (&im)
   }
 }
 
-// One dense opcode per gate (planner-assigned, qb_internal.h): a single jump-table dispatch.
-// The control predicate (thread-id / external masks) is only evaluated in the arms that need it.
-#define QB_ARM(BASE, FN, FL, JJ)                                                        \
-  case (BASE + FL * 5 + JJ):                                                            \
-    if constexpr (JJ < R) FN<R, JJ, FL>(re, im, g, (FL == 2) ? ok_thr(g, tid, basefull) : true, f); \
+// Rotation [[c,-s],[s,c]], c >= 0, as three shears applied IN PLACE:
+//   x0 += t x1;  x1 += s x0;  x0 += t x1      (t = -tan(theta/2), |t| <= 1;  s = sin(theta))
+// 3 DFMA per component pair instead of 4 (a DFMA holds the issue port for two cycles on this
+// machine, so FP64 instructions are the unit of cost), no temporaries, and each of the three
+// sweeps is 2^R independent operations, far longer than the DFMA latency.  With the pair
+// order reversed (flip mask) the same rotation is the one by -theta: both coefficients change sign.
+template <int R, int J, int FL>
+__device__ __forceinline__ void gate_rot(double (&re)[1 << R], double (&im)[1 << R], const DevGate &g,
+                                         bool ok_thr, uint32_t f) {
+  double t = g.m[0], s = g.m[1];
+  if (FL != 0) {
+    const long long sg = (long long)((unsigned long long)((f >> J) & 1u) << 63);
+    t = __longlong_as_double(__double_as_longlong(t) ^ sg);
+    s = __longlong_as_double(__double_as_longlong(s) ^ sg);
+  }
+  if (FL != 2) {
+#pragma unroll
+    for (int p = 0; p < (1 << (R - 1)); ++p) {
+      const int i0 = ((p >> J) << (J + 1)) | (p & ((1 << J) - 1)), i1 = i0 | (1 << J);
+      re[i0] = fma(t, re[i1], re[i0]);
+      im[i0] = fma(t, im[i1], im[i0]);
+    }
+#pragma unroll
+    for (int p = 0; p < (1 << (R - 1)); ++p) {
+      const int i0 = ((p >> J) << (J + 1)) | (p & ((1 << J) - 1)), i1 = i0 | (1 << J);
+      re[i1] = fma(s, re[i0], re[i1]);
+      im[i1] = fma(s, im[i0], im[i1]);
+    }
+#pragma unroll
+    for (int p = 0; p < (1 << (R - 1)); ++p) {
+      const int i0 = ((p >> J) << (J + 1)) | (p & ((1 << J) - 1)), i1 = i0 | (1 << J);
+      re[i0] = fma(t, re[i1], re[i0]);
+      im[i0] = fma(t, im[i1], im[i0]);
+    }
+  } else {
+    const uint32_t creg = g.creg;
+#pragma unroll
+    for (int p = 0; p < (1 << (R - 1)); ++p) {
+      const int i0 = ((p >> J) << (J + 1)) | (p & ((1 << J) - 1)), i1 = i0 | (1 << J);
+      if (ok_thr && (((uint32_t(i0) ^ f) & creg) == creg)) {
+        re[i0] = fma(t, re[i1], re[i0]);
+        im[i0] = fma(t, im[i1], im[i0]);
+        re[i1] = fma(s, re[i0], re[i1]);
+        im[i1] = fma(s, im[i0], im[i1]);
+        re[i0] = fma(t, re[i1], re[i0]);
+        im[i0] = fma(t, im[i1], im[i0]);
+      }
+    }
+  }
+}
+
+// One opcode per gate, DENSE for this R (planner-assigned, qb_internal.h): a single jump-table
+// dispatch.  The control predicate (thread-id / external masks) is only evaluated in the arms
+// that need it.  Labels for J >= R do not exist for this instantiation: they are pushed out of
+// the dense range and compile to nothing.
+#define QB_LABEL(CLS, FL, JJ) ((JJ) < R ? op_arith(R, CLS, FL, JJ) : 0x1000u + ((CLS) * 3u + (FL)) * 8u + (JJ))
+#define QB_ARM(CLS, FN, FL, JJ)                                                                       \
+  case QB_LABEL(CLS, FL, JJ):                                                                         \
+    if constexpr (JJ < R) FN<R, JJ, FL>(re, im, g, (FL == 2) ? ok_thr(g, tid, basefull) : true, f);   \
     break;
-#define QB_ARMS_FL(BASE, FN, FL) QB_ARM(BASE, FN, FL, 0) QB_ARM(BASE, FN, FL, 1) QB_ARM(BASE, FN, FL, 2) QB_ARM(BASE, FN, FL, 3) QB_ARM(BASE, FN, FL, 4)
-#define QB_ARMS(BASE, FN) QB_ARMS_FL(BASE, FN, 0) QB_ARMS_FL(BASE, FN, 1) QB_ARMS_FL(BASE, FN, 2)
+#define QB_ARMS_FL(CLS, FN, FL) QB_ARM(CLS, FN, FL, 0) QB_ARM(CLS, FN, FL, 1) QB_ARM(CLS, FN, FL, 2) QB_ARM(CLS, FN, FL, 3) QB_ARM(CLS, FN, FL, 4)
+#define QB_ARMS(CLS, FN) QB_ARMS_FL(CLS, FN, 0) QB_ARMS_FL(CLS, FN, 1) QB_ARMS_FL(CLS, FN, 2)
+#define QB_SWAP_ARM(JJ)                                                                \
+  case ((JJ) < R ? op_swap_reg(R, JJ) : 0x2000u + (JJ)):                               \
+    if constexpr (JJ < R) gate_swap<R, JJ, 2>(re, im, g, ok_thr(g, tid, basefull), f); \
+    break;
 
 __device__ __forceinline__ bool ok_thr(const DevGate &g, uint32_t tid, uint64_t basefull) {
   return ((tid & g.cthr) == g.cthr) && ((basefull & g.cext) == g.cext);
@@ -206,22 +266,112 @@ template <int R>
 __device__ __forceinline__ void apply_gate(double (&re)[1 << R], double (&im)[1 << R], const DevGate &g, uint32_t tid,
                                            uint64_t basefull, uint32_t &f) {
   switch (g.op) {
-    QB_ARMS(OP_GENERAL, gate_general)
-    QB_ARMS(OP_REAL, gate_real)
-    QB_ARMS(OP_DIAG_REG, gate_diag_reg)
-    case OP_SWAP_REG + 0: gate_swap<R, 0, 2>(re, im, g, ok_thr(g, tid, basefull), f); break;
-    case OP_SWAP_REG + 1: gate_swap<R, 1, 2>(re, im, g, ok_thr(g, tid, basefull), f); break;
-    case OP_SWAP_REG + 2: gate_swap<R, 2, 2>(re, im, g, ok_thr(g, tid, basefull), f); break;
-    case OP_SWAP_REG + 3: if constexpr (R > 3) gate_swap<R, 3, 2>(re, im, g, ok_thr(g, tid, basefull), f); break;
-    case OP_SWAP_REG + 4: if constexpr (R > 4) gate_swap<R, 4, 2>(re, im, g, ok_thr(g, tid, basefull), f); break;
-    case OP_TOGGLE:  // flip-mask toggle: no data movement
+    QB_ARMS(C_GENERAL, gate_general)
+    QB_ARMS(C_REAL, gate_real)
+    QB_ARMS(C_ROT, gate_rot)
+    QB_ARMS(C_DIAG_REG, gate_diag_reg)
+    QB_SWAP_ARM(0) QB_SWAP_ARM(1) QB_SWAP_ARM(2) QB_SWAP_ARM(3) QB_SWAP_ARM(4)
+    case op_toggle(R):  // flip-mask toggle: no data movement
       f ^= ok_thr(g, tid, basefull) ? (1u << (g.treg & 0xffu)) : 0u;
       break;
-    case OP_DIAG_THR: {
+    case op_diag_thr(R): {
       const bool one = ((tid & g.dthr) != 0) || ((basefull & g.dext) != 0);
       gate_diag_thr<R>(re, im, g, ok_thr(g, tid, basefull), one, f);
     } break;
     default: break;
+  }
+}
+
+// ---- LITE passes: uncontrolled rotations and X / CX only (what circuits of U(theta,phi,0) and CX
+// layers compile to).  The planner packed each round into DevSteps; a step is straight-line
+// code behind uniform skip-branches: no opcode fetch, no dispatch tree, no jump table.
+template <int R, int J>
+__device__ __forceinline__ void step_rot(double (&re)[1 << R], double (&im)[1 << R], const DevStep &S, uint32_t f) {
+  if ((S.rot_mask >> J) & 1u) {
+    const double t = S.rot[J][0], s = S.rot[J][1];
+    if ((S.rot_flip >> J) & 1u) {  // a flip may be pending on this bit: per-thread sign
+      const long long sg = (long long)((unsigned long long)((f >> J) & 1u) << 63);
+      const double tv = __longlong_as_double(__double_as_longlong(t) ^ sg);
+      const double sv = __longlong_as_double(__double_as_longlong(s) ^ sg);
+#pragma unroll
+      for (int p = 0; p < (1 << (R - 1)); ++p) {
+        const int i0 = ((p >> J) << (J + 1)) | (p & ((1 << J) - 1)), i1 = i0 | (1 << J);
+        re[i0] = fma(tv, re[i1], re[i0]);
+        im[i0] = fma(tv, im[i1], im[i0]);
+      }
+#pragma unroll
+      for (int p = 0; p < (1 << (R - 1)); ++p) {
+        const int i0 = ((p >> J) << (J + 1)) | (p & ((1 << J) - 1)), i1 = i0 | (1 << J);
+        re[i1] = fma(sv, re[i0], re[i1]);
+        im[i1] = fma(sv, im[i0], im[i1]);
+      }
+#pragma unroll
+      for (int p = 0; p < (1 << (R - 1)); ++p) {
+        const int i0 = ((p >> J) << (J + 1)) | (p & ((1 << J) - 1)), i1 = i0 | (1 << J);
+        re[i0] = fma(tv, re[i1], re[i0]);
+        im[i0] = fma(tv, im[i1], im[i0]);
+      }
+    } else {  // coefficients straight from the uniform datapath
+#pragma unroll
+      for (int p = 0; p < (1 << (R - 1)); ++p) {
+        const int i0 = ((p >> J) << (J + 1)) | (p & ((1 << J) - 1)), i1 = i0 | (1 << J);
+        re[i0] = fma(t, re[i1], re[i0]);
+        im[i0] = fma(t, im[i1], im[i0]);
+      }
+#pragma unroll
+      for (int p = 0; p < (1 << (R - 1)); ++p) {
+        const int i0 = ((p >> J) << (J + 1)) | (p & ((1 << J) - 1)), i1 = i0 | (1 << J);
+        re[i1] = fma(s, re[i0], re[i1]);
+        im[i1] = fma(s, im[i0], im[i1]);
+      }
+#pragma unroll
+      for (int p = 0; p < (1 << (R - 1)); ++p) {
+        const int i0 = ((p >> J) << (J + 1)) | (p & ((1 << J) - 1)), i1 = i0 | (1 << J);
+        re[i0] = fma(t, re[i1], re[i0]);
+        im[i0] = fma(t, im[i1], im[i0]);
+      }
+    }
+  }
+}
+
+template <int R, int J>
+__device__ __forceinline__ void step_swap(double (&re)[1 << R], double (&im)[1 << R], const DevStep &S, uint32_t tid,
+                                          uint64_t basefull, uint32_t f) {
+  const bool okt = ((tid & S.swap_cthr) == S.swap_cthr) && ((basefull & S.swap_cext) == S.swap_cext);
+  const uint32_t creg = S.swap_creg;
+#pragma unroll
+  for (int p = 0; p < (1 << (R - 1)); ++p) {
+    const int i0 = ((p >> J) << (J + 1)) | (p & ((1 << J) - 1)), i1 = i0 | (1 << J);
+    const bool ok = okt && (((uint32_t(i0) ^ f) & creg) == creg);
+    const unsigned long long m = ok ? ~0ull : 0ull;
+    cswap_inplace(re[i0], re[i1], m);
+    cswap_inplace(im[i0], im[i1], m);
+  }
+}
+
+template <int R>
+__device__ __forceinline__ void apply_step(double (&re)[1 << R], double (&im)[1 << R], const DevStep &S, uint32_t tid,
+                                           uint64_t basefull, uint32_t &f) {
+  step_rot<R, 0>(re, im, S, f);
+  step_rot<R, 1>(re, im, S, f);
+  step_rot<R, 2>(re, im, S, f);
+  if constexpr (R > 3) step_rot<R, 3>(re, im, S, f);
+  if constexpr (R > 4) step_rot<R, 4>(re, im, S, f);
+  const uint32_t ntog = S.ntog;
+#pragma unroll
+  for (int k = 0; k < kStepToggles; ++k) {
+    if (k < ntog) {
+      const bool ok = ((tid & S.tog[k].cthr) == S.tog[k].cthr) && ((basefull & S.tog[k].cext) == S.tog[k].cext);
+      f ^= ok ? (1u << S.tog[k].bit) : 0u;
+    }
+  }
+  const uint32_t sj = S.swap_j;
+  if (sj < 8u) {
+    if (sj == 0) step_swap<R, 0>(re, im, S, tid, basefull, f);
+    else if (sj == 1) step_swap<R, 1>(re, im, S, tid, basefull, f);
+    else if (sj == 2) step_swap<R, 2>(re, im, S, tid, basefull, f);
+    else if (sj == 3) { if constexpr (R > 3) step_swap<R, 3>(re, im, S, tid, basefull, f); }
+    else { if constexpr (R > 4) step_swap<R, 4>(re, im, S, tid, basefull, f); }
   }
 }
 
@@ -247,145 +397,97 @@ __device__ __forceinline__ uint64_t thread_goff(const DevPass &P, const DevRound
 // shared memory, no upload, and no shared-memory round trip per gate.
 struct PassProgram {
   DevPass hdr;
-  DevGate gates[kMaxPassGates];
+  union {
+    DevGate gates[kMaxPassGates];
+    DevStep steps[kMaxPassGates];  // lite passes
+  };
 };
 static_assert(sizeof(PassProgram) <= 32000, "kernel parameter space");
 
-template <int T, int R, int MINB>
-__global__ void __launch_bounds__(1 << (T - R), MINB)
+// ---- phase tokens (GR > 1) -------------------------------------------------------------------
+// Co-resident CTAs that run the same program bunch up: all of them sit in the shared-memory /
+// load-store phases at once, then all in the FP64 phases, and the pass costs the SUM of the two
+// instead of the maximum (measured: 3 CTAs/SM, issue slots 47 % busy, LSU and FP64 pipes each
+// ~1/3 busy).  With GR > 1 one CTA holds GR independent thread groups, each with its own tile,
+// and two tokens travel round-robin between the groups through named barriers: "M" is needed for
+// every LSU-heavy phase (global load / store issue, shared-memory transposes), "F" for every
+// gate phase.  At any moment one group computes, one moves data and the third waits for HBM.
+template <int GR, int NT>
+__device__ __forceinline__ void tok_acquire(uint32_t res, uint32_t grp) {
+  if constexpr (GR > 1) asm volatile("bar.sync %0, %1;" ::"r"(4u + res * GR + grp), "n"(2 * NT) : "memory");
+}
+template <int GR, int NT>
+__device__ __forceinline__ void tok_release(uint32_t res, uint32_t grp) {
+  if constexpr (GR > 1)
+    asm volatile("bar.arrive %0, %1;" ::"r"(4u + res * GR + (grp + 1u == GR ? 0u : grp + 1u)), "n"(2 * NT) : "memory");
+}
+template <int GR, int NT>
+__device__ __forceinline__ void group_sync(uint32_t grp) {
+  if constexpr (GR > 1) asm volatile("bar.sync %0, %1;" ::"r"(1u + grp), "n"(NT) : "memory");
+  else __syncthreads();
+}
+constexpr uint32_t TOK_M = 0, TOK_F = 1;
+
+template <int T, int R>
+__host__ __device__ constexpr size_t fused_group_smem() {
+  return (size_t(16) << T) + size_t(kMaxRounds) * (size_t(1) << (T - R)) * sizeof(uint16_t) +
+         size_t(2) * (size_t(1) << (T - R)) * sizeof(uint64_t) + (size_t(1) << (T - 3)) * sizeof(uint32_t);
+}
+
+template <int T, int R, int MINB, bool LITE, int GR>
+__global__ void __launch_bounds__(GR << (T - R), MINB)
     k_fused_pass(double2 *__restrict__ amps, unsigned long long ntiles, const __grid_constant__ PassProgram prog) {
   constexpr int NR = 1 << R;
   constexpr int NT = 1 << (T - R);
-  extern __shared__ __align__(16) uint8_t smem_raw[];
+  extern __shared__ __align__(16) uint8_t smem_all[];
+  const uint32_t grp = (GR > 1) ? threadIdx.x / NT : 0u;  // warp-uniform
+  const uint32_t tid = (GR > 1) ? threadIdx.x % NT : threadIdx.x;
+  uint8_t *smem_raw = smem_all + size_t(grp) * fused_group_smem<T, R>();
   // after the tile: for every round, each thread's swizzled shared-memory index (computed once
   // per kernel; the persistent tile loop then needs one 16-bit load per transpose side)
   uint16_t *sidx_tab = reinterpret_cast<uint16_t *>(smem_raw + (size_t(16) << T));
   const DevPass &P = prog.hdr;
   const DevGate *G = prog.gates;
-  const uint32_t tid = threadIdx.x;
   const uint32_t nrounds = P.nrounds;
   for (uint32_t r = 0; r < nrounds; ++r) sidx_tab[r * NT + tid] = (uint16_t)thread_sidx<T, R>(P.rounds[r], tid);
   // (each thread only ever reads its own entries: no barrier needed)
-  const uint64_t goff_ld = thread_goff<T, R>(P, P.rounds[0], tid);
-  const uint64_t goff_st = thread_goff<T, R>(P, P.rounds[nrounds - 1], tid);
-
-  // Co-resident CTAs do identical work and would march in lockstep (all loading, then all
-  // computing), leaving HBM idle half of the time: start them a fraction of a tile period apart.
-  if (P.stagger_ns) {
-    const uint32_t slot = blockIdx.x / P.sm_count;
-    for (uint32_t k = 0; k < slot; ++k) __nanosleep(P.stagger_ns);
+  // ... and its element offset inside a tile for the load and the store layout (kept in shared
+  // memory, not in four registers: the gate loop needs every register it can get)
+  uint64_t *goff_tab = reinterpret_cast<uint64_t *>(sidx_tab + kMaxRounds * NT);
+  goff_tab[tid] = thread_goff<T, R>(P, P.rounds[0], tid);
+  goff_tab[NT + tid] = thread_goff<T, R>(P, P.rounds[nrounds - 1], tid);
+  // ... and the 128-byte lines of a tile this thread prefetches (offsets in units of 8 elements)
+  constexpr int LPT = 1 << (R - 3);  // lines per thread
+  uint32_t *line_tab = reinterpret_cast<uint32_t *>(goff_tab + 2 * NT);
+#pragma unroll
+  for (int k = 0; k < LPT; ++k) {
+    const uint32_t l = tid + k * NT;
+    uint64_t o = 0;
+#pragma unroll
+    for (int j = 0; j < T - 3; ++j) o |= uint64_t((l >> j) & 1u) << P.tile_pos[3 + j];
+    line_tab[k * NT + tid] = (uint32_t)(o >> 3);
   }
-  for (unsigned long long tile_id = blockIdx.x; tile_id < ntiles; tile_id += gridDim.x) {
-    // deposit the tile id into the non-tile bit positions
-    uint64_t base = 0;
-    {
-      uint64_t t = tile_id;
-      const uint32_t nruns = P.nruns;
-      for (uint32_t k = 0; k < nruns; ++k) {
-        const uint32_t len = P.run_len[k];
-        base |= (t & ((1ull << len) - 1ull)) << P.run_shift[k];
-        t >>= len;
-      }
-    }
-    const uint64_t basefull = base | P.rank_bits;
 
-    double re[NR], im[NR];
-    {  // coalesced load: lanes walk the low tile bits, registers stride over the round-0 bits
-      const double2 *src = amps + base + goff_ld;
-      uint64_t st[R];
-#pragma unroll
-      for (int j = 0; j < R; ++j) st[j] = 1ull << P.tile_pos[P.rounds[0].reg_pos[j]];
-#pragma unroll
-      for (int i = 0; i < NR; ++i) {
-        uint64_t off = 0;
-#pragma unroll
-        for (int j = 0; j < R; ++j)
-          if ((i >> j) & 1) off += st[j];
-        const double2 a = __ldcs(src + off);
-        re[i] = a.x;
-        im[i] = a.y;
-      }
-      // While this tile is in registers, pull the CTA's NEXT tile from HBM into L2 (one request
-      // per 128-byte line): its loads then hit L2 instead of waiting on DRAM, which overlaps
-      // the memory phase of tile k+1 with the gate / transpose phases of tile k.
-      const unsigned long long next_id = tile_id + gridDim.x;
-      if (P.l2_prefetch && next_id < ntiles && (tid & 7u) == 0u) {
-        uint64_t nbase = 0;
-        uint64_t t = next_id;
-        const uint32_t nruns = P.nruns;
-        for (uint32_t k = 0; k < nruns; ++k) {
-          const uint32_t len = P.run_len[k];
-          nbase |= (t & ((1ull << len) - 1ull)) << P.run_shift[k];
-          t >>= len;
-        }
-        const double2 *nsrc = amps + nbase + goff_ld;
-#pragma unroll
-        for (int i = 0; i < NR; ++i) {
-          uint64_t off = 0;
-#pragma unroll
-          for (int j = 0; j < R; ++j)
-            if ((i >> j) & 1) off += st[j];
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(nsrc + off));
-        }
-      }
-    }
-
-    uint32_t f = 0;  // flip mask: register i holds logical register index i ^ f
-    for (uint32_t r = 0; r < nrounds; ++r) {
-      const DevRound &RD = P.rounds[r];
-      if (r > 0) {  // transpose through swizzled shared memory: new register-resident bits
-        const DevRound &PR = P.rounds[r - 1];
-        // byte offsets throughout: address = tile + (thread part ^ register part)
-        uint32_t us = uint32_t(sidx_tab[(r - 1) * NT + tid]) << 4;
-        uint32_t sx[R];
-#pragma unroll
-        for (int j = 0; j < R; ++j) {
-          sx[j] = PR.reg_sx[j] << 4;
-          us ^= ((f >> j) & 1u) ? sx[j] : 0u;  // fold the flip mask into the address
-        }
-        f = 0;
-        // A warp-local transpose only touches this warp's own slots: the barriers shrink to
-        // __syncwarp() and the warps of the CTA stay decoupled.
-        const bool local = RD.warp_local != 0;
-        if (local) __syncwarp(); else __syncthreads();  // everyone finished reading the previous layout
-#pragma unroll
-        for (int i = 0; i < NR; ++i) {
-          uint32_t c = 0;  // uniform: folds at compile time into one XOR operand per register
-#pragma unroll
-          for (int j = 0; j < R; ++j)
-            if ((i >> j) & 1) c ^= sx[j];
-          *reinterpret_cast<double2 *>(smem_raw + (us ^ c)) = make_double2(re[i], im[i]);
-        }
-        if (local) __syncwarp(); else __syncthreads();
-        const uint32_t ul = uint32_t(sidx_tab[r * NT + tid]) << 4;
-#pragma unroll
-        for (int j = 0; j < R; ++j) sx[j] = RD.reg_sx[j] << 4;
-#pragma unroll
-        for (int i = 0; i < NR; ++i) {
-          uint32_t c = 0;
-#pragma unroll
-          for (int j = 0; j < R; ++j)
-            if ((i >> j) & 1) c ^= sx[j];
-          const double2 a = *reinterpret_cast<const double2 *>(smem_raw + (ul ^ c));
-          re[i] = a.x;
-          im[i] = a.y;
-        }
-      }
-      const uint32_t gend = RD.gate_end;
-      for (uint32_t gi = RD.gate_begin; gi < gend; ++gi) apply_gate<R>(re, im, G[gi], tid, basefull, f);
-    }
-
-    if (P.has_gscale) {  // deferred global scalar (folded u1-type phases, qb_scale)
-      const double sr = P.gscale[0], si = P.gscale[1];
-#pragma unroll
-      for (int i = 0; i < NR; ++i) {
-        const double xr = re[i], xi = im[i];
-        re[i] = sr * xr - si * xi;
-        im[i] = sr * xi + si * xr;
-      }
-    }
-    {  // coalesced store with the last round's layout (register strides are distinct bits, so
-       // the pending flip mask is one XOR on the element index)
+  const uint32_t ntiles32 = (uint32_t)ntiles;
+  const uint32_t stride = gridDim.x * GR;
+  const uint32_t first = blockIdx.x * GR + grp;
+  // every group runs the same number of iterations (token order), idle ones just pass the tokens
+  const uint32_t iters = (ntiles32 + stride - 1) / stride;
+  if (GR > 1 && grp == GR - 1) {  // the tokens start at group 0
+    tok_release<GR, NT>(TOK_M, grp);
+    tok_release<GR, NT>(TOK_F, grp);
+  }
+  double re[NR], im[NR];
+  uint32_t f = 0;  // flip mask: register i holds logical register index i ^ f
+  uint64_t base = 0;
+  for (uint32_t it = 0; it <= iters; ++it) {
+    const uint32_t tile_id = first + it * stride;
+    // ---------------- M phase: store the finished tile, then load the next one
+    tok_acquire<GR, NT>(TOK_M, grp);
+    const uint32_t dbg = P.stagger_ns;  // profiling switches (0 in production)
+    if (it > 0 && tile_id - stride < ntiles32 && !(dbg & 2u)) {
+      // coalesced store with the last round's layout (register strides are distinct bits, so
+      // the pending flip mask is one XOR on the element index)
       uint64_t st[R];
       uint64_t fx = 0;
 #pragma unroll
@@ -393,7 +495,7 @@ __global__ void __launch_bounds__(1 << (T - R), MINB)
         st[j] = 1ull << P.tile_pos[P.rounds[nrounds - 1].reg_pos[j]];
         fx |= ((f >> j) & 1u) ? st[j] : 0ull;
       }
-      const uint64_t at = (base + goff_st) ^ fx;
+      const uint64_t at = (base + goff_tab[NT + tid]) ^ fx;
 #pragma unroll
       for (int i = 0; i < NR; ++i) {
         uint64_t off = 0;
@@ -403,26 +505,169 @@ __global__ void __launch_bounds__(1 << (T - R), MINB)
         __stcs(amps + (at ^ off), make_double2(re[i], im[i]));
       }
     }
+    const bool active = it < iters && tile_id < ntiles32;
+    if (active) {
+      // deposit the tile id into the non-tile bit positions
+      base = 0;
+      {
+        uint64_t t = tile_id;
+        const uint32_t nruns = P.nruns;
+        for (uint32_t k = 0; k < nruns; ++k) {
+          const uint32_t len = P.run_len[k];
+          base |= (t & ((1ull << len) - 1ull)) << P.run_shift[k];
+          t >>= len;
+        }
+      }
+      // coalesced load: lanes walk the low tile bits, registers stride over the round-0 bits
+      const uint64_t goff_ld = goff_tab[tid];
+      const double2 *src = amps + base + goff_ld;
+      uint64_t st[R];
+#pragma unroll
+      for (int j = 0; j < R; ++j) st[j] = 1ull << P.tile_pos[P.rounds[0].reg_pos[j]];
+      if (!(dbg & 1u)) {
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+          uint64_t off = 0;
+#pragma unroll
+          for (int j = 0; j < R; ++j)
+            if ((i >> j) & 1) off += st[j];
+          const double2 a = __ldcs(src + off);
+          re[i] = a.x;
+          im[i] = a.y;
+        }
+      }
+      // While this tile is in registers, pull the group's NEXT tile from HBM into L2 (one request
+      // per 128-byte line): its loads then hit L2 instead of waiting on DRAM, which overlaps
+      // the memory phase of tile k+1 with the gate / transpose phases of tile k.
+      const uint32_t next_id = tile_id + stride;
+      if (P.l2_prefetch && next_id < ntiles32 && !(dbg & 1u)) {
+        uint64_t nbase = 0;
+        uint64_t t = next_id;
+        const uint32_t nruns = P.nruns;
+        for (uint32_t k = 0; k < nruns; ++k) {
+          const uint32_t len = P.run_len[k];
+          nbase |= (t & ((1ull << len) - 1ull)) << P.run_shift[k];
+          t >>= len;
+        }
+#pragma unroll
+        for (int k = 0; k < LPT; ++k)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(amps + nbase + (uint64_t(line_tab[k * NT + tid]) << 3)));
+      }
+    }
+    tok_release<GR, NT>(TOK_M, grp);
+    if (it == iters) break;
+    if (GR > 1 && active) {
+      // wait for the data BEFORE asking for the F token (the last load issued returns last, near
+      // enough): a group must not hold a token while it waits for HBM
+      im[NR - 1] = __longlong_as_double(__double_as_longlong(im[NR - 1]) ^ (long long)P.zero);
+    }
+    const uint64_t basefull = base | P.rank_bits;
+    f = 0;
+    for (uint32_t r = 0; r < nrounds; ++r) {
+      const DevRound &RD = P.rounds[r];
+      if (r > 0) {  // transpose through swizzled shared memory: new register-resident bits
+        tok_acquire<GR, NT>(TOK_M, grp);
+        if (active && !(dbg & 4u)) {
+          const DevRound &PR = P.rounds[r - 1];
+          // byte offsets throughout: address = tile + (thread part ^ register part)
+          uint32_t us = uint32_t(sidx_tab[(r - 1) * NT + tid]) << 4;
+          uint32_t sx[R];
+#pragma unroll
+          for (int j = 0; j < R; ++j) {
+            sx[j] = PR.reg_sx[j] << 4;
+            us ^= ((f >> j) & 1u) ? sx[j] : 0u;  // fold the flip mask into the address
+          }
+          f = 0;
+          // A warp-local transpose only touches this warp's own slots: the barriers shrink to
+          // __syncwarp() and the warps of the group stay decoupled.
+          const bool local = RD.warp_local != 0;
+          if (local) __syncwarp(); else group_sync<GR, NT>(grp);  // everyone finished reading the previous layout
+#pragma unroll
+          for (int i = 0; i < NR; ++i) {
+            uint32_t c = 0;  // uniform: folds at compile time into one XOR operand per register
+#pragma unroll
+            for (int j = 0; j < R; ++j)
+              if ((i >> j) & 1) c ^= sx[j];
+            *reinterpret_cast<double2 *>(smem_raw + (us ^ c)) = make_double2(re[i], im[i]);
+          }
+          if (local) __syncwarp(); else group_sync<GR, NT>(grp);
+          const uint32_t ul = uint32_t(sidx_tab[r * NT + tid]) << 4;
+#pragma unroll
+          for (int j = 0; j < R; ++j) sx[j] = RD.reg_sx[j] << 4;
+#pragma unroll
+          for (int i = 0; i < NR; ++i) {
+            uint32_t c = 0;
+#pragma unroll
+            for (int j = 0; j < R; ++j)
+              if ((i >> j) & 1) c ^= sx[j];
+            const double2 a = *reinterpret_cast<const double2 *>(smem_raw + (ul ^ c));
+            re[i] = a.x;
+            im[i] = a.y;
+          }
+        }
+        tok_release<GR, NT>(TOK_M, grp);
+      }
+      const uint32_t wb = LITE ? RD.step_begin : RD.gate_begin, we = LITE ? RD.step_end : RD.gate_end;
+      if (wb < we) {
+        tok_acquire<GR, NT>(TOK_F, grp);
+        if (active && !(dbg & 8u)) {
+          if constexpr (LITE) {
+            for (uint32_t si = wb; si < we; ++si) apply_step<R>(re, im, prog.steps[si], tid, basefull, f);
+          } else {
+            for (uint32_t gi = wb; gi < we; ++gi) apply_gate<R>(re, im, G[gi], tid, basefull, f);
+          }
+        }
+        tok_release<GR, NT>(TOK_F, grp);
+      }
+    }
+    if (P.has_gscale && active) {  // deferred global scalar (folded u1-type phases, qb_scale)
+      const double sr = P.gscale[0], si = P.gscale[1];
+#pragma unroll
+      for (int i = 0; i < NR; ++i) {
+        const double xr = re[i], xi = im[i];
+        re[i] = sr * xr - si * xi;
+        im[i] = sr * xi + si * xr;
+      }
+    }
+  }
+  if (GR > 1 && grp == 0) {  // absorb the last group's final releases
+    tok_acquire<GR, NT>(TOK_M, grp);
+    tok_acquire<GR, NT>(TOK_F, grp);
   }
 }
 
 struct FusedVariant {
   int T, R, threads, minb;
-  const void *fn;
+  const void *fn;       // every gate class
+  const void *fn_lite;  // rotations and X / CX only
+  const void *fn_g[2][2];  // [groups - 2][lite]: 2 / 3 token-passing groups in one CTA per SM (null: not built)
+  size_t group_smem;
 };
 
-#define QB_VARIANT(T_, R_, MINB_) \
-  { T_, R_, 1 << (T_ - R_), MINB_, (const void *)&k_fused_pass<T_, R_, MINB_> }
+#define QB_VARIANT(T_, R_, MINB_)                                                            \
+  {T_, R_, 1 << (T_ - R_), MINB_, (const void *)&k_fused_pass<T_, R_, MINB_, false, 1>,        \
+   (const void *)&k_fused_pass<T_, R_, MINB_, true, 1>, {{nullptr, nullptr}, {nullptr, nullptr}}, \
+   fused_group_smem<T_, R_>()}
+#define QB_VARIANT_G(T_, R_, MINB_)                                                          \
+  {T_, R_, 1 << (T_ - R_), MINB_, (const void *)&k_fused_pass<T_, R_, MINB_, false, 1>,        \
+   (const void *)&k_fused_pass<T_, R_, MINB_, true, 1>,                                       \
+   {{(const void *)&k_fused_pass<T_, R_, 1, false, 2>, (const void *)&k_fused_pass<T_, R_, 1, true, 2>},  \
+    {(const void *)&k_fused_pass<T_, R_, 1, false, 3>, (const void *)&k_fused_pass<T_, R_, 1, true, 3>}}, \
+   fused_group_smem<T_, R_>()}
 
+#ifdef QB_QUICK_COMPILE  // developer switch: only the default instantiation (fast ptxas experiments)
+static const FusedVariant kVariants[] = {QB_VARIANT_G(12, 4, 3)};
+static const FusedVariant kAltVariants[] = {QB_VARIANT(12, 4, 3)};
+#else
 static const FusedVariant kVariants[] = {
     QB_VARIANT(10, 3, 4), QB_VARIANT(10, 4, 4), QB_VARIANT(11, 3, 3), QB_VARIANT(11, 4, 4), QB_VARIANT(11, 5, 6),
-    QB_VARIANT(12, 3, 2), QB_VARIANT(12, 4, 3), QB_VARIANT(12, 5, 3), QB_VARIANT(13, 4, 1), QB_VARIANT(13, 5, 1),
+    QB_VARIANT(12, 3, 2), QB_VARIANT_G(12, 4, 3), QB_VARIANT(12, 5, 3), QB_VARIANT(13, 4, 1), QB_VARIANT(13, 5, 1),
 };
 // experimental: same (T, R) with a different register budget (selected with QB_ALT_VARIANTS=1)
 static const FusedVariant kAltVariants[] = {
-    QB_VARIANT(11, 4, 5),
-    QB_VARIANT(11, 4, 6), QB_VARIANT(12, 4, 2),
+    QB_VARIANT(12, 4, 2),
 };
+#endif
 
 static const FusedVariant *find_variant(int T, int R) {
   static const char *alt = getenv("QB_ALT_VARIANTS");
@@ -437,7 +682,9 @@ static const FusedVariant *find_variant(int T, int R) {
 }
 
 bool fused_variant_supported(int tile_bits, int reg_bits) { return find_variant(tile_bits, reg_bits) != nullptr; }
+#ifndef QB_QUICK_COMPILE
 static_assert(sizeof(kVariants) / sizeof(kVariants[0]) == sizeof(kFusedVariants) / sizeof(kFusedVariants[0]), "variant tables out of sync");
+#endif
 
 cudaError_t launch_fused_pass(double2 *amps, const uint8_t *blob, uint32_t blob_bytes, int tile_bits, int reg_bits,
                               uint64_t ntiles, int sm_count, cudaStream_t stream, int *grid_out) {
@@ -446,19 +693,29 @@ cudaError_t launch_fused_pass(double2 *amps, const uint8_t *blob, uint32_t blob_
   if (blob_bytes > sizeof(PassProgram) || blob_bytes < sizeof(DevPass)) return cudaErrorInvalidValue;
   static thread_local PassProgram prog;  // the launch copies it into the command buffer
   memcpy(&prog, blob, blob_bytes);
-  const size_t smem = (size_t(16) << tile_bits) + size_t(kMaxRounds) * v->threads * sizeof(uint16_t);
-  cudaError_t e = cudaFuncSetAttribute(v->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int lite = prog.hdr.lite ? 1 : 0;
+  const void *fn = lite ? v->fn_lite : v->fn;
+  int groups = 1;
+  if (prog.hdr.groups >= 2 && prog.hdr.groups <= 3 && v->fn_g[prog.hdr.groups - 2][lite] &&
+      ntiles >= uint64_t(sm_count) * prog.hdr.groups) {
+    groups = (int)prog.hdr.groups;
+    fn = v->fn_g[groups - 2][lite];
+  }
+  const size_t smem = v->group_smem * groups;
+  const int threads = v->threads * groups;
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int occ = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, v->fn, v->threads, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, smem);
   if (e != cudaSuccess) return e;
   if (occ < 1) return cudaErrorLaunchOutOfResources;
+  if (groups > 1) occ = 1;
   uint64_t grid = uint64_t(sm_count) * uint64_t(occ);
-  if (grid > ntiles) grid = ntiles;
+  if (grid * groups > ntiles) grid = std::max<uint64_t>(1, ntiles / groups);
   if (grid_out) *grid_out = (int)grid;
   unsigned long long nt = ntiles;
   void *args[] = {(void *)&amps, (void *)&nt, (void *)&prog};
-  return cudaLaunchKernel(v->fn, dim3((unsigned)grid), dim3(v->threads), args, smem, stream);
+  return cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(threads), args, smem, stream);
 }
 
 // ---------------------------------------------------------------- unfused kernels

@@ -52,10 +52,20 @@ bool set_opt(PlanOptions &o, const std::string &name, int64_t v) {
   } else if (name == "hot_bits") {
     if (v < 0 || v > kMaxTileBits) return false;
     o.hot_bits = (int)v;
+  } else if (name == "rot") {
+    o.rot = v ? 1 : 0;
+  } else if (name == "lite") {
+    o.lite = v ? 1 : 0;
+  } else if (name == "lane_fixed") {
+    if (v < 0 || v > kLaneFixedBits) return false;
+    o.lane_fixed = (int)v;
+  } else if (name == "groups") {
+    if (v != 1 && v != 2 && v != 3) return false;
+    o.groups = (int)v;
   } else if (name == "avoid_regswap") {
     o.avoid_regswap = v ? 1 : 0;
-  } else if (name == "stagger_ns") {
-    if (v < 0 || v > 100000) return false;
+  } else if (name == "stagger_ns" || name == "dbg_skip") {
+    if (v < 0 || v > 15) return false;
     o.stagger_ns = (int)v;
   } else {
     return false;
@@ -73,9 +83,13 @@ int64_t get_opt(const PlanOptions &o, const std::string &name) {
   if (name == "max_pass_gates") return o.max_pass_gates;
   if (name == "time_kernels") return o.time_kernels;
   if (name == "l2_prefetch") return o.l2_prefetch;
-  if (name == "stagger_ns") return o.stagger_ns;
+  if (name == "stagger_ns" || name == "dbg_skip") return o.stagger_ns;
   if (name == "avoid_regswap") return o.avoid_regswap;
   if (name == "hot_bits") return o.hot_bits;
+  if (name == "rot") return o.rot;
+  if (name == "lite") return o.lite;
+  if (name == "groups") return o.groups;
+  if (name == "lane_fixed") return o.lane_fixed;
   return -1;
 }
 
@@ -97,7 +111,46 @@ void effective_tile(const PlanOptions &o, int L, int &T, int &R) {
 }
 
 // --------------------------------------------------------------------- classification
-Classified classify_2x2(const double m[8], bool allow_phase_pull) {
+// r = k * [[c,-s],[s,c]] with c >= 0?  (k may be negative.)  Rotations run as three in-place
+// shears in the kernel: 3 instead of 4 FP64 operations per component pair, and no temporaries.
+// Only exact rotation structure qualifies (entries equal to a few ulp); allow_scale = false
+// additionally demands k = 1 (controlled gates cannot shed a scalar).
+static bool as_rotation(const double r[4], bool allow_scale, double &k, double &cs, double &sn) {
+  double scale = 0.0;
+  for (int i = 0; i < 4; ++i) scale = std::max(scale, std::fabs(r[i]));
+  if (!(scale > 0.0) || !std::isfinite(scale)) return false;
+  const double tol = 8.0 * DBL_EPSILON * scale;
+  if (!(std::fabs(r[0] - r[3]) <= tol && std::fabs(r[1] + r[2]) <= tol)) return false;
+  const double a = 0.5 * (r[0] + r[3]), c = 0.5 * (r[2] - r[1]);
+  double kk = std::hypot(a, c);
+  if (!(kk > 0.0) || !std::isfinite(kk)) return false;
+  if (!allow_scale) {
+    if (a < 0.0 || std::fabs(kk - 1.0) > 8.0 * DBL_EPSILON) return false;
+    k = 1.0;
+    cs = a;
+    sn = c;
+    return true;
+  }
+  if (kk < 0x1p-20 || kk > 0x1p20) return false;  // keep the deferred scalar well inside the exponent range
+  if (a < 0.0) kk = -kk;
+  k = kk;
+  cs = a / kk;
+  sn = c / kk;
+  return true;
+}
+
+static void set_rotation(Classified &c, double k, double cs, double sn) {
+  c.type = G_ROT;
+  std::memset(c.m, 0, sizeof(c.m));
+  c.m[0] = cs;
+  c.m[2] = -sn;
+  c.m[4] = sn;
+  c.m[6] = cs;
+  c.phase[0] *= k;
+  c.phase[1] *= k;
+}
+
+Classified classify_2x2(const double m[8], bool allow_phase_pull, bool allow_scale) {
   Classified c{};
   std::memcpy(c.m, m, sizeof(c.m));
   c.phase[0] = 1.0;
@@ -118,6 +171,9 @@ Classified classify_2x2(const double m[8], bool allow_phase_pull) {
   bool all_real = (m[1] == 0.0 && m[3] == 0.0 && m[5] == 0.0 && m[7] == 0.0);
   if (all_real) {
     c.type = G_REAL;
+    const double r[4] = {m[0], m[2], m[4], m[6]};
+    double k, cs, sn;
+    if (as_rotation(r, allow_phase_pull && allow_scale, k, cs, sn)) set_rotation(c, k, cs, sn);
     return c;
   }
   if (!allow_phase_pull) return c;
@@ -150,13 +206,16 @@ Classified classify_2x2(const double m[8], bool allow_phase_pull) {
   }
   c.phase[0] = sr;
   c.phase[1] = si;
+  double k, cs, sn;
+  if (as_rotation(r, allow_scale, k, cs, sn)) set_rotation(c, k, cs, sn);
   return c;
 }
 
 // --------------------------------------------------------------------- op queue + peephole
-void OpQueue::reset(int nqubits, bool peep) {
+void OpQueue::reset(int nqubits, bool peep, bool rot) {
   n = nqubits;
   peephole = peep;
+  use_rot = rot;
   clear();
 }
 
@@ -218,7 +277,12 @@ static void mat2_mul(const double a[8], const double b[8], double out[8]) {  // 
 
 void OpQueue::push_1q(int target_bit, uint64_t ctrl_mask, const double m[8]) {
   ++submitted;
-  Classified c = classify_2x2(m, peephole && ctrl_mask == 0);
+  // scaled rotations shed their scale into the deferred scalar only while that stays far from
+  // the exponent limits (a flush folds it back into the amplitudes)
+  const double gmag = std::fabs(gscale[0]) + std::fabs(gscale[1]);
+  const bool scale_ok = gmag > 0x1p-400 && gmag < 0x1p400;
+  Classified c = classify_2x2(m, peephole && ctrl_mask == 0, scale_ok);
+  if (c.type == G_ROT && !use_rot) c.type = G_REAL;
   const uint64_t qmask = ctrl_mask | (1ull << target_bit);
   if (peephole) {
     if (ctrl_mask == 0) {
@@ -233,7 +297,8 @@ void OpQueue::push_1q(int target_bit, uint64_t ctrl_mask, const double m[8]) {
           ops[li].nprev <= 6) {
         double prod[8];
         mat2_mul(c.m, ops[li].m, prod);
-        Classified pc = classify_2x2(prod, true);
+        Classified pc = classify_2x2(prod, true, scale_ok);
+        if (pc.type == G_ROT && !use_rot) pc.type = G_REAL;
         ++folded;
         if (pc.type == G_DIAG && pc.is_scalar) {
           mul_gscale(prod[0], prod[1]);
@@ -406,7 +471,10 @@ static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &don
   uint64_t hot_mask = 0;  // bits that carry a non-diagonal gate in this pass
   const int max_hot = (opt.hot_bits > 0 && opt.hot_bits < T) ? opt.hot_bits : 0;
   uint64_t blocked = 0;
-  const uint64_t lowfixed = (1ull << kLaneFixedBits) - 1;
+  // tile bits that must stay on lanes in the load / store rounds: 3 = whole 128-byte lines per
+  // quarter-warp, 1 = whole 32-byte sectors per lane pair (same DRAM traffic, more lines per request)
+  const int lane_fixed = std::max(0, std::min(opt.lane_fixed, kLaneFixedBits));
+  const uint64_t lowfixed = (1ull << lane_fixed) - 1;
   std::vector<RoundTmp> rounds;
   int lastround[64];
   std::fill(lastround, lastround + 64, 0);
@@ -576,7 +644,7 @@ static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &don
       for (int pass2 = 0; pass2 < 2; ++pass2)
         for (int i = T - 1; i >= 0 && popc(regm) < R; --i) {
           if ((regm | wmask) & (1u << i)) continue;
-          if (edge && i < kLaneFixedBits) continue;
+          if (edge && i < lane_fixed) continue;
           if (pass2 == 0 && (qmask & (1u << i))) continue;
           regm |= 1u << i;
         }
@@ -615,6 +683,7 @@ static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &don
   P->l2_prefetch = opt.l2_prefetch ? 1u : 0u;
   P->stagger_ns = (uint32_t)opt.stagger_ns;
   P->sm_count = 148;
+  P->groups = (uint32_t)opt.groups;
   for (int i = 0; i < T; ++i) P->tile_pos[i] = (uint8_t)tile_bits[i];
   {  // runs of non-tile local bits, ascending
     uint32_t nruns = 0;
@@ -647,7 +716,9 @@ static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &don
     std::vector<int> order;
     {
       std::vector<int> rest = lane_bits[r];
-      bool qw_ok = !edge && qw_lanes[r].size() == 3;
+      // (with lane_fixed < 3 the load / store rounds use the same rule: bit 0 is then always the
+      //  first lane, and bits 1, 2 follow whenever they are not register bits)
+      bool qw_ok = (!edge || lane_fixed < kLaneFixedBits) && qw_lanes[r].size() == 3;
       for (int q : qw_lanes[r])
         if (std::find(rest.begin(), rest.end(), q) == rest.end()) qw_ok = false;  // became a register
       if (qw_ok) {
@@ -707,14 +778,96 @@ static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &don
         const bool ctrl = (g.creg | g.cthr) != 0 || g.cext != 0;
         const uint32_t J = g.treg & 0xffu;
         const uint32_t fl = ctrl ? 2u : ((g.treg >> 8) & 1u);
-        if (g.type == G_SWAP) g.op = (g.creg == 0) ? OP_TOGGLE : OP_SWAP_REG + J;
-        else if (g.type == G_DIAG) g.op = (J < 8 && g.dreg) ? OP_DIAG_REG + fl * 5 + J : OP_DIAG_THR;
-        else g.op = (g.type == G_GENERAL ? OP_GENERAL : OP_REAL) + fl * 5 + J;
+        if (g.type == G_SWAP) g.op = (g.creg == 0) ? op_toggle(R) : op_swap_reg(R, J);
+        else if (g.type == G_DIAG) g.op = (J < 8 && g.dreg) ? op_arith(R, C_DIAG_REG, fl, J) : op_diag_thr(R);
+        else g.op = op_arith(R, g.type == G_GENERAL ? C_GENERAL : (g.type == G_ROT ? C_ROT : C_REAL), fl, J);
+        if (g.type == G_ROT) {  // shear coefficients from (cos, sin), cos >= 0 by classification
+          const double cs = op.m[0], sn = op.m[4];
+          std::memset(g.m, 0, sizeof(g.m));
+          g.m[0] = -sn / (1.0 + cs);
+          g.m[1] = sn;
+        }
       }
       out.op_index.push_back(oi);
     }
     RD.gate_end = gcount;
     out.round_regmask.push_back(rounds[r].regmask);
+  }
+  out.gates.assign(G, G + gcount);
+  {
+    bool lite = opt.lite != 0;
+    for (uint32_t gi = 0; gi < gcount && lite; ++gi) {
+      const DevGate &g = G[gi];
+      const bool ctrl = (g.creg | g.cthr) != 0 || g.cext != 0;
+      if (!(g.type == G_SWAP || (g.type == G_ROT && !ctrl))) lite = false;
+    }
+    if (lite) {
+      // ---- pack every round into steps (ASAP list scheduling; ops on disjoint qubits commute).
+      // Position = 3 * step + phase, phase 0 = rotations, 1 = toggles (list order), 2 = the
+      // register-controlled X.  An op goes to the earliest position after the last op that
+      // shares a qubit with it.
+      std::vector<DevStep> steps;
+      for (int r = 0; r < nrounds; ++r) {
+        DevRound &RD = P->rounds[r];
+        const size_t first = steps.size();
+        int last_pos[64];
+        std::fill(last_pos, last_pos + 64, -1);
+        auto step_at = [&](size_t k) -> DevStep & {
+          while (steps.size() <= first + k) {
+            DevStep s0{};
+            s0.swap_j = 0xffu;
+            steps.push_back(s0);
+          }
+          return steps[first + k];
+        };
+        for (uint32_t gi = RD.gate_begin; gi < RD.gate_end; ++gi) {
+          const DevGate &g = G[gi];
+          const PhysOp &op = ops[out.op_index[gi]];
+          const uint64_t qmask = op.ctrl | (1ull << op.target);
+          int lb = -1;
+          for (uint64_t q = qmask; q; q &= q - 1) lb = std::max(lb, last_pos[__builtin_ctzll(q)]);
+          const uint32_t J = g.treg & 0xffu;
+          int pos;
+          if (g.type == G_ROT) {
+            int k = (lb < 0) ? 0 : lb / 3 + 1;
+            DevStep &S = step_at(k);
+            S.rot[J][0] = g.m[0];
+            S.rot[J][1] = g.m[1];
+            S.rot_mask |= 1u << J;
+            if ((g.treg >> 8) & 1u) S.rot_flip |= 1u << J;
+            pos = 3 * k;
+          } else if (g.creg == 0) {  // toggle
+            int k = (lb < 0) ? 0 : (lb + 1) / 3;  // smallest k with 3k + 1 >= lb
+            while (step_at(k).ntog >= (uint32_t)kStepToggles) ++k;
+            DevStep &S = step_at(k);
+            S.tog[S.ntog].cthr = g.cthr;
+            S.tog[S.ntog].cext = g.cext;
+            S.tog[S.ntog].bit = J;
+            ++S.ntog;
+            pos = 3 * k + 1;
+          } else {  // X / CX with a register-bit control: data moves
+            int k = (lb < 0) ? 0 : (lb - 2 + 3) / 3;  // smallest k with 3k + 2 > lb
+            while (3 * k + 2 <= lb) ++k;
+            while (step_at(k).swap_j < 8u) ++k;
+            DevStep &S = step_at(k);
+            S.swap_j = J;
+            S.swap_creg = g.creg;
+            S.swap_cthr = g.cthr;
+            S.swap_cext = g.cext;
+            pos = 3 * k + 2;
+          }
+          for (uint64_t q = qmask; q; q &= q - 1) last_pos[__builtin_ctzll(q)] = pos;
+        }
+        RD.step_begin = (uint32_t)first;
+        RD.step_end = (uint32_t)steps.size();
+      }
+      P->lite = 1u;
+      P->nsteps = (uint32_t)steps.size();
+      std::vector<uint8_t> blob(sizeof(DevPass) + steps.size() * sizeof(DevStep));
+      std::memcpy(blob.data(), out.blob.data(), sizeof(DevPass));
+      if (!steps.empty()) std::memcpy(blob.data() + sizeof(DevPass), steps.data(), steps.size() * sizeof(DevStep));
+      out.blob.swap(blob);
+    }
   }
   for (auto &pr : chosen) done[pr.first] = 1;
   return true;
@@ -750,9 +903,10 @@ std::string describe_plan(const PlanResult &r) {
     const DevPass *P = reinterpret_cast<const DevPass *>(p.blob.data());
     os << "pass " << i << " T=" << p.tile_bits << " R=" << p.reg_bits << " tiles=" << p.ntiles << " tile=[";
     for (int b = 0; b < p.tile_bits; ++b) os << (b ? "," : "") << (int)P->tile_pos[b];
-    os << "] rounds=" << p.nrounds << " gates=" << p.ngates << " gscale=" << P->has_gscale;
+    os << "] rounds=" << p.nrounds << " gates=" << p.ngates << " gscale=" << P->has_gscale << " lite=" << P->lite
+       << " steps=" << P->nsteps;
     {
-      const DevGate *G = reinterpret_cast<const DevGate *>(p.blob.data() + sizeof(DevPass));
+      const DevGate *G = p.gates.data();
       int kinds[8] = {0};
       for (int g = 0; g < p.ngates; ++g) {
         const DevGate &d = G[g];

@@ -52,6 +52,13 @@ void apply_gate_host(std::vector<double> &re, std::vector<double> &im, int R, co
     const double x0r = re[i0], x0i = im[i0], x1r = re[i1], x1i = im[i1];
     if (g.type == G_SWAP) {
       re[i0] = x1r; im[i0] = x1i; re[i1] = x0r; im[i1] = x0i;
+    } else if (g.type == G_ROT) {  // three shears with the kernel's coefficients (t, s)
+      const double t = g.m[0], s = g.m[1];
+      double a0r = std::fma(t, x1r, x0r), a0i = std::fma(t, x1i, x0i);
+      const double a1r = std::fma(s, a0r, x1r), a1i = std::fma(s, a0i, x1i);
+      a0r = std::fma(t, a1r, a0r);
+      a0i = std::fma(t, a1i, a0i);
+      re[i0] = a0r; im[i0] = a0i; re[i1] = a1r; im[i1] = a1i;
     } else if (g.type == G_REAL) {
       re[i0] = g.m[0] * x0r + g.m[2] * x1r;
       im[i0] = g.m[0] * x0i + g.m[2] * x1i;
@@ -64,6 +71,59 @@ void apply_gate_host(std::vector<double> &re, std::vector<double> &im, int R, co
       im[i1] = g.m[4] * x0i + g.m[5] * x0r + g.m[6] * x1i + g.m[7] * x1r;
     }
   }
+}
+
+// One DevStep on one thread's registers, flip-mask semantics as in the kernel: register i
+// holds logical register index i ^ f.
+void apply_step_host(std::vector<double> &re, std::vector<double> &im, int R, const DevStep &S, uint32_t tid,
+                     uint64_t basefull, uint32_t &f) {
+  const int NR = 1 << R;
+  for (int J = 0; J < R; ++J) {
+    if (!((S.rot_mask >> J) & 1u)) continue;
+    double t = S.rot[J][0], s = S.rot[J][1];
+    if ((f >> J) & 1u) {
+      if (!((S.rot_flip >> J) & 1u)) std::fprintf(stderr, "emulator: flip pending on a slot the planner marked flip-free\n");
+      t = -t;
+      s = -s;
+    }
+    for (int p = 0; p < NR / 2; ++p) {
+      const int i0 = ((p >> J) << (J + 1)) | (p & ((1 << J) - 1)), i1 = i0 | (1 << J);
+      re[i0] = std::fma(t, re[i1], re[i0]);
+      im[i0] = std::fma(t, im[i1], im[i0]);
+      re[i1] = std::fma(s, re[i0], re[i1]);
+      im[i1] = std::fma(s, im[i0], im[i1]);
+      re[i0] = std::fma(t, re[i1], re[i0]);
+      im[i0] = std::fma(t, im[i1], im[i0]);
+    }
+  }
+  for (uint32_t k = 0; k < S.ntog; ++k) {
+    const auto &tg = S.tog[k];
+    if (((tid & tg.cthr) == tg.cthr) && ((basefull & tg.cext) == tg.cext)) f ^= 1u << tg.bit;
+  }
+  if (S.swap_j < 8u) {
+    const int J = (int)S.swap_j;
+    const bool ok_thr = ((tid & S.swap_cthr) == S.swap_cthr) && ((basefull & S.swap_cext) == S.swap_cext);
+    for (int p = 0; p < NR / 2; ++p) {
+      const int i0 = ((p >> J) << (J + 1)) | (p & ((1 << J) - 1)), i1 = i0 | (1 << J);
+      if (ok_thr && (((uint32_t(i0) ^ f) & S.swap_creg) == S.swap_creg)) {
+        std::swap(re[i0], re[i1]);
+        std::swap(im[i0], im[i1]);
+      }
+    }
+  }
+}
+
+// end of round: put every amplitude into the register its logical index names
+void fold_flip_host(std::vector<double> &re, std::vector<double> &im, int R, uint32_t f) {
+  if (!f) return;
+  const int NR = 1 << R;
+  std::vector<double> r2(NR), i2(NR);
+  for (int i = 0; i < NR; ++i) {
+    r2[i ^ f] = re[i];
+    i2[i ^ f] = im[i];
+  }
+  re = r2;
+  im = i2;
 }
 
 uint32_t thread_u(const DevRound &rd, int nthr_bits, uint32_t tid) {
@@ -95,7 +155,8 @@ int conflict_degree(const DevRound &rd, int T, int R, int i) {
 
 void run_pass(const PassPlan &pp, int L, std::vector<double> &amps, EmuStats &st) {
   const DevPass &P = *reinterpret_cast<const DevPass *>(pp.blob.data());
-  const DevGate *G = reinterpret_cast<const DevGate *>(pp.blob.data() + sizeof(DevPass));
+  const DevGate *G = pp.gates.data();
+  const DevStep *S = reinterpret_cast<const DevStep *>(pp.blob.data() + sizeof(DevPass));
   const int T = P.tile_bits, R = P.reg_bits, NT = 1 << (T - R), NR = 1 << R;
   std::vector<double> tile_re(size_t(1) << T), tile_im(size_t(1) << T);
   std::vector<char> written(size_t(1) << T);
@@ -154,8 +215,19 @@ void run_pass(const PassPlan &pp, int L, std::vector<double> &amps, EmuStats &st
             }
         }
       }
-      for (uint32_t gi = RD.gate_begin; gi < RD.gate_end; ++gi)
-        for (int tid = 0; tid < NT; ++tid) apply_gate_host(re[tid], im[tid], R, G[gi], tid, basefull);
+      if (P.lite) {
+        // lite passes carry STEPS, not gates: run them exactly as the kernel does (rotation
+        // slots in register-bit order, then the toggles, then the register-controlled X), with a
+        // per-thread flip mask that folds into the data at the end of the round
+        for (int tid = 0; tid < NT; ++tid) {
+          uint32_t f = 0;
+          for (uint32_t si = RD.step_begin; si < RD.step_end; ++si) apply_step_host(re[tid], im[tid], R, S[si], tid, basefull, f);
+          fold_flip_host(re[tid], im[tid], R, f);
+        }
+      } else {
+        for (uint32_t gi = RD.gate_begin; gi < RD.gate_end; ++gi)
+          for (int tid = 0; tid < NT; ++tid) apply_gate_host(re[tid], im[tid], R, G[gi], tid, basefull);
+      }
       st.gates += RD.gate_end - RD.gate_begin;
     }
     for (int tid = 0; tid < NT; ++tid)
@@ -203,7 +275,7 @@ int qbe_run(int nlocal, const qb_op *ops, int64_t nops, const char *options, dou
     }
   }
   OpQueue q;
-  q.reset(nlocal, opt.peephole != 0);
+  q.reset(nlocal, opt.peephole != 0, opt.rot != 0);
   static const double X[8] = {0, 0, 1, 0, 1, 0, 0, 0};
   for (int64_t i = 0; i < nops; ++i) {
     const qb_op &o = ops[i];
@@ -280,7 +352,7 @@ int qbe_run_rank(int n, int nranks, int rank, const qb_op *ops, int64_t nops, co
   while ((1 << pbits) < nranks) ++pbits;
   const int L = n - pbits;
   OpQueue q;
-  q.reset(n, opt.peephole != 0);
+  q.reset(n, opt.peephole != 0, opt.rot != 0);
   static const double X[8] = {0, 0, 1, 0, 1, 0, 0, 0};
   for (int64_t i = 0; i < nops; ++i) {
     const qb_op &o = ops[i];

@@ -132,6 +132,27 @@ def test_fused_passes_planner_knobs(default_opts, opts):
     assert close(sv.to_host(), S.run_ops(n, ops, v), 1e-11 if opts.get("peephole") == 0 else TOL)
 
 
+@pytest.mark.parametrize("groups", [1, 2, 3])
+@pytest.mark.parametrize("lite", [1, 0])
+def test_phase_token_groups_and_lite_steps_vs_oracle(default_opts, groups, lite):
+    """22 qubits = 1024 tiles: enough for the one-CTA-per-SM kernel with 2 / 3 token-passing tile
+    groups (ragged: 1024 is not a multiple of 148 * groups, so idle groups must keep passing the
+    tokens), with the step-packed LITE program and with the gate interpreter."""
+    ctx = default_opts
+    ctx.set_option("groups", groups)
+    ctx.set_option("lite", lite)
+    n = 22
+    rng = np.random.default_rng(groups * 10 + lite)
+    v = S.gen_state(n, rng)
+    ops = random_layers(n, 3, seed=3, lam0=True) + qft_ops(n) + random_layers(n, 1, seed=4, lam0=False)
+    ref = S.run_ops(n, ops, v)
+    sv = Q.StateVec.from_host(v)
+    ctx.reset_stats()
+    sv.submit(ops)
+    assert close(sv.to_host(), ref)
+    assert ctx.stats()["simple_launches"] == 0
+
+
 def test_submit_equals_per_gate_calls(ctx):
     n = 13
     v = S.gen_state(n, np.random.default_rng(3))

@@ -60,7 +60,8 @@ def test_product_does_not_import_oracle():
 # ------------------------------------------------------------------ planner + emulator parity
 OPTION_SETS = ["", "reg_bits=5", "reg_bits=3", "tile_bits=11,reg_bits=4", "tile_bits=10,reg_bits=3", "peephole=0",
                "fuse=0", "max_rounds=3", "low_bits=3", "low_bits=7", "max_pass_gates=5",
-               "tile_bits=13,reg_bits=5,low_bits=7", "tile_bits=13,reg_bits=4"]
+               "tile_bits=13,reg_bits=5,low_bits=7", "tile_bits=13,reg_bits=4", "lane_fixed=1", "lane_fixed=2,reg_bits=5",
+               "lane_fixed=1,tile_bits=11,reg_bits=3", "lane_fixed=0", "lane_fixed=0,reg_bits=5"]
 
 
 def extras(n):
@@ -88,6 +89,25 @@ def test_emulated_passes_match_oracle(emul, n, opts):
         assert st["local"] * 2 >= st["transposes"], "most transposes should be warp-local"
     if "fuse=0" not in opts and "max_pass_gates" not in opts:
         assert st["passes"] <= 6
+
+
+@pytest.mark.parametrize("opts", ["", "rot=0", "lite=0", "reg_bits=3", "reg_bits=5", "tile_bits=10,reg_bits=4", "low_bits=5"])
+def test_emulated_lite_passes_rotations_and_cx(emul, opts):
+    """Circuits of U(theta, phi, 0) and CX layers plan into LITE passes (rotation steps, flip-mask
+    toggles, register-controlled X): the step packing must reproduce the oracle."""
+    n = 13
+    ops = random_layers(n, 6, seed=77, lam0=True)
+    txt = capi.plan_describe(n, ops, opts)
+    if opts not in ("rot=0", "lite=0"):
+        assert "lite=1" in txt and "lite=0" not in txt
+        assert all(int(m) > 0 for m in re.findall(r"lite=1 steps=(\d+)", txt))
+    else:
+        assert "lite=1" not in txt
+    rng = np.random.default_rng(5)
+    v = S.gen_state(n, rng)
+    ref = S.run_ops(n, ops, v)
+    out, st = emul(n, ops, v, opts)
+    assert np.abs(out - ref).max() < 1e-13
 
 
 def test_emulated_reference_semantics_qft_and_adder(emul):

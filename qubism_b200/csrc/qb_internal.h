@@ -104,13 +104,13 @@ struct DevPass {
   double gscale[2];                   // deferred global scalar applied on the way out (1,0 = none)
   uint32_t has_gscale;
   uint32_t l2_prefetch;               // prefetch the CTA's next tile into L2 while this one computes
-  uint32_t stagger_ns;                // PROFILING ONLY (results are wrong): bit 0 skip global loads, bit 1 skip
+  uint32_t dbg_skip;                  // PROFILING ONLY (results are wrong): bit 0 skip global loads, bit 1 skip
                                       // global stores, bit 2 skip the shared-memory transposes, bit 3 skip gates
   uint32_t sm_count;
   uint32_t lite;                      // only uncontrolled rotations and X / CX: rounds index DevSteps, not DevGates
   uint32_t nsteps;
   uint32_t zero;                      // always 0 (a run-time zero the kernel uses to touch a register)
-  uint32_t groups;                    // thread groups per CTA (phase tokens), 1 = plain CTAs
+  uint32_t _pad3;
   DevRound rounds[kMaxRounds];
   // followed in memory by ngates DevGate records (lite: by nsteps DevStep records)
 };
@@ -153,11 +153,10 @@ struct PlanOptions {
   int max_pass_gates = kMaxPassGates;
   int time_kernels = 0;
   int l2_prefetch = 1;
-  int stagger_ns = 0;     // profiling switches, see DevPass::stagger_ns (named "dbg_skip" in set_option)
+  int dbg_skip = 0;       // profiling switches, see DevPass::dbg_skip
   int avoid_regswap = 0;  // planner: refuse rounds where a CX control would be a register bit
   int rot = 1;            // rotations [[c,-s],[s,c]] run as three in-place shears (G_ROT) instead of G_REAL
-  int lane_fixed = 3;     // low tile bits that stay on lanes in the load / store rounds (1..3)
-  int groups = 1;         // 3: one CTA per SM with three tile groups that pass phase tokens (k_fused_pass)
+  int lane_fixed = 1;     // low tile bits that stay on lanes in the load / store rounds (1..3)
   int lite = 1;           // passes of rotations and X / CX only use the lean kernel instantiation
   int hot_bits = 0;       // planner: max distinct TARGET bits per pass (0 = tile_bits).  With
                           // hot_bits <= tile_bits - warp bits every transpose can stay warp-local.

@@ -404,45 +404,19 @@ struct PassProgram {
 };
 static_assert(sizeof(PassProgram) <= 32000, "kernel parameter space");
 
-// ---- phase tokens (GR > 1) -------------------------------------------------------------------
-// Co-resident CTAs that run the same program bunch up: all of them sit in the shared-memory /
-// load-store phases at once, then all in the FP64 phases, and the pass costs the SUM of the two
-// instead of the maximum (measured: 3 CTAs/SM, issue slots 47 % busy, LSU and FP64 pipes each
-// ~1/3 busy).  With GR > 1 one CTA holds GR independent thread groups, each with its own tile,
-// and two tokens travel round-robin between the groups through named barriers: "M" is needed for
-// every LSU-heavy phase (global load / store issue, shared-memory transposes), "F" for every
-// gate phase.  At any moment one group computes, one moves data and the third waits for HBM.
-template <int GR, int NT>
-__device__ __forceinline__ void tok_acquire(uint32_t res, uint32_t grp) {
-  if constexpr (GR > 1) asm volatile("bar.sync %0, %1;" ::"r"(4u + res * GR + grp), "n"(2 * NT) : "memory");
-}
-template <int GR, int NT>
-__device__ __forceinline__ void tok_release(uint32_t res, uint32_t grp) {
-  if constexpr (GR > 1)
-    asm volatile("bar.arrive %0, %1;" ::"r"(4u + res * GR + (grp + 1u == GR ? 0u : grp + 1u)), "n"(2 * NT) : "memory");
-}
-template <int GR, int NT>
-__device__ __forceinline__ void group_sync(uint32_t grp) {
-  if constexpr (GR > 1) asm volatile("bar.sync %0, %1;" ::"r"(1u + grp), "n"(NT) : "memory");
-  else __syncthreads();
-}
-constexpr uint32_t TOK_M = 0, TOK_F = 1;
-
 template <int T, int R>
-__host__ __device__ constexpr size_t fused_group_smem() {
+__host__ __device__ constexpr size_t fused_smem_bytes() {
   return (size_t(16) << T) + size_t(kMaxRounds) * (size_t(1) << (T - R)) * sizeof(uint16_t) +
          size_t(2) * (size_t(1) << (T - R)) * sizeof(uint64_t) + (size_t(1) << (T - 3)) * sizeof(uint32_t);
 }
 
-template <int T, int R, int MINB, bool LITE, int GR>
-__global__ void __launch_bounds__(GR << (T - R), MINB)
+template <int T, int R, int MINB, bool LITE>
+__global__ void __launch_bounds__(1 << (T - R), MINB)
     k_fused_pass(double2 *__restrict__ amps, unsigned long long ntiles, const __grid_constant__ PassProgram prog) {
   constexpr int NR = 1 << R;
   constexpr int NT = 1 << (T - R);
-  extern __shared__ __align__(16) uint8_t smem_all[];
-  const uint32_t grp = (GR > 1) ? threadIdx.x / NT : 0u;  // warp-uniform
-  const uint32_t tid = (GR > 1) ? threadIdx.x % NT : threadIdx.x;
-  uint8_t *smem_raw = smem_all + size_t(grp) * fused_group_smem<T, R>();
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const uint32_t tid = threadIdx.x;
   // after the tile: for every round, each thread's swizzled shared-memory index (computed once
   // per kernel; the persistent tile loop then needs one 16-bit load per transpose side)
   uint16_t *sidx_tab = reinterpret_cast<uint16_t *>(smem_raw + (size_t(16) << T));
@@ -469,22 +443,16 @@ __global__ void __launch_bounds__(GR << (T - R), MINB)
   }
 
   const uint32_t ntiles32 = (uint32_t)ntiles;
-  const uint32_t stride = gridDim.x * GR;
-  const uint32_t first = blockIdx.x * GR + grp;
-  // every group runs the same number of iterations (token order), idle ones just pass the tokens
+  const uint32_t stride = gridDim.x;
+  const uint32_t first = blockIdx.x;
   const uint32_t iters = (ntiles32 + stride - 1) / stride;
-  if (GR > 1 && grp == GR - 1) {  // the tokens start at group 0
-    tok_release<GR, NT>(TOK_M, grp);
-    tok_release<GR, NT>(TOK_F, grp);
-  }
   double re[NR], im[NR];
   uint32_t f = 0;  // flip mask: register i holds logical register index i ^ f
   uint64_t base = 0;
   for (uint32_t it = 0; it <= iters; ++it) {
     const uint32_t tile_id = first + it * stride;
-    // ---------------- M phase: store the finished tile, then load the next one
-    tok_acquire<GR, NT>(TOK_M, grp);
-    const uint32_t dbg = P.stagger_ns;  // profiling switches (0 in production)
+    // ---------------- store the finished tile, then load the next one
+    const uint32_t dbg = P.dbg_skip;  // profiling switches (0 in production)
     if (it > 0 && tile_id - stride < ntiles32 && !(dbg & 2u)) {
       // coalesced store with the last round's layout (register strides are distinct bits, so
       // the pending flip mask is one XOR on the element index)
@@ -554,20 +522,13 @@ __global__ void __launch_bounds__(GR << (T - R), MINB)
           asm volatile("prefetch.global.L2 [%0];" ::"l"(amps + nbase + (uint64_t(line_tab[k * NT + tid]) << 3)));
       }
     }
-    tok_release<GR, NT>(TOK_M, grp);
-    if (it == iters) break;
-    if (GR > 1 && active) {
-      // wait for the data BEFORE asking for the F token (the last load issued returns last, near
-      // enough): a group must not hold a token while it waits for HBM
-      im[NR - 1] = __longlong_as_double(__double_as_longlong(im[NR - 1]) ^ (long long)P.zero);
-    }
+    if (!active) break;
     const uint64_t basefull = base | P.rank_bits;
     f = 0;
     for (uint32_t r = 0; r < nrounds; ++r) {
       const DevRound &RD = P.rounds[r];
       if (r > 0) {  // transpose through swizzled shared memory: new register-resident bits
-        tok_acquire<GR, NT>(TOK_M, grp);
-        if (active && !(dbg & 4u)) {
+        if (!(dbg & 4u)) {
           const DevRound &PR = P.rounds[r - 1];
           // byte offsets throughout: address = tile + (thread part ^ register part)
           uint32_t us = uint32_t(sidx_tab[(r - 1) * NT + tid]) << 4;
@@ -581,7 +542,7 @@ __global__ void __launch_bounds__(GR << (T - R), MINB)
           // A warp-local transpose only touches this warp's own slots: the barriers shrink to
           // __syncwarp() and the warps of the group stay decoupled.
           const bool local = RD.warp_local != 0;
-          if (local) __syncwarp(); else group_sync<GR, NT>(grp);  // everyone finished reading the previous layout
+          if (local) __syncwarp(); else __syncthreads();  // everyone finished reading the previous layout
 #pragma unroll
           for (int i = 0; i < NR; ++i) {
             uint32_t c = 0;  // uniform: folds at compile time into one XOR operand per register
@@ -590,7 +551,7 @@ __global__ void __launch_bounds__(GR << (T - R), MINB)
               if ((i >> j) & 1) c ^= sx[j];
             *reinterpret_cast<double2 *>(smem_raw + (us ^ c)) = make_double2(re[i], im[i]);
           }
-          if (local) __syncwarp(); else group_sync<GR, NT>(grp);
+          if (local) __syncwarp(); else __syncthreads();
           const uint32_t ul = uint32_t(sidx_tab[r * NT + tid]) << 4;
 #pragma unroll
           for (int j = 0; j < R; ++j) sx[j] = RD.reg_sx[j] << 4;
@@ -605,22 +566,17 @@ __global__ void __launch_bounds__(GR << (T - R), MINB)
             im[i] = a.y;
           }
         }
-        tok_release<GR, NT>(TOK_M, grp);
       }
       const uint32_t wb = LITE ? RD.step_begin : RD.gate_begin, we = LITE ? RD.step_end : RD.gate_end;
-      if (wb < we) {
-        tok_acquire<GR, NT>(TOK_F, grp);
-        if (active && !(dbg & 8u)) {
-          if constexpr (LITE) {
-            for (uint32_t si = wb; si < we; ++si) apply_step<R>(re, im, prog.steps[si], tid, basefull, f);
-          } else {
-            for (uint32_t gi = wb; gi < we; ++gi) apply_gate<R>(re, im, G[gi], tid, basefull, f);
-          }
+      if (wb < we && !(dbg & 8u)) {
+        if constexpr (LITE) {
+          for (uint32_t si = wb; si < we; ++si) apply_step<R>(re, im, prog.steps[si], tid, basefull, f);
+        } else {
+          for (uint32_t gi = wb; gi < we; ++gi) apply_gate<R>(re, im, G[gi], tid, basefull, f);
         }
-        tok_release<GR, NT>(TOK_F, grp);
       }
     }
-    if (P.has_gscale && active) {  // deferred global scalar (folded u1-type phases, qb_scale)
+    if (P.has_gscale) {  // deferred global scalar (folded u1-type phases, qb_scale)
       const double sr = P.gscale[0], si = P.gscale[1];
 #pragma unroll
       for (int i = 0; i < NR; ++i) {
@@ -630,52 +586,33 @@ __global__ void __launch_bounds__(GR << (T - R), MINB)
       }
     }
   }
-  if (GR > 1 && grp == 0) {  // absorb the last group's final releases
-    tok_acquire<GR, NT>(TOK_M, grp);
-    tok_acquire<GR, NT>(TOK_F, grp);
-  }
 }
 
 struct FusedVariant {
-  int T, R, threads, minb;
-  const void *fn;       // every gate class
-  const void *fn_lite;  // rotations and X / CX only
-  const void *fn_g[2][2];  // [groups - 2][lite]: 2 / 3 token-passing groups in one CTA per SM (null: not built)
-  size_t group_smem;
+  int T, R, threads;
+  int minb, minb_lite;   // resident CTAs per SM each instantiation is compiled for
+  const void *fn;        // every gate class (interpreter)
+  const void *fn_lite;   // rotations and X / CX only (steps)
+  size_t smem;
 };
 
-#define QB_VARIANT(T_, R_, MINB_)                                                            \
-  {T_, R_, 1 << (T_ - R_), MINB_, (const void *)&k_fused_pass<T_, R_, MINB_, false, 1>,        \
-   (const void *)&k_fused_pass<T_, R_, MINB_, true, 1>, {{nullptr, nullptr}, {nullptr, nullptr}}, \
-   fused_group_smem<T_, R_>()}
-#define QB_VARIANT_G(T_, R_, MINB_)                                                          \
-  {T_, R_, 1 << (T_ - R_), MINB_, (const void *)&k_fused_pass<T_, R_, MINB_, false, 1>,        \
-   (const void *)&k_fused_pass<T_, R_, MINB_, true, 1>,                                       \
-   {{(const void *)&k_fused_pass<T_, R_, 1, false, 2>, (const void *)&k_fused_pass<T_, R_, 1, true, 2>},  \
-    {(const void *)&k_fused_pass<T_, R_, 1, false, 3>, (const void *)&k_fused_pass<T_, R_, 1, true, 3>}}, \
-   fused_group_smem<T_, R_>()}
+// MINB_ / MINBL_: the interpreter wants occupancy (its arms are short dependent chains); the
+// step kernel wants registers (128: no spills, every sweep is 2^R independent DFMAs) -- measured.
+#define QB_VARIANT(T_, R_, MINB_, MINBL_)                                                               \
+  {T_, R_, 1 << (T_ - R_), MINB_, MINBL_, (const void *)&k_fused_pass<T_, R_, MINB_, false>,            \
+   (const void *)&k_fused_pass<T_, R_, MINBL_, true>, fused_smem_bytes<T_, R_>()}
 
 #ifdef QB_QUICK_COMPILE  // developer switch: only the default instantiation (fast ptxas experiments)
-static const FusedVariant kVariants[] = {QB_VARIANT_G(12, 4, 3)};
-static const FusedVariant kAltVariants[] = {QB_VARIANT(12, 4, 3)};
+static const FusedVariant kVariants[] = {QB_VARIANT(12, 4, 3, 2)};
 #else
 static const FusedVariant kVariants[] = {
-    QB_VARIANT(10, 3, 4), QB_VARIANT(10, 4, 4), QB_VARIANT(11, 3, 3), QB_VARIANT(11, 4, 4), QB_VARIANT(11, 5, 6),
-    QB_VARIANT(12, 3, 2), QB_VARIANT_G(12, 4, 3), QB_VARIANT(12, 5, 3), QB_VARIANT(13, 4, 1), QB_VARIANT(13, 5, 1),
-};
-// experimental: same (T, R) with a different register budget (selected with QB_ALT_VARIANTS=1)
-static const FusedVariant kAltVariants[] = {
-    QB_VARIANT(12, 4, 2),
+    QB_VARIANT(10, 3, 4, 4), QB_VARIANT(10, 4, 4, 4), QB_VARIANT(11, 3, 3, 3), QB_VARIANT(11, 4, 4, 4),
+    QB_VARIANT(11, 5, 6, 6), QB_VARIANT(12, 3, 2, 2), QB_VARIANT(12, 4, 3, 2), QB_VARIANT(12, 5, 3, 3),
+    QB_VARIANT(13, 4, 1, 1), QB_VARIANT(13, 5, 1, 1),
 };
 #endif
 
 static const FusedVariant *find_variant(int T, int R) {
-  static const char *alt = getenv("QB_ALT_VARIANTS");
-  if (alt && *alt) {
-    const int want = atoi(alt);
-    for (const auto &v : kAltVariants)
-      if (v.T == T && v.R == R && v.minb == want) return &v;
-  }
   for (const auto &v : kVariants)
     if (v.T == T && v.R == R) return &v;
   return nullptr;
@@ -693,25 +630,17 @@ cudaError_t launch_fused_pass(double2 *amps, const uint8_t *blob, uint32_t blob_
   if (blob_bytes > sizeof(PassProgram) || blob_bytes < sizeof(DevPass)) return cudaErrorInvalidValue;
   static thread_local PassProgram prog;  // the launch copies it into the command buffer
   memcpy(&prog, blob, blob_bytes);
-  const int lite = prog.hdr.lite ? 1 : 0;
-  const void *fn = lite ? v->fn_lite : v->fn;
-  int groups = 1;
-  if (prog.hdr.groups >= 2 && prog.hdr.groups <= 3 && v->fn_g[prog.hdr.groups - 2][lite] &&
-      ntiles >= uint64_t(sm_count) * prog.hdr.groups) {
-    groups = (int)prog.hdr.groups;
-    fn = v->fn_g[groups - 2][lite];
-  }
-  const size_t smem = v->group_smem * groups;
-  const int threads = v->threads * groups;
+  const void *fn = prog.hdr.lite ? v->fn_lite : v->fn;
+  const size_t smem = v->smem;
+  const int threads = v->threads;
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int occ = 0;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, smem);
   if (e != cudaSuccess) return e;
   if (occ < 1) return cudaErrorLaunchOutOfResources;
-  if (groups > 1) occ = 1;
   uint64_t grid = uint64_t(sm_count) * uint64_t(occ);
-  if (grid * groups > ntiles) grid = std::max<uint64_t>(1, ntiles / groups);
+  if (grid > ntiles) grid = ntiles;
   if (grid_out) *grid_out = (int)grid;
   unsigned long long nt = ntiles;
   void *args[] = {(void *)&amps, (void *)&nt, (void *)&prog};

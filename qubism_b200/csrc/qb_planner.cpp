@@ -59,14 +59,12 @@ bool set_opt(PlanOptions &o, const std::string &name, int64_t v) {
   } else if (name == "lane_fixed") {
     if (v < 0 || v > kLaneFixedBits) return false;
     o.lane_fixed = (int)v;
-  } else if (name == "groups") {
-    if (v != 1 && v != 2 && v != 3) return false;
-    o.groups = (int)v;
+
   } else if (name == "avoid_regswap") {
     o.avoid_regswap = v ? 1 : 0;
-  } else if (name == "stagger_ns" || name == "dbg_skip") {
+  } else if (name == "dbg_skip") {
     if (v < 0 || v > 15) return false;
-    o.stagger_ns = (int)v;
+    o.dbg_skip = (int)v;
   } else {
     return false;
   }
@@ -83,12 +81,11 @@ int64_t get_opt(const PlanOptions &o, const std::string &name) {
   if (name == "max_pass_gates") return o.max_pass_gates;
   if (name == "time_kernels") return o.time_kernels;
   if (name == "l2_prefetch") return o.l2_prefetch;
-  if (name == "stagger_ns" || name == "dbg_skip") return o.stagger_ns;
+  if (name == "dbg_skip") return o.dbg_skip;
   if (name == "avoid_regswap") return o.avoid_regswap;
   if (name == "hot_bits") return o.hot_bits;
   if (name == "rot") return o.rot;
   if (name == "lite") return o.lite;
-  if (name == "groups") return o.groups;
   if (name == "lane_fixed") return o.lane_fixed;
   return -1;
 }
@@ -681,9 +678,8 @@ static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &don
   P->gscale[1] = 0.0;
   P->has_gscale = 0;
   P->l2_prefetch = opt.l2_prefetch ? 1u : 0u;
-  P->stagger_ns = (uint32_t)opt.stagger_ns;
+  P->dbg_skip = (uint32_t)opt.dbg_skip;
   P->sm_count = 148;
-  P->groups = (uint32_t)opt.groups;
   for (int i = 0; i < T; ++i) P->tile_pos[i] = (uint8_t)tile_bits[i];
   {  // runs of non-tile local bits, ascending
     uint32_t nruns = 0;

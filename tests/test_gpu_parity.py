@@ -132,17 +132,16 @@ def test_fused_passes_planner_knobs(default_opts, opts):
     assert close(sv.to_host(), S.run_ops(n, ops, v), 1e-11 if opts.get("peephole") == 0 else TOL)
 
 
-@pytest.mark.parametrize("groups", [1, 2, 3])
+@pytest.mark.parametrize("lane_fixed", [3, 1, 0])
 @pytest.mark.parametrize("lite", [1, 0])
-def test_phase_token_groups_and_lite_steps_vs_oracle(default_opts, groups, lite):
-    """22 qubits = 1024 tiles: enough for the one-CTA-per-SM kernel with 2 / 3 token-passing tile
-    groups (ragged: 1024 is not a multiple of 148 * groups, so idle groups must keep passing the
-    tokens), with the step-packed LITE program and with the gate interpreter."""
+def test_lite_steps_and_interpreter_vs_oracle_20q(default_opts, lane_fixed, lite):
+    """20 qubits = 256 tiles over 148 SMs (ragged persistent grid): the step-packed LITE program
+    and the gate interpreter against the structured oracle, with every load / store lane rule."""
     ctx = default_opts
-    ctx.set_option("groups", groups)
+    ctx.set_option("lane_fixed", lane_fixed)
     ctx.set_option("lite", lite)
-    n = 22
-    rng = np.random.default_rng(groups * 10 + lite)
+    n = 20
+    rng = np.random.default_rng(lane_fixed * 10 + lite)
     v = S.gen_state(n, rng)
     ops = random_layers(n, 3, seed=3, lam0=True) + qft_ops(n) + random_layers(n, 1, seed=4, lam0=False)
     ref = S.run_ops(n, ops, v)

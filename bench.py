@@ -325,7 +325,7 @@ def run_ours(args):
     achieved = alg_bytes / (fused_ms / 1e3) / 1e9 if fused_ms > 0 else None
     traffic = None
     try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "r01_fused_pass_summary.json")))
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r01c_fused_pass_summary.json")))
         traffic = prof.get("dram_bytes_per_launch_scaled_to", {}).get(str(L))
     except (OSError, ValueError):
         pass
@@ -349,7 +349,7 @@ def run_ours(args):
         "config": {"workload": workload_name(n), "qubits": n, "local_qubits": L, "primitive_ops_per_step": nops,
                    "state_bytes_per_gpu": 16 << L, "l2_policy": "inputs larger than L2 (state >= 16 GiB >> 126 MB)",
                    "parallelism": f"shard{world}" if world > 1 else "single",
-                   "planner": {k: ctx.get_option(k) for k in ("tile_bits", "reg_bits", "low_bits", "max_rounds", "peephole")},
+                   "planner": {k: ctx.get_option(k) for k in ("tile_bits", "reg_bits", "low_bits", "lane_fixed", "max_rounds", "peephole", "rot", "lite")},
                    "ops_executed_per_step": st["ops_executed"] / args.steps,
                    "ops_folded_per_step": st["ops_folded"] / args.steps,
                    "passes_per_step": passes, "rounds_per_step": st["rounds"] / args.steps,

@@ -913,6 +913,10 @@ std::string describe_plan(const PlanResult &r) {
         else if ((d.treg >> 8) & 1) kinds[3]++;                    // uncontrolled, flip-aware
         else kinds[4]++;                                           // plain
       }
+      int types[5] = {0};
+      for (int g = 0; g < p.ngates; ++g) types[G[g].type < 5 ? G[g].type : 0]++;
+      os << " types[general,real,diag,swap,rot]=" << types[0] << "," << types[1] << "," << types[2] << "," << types[3] << ","
+         << types[4];
       os << " kinds[toggle,regswap,ctrl,flipaware,plain]=" << kinds[0] << "," << kinds[1] << "," << kinds[2] << ","
          << kinds[3] << "," << kinds[4];
     }

@@ -73,7 +73,9 @@ struct alignas(16) DevStep {
   uint32_t rot_mask;           // bit J: slot J holds a rotation
   uint32_t rot_flip;           // bit J: a flip may be pending on register bit J (sign-aware flavour)
   uint32_t ntog;               // toggles applied after the rotations
-  uint32_t swap_j;             // >= 8: none; else X / CX with register-bit control(s) on target register bit swap_j
+  uint32_t swap_j;             // 0xff: none; else bits 0-2 = target register bit of an X / CX with register-bit
+                               // control(s), bit 4 = static flavour (one control, a register bit without a
+                               // pending flip, no other controls: the same pairs swap in every thread)
   struct Tog {
     uint32_t cthr, bit;
     uint64_t cext;

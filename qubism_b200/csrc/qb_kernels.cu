@@ -349,6 +349,42 @@ __device__ __forceinline__ void step_swap(double (&re)[1 << R], double (&im)[1 <
   }
 }
 
+// XOR swap in place (inline PTX so that the optimiser cannot rename the registers: a renamed
+// arm is repaired with moves at the join)
+__device__ __forceinline__ void swap_inplace(double &a, double &b) {
+  asm volatile(
+      "xor.b64 %0, %0, %1;\n"
+      "xor.b64 %1, %1, %0;\n"
+      "xor.b64 %0, %0, %1;"
+      : "+d"(a), "+d"(b));
+}
+
+template <int R, int J, int K>
+__device__ __forceinline__ void step_swap_static(double (&re)[1 << R], double (&im)[1 << R]) {
+#pragma unroll
+  for (int p = 0; p < (1 << (R - 1)); ++p) {
+    const int i0 = ((p >> J) << (J + 1)) | (p & ((1 << J) - 1)), i1 = i0 | (1 << J);
+    if ((i0 >> K) & 1) {
+      swap_inplace(re[i0], re[i1]);
+      swap_inplace(im[i0], im[i1]);
+    }
+  }
+}
+
+template <int R>
+__device__ __forceinline__ void step_swap_static_dispatch(double (&re)[1 << R], double (&im)[1 << R], uint32_t jk) {
+#define QB_SS(JJ, KK)                                                             \
+  case (JJ) * 8 + (KK):                                                           \
+    if constexpr ((JJ) < R && (KK) < R && (JJ) != (KK)) step_swap_static<R, JJ, KK>(re, im); \
+    break;
+  switch (jk) {
+    QB_SS(0, 1) QB_SS(0, 2) QB_SS(0, 3) QB_SS(0, 4) QB_SS(1, 0) QB_SS(1, 2) QB_SS(1, 3) QB_SS(1, 4) QB_SS(2, 0) QB_SS(2, 1)
+    QB_SS(2, 3) QB_SS(2, 4) QB_SS(3, 0) QB_SS(3, 1) QB_SS(3, 2) QB_SS(3, 4) QB_SS(4, 0) QB_SS(4, 1) QB_SS(4, 2) QB_SS(4, 3)
+    default: break;
+  }
+#undef QB_SS
+}
+
 template <int R>
 __device__ __forceinline__ void apply_step(double (&re)[1 << R], double (&im)[1 << R], const DevStep &S, uint32_t tid,
                                            uint64_t basefull, uint32_t &f) {
@@ -366,12 +402,18 @@ __device__ __forceinline__ void apply_step(double (&re)[1 << R], double (&im)[1 
     }
   }
   const uint32_t sj = S.swap_j;
-  if (sj < 8u) {
-    if (sj == 0) step_swap<R, 0>(re, im, S, tid, basefull, f);
-    else if (sj == 1) step_swap<R, 1>(re, im, S, tid, basefull, f);
-    else if (sj == 2) step_swap<R, 2>(re, im, S, tid, basefull, f);
-    else if (sj == 3) { if constexpr (R > 3) step_swap<R, 3>(re, im, S, tid, basefull, f); }
-    else { if constexpr (R > 4) step_swap<R, 4>(re, im, S, tid, basefull, f); }
+  if (sj != 0xffu) {
+    if (sj & 16u) {  // static: the pairs whose index has control bit K set swap, in every thread
+      const uint32_t jk = (sj & 7u) * 8u + (uint32_t)(__ffs((int)S.swap_creg) - 1);
+      step_swap_static_dispatch<R>(re, im, jk);
+    } else {
+      const uint32_t j = sj & 7u;
+      if (j == 0) step_swap<R, 0>(re, im, S, tid, basefull, f);
+      else if (j == 1) step_swap<R, 1>(re, im, S, tid, basefull, f);
+      else if (j == 2) step_swap<R, 2>(re, im, S, tid, basefull, f);
+      else if (j == 3) { if constexpr (R > 3) step_swap<R, 3>(re, im, S, tid, basefull, f); }
+      else { if constexpr (R > 4) step_swap<R, 4>(re, im, S, tid, basefull, f); }
+    }
   }
 }
 
@@ -540,9 +582,13 @@ __global__ void __launch_bounds__(1 << (T - R), MINB)
           }
           f = 0;
           // A warp-local transpose only touches this warp's own slots: the barriers shrink to
-          // __syncwarp() and the warps of the group stay decoupled.
+          // __syncwarp() and the warps of the CTA stay decoupled.  For a CTA-wide transpose the
+          // barrier that frees the buffer ("everyone finished reading the previous layout") was
+          // taken EARLY, right after the previous transpose's loads (below), when the warps had
+          // just left a barrier together: taking it here would make every warp wait for the
+          // slowest one's whole gate phase and then send all the stores to the LSU at once.
           const bool local = RD.warp_local != 0;
-          if (local) __syncwarp(); else __syncthreads();  // everyone finished reading the previous layout
+          if (local) __syncwarp();
 #pragma unroll
           for (int i = 0; i < NR; ++i) {
             uint32_t c = 0;  // uniform: folds at compile time into one XOR operand per register
@@ -565,6 +611,9 @@ __global__ void __launch_bounds__(1 << (T - R), MINB)
             re[i] = a.x;
             im[i] = a.y;
           }
+          // free the buffer for the next CTA-wide transpose (of this tile, or the first one of the
+          // next tile) now
+          if (P.rounds[(r + 1 < nrounds) ? r + 1 : 1].warp_local == 0) __syncthreads();
         }
       }
       const uint32_t wb = LITE ? RD.step_begin : RD.gate_begin, we = LITE ? RD.step_end : RD.gate_end;

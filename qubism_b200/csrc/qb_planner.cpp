@@ -770,6 +770,11 @@ static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &don
       } else if (g.treg < 8 && (flip_possible & (1u << g.treg))) {
         g.treg |= 1u << 8;
       }
+      // bit 9 of treg: X with exactly one control, a register bit that no earlier toggle of this
+      // round can have flipped, and no thread / external controls: WHICH register pairs swap is
+      // then the same in every thread (static register swap in the step kernel)
+      if (op.type == G_SWAP && popc(g.creg) == 1 && g.cthr == 0 && g.cext == 0 && !(flip_possible & g.creg))
+        g.treg |= 1u << 9;
       {  // dense opcode for the kernel's jump table
         const bool ctrl = (g.creg | g.cthr) != 0 || g.cext != 0;
         const uint32_t J = g.treg & 0xffu;
@@ -811,7 +816,7 @@ static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &don
         auto step_at = [&](size_t k) -> DevStep & {
           while (steps.size() <= first + k) {
             DevStep s0{};
-            s0.swap_j = 0xffu;
+            s0.swap_j = 0xffu;  // none
             steps.push_back(s0);
           }
           return steps[first + k];
@@ -844,9 +849,9 @@ static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &don
           } else {  // X / CX with a register-bit control: data moves
             int k = (lb < 0) ? 0 : (lb - 2 + 3) / 3;  // smallest k with 3k + 2 > lb
             while (3 * k + 2 <= lb) ++k;
-            while (step_at(k).swap_j < 8u) ++k;
+            while (step_at(k).swap_j < 0x80u) ++k;
             DevStep &S = step_at(k);
-            S.swap_j = J;
+            S.swap_j = J | (((g.treg >> 9) & 1u) << 4);  // bit 4: static flavour
             S.swap_creg = g.creg;
             S.swap_cthr = g.cthr;
             S.swap_cext = g.cext;

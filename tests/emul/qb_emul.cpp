@@ -100,8 +100,10 @@ void apply_step_host(std::vector<double> &re, std::vector<double> &im, int R, co
     const auto &tg = S.tog[k];
     if (((tid & tg.cthr) == tg.cthr) && ((basefull & tg.cext) == tg.cext)) f ^= 1u << tg.bit;
   }
-  if (S.swap_j < 8u) {
-    const int J = (int)S.swap_j;
+  if (S.swap_j != 0xffu) {
+    const int J = (int)(S.swap_j & 7u);
+    if ((S.swap_j & 16u) && ((f & S.swap_creg) || S.swap_cthr || S.swap_cext || __builtin_popcount(S.swap_creg) != 1))
+      std::fprintf(stderr, "emulator: static register swap flagged wrongly\n");
     const bool ok_thr = ((tid & S.swap_cthr) == S.swap_cthr) && ((basefull & S.swap_cext) == S.swap_cext);
     for (int p = 0; p < NR / 2; ++p) {
       const int i0 = ((p >> J) << (J + 1)) | (p & ((1 << J) - 1)), i1 = i0 | (1 << J);

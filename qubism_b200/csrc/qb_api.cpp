@@ -74,6 +74,15 @@ struct qb_state {
   std::vector<int> perm;  // logical bit -> physical bit (bits >= L are rank bits)
   std::vector<double2 *> peers;  // distributed: every rank's shard through CUDA IPC (empty: NCCL swaps)
   OpQueue q;
+  // SUPPORT of the amplitudes on the device: every non-zero amplitude has
+  // (logical index & zmask) == zval.  |0...0> knows every bit, a collapse learns one, a
+  // non-diagonal gate forgets its target.  Measurement works on the live sub-cube only.
+  uint64_t zmask = 0, zval = 0;
+  // deferred scalar that no pass has taken yet (collapse normalisation, qb_scale on an idle state):
+  // true amplitudes = pscale * device amplitudes.  Reductions apply it arithmetically; everything
+  // that exposes raw amplitudes forces it first (force_scale).
+  double pscale[2] = {1.0, 0.0};
+  bool all_finite = false;  // no NaN / inf can be in the amplitudes (created here, only finite gates since)
 };
 
 namespace {
@@ -289,18 +298,85 @@ int run_fused_segment(qb_state *s, std::vector<const HostOp *> seg, const double
   return QB_OK;
 }
 
-int flush_locked(qb_state *s) {
+// The live sub-cube of this rank's shard in PHYSICAL local bits.  Returns false if the support
+// cannot be used (nothing known, or too fragmented for the kernels); *dead = this rank holds
+// only zeros (a known global bit has the other value here).
+bool live_cube(const qb_state *s, uint64_t *mask, uint64_t *val, bool *dead) {
+  *mask = *val = 0;
+  *dead = false;
+  if (!s->zmask) return false;
+  for (int lb = 0; lb < s->n; ++lb) {
+    if (!((s->zmask >> lb) & 1ull)) continue;
+    const int pb = s->perm[lb];
+    const uint64_t v = (s->zval >> lb) & 1ull;
+    if (pb < s->L) {
+      *mask |= 1ull << pb;
+      *val |= v << pb;
+    } else if ((uint64_t)((s->ctx->rank >> (pb - s->L)) & 1) != v) {
+      *dead = true;
+    }
+  }
+  if (cube_runs(s->L, *mask) > kMaxRuns) {
+    *mask = *val = 0;
+    return *dead;
+  }
+  return true;
+}
+
+static bool finite8(const double *m) {
+  for (int i = 0; i < 8; ++i)
+    if (!std::isfinite(m[i])) return false;
+  return true;
+}
+
+// what the queued ops do to the support once they have run
+void support_after_ops(qb_state *s) {
+  for (const auto &op : s->q.ops) {
+    if (op.dead) continue;
+    if (op.kind == 2) {
+      for (int j = 0; j < op.k; ++j) s->zmask &= ~(1ull << op.kq_bits[j]);
+      for (double x : op.kq_m)
+        if (!std::isfinite(x)) {
+          s->zmask = 0;
+          s->all_finite = false;
+        }
+      continue;
+    }
+    if (!finite8(op.m)) {  // 0 * NaN = NaN: nothing stays zero (zero-weight collapse, StateVec.hs:92)
+      s->zmask = 0;
+      s->all_finite = false;
+    }
+    if (op.type != G_DIAG) s->zmask &= ~(1ull << op.target);
+  }
+  s->zval &= s->zmask;
+}
+
+// run the queued ops.  The deferred scalar rides on the last fused pass if there is one;
+// otherwise it stays pending in s->pscale (no sweep just to scale).
+int flush_ops_locked(qb_state *s) {
   qb_ctx *c = s->ctx;
   OpQueue &q = s->q;
   c->stats.ops_submitted += q.submitted;
   c->stats.ops_folded += q.folded;
   q.submitted = q.folded = 0;
+  {  // total pending scalar = state-level * queue-level
+    const double r = s->pscale[0] * q.gscale[0] - s->pscale[1] * q.gscale[1];
+    const double i = s->pscale[0] * q.gscale[1] + s->pscale[1] * q.gscale[0];
+    s->pscale[0] = r;
+    s->pscale[1] = i;
+    q.gscale[0] = 1.0;
+    q.gscale[1] = 0.0;
+  }
+  if (!(std::isfinite(s->pscale[0]) && std::isfinite(s->pscale[1]))) {
+    s->zmask = s->zval = 0;
+    s->all_finite = false;
+  }
   if (q.empty()) {
     q.clear();
     return QB_OK;
   }
-  const bool has_g = !(q.gscale[0] == 1.0 && q.gscale[1] == 0.0);
-  const double g[2] = {q.gscale[0], q.gscale[1]};
+  const bool has_g = !(s->pscale[0] == 1.0 && s->pscale[1] == 0.0);
+  const double g[2] = {s->pscale[0], s->pscale[1]};
   bool g_done = !has_g;
   int T, R;
   effective_tile(c->opt, s->L, T, R);
@@ -318,9 +394,6 @@ int flush_locked(qb_state *s) {
     }
   } else {
     std::vector<const HostOp *> seg;
-    size_t last_live = 0;
-    for (size_t i = 0; i < q.ops.size(); ++i)
-      if (!q.ops[i].dead) last_live = i;
     for (size_t i = 0; i < q.ops.size() && rc == QB_OK; ++i) {
       const HostOp &op = q.ops[i];
       if (op.dead) continue;
@@ -334,26 +407,74 @@ int flush_locked(qb_state *s) {
       }
       if (rc == QB_OK) rc = run_simple(s, op);
     }
-    (void)last_live;
     if (rc == QB_OK && !seg.empty()) rc = run_fused_segment(s, seg, has_g ? g : nullptr, &g_done);
   }
-  if (rc == QB_OK && !g_done) rc = run_gscale_simple(s, g);
+  if (rc == QB_OK && g_done) {
+    s->pscale[0] = 1.0;
+    s->pscale[1] = 0.0;
+  }
+  support_after_ops(s);
   q.clear();
   return rc;
+}
+
+// apply the pending scalar to the device amplitudes (live sub-cube only when the support is known)
+int force_scale(qb_state *s) {
+  if (s->pscale[0] == 1.0 && s->pscale[1] == 0.0) return QB_OK;
+  qb_ctx *c = s->ctx;
+  uint64_t mask, val;
+  bool dead;
+  const bool finite = std::isfinite(s->pscale[0]) && std::isfinite(s->pscale[1]);
+  if (finite && live_cube(s, &mask, &val, &dead)) {
+    if (!dead) {
+      QB_CUDA(launch_cube_update(s->amps, s->L, mask, val, 1, s->pscale, c->sm_count, c->stream));
+      c->stats.simple_launches++;
+    }
+  } else {
+    if (!finite) s->zmask = s->zval = 0;
+    QB_TRY(run_gscale_simple(s, s->pscale));
+  }
+  s->pscale[0] = 1.0;
+  s->pscale[1] = 0.0;
+  return QB_OK;
+}
+
+// run the queued ops AND materialise the deferred scalar: the device holds the true amplitudes
+int flush_locked(qb_state *s) {
+  QB_TRY(flush_ops_locked(s));
+  return force_scale(s);
 }
 
 // reduce (S0, S1) split by a logical bit (lb < 0: total) into host doubles; all-reduced when distributed
 int sumsq_locked(qb_state *s, int lb, double *s0, double *s1) {
   qb_ctx *c = s->ctx;
-  QB_TRY(flush_locked(s));
+  QB_TRY(flush_ops_locked(s));
+  if (!(std::isfinite(s->pscale[0]) && std::isfinite(s->pscale[1]))) QB_TRY(force_scale(s));  // NaN / inf must reach the data
   const int pb = lb < 0 ? -1 : s->perm[lb];
-  const int kbit = (pb >= 0 && pb < s->L) ? pb : -1;
-  QB_CUDA(launch_sumsq(s->amps, 1ull << s->L, kbit, c->red_partials, c->red_out, c->sm_count, c->stream));
-  c->stats.reduce_launches += 2;
-  QB_CUDA(cudaMemcpyAsync(c->red_host, c->red_out, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  QB_CUDA(cudaStreamSynchronize(c->stream));
-  double a0 = c->red_host[0], a1 = c->red_host[1];
-  if (pb >= s->L) {  // global bit: this rank's whole shard has one value of it
+  const bool known = lb >= 0 && ((s->zmask >> lb) & 1ull);
+  const int kbit = (pb >= 0 && pb < s->L && !known) ? pb : -1;
+  uint64_t mask, val;
+  bool dead;
+  const bool cube = live_cube(s, &mask, &val, &dead);
+  double a0 = 0.0, a1 = 0.0;
+  if (!(cube && dead)) {
+    if (cube && mask) {
+      QB_CUDA(launch_sumsq_cube(s->amps, s->L, mask, val, kbit, c->red_partials, c->red_out, c->sm_count, c->stream));
+    } else {
+      QB_CUDA(launch_sumsq(s->amps, 1ull << s->L, kbit, c->red_partials, c->red_out, c->sm_count, c->stream));
+    }
+    c->stats.reduce_launches += 2;
+    QB_CUDA(cudaMemcpyAsync(c->red_host, c->red_out, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    QB_CUDA(cudaStreamSynchronize(c->stream));
+    a0 = c->red_host[0];
+    a1 = c->red_host[1];
+  }
+  if (known) {  // every live amplitude has the known value of this bit
+    if ((s->zval >> lb) & 1ull) {
+      a1 = a0;
+      a0 = 0.0;
+    }
+  } else if (pb >= s->L) {  // global bit: this rank's whole shard has one value of it
     if ((c->rank >> (pb - s->L)) & 1) {
       a1 = a0;
       a0 = 0.0;
@@ -366,21 +487,55 @@ int sumsq_locked(qb_state *s, int lb, double *s0, double *s1) {
     a0 = v[0];
     a1 = v[1];
   }
+  const double g2 = s->pscale[0] * s->pscale[0] + s->pscale[1] * s->pscale[1];  // the pending scalar, arithmetically
+  if (g2 != 1.0) {
+    a0 *= g2;
+    a1 *= g2;
+  }
   if (s0) *s0 = a0;
   if (s1) *s1 = a1;
   return QB_OK;
 }
 
+// collapse (StateVec.hs:104-114) right after sumsq_locked (queue empty): zero-fill the half of
+// the live sub-cube that dies, learn the bit, defer the normalisation.  No read, no full pass.
 int collapse_with(qb_state *s, int lb, int bit, double weight) {
-  double m[8] = {0};
-  if (weight == 0.0 || std::isnan(weight)) {
+  qb_ctx *c = s->ctx;
+  if (weight == 0.0 || !std::isfinite(weight)) {
     // the reference divides by norm_2 = 0: every amplitude becomes NaN (StateVec.hs:92,107)
+    double m[8] = {0};
     m[0] = m[6] = NAN;
-  } else {
-    const double f = 1.0 / std::sqrt(weight);
-    m[bit ? 6 : 0] = f;
+    s->q.push_1q(lb, 0, m);
+    return QB_OK;
   }
-  s->q.push_1q(lb, 0, m);
+  const double f = 1.0 / std::sqrt(weight);
+  const bool known = (s->zmask >> lb) & 1ull;  // then the other value has weight 0 and was handled above
+  if (!known) {
+    uint64_t mask, val;
+    bool dead;
+    const bool cube = live_cube(s, &mask, &val, &dead);
+    const int pb = s->perm[lb];
+    if (!(cube && dead)) {
+      if (pb < s->L) {
+        const uint64_t m2 = mask | (1ull << pb), v2 = val | (uint64_t(bit ? 0 : 1) << pb);
+        if (cube_runs(s->L, m2) <= kMaxRuns) {
+          QB_CUDA(launch_cube_update(s->amps, s->L, m2, v2, 0, nullptr, c->sm_count, c->stream));
+        } else {  // too fragmented for the cube kernels: the plain diagonal sweep
+          const double d0[2] = {bit ? 0.0 : 1.0, 0.0}, d1[2] = {bit ? 1.0 : 0.0, 0.0};
+          QB_CUDA(launch_simple_diag(s->amps, s->L, 1ull << pb, 0, 0, d0, d1, c->sm_count, c->stream));
+        }
+        c->stats.simple_launches++;
+      } else if (((c->rank >> (pb - s->L)) & 1) != bit) {  // this rank holds the half that dies
+        QB_CUDA(launch_cube_update(s->amps, s->L, mask, val, 0, nullptr, c->sm_count, c->stream));
+        c->stats.simple_launches++;
+      }
+    }
+    s->zmask |= 1ull << lb;
+    s->zval = (s->zval & ~(1ull << lb)) | (uint64_t(bit) << lb);
+  }
+  const double r = s->pscale[0] * f, i = s->pscale[1] * f;
+  s->pscale[0] = r;
+  s->pscale[1] = i;
   return QB_OK;
 }
 
@@ -485,6 +640,11 @@ int qb_state_create(qb_ctx *ctx, int nqubits, int basis, qb_state **out) {
     qb_state_free(s);
     return fail(QB_ERR_CUDA, "state init: %s", cudaGetErrorString(e));
   }
+  if (basis) {  // |0...0>: every index bit of the one non-zero amplitude is known
+    s->zmask = (nqubits >= 64) ? ~0ull : ((1ull << nqubits) - 1ull);
+    s->zval = 0;
+  }
+  s->all_finite = true;
   *out = s;
   return QB_OK;
 }
@@ -507,10 +667,15 @@ int qb_state_from_host(qb_ctx *ctx, int nqubits, const qb_c64 *amps, qb_state **
 int qb_state_clone(qb_state *src, qb_state **out) {
   if (!src || !out) return fail(QB_ERR_ARG, "null argument");
   Guard g(src->ctx);
-  QB_TRY(flush_locked(src));
+  QB_TRY(flush_ops_locked(src));
   qb_state *s = nullptr;
   QB_TRY(alloc_state(src->ctx, src->n, &s));
   s->perm = src->perm;
+  s->zmask = src->zmask;
+  s->zval = src->zval;
+  s->all_finite = src->all_finite;
+  s->pscale[0] = src->pscale[0];
+  s->pscale[1] = src->pscale[1];
   cudaError_t e =
       cudaMemcpyAsync(s->amps, src->amps, sizeof(double2) << s->L, cudaMemcpyDeviceToDevice, src->ctx->stream);
   if (e != cudaSuccess) {
@@ -550,6 +715,10 @@ int qb_state_write_local(qb_state *s, uint64_t first, uint64_t count, const qb_c
   if (first + count > (1ull << s->L)) return fail(QB_ERR_ARG, "range beyond the local shard");
   Guard g(s->ctx);
   s->q.clear();
+  s->zmask = s->zval = 0;
+  s->all_finite = false;
+  s->pscale[0] = 1.0;
+  s->pscale[1] = 0.0;
   for (int i = 0; i < s->n; ++i) s->perm[i] = i;
   QB_CUDA(cudaMemcpyAsync(s->amps + first, amps, count * sizeof(double2), cudaMemcpyHostToDevice, s->ctx->stream));
   return QB_OK;
@@ -723,6 +892,11 @@ int qb_axpy(qb_state *y, qb_c64 z, qb_state *x) {
   if (y->perm != x->perm) return fail(QB_ERR_UNSUPPORTED, "operands have different qubit layouts");
   const double zz[2] = {z.re, z.im};
   QB_CUDA(launch_axpy(y->amps, x->amps, 1ull << y->L, zz, c->sm_count, c->stream));
+  // the sum is non-zero only where one of the operands is: keep the bits both know with the same value
+  y->zmask = y->zmask & x->zmask & ~(y->zval ^ x->zval);
+  y->zval &= y->zmask;
+  y->all_finite = y->all_finite && x->all_finite && std::isfinite(z.re) && std::isfinite(z.im);
+  if (!y->all_finite) y->zmask = y->zval = 0;
   return QB_OK;
 }
 
@@ -779,6 +953,12 @@ int qb_tensor(qb_state *a, qb_state *b, qb_state **out) {
   if (e != cudaSuccess) {
     qb_state_free(s);
     return fail(QB_ERR_CUDA, "tensor: %s", cudaGetErrorString(e));
+  }
+  // a's bits are the high ones (StateVec.hs:98-100); a known zero stays zero only against finite factors
+  s->all_finite = a->all_finite && b->all_finite;
+  if (s->all_finite) {
+    s->zmask = (a->zmask << b->n) | b->zmask;
+    s->zval = (a->zval << b->n) | b->zval;
   }
   *out = s;
   return QB_OK;

@@ -985,6 +985,118 @@ cudaError_t launch_dotc(const double2 *a, const double2 *b, uint64_t n, double *
   return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------- live sub-cube kernels
+// After a collapse (StateVec.hs:104-114) half of the state is exactly zero, and a fresh
+// |0...0> is zero outside one amplitude.  The host tracks the index bits whose value is KNOWN
+// for every non-zero amplitude (qb_api.cpp, "support"); measurement then only ever touches the
+// live sub-cube {i : i & fixed_mask == fixed_val}: the reduction of `measure` on qubit k reads
+// 2^(n-k) amplitudes instead of 2^n, and a collapse is a zero-fill of the half that dies (no
+// read, no full pass) plus a deferred scalar.  `measure` on all n qubits is ~3 sweep-equivalents
+// instead of 2n.
+struct CubeGeom {
+  uint32_t nruns;
+  uint32_t run_shift[kMaxRuns];  // deposit of the free index into the unknown local bits
+  uint32_t run_len[kMaxRuns];
+  uint64_t fixed;                // the known local bits, at their known value
+};
+
+__device__ __forceinline__ uint64_t cube_index(const CubeGeom &geo, uint64_t j) {
+  if (geo.nruns == 1 && geo.run_shift[0] == 0) return j | geo.fixed;  // contiguous block (top bits known)
+  uint64_t idx = geo.fixed, rest = j;
+  for (uint32_t k = 0; k < geo.nruns; ++k) {
+    idx |= (rest & ((1ull << geo.run_len[k]) - 1ull)) << geo.run_shift[k];
+    rest >>= geo.run_len[k];
+  }
+  return idx;
+}
+
+__global__ void __launch_bounds__(kRedThreads) k_sumsq_cube(const double2 *__restrict__ amps, uint64_t n, int bit,
+                                                           double *__restrict__ partials, const __grid_constant__ CubeGeom geo) {
+  double acc[2] = {0.0, 0.0};
+  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+  for (uint64_t j = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; j < n; j += stride) {
+    const uint64_t i = cube_index(geo, j);
+    const double2 z = __ldcs(amps + i);
+    const double w = z.x * z.x + z.y * z.y;
+    if (bit >= 0 && ((i >> bit) & 1ull)) acc[1] += w; else acc[0] += w;
+  }
+  block_reduce_store<2>(acc, partials + 2 * blockIdx.x);
+}
+
+// mode 0: amps[i] = 0;  mode 1: amps[i] *= (zr, zi)
+__global__ void __launch_bounds__(256) k_cube_update(double2 *__restrict__ amps, uint64_t n, int mode, double zr, double zi,
+                                                    const __grid_constant__ CubeGeom geo) {
+  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+  for (uint64_t j = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; j < n; j += stride) {
+    const uint64_t i = cube_index(geo, j);
+    if (mode == 0) {
+      amps[i] = make_double2(0.0, 0.0);
+    } else {
+      const double2 x = amps[i];
+      amps[i] = make_double2(zr * x.x - zi * x.y, zr * x.y + zi * x.x);
+    }
+  }
+}
+
+static uint64_t make_cube(int local_bits, uint64_t fixed_mask, uint64_t fixed_val, CubeGeom &geo) {
+  geo = CubeGeom{};
+  geo.fixed = fixed_val & fixed_mask & ((1ull << local_bits) - 1ull);
+  int nfree = 0, b = 0;
+  while (b < local_bits) {
+    if (fixed_mask & (1ull << b)) {
+      ++b;
+      continue;
+    }
+    int e = b;
+    while (e < local_bits && !(fixed_mask & (1ull << e))) ++e;
+    if (geo.nruns >= (uint32_t)kMaxRuns) return 0;  // cannot happen: at most local_bits / 2 + 1 runs <= 16 for <= 31 bits ... guarded by the caller
+    geo.run_shift[geo.nruns] = b;
+    geo.run_len[geo.nruns] = e - b;
+    ++geo.nruns;
+    nfree += e - b;
+    b = e;
+  }
+  if (geo.nruns == 0) {  // a single element
+    geo.nruns = 1;
+    geo.run_shift[0] = 0;
+    geo.run_len[0] = 0;
+  }
+  return 1ull << nfree;
+}
+
+int cube_runs(int local_bits, uint64_t fixed_mask) {
+  int runs = 0, b = 0;
+  while (b < local_bits) {
+    if (fixed_mask & (1ull << b)) {
+      ++b;
+      continue;
+    }
+    while (b < local_bits && !(fixed_mask & (1ull << b))) ++b;
+    ++runs;
+  }
+  return runs;
+}
+
+cudaError_t launch_sumsq_cube(const double2 *amps, int local_bits, uint64_t fixed_mask, uint64_t fixed_val, int bit,
+                              double *partials_dev, double *out_dev, int sm_count, cudaStream_t stream) {
+  CubeGeom geo;
+  const uint64_t n = make_cube(local_bits, fixed_mask, fixed_val, geo);
+  if (n == 0) return cudaErrorInvalidValue;
+  const int g = reduce_grid(n, sm_count);
+  k_sumsq_cube<<<g, kRedThreads, 0, stream>>>(amps, n, bit, partials_dev, geo);
+  k_reduce_final<<<1, kRedThreads, 0, stream>>>(partials_dev, g, out_dev);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_cube_update(double2 *amps, int local_bits, uint64_t fixed_mask, uint64_t fixed_val, int mode,
+                               const double z[2], int sm_count, cudaStream_t stream) {
+  CubeGeom geo;
+  const uint64_t n = make_cube(local_bits, fixed_mask, fixed_val, geo);
+  if (n == 0) return cudaErrorInvalidValue;
+  k_cube_update<<<grid_for(n, 256 * 4, sm_count, 8), 256, 0, stream>>>(amps, n, mode, z ? z[0] : 0.0, z ? z[1] : 0.0, geo);
+  return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------- element-wise kernels
 __global__ void __launch_bounds__(256) k_axpy(double2 *__restrict__ y, const double2 *__restrict__ x, uint64_t n,
                                               double zr, double zi) {

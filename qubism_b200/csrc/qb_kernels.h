@@ -36,6 +36,14 @@ cudaError_t launch_sumsq(const double2 *amps, uint64_t n, int bit, double *parti
 cudaError_t launch_dotc(const double2 *a, const double2 *b, uint64_t n, double *partials_dev, double *out_dev,
                         int sm_count, cudaStream_t stream);
 
+// Live sub-cube {i : i & fixed_mask == fixed_val} of the shard (see "support" in qb_api.cpp): the
+// reduction of launch_sumsq restricted to it, and zero-fill (mode 0) / scaling (mode 1) of it.
+int cube_runs(int local_bits, uint64_t fixed_mask);  // must be <= kMaxRuns for the launchers below
+cudaError_t launch_sumsq_cube(const double2 *amps, int local_bits, uint64_t fixed_mask, uint64_t fixed_val, int bit,
+                              double *partials_dev, double *out_dev, int sm_count, cudaStream_t stream);
+cudaError_t launch_cube_update(double2 *amps, int local_bits, uint64_t fixed_mask, uint64_t fixed_val, int mode,
+                               const double z[2], int sm_count, cudaStream_t stream);
+
 cudaError_t launch_axpy(double2 *y, const double2 *x, uint64_t n, const double z[2], int sm_count,
                         cudaStream_t stream);
 cudaError_t launch_tensor(double2 *out, const double2 *a, const double2 *b, int abits, int bbits, int sm_count,

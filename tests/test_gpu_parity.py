@@ -211,6 +211,62 @@ def test_measure_qubit_and_measure_all(ctx):
         assert bits == ref_bits and close(sv.to_host(), w)
 
 
+def test_support_tracking_from_basis_state_measure_reset_and_observers(ctx):
+    """|0...0> knows every index bit, a collapse learns one, a non-diagonal gate forgets its target:
+    measurement reductions run on the live sub-cube, a collapse is a zero-fill + deferred scalar.
+    Everything observable (amplitudes, S0/S1, norms, dot products, sums, clones, tensor) must
+    still match the oracle, in every interleaving of gates, measurements and raw reads."""
+    rng = np.random.default_rng(77)
+    for n in (4, 11, 15):
+        ops = (random_layers(n, 1, seed=3, lam0=True)[: n // 2] + [("MEASURE", 0, 0.5), ("U", 1, D.hadamard()), ("MEASURE", n - 1, 0.2)]
+               + random_layers(n, 1, seed=4, lam0=False) + [("COLLAPSE", n // 2, 1), ("MEASURE", n // 2, 0.9), ("CX", 0, 1),
+               ("MEASURE", 1, 0.1), ("COLLAPSE", n - 2, 0)] + random_layers(n, 1, seed=5, lam0=True))
+        v0 = np.zeros(1 << n, complex)
+        v0[0] = 1
+        rec_ref = []
+        ref = S.run_ops(n, ops, v0, record=rec_ref)
+        sv = Q.mkStateVec(n)
+        rec = sv.run_ops(ops)
+        assert [(q, b) for q, b, _ in rec] == [(q, b) for q, b, _ in rec_ref]
+        assert all(abs(p - pr) < TOL for (_, _, p), (_, _, pr) in zip(rec, rec_ref)), (n, rec, rec_ref)
+        assert close(sv.to_host(), ref)
+    # observers with a pending scalar and a known support
+    n = 12
+    sv = Q.mkStateVec(n)
+    pre = [("U", q, D.unitary(0.3 + q, 0.1, 0.0)) for q in range(n)] + [("CX", 0, 5), ("CX", 7, 2)]
+    sv.run_ops(pre)
+    v = S.run_ops(n, pre, np.eye(1, 1 << n, 0, dtype=complex)[0])
+    sv.collapse_(3, 1).collapse_(0, 0)
+    v = S.collapse(n, 0, 0, S.collapse(n, 3, 1, v))
+    for q in (0, 3, 4, n - 1):  # known bits and unknown ones
+        s0, s1 = sv.sumsq(q)
+        r0, r1 = S.sumsq(n, q, v)
+        assert abs(s0 - r0) < TOL and abs(s1 - r1) < TOL
+    assert abs(sv.norm2() - np.linalg.norm(v)) < TOL
+    c = sv.clone()  # carries support + pending scalar
+    assert close(c.to_host(), v)
+    w = S.gen_state(n, rng)
+    other = Q.StateVec.from_host(w)
+    assert abs(sv.inner(other) - np.vdot(v, w)) < 1e-11
+    assert close((sv + other).to_host(), v + w) and close((other - sv).to_host(), w - v)
+    assert close((2j * sv).to_host(), 2j * v)
+    sv.collapse_(3, 0)  # the dead value of a known bit: weight 0 -> NaN everywhere, as the reference
+    assert np.isnan(sv.to_host()).all()
+    # measuring every qubit of a 20-qubit state: total traffic ~3 sweeps, not 2 n
+    n = 20
+    layer = [("U", q, D.unitary(0.2 + 0.1 * q, 0.3, 0.0)) for q in range(n)] + [("CX", q, (q + 7) % n) for q in range(0, n, 3)]
+    rs = list(rng.uniform(0, 1, n))
+    sv = Q.mkStateVec(n)
+    sv.run_ops(layer)
+    vv = S.run_ops(n, layer, np.eye(1, 1 << n, 0, dtype=complex)[0])
+    bits = Q.measure(sv, rs)
+    ref_bits = []
+    for q in range(n):
+        b, vv, _ = S.measure_qubit(n, q, rs[q], vv)
+        ref_bits.append(b)
+    assert bits == ref_bits and close(sv.to_host(), vv)
+
+
 def test_quickcheck_measurement_is_idempotent(ctx):
     # test/Qubism/StateVecSpec.hs:35-62 (n = 1) and wider
     rng = np.random.default_rng(22)

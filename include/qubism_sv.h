@@ -170,14 +170,17 @@ typedef struct {
   double fused_ms;          /* device time inside fused-pass kernels (CUDA events on the
                                launching stream), accumulated while option "time_kernels"=1 */
   uint64_t fused_timed;     /* number of fused launches that were timed                    */
+  uint64_t tiles;           /* tiles the fused passes visited (all-zero tiles are skipped)  */
 } qb_stats;
 int qb_get_stats(const qb_ctx *ctx, qb_stats *out);
 int qb_reset_stats(qb_ctx *ctx);
 /* Raw CUDA stream of the context (cudaStream_t as void*), for event timing by callers. */
 void *qb_ctx_stream(qb_ctx *ctx);
-/* Tuning knobs: "tile_bits", "reg_bits", "low_bits", "max_rounds", "max_pass_gates",
- * "peephole", "fuse" (0 = one pass per op), "time_kernels" (bracket every fused launch with
- * CUDA events).  Returns QB_ERR_ARG for unknown names / bad values. */
+/* Tuning knobs: "tile_bits", "reg_bits", "low_bits", "lane_fixed", "max_rounds",
+ * "max_pass_gates", "peephole", "fuse" (0 = one pass per op), "rot" (rotations as shears),
+ * "lite" (step-packed passes), "skip_dead" (skip all-zero tiles using the tracked support),
+ * "time_kernels" (bracket every fused launch with CUDA events).  Returns QB_ERR_ARG for unknown
+ * names / bad values. */
 int qb_set_option(qb_ctx *ctx, const char *name, int64_t value);
 int64_t qb_get_option(const qb_ctx *ctx, const char *name);
 /* Host-only planner entry point (no device needed): plan `nops` ops for an n-qubit local

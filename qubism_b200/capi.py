@@ -36,7 +36,7 @@ class QbStats(C.Structure):
     _fields_ = [("ops_submitted", C.c_uint64), ("ops_folded", C.c_uint64), ("ops_executed", C.c_uint64),
                 ("passes", C.c_uint64), ("rounds", C.c_uint64), ("simple_launches", C.c_uint64),
                 ("reduce_launches", C.c_uint64), ("exchange_bytes", C.c_uint64), ("exchanges", C.c_uint64),
-                ("plan_ms", C.c_double), ("fused_ms", C.c_double), ("fused_timed", C.c_uint64)]
+                ("plan_ms", C.c_double), ("fused_ms", C.c_double), ("fused_timed", C.c_uint64), ("tiles", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -104,7 +104,7 @@ int init_common(qb_ctx *c) {
   QB_CUDA(cudaMallocHost(&c->red_host, sizeof(double) * 4));
   QB_CUDA(cudaMalloc(&c->kq_bits_dev, sizeof(int) * 2 * QB_MAX_KQ));
   QB_CUDA(cudaMalloc(&c->kq_mat_dev, sizeof(double2) << (2 * QB_MAX_KQ)));
-  for (const char *name : {"tile_bits", "reg_bits", "low_bits", "max_rounds", "peephole", "fuse", "max_pass_gates", "l2_prefetch", "avoid_regswap", "hot_bits", "rot", "lite", "dbg_skip", "lane_fixed"}) {
+  for (const char *name : {"tile_bits", "reg_bits", "low_bits", "max_rounds", "peephole", "fuse", "max_pass_gates", "l2_prefetch", "avoid_regswap", "hot_bits", "rot", "lite", "dbg_skip", "lane_fixed", "skip_dead"}) {
     std::string env = "QB_";
     for (const char *p = name; *p; ++p) env.push_back((char)toupper(*p));
     const char *v = getenv(env.c_str());
@@ -240,64 +240,6 @@ int make_local(qb_state *s, const std::vector<const HostOp *> &pending) {
   return QB_OK;
 }
 
-int run_fused_segment(qb_state *s, std::vector<const HostOp *> seg, const double *gscale, bool *gscale_done) {
-  qb_ctx *c = s->ctx;
-  int T, R;
-  effective_tile(c->opt, s->L, T, R);
-  PlanOptions opt = c->opt;
-  opt.tile_bits = T;
-  opt.reg_bits = R;
-  if (!opt.fuse) opt.max_pass_gates = 1;
-  while (!seg.empty()) {
-    std::vector<PhysOp> pops(seg.size());
-    for (size_t i = 0; i < seg.size(); ++i) {
-      const HostOp &h = *seg[i];
-      pops[i].type = h.type;
-      pops[i].target = s->perm[h.target];
-      pops[i].ctrl = phys_mask(s, h.ctrl);
-      memcpy(pops[i].m, h.m, sizeof(h.m));
-    }
-    auto t0 = std::chrono::steady_clock::now();
-    PlanResult plan = plan_passes(pops, s->L, c->rank, opt, nullptr);
-    const bool all = plan.consumed == seg.size();
-    if (all && gscale && !*gscale_done && !plan.passes.empty()) {
-      DevPass *P = reinterpret_cast<DevPass *>(plan.passes.back().blob.data());
-      P->gscale[0] = gscale[0];
-      P->gscale[1] = gscale[1];
-      P->has_gscale = 1;
-      *gscale_done = true;
-    }
-    c->stats.plan_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    for (const PassPlan &p : plan.passes) {
-      cudaEvent_t e0 = nullptr, e1 = nullptr;
-      if (c->opt.time_kernels) {
-        QB_TRY(get_event(c, &e0));
-        QB_TRY(get_event(c, &e1));
-        QB_CUDA(cudaEventRecord(e0, c->stream));
-      }
-      QB_CUDA(launch_fused_pass(s->amps, p.blob.data(), (uint32_t)p.blob.size(), p.tile_bits, p.reg_bits, p.ntiles,
-                                c->sm_count, c->stream, nullptr));
-      if (e0) {
-        QB_CUDA(cudaEventRecord(e1, c->stream));
-        c->timed.emplace_back(e0, e1);
-      }
-      c->stats.passes++;
-      c->stats.rounds += p.nrounds;
-      c->stats.ops_executed += p.ngates;
-    }
-    if (all) break;
-    std::vector<const HostOp *> rest;
-    for (size_t i = 0; i < seg.size(); ++i)
-      if (!plan.done[i]) rest.push_back(seg[i]);
-    if (plan.passes.empty() || true) {
-      // whatever is left starts with gates on global qubits: remap them into the shard
-      QB_TRY(make_local(s, rest));
-    }
-    seg.swap(rest);
-  }
-  return QB_OK;
-}
-
 // The live sub-cube of this rank's shard in PHYSICAL local bits.  Returns false if the support
 // cannot be used (nothing known, or too fragmented for the kernels); *dead = this rank holds
 // only zeros (a known global bit has the other value here).
@@ -327,6 +269,92 @@ static bool finite8(const double *m) {
   for (int i = 0; i < 8; ++i)
     if (!std::isfinite(m[i])) return false;
   return true;
+}
+
+int run_fused_segment(qb_state *s, std::vector<const HostOp *> seg, const double *gscale, bool *gscale_done) {
+  qb_ctx *c = s->ctx;
+  int T, R;
+  effective_tile(c->opt, s->L, T, R);
+  PlanOptions opt = c->opt;
+  opt.tile_bits = T;
+  opt.reg_bits = R;
+  if (!opt.fuse) opt.max_pass_gates = 1;
+  while (!seg.empty()) {
+    std::vector<PhysOp> pops(seg.size());
+    for (size_t i = 0; i < seg.size(); ++i) {
+      const HostOp &h = *seg[i];
+      pops[i].type = h.type;
+      pops[i].target = s->perm[h.target];
+      pops[i].ctrl = phys_mask(s, h.ctrl);
+      memcpy(pops[i].m, h.m, sizeof(h.m));
+    }
+    // the support in today's physical bits (it changes with every global<->local swap); a rank
+    // whose known global bits contradict its rank number holds only zeros: no pass at all
+    bool rank_dead = false;
+    {
+      uint64_t mask, val;
+      opt.known_mask = opt.known_val = 0;
+      if (c->opt.skip_dead && live_cube(s, &mask, &val, &rank_dead)) {
+        opt.known_mask = mask;
+        opt.known_val = val;
+      } else {
+        rank_dead = false;
+      }
+      if (gscale && !(std::isfinite(gscale[0]) && std::isfinite(gscale[1]))) {
+        opt.known_mask = opt.known_val = 0;
+        rank_dead = false;
+      }
+      for (const auto &po : pops)
+        if (!finite8(po.m)) rank_dead = false;
+    }
+    auto t0 = std::chrono::steady_clock::now();
+    PlanResult plan = plan_passes(pops, s->L, c->rank, opt, nullptr);
+    const bool all = plan.consumed == seg.size();
+    if (all && gscale && !*gscale_done && !plan.passes.empty()) {
+      DevPass *P = reinterpret_cast<DevPass *>(plan.passes.back().blob.data());
+      P->gscale[0] = gscale[0];
+      P->gscale[1] = gscale[1];
+      P->has_gscale = 1;
+      *gscale_done = true;
+    }
+    c->stats.plan_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    for (const PassPlan &p : plan.passes) {
+      cudaEvent_t e0 = nullptr, e1 = nullptr;
+      if (c->opt.time_kernels) {
+        QB_TRY(get_event(c, &e0));
+        QB_TRY(get_event(c, &e1));
+        QB_CUDA(cudaEventRecord(e0, c->stream));
+      }
+      if (!rank_dead)
+        QB_CUDA(launch_fused_pass(s->amps, p.blob.data(), (uint32_t)p.blob.size(), p.tile_bits, p.reg_bits, p.ntiles,
+                                  c->sm_count, c->stream, nullptr));
+      c->stats.tiles += rank_dead ? 0 : p.ntiles;
+      if (e0) {
+        QB_CUDA(cudaEventRecord(e1, c->stream));
+        c->timed.emplace_back(e0, e1);
+      }
+      c->stats.passes++;
+      c->stats.rounds += p.nrounds;
+      c->stats.ops_executed += p.ngates;
+    }
+    for (size_t i = 0; i < seg.size(); ++i) {  // the scheduled ops now shape the support
+      if (!plan.done[i]) continue;
+      const HostOp &h = *seg[i];
+      if (!finite8(h.m)) s->zmask = 0;
+      if (h.type != G_DIAG) s->zmask &= ~(1ull << h.target);
+    }
+    s->zval &= s->zmask;
+    if (all) break;
+    std::vector<const HostOp *> rest;
+    for (size_t i = 0; i < seg.size(); ++i)
+      if (!plan.done[i]) rest.push_back(seg[i]);
+    if (plan.passes.empty() || true) {
+      // whatever is left starts with gates on global qubits: remap them into the shard
+      QB_TRY(make_local(s, rest));
+    }
+    seg.swap(rest);
+  }
+  return QB_OK;
 }
 
 // what the queued ops do to the support once they have run

@@ -111,8 +111,9 @@ struct DevPass {
   uint32_t sm_count;
   uint32_t lite;                      // only uncontrolled rotations and X / CX: rounds index DevSteps, not DevGates
   uint32_t nsteps;
-  uint32_t zero;                      // always 0 (a run-time zero the kernel uses to touch a register)
-  uint32_t _pad3;
+  uint32_t _pad3[2];
+  uint64_t base_fixed;                // known non-tile bits at their known value: OR-ed into every live tile's base
+  uint64_t _pad4;
   DevRound rounds[kMaxRounds];
   // followed in memory by ngates DevGate records (lite: by nsteps DevStep records)
 };
@@ -158,6 +159,9 @@ struct PlanOptions {
   int dbg_skip = 0;       // profiling switches, see DevPass::dbg_skip
   int avoid_regswap = 0;  // planner: refuse rounds where a CX control would be a register bit
   int rot = 1;            // rotations [[c,-s],[s,c]] run as three in-place shears (G_ROT) instead of G_REAL
+  int skip_dead = 1;        // use the state's support: fused passes skip all-zero tiles
+  uint64_t known_mask = 0;  // PHYSICAL local bits whose value is the same for every non-zero amplitude ...
+  uint64_t known_val = 0;   // ... and that value: tiles that contradict it are all zero and are skipped
   int lane_fixed = 1;     // low tile bits that stay on lanes in the load / store rounds (1..3)
   int lite = 1;           // passes of rotations and X / CX only use the lean kernel instantiation
   int hot_bits = 0;       // planner: max distinct TARGET bits per pass (0 = tile_bits).  With
@@ -199,6 +203,7 @@ struct PlanResult {
   std::vector<PassPlan> passes;
   size_t consumed = 0;           // number of input ops that were scheduled
   std::vector<char> done;        // per input op: scheduled?
+  uint64_t known_mask = 0, known_val = 0;  // the support after the scheduled passes (PlanOptions::known_*)
 };
 
 // Plan fused passes for `ops` on a shard with `local_bits` local qubits.  Ops that cannot run

@@ -527,6 +527,7 @@ __global__ void __launch_bounds__(1 << (T - R), MINB)
           base |= (t & ((1ull << len) - 1ull)) << P.run_shift[k];
           t >>= len;
         }
+        base |= P.base_fixed;  // only live tiles are enumerated (qb_planner.cpp, "dead tiles")
       }
       // coalesced load: lanes walk the low tile bits, registers stride over the round-0 bits
       const uint64_t goff_ld = goff_tab[tid];
@@ -559,6 +560,7 @@ __global__ void __launch_bounds__(1 << (T - R), MINB)
           nbase |= (t & ((1ull << len) - 1ull)) << P.run_shift[k];
           t >>= len;
         }
+        nbase |= P.base_fixed;
 #pragma unroll
         for (int k = 0; k < LPT; ++k)
           asm volatile("prefetch.global.L2 [%0];" ::"l"(amps + nbase + (uint64_t(line_tab[k * NT + tid]) << 3)));

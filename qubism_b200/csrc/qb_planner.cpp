@@ -56,6 +56,12 @@ bool set_opt(PlanOptions &o, const std::string &name, int64_t v) {
     o.rot = v ? 1 : 0;
   } else if (name == "lite") {
     o.lite = v ? 1 : 0;
+  } else if (name == "skip_dead") {
+    o.skip_dead = v ? 1 : 0;
+  } else if (name == "known_mask") {
+    o.known_mask = (uint64_t)v;
+  } else if (name == "known_val") {
+    o.known_val = (uint64_t)v;
   } else if (name == "lane_fixed") {
     if (v < 0 || v > kLaneFixedBits) return false;
     o.lane_fixed = (int)v;
@@ -87,6 +93,7 @@ int64_t get_opt(const PlanOptions &o, const std::string &name) {
   if (name == "rot") return o.rot;
   if (name == "lite") return o.lite;
   if (name == "lane_fixed") return o.lane_fixed;
+  if (name == "skip_dead") return o.skip_dead;
   return -1;
 }
 
@@ -553,12 +560,14 @@ static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &don
   if (rounds.back().regmask & lowfixed) rounds.emplace_back();
   if (rounds[0].regmask & lowfixed) return false;  // cannot happen (edge rule), defensive
 
-  // fill the tile with the lowest unused local bits
-  for (int b = 0; b < L && ntile < T; ++b)
-    if (!(tile_mask & (1ull << b))) {
-      tile_mask |= 1ull << b;
-      ++ntile;
-    }
+  // fill the tile with the lowest unused local bits -- bits whose value is KNOWN for every
+  // non-zero amplitude last: outside the tile each of them halves the number of live tiles
+  for (int pass2 = 0; pass2 < 2; ++pass2)
+    for (int b = 0; b < L && ntile < T; ++b)
+      if (!(tile_mask & (1ull << b)) && (pass2 == 1 || !(opt.known_mask & (1ull << b)))) {
+        tile_mask |= 1ull << b;
+        ++ntile;
+      }
   std::vector<int> tile_bits;
   for (int b = 0; b < L; ++b)
     if (tile_mask & (1ull << b)) tile_bits.push_back(b);
@@ -664,7 +673,27 @@ static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &don
   out.nrounds = nrounds;
   out.ngates = (int)chosen.size();
   out.tile_mask = tile_mask;
-  out.ntiles = 1ull << (L - T);
+  // dead tiles: a non-tile bit with a known value selects, for every tile, whether it holds
+  // anything but zeros.  Finite gates map zero tiles to zero tiles, so the dead ones are
+  // never read or written (a fresh |0...0>, everything after a collapse / reset).
+  uint64_t kmask = opt.known_mask & ~tile_mask & ((L >= 64) ? ~0ull : ((1ull << L) - 1ull));
+  for (auto &pr : chosen)
+    for (int k = 0; k < 8; ++k)
+      if (!std::isfinite(ops[pr.first].m[k])) kmask = 0;  // 0 * NaN = NaN: every tile is live
+  {
+    int nr = 0, b = 0;
+    const uint64_t skip = tile_mask | kmask;
+    while (b < L) {
+      if (skip & (1ull << b)) {
+        ++b;
+        continue;
+      }
+      while (b < L && !(skip & (1ull << b))) ++b;
+      ++nr;
+    }
+    if (nr > kMaxRuns) kmask = 0;
+  }
+  out.ntiles = 1ull << (L - T - popc(kmask));
   out.blob.assign(pass_bytes((uint32_t)chosen.size()), 0);
   DevPass *P = reinterpret_cast<DevPass *>(out.blob.data());
   DevGate *G = reinterpret_cast<DevGate *>(out.blob.data() + sizeof(DevPass));
@@ -681,16 +710,18 @@ static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &don
   P->dbg_skip = (uint32_t)opt.dbg_skip;
   P->sm_count = 148;
   for (int i = 0; i < T; ++i) P->tile_pos[i] = (uint8_t)tile_bits[i];
-  {  // runs of non-tile local bits, ascending
+  P->base_fixed = opt.known_val & kmask;
+  {  // runs of the free (non-tile, not known) local bits, ascending
     uint32_t nruns = 0;
     int b = 0;
+    const uint64_t skip = tile_mask | kmask;
     while (b < L) {
-      if (tile_mask & (1ull << b)) {
+      if (skip & (1ull << b)) {
         ++b;
         continue;
       }
       int e = b;
-      while (e < L && !(tile_mask & (1ull << e))) ++e;
+      while (e < L && !(skip & (1ull << e))) ++e;
       P->run_shift[nruns] = b;
       P->run_len[nruns] = e - b;
       ++nruns;
@@ -874,19 +905,31 @@ static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &don
   return true;
 }
 
-PlanResult plan_passes(const std::vector<PhysOp> &ops, int local_bits, int rank, const PlanOptions &opt,
+PlanResult plan_passes(const std::vector<PhysOp> &ops, int local_bits, int rank, const PlanOptions &opt_in,
                        const double *gscale) {
   PlanResult res;
+  PlanOptions opt = opt_in;  // known_mask / known_val evolve pass by pass
+  if (gscale && !(std::isfinite(gscale[0]) && std::isfinite(gscale[1]))) opt.known_mask = 0;
   std::vector<char> done(ops.size(), 0);
   size_t ndone = 0;
   while (ndone < ops.size()) {
     PassPlan p;
     if (!plan_one_pass(ops, done, local_bits, rank, opt, p)) break;
     ndone += p.op_index.size();
+    // a non-diagonal gate forgets its target; a non-finite matrix forgets everything
+    for (int oi : p.op_index) {
+      const PhysOp &op = ops[oi];
+      if (op.type != G_DIAG) opt.known_mask &= ~(1ull << op.target);
+      for (int k = 0; k < 8; ++k)
+        if (!std::isfinite(op.m[k])) opt.known_mask = 0;
+    }
+    opt.known_val &= opt.known_mask;
     res.passes.push_back(std::move(p));
   }
   res.consumed = ndone;
   res.done = done;
+  res.known_mask = opt.known_mask;
+  res.known_val = opt.known_val;
   if (gscale && !res.passes.empty() && !(gscale[0] == 1.0 && gscale[1] == 0.0)) {
     DevPass *P = reinterpret_cast<DevPass *>(res.passes.back().blob.data());
     P->gscale[0] = gscale[0];

@@ -181,6 +181,7 @@ void run_pass(const PassPlan &pp, int L, std::vector<double> &amps, EmuStats &st
       base |= (t & ((1ull << P.run_len[k]) - 1)) << P.run_shift[k];
       t >>= P.run_len[k];
     }
+    base |= P.base_fixed;
     const uint64_t basefull = base | P.rank_bits;
     for (int tid = 0; tid < NT; ++tid)
       for (int i = 0; i < NR; ++i) {

@@ -228,7 +228,8 @@ def test_support_tracking_from_basis_state_measure_reset_and_observers(ctx):
         sv = Q.mkStateVec(n)
         rec = sv.run_ops(ops)
         assert [(q, b) for q, b, _ in rec] == [(q, b) for q, b, _ in rec_ref]
-        assert all(abs(p - pr) < TOL for (_, _, p), (_, _, pr) in zip(rec, rec_ref)), (n, rec, rec_ref)
+        # (pone is 0 through the ABI where the reference has NaN: zero weight, include/qubism_sv.h)
+        assert all(abs(p - pr) < TOL or (p == 0.0 and np.isnan(pr)) for (_, _, p), (_, _, pr) in zip(rec, rec_ref)), (n, rec, rec_ref)
         assert close(sv.to_host(), ref)
     # observers with a pending scalar and a known support
     n = 12

@@ -110,6 +110,35 @@ def test_emulated_lite_passes_rotations_and_cx(emul, opts):
     assert np.abs(out - ref).max() < 1e-13
 
 
+@pytest.mark.parametrize("opts", ["", "lite=0", "tile_bits=10,reg_bits=3", "max_pass_gates=6"])
+def test_emulated_dead_tiles_are_skipped_with_a_known_support(emul, opts):
+    """PlanOptions.known_mask / known_val (PHYSICAL bits whose value every non-zero amplitude
+    shares): passes enumerate only the live tiles.  A fresh |0...0> knows every bit; after a
+    collapse one bit is known.  Results must equal the oracle's, which touches everything."""
+    n = 14
+    ops = random_layers(n, 3, seed=11, lam0=True) + extras(n)[:6]
+    # (a) |0...0>, everything known
+    v = np.zeros(1 << n, complex)
+    v[0] = 1.0
+    ref = S.run_ops(n, ops, v)
+    o = ",".join(x for x in (opts, f"known_mask={(1 << n) - 1}", "known_val=0") if x)
+    out, st = emul(n, ops, v, o)
+    assert np.abs(out - ref).max() < 1e-13
+    txt = capi.plan_describe(n, ops, o)
+    tiles = [int(t) for t in re.findall(r"tiles=(\d+)", txt)]
+    full = 1 << (n - (10 if "tile_bits=10" in opts else 12))
+    assert tiles[0] == 1 and min(tiles) < full, "the first pass of a basis state has one live tile"
+    # (b) a random state collapsed on two qubits: two known bits, one of them 1
+    rng = np.random.default_rng(3)
+    w = S.collapse(n, 2, 1, S.collapse(n, n - 4, 0, S.gen_state(n, rng)))
+    kmask = (1 << (n - 1 - 2)) | (1 << 3)
+    kval = 1 << (n - 1 - 2)
+    ops2 = [op for op in random_layers(n, 2, seed=12, lam0=True) if not (op[0] == "U" and op[1] in (2, n - 4))]
+    o = ",".join(x for x in (opts, f"known_mask={kmask}", f"known_val={kval}") if x)
+    out, st = emul(n, ops2, w, o)
+    assert np.abs(out - S.run_ops(n, ops2, w)).max() < 1e-13
+
+
 def test_emulated_reference_semantics_qft_and_adder(emul):
     for n, ops in ((12, qft_ops(12)), (12, adder_ops(5)), (13, proper_unitary_layers(13, 2))):
         rng = np.random.default_rng(n)

@@ -104,7 +104,7 @@ int init_common(qb_ctx *c) {
   QB_CUDA(cudaMallocHost(&c->red_host, sizeof(double) * 4));
   QB_CUDA(cudaMalloc(&c->kq_bits_dev, sizeof(int) * 2 * QB_MAX_KQ));
   QB_CUDA(cudaMalloc(&c->kq_mat_dev, sizeof(double2) << (2 * QB_MAX_KQ)));
-  for (const char *name : {"tile_bits", "reg_bits", "low_bits", "max_rounds", "peephole", "fuse", "max_pass_gates", "l2_prefetch", "avoid_regswap", "hot_bits", "rot", "lite", "dbg_skip", "lane_fixed", "skip_dead"}) {
+  for (const char *name : {"tile_bits", "reg_bits", "low_bits", "max_rounds", "peephole", "fuse", "max_pass_gates", "l2_prefetch", "avoid_regswap", "hot_bits", "rot", "lite", "dbg_skip", "lane_fixed", "skip_dead", "support"}) {
     std::string env = "QB_";
     for (const char *p = name; *p; ++p) env.push_back((char)toupper(*p));
     const char *v = getenv(env.c_str());
@@ -246,7 +246,7 @@ int make_local(qb_state *s, const std::vector<const HostOp *> &pending) {
 bool live_cube(const qb_state *s, uint64_t *mask, uint64_t *val, bool *dead) {
   *mask = *val = 0;
   *dead = false;
-  if (!s->zmask) return false;
+  if (!s->zmask || !s->ctx->opt.support) return false;
   for (int lb = 0; lb < s->n; ++lb) {
     if (!((s->zmask >> lb) & 1ull)) continue;
     const int pb = s->perm[lb];
@@ -537,6 +537,12 @@ int collapse_with(qb_state *s, int lb, int bit, double weight) {
     return QB_OK;
   }
   const double f = 1.0 / std::sqrt(weight);
+  if (!c->opt.support) {  // A/B switch: the collapse as a queued diagonal gate (a full pass later)
+    double m[8] = {0};
+    m[bit ? 6 : 0] = f;
+    s->q.push_1q(lb, 0, m);
+    return QB_OK;
+  }
   const bool known = (s->zmask >> lb) & 1ull;  // then the other value has weight 0 and was handled above
   if (!known) {
     uint64_t mask, val;

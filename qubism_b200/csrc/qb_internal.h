@@ -159,6 +159,8 @@ struct PlanOptions {
   int dbg_skip = 0;       // profiling switches, see DevPass::dbg_skip
   int avoid_regswap = 0;  // planner: refuse rounds where a CX control would be a register bit
   int rot = 1;            // rotations [[c,-s],[s,c]] run as three in-place shears (G_ROT) instead of G_REAL
+  int support = 1;          // track the support (known index bits of the non-zero amplitudes): live sub-cube
+                            // reductions, collapse = zero-fill + deferred scalar.  0 = A/B baseline
   int skip_dead = 1;        // use the state's support: fused passes skip all-zero tiles
   uint64_t known_mask = 0;  // PHYSICAL local bits whose value is the same for every non-zero amplitude ...
   uint64_t known_val = 0;   // ... and that value: tiles that contradict it are all zero and are skipped

@@ -56,6 +56,8 @@ bool set_opt(PlanOptions &o, const std::string &name, int64_t v) {
     o.rot = v ? 1 : 0;
   } else if (name == "lite") {
     o.lite = v ? 1 : 0;
+  } else if (name == "support") {
+    o.support = v ? 1 : 0;
   } else if (name == "skip_dead") {
     o.skip_dead = v ? 1 : 0;
   } else if (name == "known_mask") {
@@ -94,6 +96,7 @@ int64_t get_opt(const PlanOptions &o, const std::string &name) {
   if (name == "lite") return o.lite;
   if (name == "lane_fixed") return o.lane_fixed;
   if (name == "skip_dead") return o.skip_dead;
+  if (name == "support") return o.support;
   return -1;
 }
 

@@ -164,7 +164,7 @@ struct PlanOptions {
   int skip_dead = 1;        // use the state's support: fused passes skip all-zero tiles
   uint64_t known_mask = 0;  // PHYSICAL local bits whose value is the same for every non-zero amplitude ...
   uint64_t known_val = 0;   // ... and that value: tiles that contradict it are all zero and are skipped
-  int lane_fixed = 1;     // low tile bits that stay on lanes in the load / store rounds (1..3)
+  int lane_fixed = 0;     // low tile bits that stay on lanes in the load / store rounds (1..3)
   int lite = 1;           // passes of rotations and X / CX only use the lean kernel instantiation
   int hot_bits = 0;       // planner: max distinct TARGET bits per pass (0 = tile_bits).  With
                           // hot_bits <= tile_bits - warp bits every transpose can stay warp-local.

@@ -446,6 +446,16 @@ struct PassProgram {
 };
 static_assert(sizeof(PassProgram) <= 32000, "kernel parameter space");
 
+// 256-bit global accesses (sm_100: LDG.256 / STG.256): when tile bit 0 is a REGISTER bit of the
+// load / store round, the two registers of a pair are one whole 32-byte sector of the same
+// thread -- one instruction instead of two, and no half-sector requests.
+__device__ __forceinline__ void ld_pair256(const double2 *p, double &a0, double &a1, double &b0, double &b1) {
+  asm volatile("ld.global.cs.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a0), "=d"(a1), "=d"(b0), "=d"(b1) : "l"(p));
+}
+__device__ __forceinline__ void st_pair256(double2 *p, double a0, double a1, double b0, double b1) {
+  asm volatile("st.global.cs.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a0), "d"(a1), "d"(b0), "d"(b1) : "memory");
+}
+
 template <int T, int R>
 __host__ __device__ constexpr size_t fused_smem_bytes() {
   return (size_t(16) << T) + size_t(kMaxRounds) * (size_t(1) << (T - R)) * sizeof(uint16_t) +
@@ -505,14 +515,28 @@ __global__ void __launch_bounds__(1 << (T - R), MINB)
         st[j] = 1ull << P.tile_pos[P.rounds[nrounds - 1].reg_pos[j]];
         fx |= ((f >> j) & 1u) ? st[j] : 0ull;
       }
-      const uint64_t at = (base + goff_tab[NT + tid]) ^ fx;
+      if (st[0] == 1ull) {  // register bit 0 is physical bit 0: 32-byte stores of register pairs
+        const uint64_t at = (base + goff_tab[NT + tid]) ^ (fx & ~1ull);
+        const bool sw = (f & 1u) != 0;  // pending flip on that bit: the pair goes out in reverse order
 #pragma unroll
-      for (int i = 0; i < NR; ++i) {
-        uint64_t off = 0;
+        for (int i = 0; i < NR; i += 2) {
+          uint64_t off = 0;
 #pragma unroll
-        for (int j = 0; j < R; ++j)
-          if ((i >> j) & 1) off |= st[j];
-        __stcs(amps + (at ^ off), make_double2(re[i], im[i]));
+          for (int j = 1; j < R; ++j)
+            if ((i >> j) & 1) off |= st[j];
+          st_pair256(amps + (at ^ off), sw ? re[i + 1] : re[i], sw ? im[i + 1] : im[i], sw ? re[i] : re[i + 1],
+                     sw ? im[i] : im[i + 1]);
+        }
+      } else {
+        const uint64_t at = (base + goff_tab[NT + tid]) ^ fx;
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+          uint64_t off = 0;
+#pragma unroll
+          for (int j = 0; j < R; ++j)
+            if ((i >> j) & 1) off |= st[j];
+          __stcs(amps + (at ^ off), make_double2(re[i], im[i]));
+        }
       }
     }
     const bool active = it < iters && tile_id < ntiles32;
@@ -536,15 +560,26 @@ __global__ void __launch_bounds__(1 << (T - R), MINB)
 #pragma unroll
       for (int j = 0; j < R; ++j) st[j] = 1ull << P.tile_pos[P.rounds[0].reg_pos[j]];
       if (!(dbg & 1u)) {
+        if (st[0] == 1ull) {  // register bit 0 is physical bit 0: 32-byte loads of register pairs
 #pragma unroll
-        for (int i = 0; i < NR; ++i) {
-          uint64_t off = 0;
+          for (int i = 0; i < NR; i += 2) {
+            uint64_t off = 0;
 #pragma unroll
-          for (int j = 0; j < R; ++j)
-            if ((i >> j) & 1) off += st[j];
-          const double2 a = __ldcs(src + off);
-          re[i] = a.x;
-          im[i] = a.y;
+            for (int j = 1; j < R; ++j)
+              if ((i >> j) & 1) off += st[j];
+            ld_pair256(src + off, re[i], im[i], re[i + 1], im[i + 1]);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < NR; ++i) {
+            uint64_t off = 0;
+#pragma unroll
+            for (int j = 0; j < R; ++j)
+              if ((i >> j) & 1) off += st[j];
+            const double2 a = __ldcs(src + off);
+            re[i] = a.x;
+            im[i] = a.y;
+          }
         }
       }
       // While this tile is in registers, pull the group's NEXT tile from HBM into L2 (one request

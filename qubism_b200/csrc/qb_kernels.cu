@@ -500,7 +500,7 @@ __global__ void __launch_bounds__(1 << (T - R), MINB)
   const uint32_t iters = (ntiles32 + stride - 1) / stride;
   double re[NR], im[NR];
   uint32_t f = 0;  // flip mask: register i holds logical register index i ^ f
-  uint64_t base = 0;
+  uint64_t base = 0, next_base = 0;
   for (uint32_t it = 0; it <= iters; ++it) {
     const uint32_t tile_id = first + it * stride;
     // ---------------- store the finished tile, then load the next one
@@ -541,9 +541,12 @@ __global__ void __launch_bounds__(1 << (T - R), MINB)
     }
     const bool active = it < iters && tile_id < ntiles32;
     if (active) {
-      // deposit the tile id into the non-tile bit positions
-      base = 0;
-      {
+      // deposit the tile id into the free non-tile bit positions (the prefetch of the previous
+      // iteration already did it for this tile)
+      if (it > 0 && P.l2_prefetch == 1 && !(dbg & 1u)) {
+        base = next_base;
+      } else {
+        base = 0;
         uint64_t t = tile_id;
         const uint32_t nruns = P.nruns;
         for (uint32_t k = 0; k < nruns; ++k) {
@@ -585,7 +588,7 @@ __global__ void __launch_bounds__(1 << (T - R), MINB)
       // While this tile is in registers, pull the group's NEXT tile from HBM into L2 (one request
       // per 128-byte line): its loads then hit L2 instead of waiting on DRAM, which overlaps
       // the memory phase of tile k+1 with the gate / transpose phases of tile k.
-      const uint32_t next_id = tile_id + stride;
+      const uint32_t next_id = tile_id + stride * P.l2_prefetch;  // prefetch distance in tiles of this CTA
       if (P.l2_prefetch && next_id < ntiles32 && !(dbg & 1u)) {
         uint64_t nbase = 0;
         uint64_t t = next_id;
@@ -596,6 +599,7 @@ __global__ void __launch_bounds__(1 << (T - R), MINB)
           t >>= len;
         }
         nbase |= P.base_fixed;
+        next_base = nbase;
 #pragma unroll
         for (int k = 0; k < LPT; ++k)
           asm volatile("prefetch.global.L2 [%0];" ::"l"(amps + nbase + (uint64_t(line_tab[k * NT + tid]) << 3)));

@@ -48,7 +48,8 @@ bool set_opt(PlanOptions &o, const std::string &name, int64_t v) {
   } else if (name == "time_kernels") {
     o.time_kernels = v ? 1 : 0;
   } else if (name == "l2_prefetch") {
-    o.l2_prefetch = v ? 1 : 0;
+    if (v < 0 || v > 4) return false;
+    o.l2_prefetch = (int)v;
   } else if (name == "hot_bits") {
     if (v < 0 || v > kMaxTileBits) return false;
     o.hot_bits = (int)v;
@@ -709,7 +710,7 @@ static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &don
   P->gscale[0] = 1.0;
   P->gscale[1] = 0.0;
   P->has_gscale = 0;
-  P->l2_prefetch = opt.l2_prefetch ? 1u : 0u;
+  P->l2_prefetch = (uint32_t)opt.l2_prefetch;
   P->dbg_skip = (uint32_t)opt.dbg_skip;
   P->sm_count = 148;
   for (int i = 0; i < T; ++i) P->tile_pos[i] = (uint8_t)tile_bits[i];

@@ -129,3 +129,34 @@ def adder_ops(k: int):
         ops += unmaj(a(i - 1), b(i), a(i))
     ops += unmaj(cin, b(0), a(0))
     return ops
+
+
+def random_mixed(n: int, nops: int, seed: int):
+    """A random mix of every op kind the ABI takes -- rotations (lambda = 0), general `unitary`
+    matrices, Paulis / Hadamard / a phase gate, CX (dense, so that flip-mask toggles, static and
+    masked register swaps all occur) and multi-controlled gates -- for the randomised parity
+    sweeps.  Same stream format as the other generators plus ("CU", ctrls, t, 2x2)."""
+    rng = np.random.default_rng(seed)
+    had = np.array([[1, 1], [1, -1]], dtype=complex) / np.sqrt(2)
+    fixed = [had, np.array([[0, 1], [1, 0]], dtype=complex), np.array([[0, -1j], [1j, 0]]),
+             np.diag([1, -1]).astype(complex), np.diag([1, 1j])]
+    ops = []
+    while len(ops) < nops:
+        kind = int(rng.integers(0, 8))
+        q = int(rng.integers(0, n))
+        if kind <= 1:
+            ops.append(("U", q, unitary_matrix(float(rng.uniform(0, 12)), float(rng.uniform(0, 12)), 0.0)))
+        elif kind == 2:
+            ops.append(("U", q, unitary_matrix(*[float(a) for a in rng.uniform(0, 12, 3)])))
+        elif kind == 3:
+            ops.append(("U", q, fixed[int(rng.integers(0, len(fixed)))]))
+        elif kind <= 6:
+            c = int(rng.integers(0, n))
+            if c != q:
+                ops.append(("CX", c, q))
+        elif n >= 3:
+            cs = [int(a) for a in rng.choice([a for a in range(n) if a != q], int(rng.integers(1, 3)), replace=False)]
+            m = unitary_matrix(*[float(a) for a in rng.uniform(0, 12, 3)]) if rng.integers(0, 2) else \
+                np.array([[np.cos(.4), -np.sin(.4)], [np.sin(.4), np.cos(.4)]], dtype=complex)
+            ops.append(("CU", cs, q, m))
+    return ops

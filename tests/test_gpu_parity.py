@@ -152,6 +152,38 @@ def test_lite_steps_and_interpreter_vs_oracle_20q(default_opts, lane_fixed, lite
     assert ctx.stats()["simple_launches"] == 0
 
 
+@pytest.mark.parametrize("seed", range(10))
+def test_random_mixed_circuits_random_knobs(default_opts, seed):
+    """Randomised sweep through the real kernels: every op kind, random planner knobs, with and
+    without a tracked support (fresh |0...0> vs uploaded state), against the structured oracle."""
+    from qubism_b200.circuits import random_mixed
+    ctx = default_opts
+    rng = np.random.default_rng(500 + seed)
+    n = int(rng.integers(11, 19))
+    ops = random_mixed(n, int(rng.integers(30, 120)), 700 + seed)
+    T, R = [(12, 4), (12, 4), (11, 4), (10, 3), (12, 5), (12, 3), (13, 4)][int(rng.integers(0, 7))]
+    if T <= n:
+        ctx.set_option("tile_bits", T)
+        ctx.set_option("reg_bits", R)
+    ctx.set_option("lane_fixed", int(rng.integers(0, 4)))
+    ctx.set_option("lite", int(rng.integers(0, 4) > 0))
+    ctx.set_option("rot", int(rng.integers(0, 4) > 0))
+    if rng.integers(0, 2):
+        v = np.zeros(1 << n, complex)
+        v[0] = 1
+        sv = Q.mkStateVec(n)  # support fully known
+        mid = [("MEASURE", int(rng.integers(0, n)), float(rng.uniform(0, 1))) for _ in range(2)]
+        ops = ops[: len(ops) // 2] + mid + ops[len(ops) // 2:]
+    else:
+        v = S.gen_state(n, rng)
+        sv = Q.StateVec.from_host(v)
+    rec_ref = []
+    ref = S.run_ops(n, ops, v, record=rec_ref)
+    rec = sv.run_ops(ops)
+    assert [(q, b) for q, b, _ in rec] == [(q, b) for q, b, _ in rec_ref]
+    assert close(sv.to_host(), ref, 1e-11)
+
+
 def test_submit_equals_per_gate_calls(ctx):
     n = 13
     v = S.gen_state(n, np.random.default_rng(3))

@@ -139,6 +139,61 @@ def test_emulated_dead_tiles_are_skipped_with_a_known_support(emul, opts):
     assert np.abs(out - S.run_ops(n, ops2, w)).max() < 1e-13
 
 
+@pytest.mark.parametrize("seed", range(12))
+def test_emulated_random_circuits_random_knobs(emul, seed):
+    """Randomised sweep: random mixes of rotations, reflections, general / diagonal / controlled
+    gates and CX (dense in CX so that toggles, static and masked register swaps all occur), random
+    planner knobs, random known support -- always against the structured oracle."""
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(10, 14))
+    ops = []
+    for _ in range(int(rng.integers(20, 90))):
+        kind = rng.integers(0, 8)
+        q = int(rng.integers(0, n))
+        if kind <= 1:
+            ops.append(("U", q, D.unitary(float(rng.uniform(0, 12)), float(rng.uniform(0, 12)), 0.0)))
+        elif kind == 2:
+            ops.append(("U", q, D.unitary(*[float(x) for x in rng.uniform(0, 12, 3)])))
+        elif kind == 3:
+            ops.append(("U", q, [D.hadamard(), D.pauliX(), D.pauliY(), D.pauliZ(), np.diag([1, 1j])][int(rng.integers(0, 5))]))
+        elif kind <= 6:
+            c = int(rng.integers(0, n))
+            if c != q:
+                ops.append(("CX", c, q))
+        else:
+            cs = [int(x) for x in rng.choice([x for x in range(n) if x != q], int(rng.integers(1, 3)), replace=False)]
+            ops.append(("CU", cs, q, D.unitary(*[float(x) for x in rng.uniform(0, 12, 3)]) if rng.integers(0, 2) else
+                        np.array([[np.cos(.4), -np.sin(.4)], [np.sin(.4), np.cos(.4)]])))
+    knobs = []
+    if rng.integers(0, 2): knobs.append(f"reg_bits={int(rng.choice([3, 4, 5]))}")
+    if rng.integers(0, 2): knobs.append(f"tile_bits={int(rng.choice([10, 11, 12] if n >= 12 else [10]))}")
+    if rng.integers(0, 2): knobs.append(f"lane_fixed={int(rng.integers(0, 4))}")
+    if rng.integers(0, 2): knobs.append(f"low_bits={int(rng.integers(3, 6))}")
+    if rng.integers(0, 3) == 0: knobs.append("lite=0")
+    if rng.integers(0, 3) == 0: knobs.append("rot=0")
+    if rng.integers(0, 3) == 0: knobs.append(f"max_pass_gates={int(rng.integers(3, 20))}")
+    if rng.integers(0, 3) == 0: knobs.append(f"max_rounds={int(rng.integers(3, 8))}")
+    v = S.gen_state(n, rng)
+    if rng.integers(0, 2):  # a known support: collapse two qubits first
+        qa, qb = [int(x) for x in rng.choice(n, 2, replace=False)]
+        ba, bb = int(rng.integers(0, 2)), int(rng.integers(0, 2))
+        v = S.collapse(n, qa, ba, S.collapse(n, qb, bb, v))
+        knobs.append(f"known_mask={(1 << (n - 1 - qa)) | (1 << (n - 1 - qb))}")
+        knobs.append(f"known_val={(ba << (n - 1 - qa)) | (bb << (n - 1 - qb))}")
+    opts = ",".join(knobs)
+    if not capi_variant_ok(opts, n):
+        pytest.skip("kernel variant not built for this (tile_bits, reg_bits)")
+    ref = S.run_ops(n, ops, v)
+    out, st = emul(n, ops, v, opts)
+    assert np.abs(out - ref).max() < 1e-12, opts
+
+
+def capi_variant_ok(opts: str, n: int) -> bool:
+    kv = dict(x.split("=") for x in opts.split(",") if x)
+    T, R = int(kv.get("tile_bits", 12)), int(kv.get("reg_bits", 4))
+    return (min(T, n), R) in {(10, 3), (10, 4), (11, 3), (11, 4), (11, 5), (12, 3), (12, 4), (12, 5), (13, 4), (13, 5)}
+
+
 def test_emulated_reference_semantics_qft_and_adder(emul):
     for n, ops in ((12, qft_ops(12)), (12, adder_ops(5)), (13, proper_unitary_layers(13, 2))):
         rng = np.random.default_rng(n)

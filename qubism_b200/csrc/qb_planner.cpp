@@ -70,7 +70,8 @@ bool set_opt(PlanOptions &o, const std::string &name, int64_t v) {
     o.lane_fixed = (int)v;
 
   } else if (name == "avoid_regswap") {
-    o.avoid_regswap = v ? 1 : 0;
+    if (v < 0 || v > 2) return false;
+    o.avoid_regswap = (int)v;
   } else if (name == "dbg_skip") {
     if (v < 0 || v > 15) return false;
     o.dbg_skip = (int)v;
@@ -522,8 +523,12 @@ static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &don
       // Two attempts: first refuse rounds where an X / CX would end up with a control on a
       // REGISTER bit (that flavour moves data, ~150 instructions per thread, instead of toggling
       // the flip mask); if no round qualifies, accept such a round.
+      // (avoid_regswap = 2: the first attempt only looks at rounds that already exist -- never
+      //  pay a new round, i.e. a transpose, to save a register swap)
+      const int nexisting = (int)rounds.size();
       for (int attempt = opt.avoid_regswap ? 0 : 1; attempt < 2 && place < 0; ++attempt) {
         for (int r = r0; r < max_rounds; ++r) {
+          if (attempt == 0 && opt.avoid_regswap == 2 && r >= std::max(nexisting, 1)) break;
           const bool edge = (r == 0) || (r == max_rounds - 1);  // load round / last possible store round
           if (edge && (tb & lowfixed)) continue;
           while ((int)rounds.size() <= r) rounds.emplace_back();
@@ -650,12 +655,18 @@ static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &don
       std::sort(qw_lanes[r].begin(), qw_lanes[r].end());
       // fill the register set to exactly R bits: highest free bits (not warp bits, not the
       // quarter-warp lanes, and never bits 0..2 in a load / store round)
+      // Filler bits that are CONTROLS of an X / CX of this round come last: a control that is not
+      // a register bit keeps the gate a flip-mask toggle instead of a register swap.
+      uint32_t ctl = 0;
+      for (int i = 0; i < T; ++i)
+        if (rounds[r].swap_ctrl & (1ull << tile_bits[i])) ctl |= 1u << i;
       uint32_t regm = req[r];
-      for (int pass2 = 0; pass2 < 2; ++pass2)
+      for (int pass2 = 0; pass2 < 3; ++pass2)
         for (int i = T - 1; i >= 0 && popc(regm) < R; --i) {
           if ((regm | wmask) & (1u << i)) continue;
           if (edge && i < lane_fixed) continue;
-          if (pass2 == 0 && (qmask & (1u << i))) continue;
+          if (pass2 == 0 && ((qmask | ctl) & (1u << i))) continue;
+          if (pass2 == 1 && (qmask & (1u << i))) continue;
           regm |= 1u << i;
         }
       rounds[r].regmask = 0;

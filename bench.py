@@ -327,7 +327,7 @@ def run_ours(args):
     achieved = alg_bytes / (fused_ms / 1e3) / 1e9 if fused_ms > 0 else None
     traffic = None
     try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "r01c_fused_pass_summary.json")))
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r01d_fused_pass_summary.json")))
         traffic = prof.get("dram_bytes_per_launch_scaled_to", {}).get(str(L))
     except (OSError, ValueError):
         pass

@@ -50,6 +50,31 @@ for n in ([int(sys.argv[1])] if len(sys.argv) > 1 else [pbits + 4, 14, 18]):
         print(f"n={n} world={world}: amp err {err:.2e}, sumsq err {red_err:.2e}, measure bit {bit}=={rb} err {merr:.2e}, "
               f"exchanges {st['exchanges']} ({st['exchange_bytes']/2**20:.1f} MiB/rank), passes {st['passes']}, simple {st['simple_launches']} -> "
               f"{'OK' if good else 'FAIL'}", flush=True)
+# C4: the widened ripple-carry adder (Toffolis through qelib1.inc's ccx), started
+# from a fresh |0...0> -- the support is fully known, ranks other than 0 hold only zeros until a
+# gate reaches a global qubit -- followed by a random mix of every op kind and two measurements
+from qubism_b200.circuits import adder_ops, random_mixed
+for k in (6, 8):
+    n = 2 * k + 2
+    if n - pbits < 4:
+        continue
+    ops = adder_ops(k) + [("MEASURE", 0, 0.3)] + random_mixed(n, 60, 40 + k) + [("MEASURE", n - 1, 0.6), ("MEASURE", 1, 0.5)]
+    v0 = np.zeros(1 << n, complex)
+    v0[0] = 1
+    rec_ref = []
+    ref = S.run_ops(n, ops, v0, record=rec_ref)
+    sv = Q.mkStateVec(n, ctx)
+    ctx.reset_stats()
+    rec = sv.run_ops(ops)
+    got = sv.to_host(0, 1 << n)
+    err = float(np.abs(got - ref).max())
+    bits_ok = [(q, b) for q, b, _ in rec] == [(q, b) for q, b, _ in rec_ref]
+    st = ctx.stats()
+    good = err < 1e-11 and bits_ok
+    ok = ok and good
+    if rank == 0:
+        print(f"adder k={k} (n={n}) + mixed from |0>: amp err {err:.2e}, measured bits match {bits_ok}, exchanges {st['exchanges']}, "
+              f"passes {st['passes']}, tiles {st['tiles']} -> {'OK' if good else 'FAIL'}", flush=True)
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 ctx.barrier()

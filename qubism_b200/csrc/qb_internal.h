@@ -62,17 +62,23 @@ QB_HD constexpr uint32_t op_diag_thr(int R) { return op_toggle(R) + 1u; }  // di
 QB_HD constexpr uint32_t op_count(int R) { return op_toggle(R) + 2u; }
 static_assert(sizeof(DevGate) == 112, "DevGate layout");
 
-// LITE passes (uncontrolled rotations and X / CX only) are not interpreted gate by gate: the
-// planner packs each round into STEPS of mutually independent work -- one rotation slot per
-// register bit, then up to four flip-mask toggles, then at most one register-controlled X --
+// LITE passes (uncontrolled 1-qubit gates of the rotation / real / general class and X / CX only:
+// everything the reference interpreter ever sends, QASM/Simulation.hs:94-122,163-171) are not
+// interpreted gate by gate: the planner packs each round into STEPS of mutually independent
+// work -- one 1-qubit slot per register bit, then up to four flip-mask toggles, then at most one
+// register-controlled X --
 // which the kernel runs as straight-line code behind a few uniform skip-branches.  No opcode
 // fetch, no dispatch tree, no jump table: per step ONE header read, per gate two constants.
 constexpr int kStepToggles = 4;
+constexpr int kMaxSteps = 72;  // steps per pass (kernel parameter space: 72 * 416 B + header < 32 KB)
+// slot kinds (4 bits per register bit in DevStep::kinds): class in bits 0-1, bit 2 = a flip may
+// be pending on that register bit (flip-aware flavour)
+enum : uint32_t { SLOT_NONE = 0, SLOT_ROT = 1, SLOT_REAL = 2, SLOT_GENERAL = 3, SLOT_FLIP = 4 };
 struct alignas(16) DevStep {
-  double rot[kMaxRegBits][2];  // (t, s) of the rotation on register bit J
-  uint32_t rot_mask;           // bit J: slot J holds a rotation
-  uint32_t rot_flip;           // bit J: a flip may be pending on register bit J (sign-aware flavour)
-  uint32_t ntog;               // toggles applied after the rotations
+  double slot[kMaxRegBits][8];  // the 1-qubit gate on register bit J: ROT (t, s); REAL a b c d; GENERAL = DevGate::m
+  uint32_t kinds;              // slot kind of register bit J in bits 4J .. 4J+3
+  uint32_t _pad;
+  uint32_t ntog;               // toggles applied after the slots
   uint32_t swap_j;             // 0xff: none; else bits 0-2 = target register bit of an X / CX with register-bit
                                // control(s), bit 4 = static flavour (one control, a register bit without a
                                // pending flip, no other controls: the same pairs swap in every thread)
@@ -83,7 +89,7 @@ struct alignas(16) DevStep {
   uint32_t swap_creg, swap_cthr;
   uint64_t swap_cext;
 };
-static_assert(sizeof(DevStep) == 176, "DevStep layout");
+static_assert(sizeof(DevStep) == 416, "DevStep layout");
 
 struct DevRound {
   uint32_t gate_begin, gate_end;
@@ -109,7 +115,8 @@ struct DevPass {
   uint32_t dbg_skip;                  // PROFILING ONLY (results are wrong): bit 0 skip global loads, bit 1 skip
                                       // global stores, bit 2 skip the shared-memory transposes, bit 3 skip gates
   uint32_t sm_count;
-  uint32_t lite;                      // only uncontrolled rotations and X / CX: rounds index DevSteps, not DevGates
+  uint32_t lite;                      // 0: rounds index DevGates (interpreter); 1 / 2: DevSteps (1 = every slot is a
+                                      // rotation, 2 = rotation / real / general slots)
   uint32_t nsteps;
   uint32_t _pad3[2];
   uint64_t base_fixed;                // known non-tile bits at their known value: OR-ed into every live tile's base

@@ -54,10 +54,10 @@ __device__ __forceinline__ uint32_t swz(uint32_t u) {
 // the switch arms leave every amplitude in the register it came in (no shuffle MOVs between
 // gates -- they were 55% of all executed instructions in the first version, ncu r01).
 template <int R, int J, int FL>
-__device__ __forceinline__ void gate_general(double (&re)[1 << R], double (&im)[1 << R], const DevGate &g,
-                                             bool ok_thr, uint32_t f) {
-  double Ar = g.m[0], Ai = g.m[1], Br = g.m[2], Bi = g.m[3];
-  double Cr = g.m[4], Ci = g.m[5], Dr = g.m[6], Di = g.m[7];
+__device__ __forceinline__ void gate_general_m(double (&re)[1 << R], double (&im)[1 << R], const double *m, uint32_t creg_in,
+                                               bool ok_thr, uint32_t f) {
+  double Ar = m[0], Ai = m[1], Br = m[2], Bi = m[3];
+  double Cr = m[4], Ci = m[5], Dr = m[6], Di = m[7];
   if (FL != 0 && ((f >> J) & 1u)) {  // logical pair order is reversed in this thread
     double t;
     t = Ar; Ar = Dr; Dr = t;
@@ -65,7 +65,7 @@ __device__ __forceinline__ void gate_general(double (&re)[1 << R], double (&im)[
     t = Br; Br = Cr; Cr = t;
     t = Bi; Bi = Ci; Ci = t;
   }
-  const uint32_t creg = (FL == 2) ? g.creg : 0u;
+  const uint32_t creg = (FL == 2) ? creg_in : 0u;
 #pragma unroll
   for (int p = 0; p < (1 << (R - 1)); ++p) {
     const int i0 = ((p >> J) << (J + 1)) | (p & ((1 << J) - 1));
@@ -94,15 +94,20 @@ __device__ __forceinline__ void gate_general(double (&re)[1 << R], double (&im)[
 }
 
 template <int R, int J, int FL>
-__device__ __forceinline__ void gate_real(double (&re)[1 << R], double (&im)[1 << R], const DevGate &g,
-                                          bool ok_thr, uint32_t f) {
-  double a = g.m[0], b = g.m[2], c = g.m[4], d = g.m[6];
+__device__ __forceinline__ void gate_general(double (&re)[1 << R], double (&im)[1 << R], const DevGate &g,
+                                             bool ok_thr, uint32_t f) {
+  gate_general_m<R, J, FL>(re, im, g.m, g.creg, ok_thr, f);
+}
+
+template <int R, int J, int FL>
+__device__ __forceinline__ void gate_real_m(double (&re)[1 << R], double (&im)[1 << R], double a, double b, double c,
+                                            double d, uint32_t creg_in, bool ok_thr, uint32_t f) {
   if (FL != 0 && ((f >> J) & 1u)) {
     double t;
     t = a; a = d; d = t;
     t = b; b = c; c = t;
   }
-  const uint32_t creg = (FL == 2) ? g.creg : 0u;
+  const uint32_t creg = (FL == 2) ? creg_in : 0u;
 #pragma unroll
   for (int p = 0; p < (1 << (R - 1)); ++p) {
     const int i0 = ((p >> J) << (J + 1)) | (p & ((1 << J) - 1));
@@ -118,6 +123,12 @@ __device__ __forceinline__ void gate_real(double (&re)[1 << R], double (&im)[1 <
       im[i1] = fma(d, im[i1], Ti);
     }
   }
+}
+
+template <int R, int J, int FL>
+__device__ __forceinline__ void gate_real(double (&re)[1 << R], double (&im)[1 << R], const DevGate &g,
+                                          bool ok_thr, uint32_t f) {
+  gate_real_m<R, J, FL>(re, im, g.m[0], g.m[2], g.m[4], g.m[6], g.creg, ok_thr, f);
 }
 
 // Conditional swap IN PLACE with the masked-XOR trick (t = (a ^ b) & m; a ^= t; b ^= t), in
@@ -286,10 +297,11 @@ __device__ __forceinline__ void apply_gate(double (&re)[1 << R], double (&im)[1 
 // layers compile to).  The planner packed each round into DevSteps; a step is straight-line
 // code behind uniform skip-branches: no opcode fetch, no dispatch tree, no jump table.
 template <int R, int J>
-__device__ __forceinline__ void step_rot(double (&re)[1 << R], double (&im)[1 << R], const DevStep &S, uint32_t f) {
-  if ((S.rot_mask >> J) & 1u) {
-    const double t = S.rot[J][0], s = S.rot[J][1];
-    if ((S.rot_flip >> J) & 1u) {  // a flip may be pending on this bit: per-thread sign
+__device__ __forceinline__ void step_rot(double (&re)[1 << R], double (&im)[1 << R], const DevStep &S, uint32_t f,
+                                         bool flip) {
+  {
+    const double t = S.slot[J][0], s = S.slot[J][1];
+    if (flip) {  // a flip may be pending on this bit: per-thread sign
       const long long sg = (long long)((unsigned long long)((f >> J) & 1u) << 63);
       const double tv = __longlong_as_double(__double_as_longlong(t) ^ sg);
       const double sv = __longlong_as_double(__double_as_longlong(s) ^ sg);
@@ -331,6 +343,27 @@ __device__ __forceinline__ void step_rot(double (&re)[1 << R], double (&im)[1 <<
         im[i0] = fma(t, im[i1], im[i0]);
       }
     }
+  }
+}
+
+// the 1-qubit slot of register bit J: uniform branches on the slot kind
+// (ROT_ONLY: the instantiation for passes whose slots are all rotations -- a third of the code)
+template <int R, int J, bool ROT_ONLY>
+__device__ __forceinline__ void step_slot(double (&re)[1 << R], double (&im)[1 << R], const DevStep &S, uint32_t kinds,
+                                          uint32_t f) {
+  const uint32_t kind = (kinds >> (4 * J)) & 15u;
+  if (kind == SLOT_NONE) return;
+  const bool flip = (kind & SLOT_FLIP) != 0;
+  const uint32_t cls = kind & 3u;
+  if (ROT_ONLY || cls == SLOT_ROT) {
+    step_rot<R, J>(re, im, S, f, flip);
+  } else if (cls == SLOT_REAL) {
+    const double a = S.slot[J][0], b = S.slot[J][1], c = S.slot[J][2], d = S.slot[J][3];
+    if (flip) gate_real_m<R, J, 1>(re, im, a, b, c, d, 0u, true, f);
+    else gate_real_m<R, J, 0>(re, im, a, b, c, d, 0u, true, f);
+  } else {
+    if (flip) gate_general_m<R, J, 1>(re, im, S.slot[J], 0u, true, f);
+    else gate_general_m<R, J, 0>(re, im, S.slot[J], 0u, true, f);
   }
 }
 
@@ -385,14 +418,15 @@ __device__ __forceinline__ void step_swap_static_dispatch(double (&re)[1 << R], 
 #undef QB_SS
 }
 
-template <int R>
+template <int R, bool ROT_ONLY>
 __device__ __forceinline__ void apply_step(double (&re)[1 << R], double (&im)[1 << R], const DevStep &S, uint32_t tid,
                                            uint64_t basefull, uint32_t &f) {
-  step_rot<R, 0>(re, im, S, f);
-  step_rot<R, 1>(re, im, S, f);
-  step_rot<R, 2>(re, im, S, f);
-  if constexpr (R > 3) step_rot<R, 3>(re, im, S, f);
-  if constexpr (R > 4) step_rot<R, 4>(re, im, S, f);
+  const uint32_t kinds = S.kinds;
+  step_slot<R, 0, ROT_ONLY>(re, im, S, kinds, f);
+  step_slot<R, 1, ROT_ONLY>(re, im, S, kinds, f);
+  step_slot<R, 2, ROT_ONLY>(re, im, S, kinds, f);
+  if constexpr (R > 3) step_slot<R, 3, ROT_ONLY>(re, im, S, kinds, f);
+  if constexpr (R > 4) step_slot<R, 4, ROT_ONLY>(re, im, S, kinds, f);
   const uint32_t ntog = S.ntog;
 #pragma unroll
   for (int k = 0; k < kStepToggles; ++k) {
@@ -441,7 +475,7 @@ struct PassProgram {
   DevPass hdr;
   union {
     DevGate gates[kMaxPassGates];
-    DevStep steps[kMaxPassGates];  // lite passes
+    DevStep steps[kMaxSteps];  // lite passes
   };
 };
 static_assert(sizeof(PassProgram) <= 32000, "kernel parameter space");
@@ -462,7 +496,7 @@ __host__ __device__ constexpr size_t fused_smem_bytes() {
          size_t(2) * (size_t(1) << (T - R)) * sizeof(uint64_t) + (size_t(1) << (T - 3)) * sizeof(uint32_t);
 }
 
-template <int T, int R, int MINB, bool LITE>
+template <int T, int R, int MINB, int LITE>
 __global__ void __launch_bounds__(1 << (T - R), MINB)
     k_fused_pass(double2 *__restrict__ amps, unsigned long long ntiles, const __grid_constant__ PassProgram prog) {
   constexpr int NR = 1 << R;
@@ -657,10 +691,10 @@ __global__ void __launch_bounds__(1 << (T - R), MINB)
           if (P.rounds[(r + 1 < nrounds) ? r + 1 : 1].warp_local == 0) __syncthreads();
         }
       }
-      const uint32_t wb = LITE ? RD.step_begin : RD.gate_begin, we = LITE ? RD.step_end : RD.gate_end;
+      const uint32_t wb = LITE != 0 ? RD.step_begin : RD.gate_begin, we = LITE != 0 ? RD.step_end : RD.gate_end;
       if (wb < we && !(dbg & 8u)) {
-        if constexpr (LITE) {
-          for (uint32_t si = wb; si < we; ++si) apply_step<R>(re, im, prog.steps[si], tid, basefull, f);
+        if constexpr (LITE != 0) {
+          for (uint32_t si = wb; si < we; ++si) apply_step<R, LITE == 1>(re, im, prog.steps[si], tid, basefull, f);
         } else {
           for (uint32_t gi = wb; gi < we; ++gi) apply_gate<R>(re, im, G[gi], tid, basefull, f);
         }
@@ -681,16 +715,18 @@ __global__ void __launch_bounds__(1 << (T - R), MINB)
 struct FusedVariant {
   int T, R, threads;
   int minb, minb_lite;   // resident CTAs per SM each instantiation is compiled for
-  const void *fn;        // every gate class (interpreter)
-  const void *fn_lite;   // rotations and X / CX only (steps)
+  const void *fn[3];     // [0] interpreter (every gate class), [1] steps of rotations and X / CX, [2] steps of
+                         // rotation / real / general slots and X / CX
   size_t smem;
 };
 
 // MINB_ / MINBL_: the interpreter wants occupancy (its arms are short dependent chains); the
-// step kernel wants registers (128: no spills, every sweep is 2^R independent DFMAs) -- measured.
-#define QB_VARIANT(T_, R_, MINB_, MINBL_)                                                               \
-  {T_, R_, 1 << (T_ - R_), MINB_, MINBL_, (const void *)&k_fused_pass<T_, R_, MINB_, false>,            \
-   (const void *)&k_fused_pass<T_, R_, MINBL_, true>, fused_smem_bytes<T_, R_>()}
+// step kernels want registers (128: no spills, every sweep is 2^R independent DFMAs) -- measured.
+#define QB_VARIANT(T_, R_, MINB_, MINBL_)                                                          \
+  {T_, R_, 1 << (T_ - R_), MINB_, MINBL_,                                                          \
+   {(const void *)&k_fused_pass<T_, R_, MINB_, 0>, (const void *)&k_fused_pass<T_, R_, MINBL_, 1>, \
+    (const void *)&k_fused_pass<T_, R_, MINBL_, 2>},                                               \
+   fused_smem_bytes<T_, R_>()}
 
 #ifdef QB_QUICK_COMPILE  // developer switch: only the default instantiation (fast ptxas experiments)
 static const FusedVariant kVariants[] = {QB_VARIANT(12, 4, 3, 2)};
@@ -720,7 +756,7 @@ cudaError_t launch_fused_pass(double2 *amps, const uint8_t *blob, uint32_t blob_
   if (blob_bytes > sizeof(PassProgram) || blob_bytes < sizeof(DevPass)) return cudaErrorInvalidValue;
   static thread_local PassProgram prog;  // the launch copies it into the command buffer
   memcpy(&prog, blob, blob_bytes);
-  const void *fn = prog.hdr.lite ? v->fn_lite : v->fn;
+  const void *fn = v->fn[prog.hdr.lite <= 2 ? prog.hdr.lite : 0];
   const size_t smem = v->smem;
   const int threads = v->threads;
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -846,14 +846,14 @@ static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &don
     for (uint32_t gi = 0; gi < gcount && lite; ++gi) {
       const DevGate &g = G[gi];
       const bool ctrl = (g.creg | g.cthr) != 0 || g.cext != 0;
-      if (!(g.type == G_SWAP || (g.type == G_ROT && !ctrl))) lite = false;
+      if (!(g.type == G_SWAP || ((g.type == G_ROT || g.type == G_REAL || g.type == G_GENERAL) && !ctrl))) lite = false;
     }
+    std::vector<DevStep> steps;
     if (lite) {
       // ---- pack every round into steps (ASAP list scheduling; ops on disjoint qubits commute).
-      // Position = 3 * step + phase, phase 0 = rotations, 1 = toggles (list order), 2 = the
+      // Position = 3 * step + phase, phase 0 = 1-qubit slots, 1 = toggles (list order), 2 = the
       // register-controlled X.  An op goes to the earliest position after the last op that
       // shares a qubit with it.
-      std::vector<DevStep> steps;
       for (int r = 0; r < nrounds; ++r) {
         DevRound &RD = P->rounds[r];
         const size_t first = steps.size();
@@ -875,13 +875,23 @@ static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &don
           for (uint64_t q = qmask; q; q &= q - 1) lb = std::max(lb, last_pos[__builtin_ctzll(q)]);
           const uint32_t J = g.treg & 0xffu;
           int pos;
-          if (g.type == G_ROT) {
+          if (g.type != G_SWAP) {  // a 1-qubit slot
             int k = (lb < 0) ? 0 : lb / 3 + 1;
             DevStep &S = step_at(k);
-            S.rot[J][0] = g.m[0];
-            S.rot[J][1] = g.m[1];
-            S.rot_mask |= 1u << J;
-            if ((g.treg >> 8) & 1u) S.rot_flip |= 1u << J;
+            uint32_t kind;
+            if (g.type == G_ROT) {
+              kind = SLOT_ROT;
+              S.slot[J][0] = g.m[0];
+              S.slot[J][1] = g.m[1];
+            } else if (g.type == G_REAL) {
+              kind = SLOT_REAL;
+              for (int e = 0; e < 4; ++e) S.slot[J][e] = g.m[2 * e];
+            } else {
+              kind = SLOT_GENERAL;
+              std::memcpy(S.slot[J], g.m, sizeof(g.m));
+            }
+            if ((g.treg >> 8) & 1u) kind |= SLOT_FLIP;
+            S.kinds |= kind << (4 * J);
             pos = 3 * k;
           } else if (g.creg == 0) {  // toggle
             int k = (lb < 0) ? 0 : (lb + 1) / 3;  // smallest k with 3k + 1 >= lb
@@ -908,7 +918,16 @@ static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &don
         RD.step_begin = (uint32_t)first;
         RD.step_end = (uint32_t)steps.size();
       }
-      P->lite = 1u;
+      if ((int)steps.size() > kMaxSteps) lite = false;  // (never seen: a pass holds <= 96 gates) -> interpreter
+    }
+    if (lite) {
+      bool rot_only = true;
+      for (const DevStep &st : steps)
+        for (int J = 0; J < kMaxRegBits; ++J) {
+          const uint32_t cls = (st.kinds >> (4 * J)) & 3u;
+          if (cls != SLOT_NONE && cls != SLOT_ROT) rot_only = false;
+        }
+      P->lite = rot_only ? 1u : 2u;  // which step-kernel instantiation (qb_kernels.cu)
       P->nsteps = (uint32_t)steps.size();
       std::vector<uint8_t> blob(sizeof(DevPass) + steps.size() * sizeof(DevStep));
       std::memcpy(blob.data(), out.blob.data(), sizeof(DevPass));

@@ -79,21 +79,37 @@ void apply_step_host(std::vector<double> &re, std::vector<double> &im, int R, co
                      uint64_t basefull, uint32_t &f) {
   const int NR = 1 << R;
   for (int J = 0; J < R; ++J) {
-    if (!((S.rot_mask >> J) & 1u)) continue;
-    double t = S.rot[J][0], s = S.rot[J][1];
-    if ((f >> J) & 1u) {
-      if (!((S.rot_flip >> J) & 1u)) std::fprintf(stderr, "emulator: flip pending on a slot the planner marked flip-free\n");
-      t = -t;
-      s = -s;
-    }
+    const uint32_t kind = (S.kinds >> (4 * J)) & 15u;
+    if ((kind & 3u) == SLOT_NONE) continue;
+    const bool fl = (f >> J) & 1u;
+    if (fl && !(kind & SLOT_FLIP)) std::fprintf(stderr, "emulator: flip pending on a slot the planner marked flip-free\n");
+    const double *m = S.slot[J];
     for (int p = 0; p < NR / 2; ++p) {
       const int i0 = ((p >> J) << (J + 1)) | (p & ((1 << J) - 1)), i1 = i0 | (1 << J);
-      re[i0] = std::fma(t, re[i1], re[i0]);
-      im[i0] = std::fma(t, im[i1], im[i0]);
-      re[i1] = std::fma(s, re[i0], re[i1]);
-      im[i1] = std::fma(s, im[i0], im[i1]);
-      re[i0] = std::fma(t, re[i1], re[i0]);
-      im[i0] = std::fma(t, im[i1], im[i0]);
+      if ((kind & 3u) == SLOT_ROT) {
+        const double t = fl ? -m[0] : m[0], s = fl ? -m[1] : m[1];
+        re[i0] = std::fma(t, re[i1], re[i0]);
+        im[i0] = std::fma(t, im[i1], im[i0]);
+        re[i1] = std::fma(s, re[i0], re[i1]);
+        im[i1] = std::fma(s, im[i0], im[i1]);
+        re[i0] = std::fma(t, re[i1], re[i0]);
+        im[i0] = std::fma(t, im[i1], im[i0]);
+        continue;
+      }
+      // logical pair: register i holds logical index i ^ f
+      const int l0 = fl ? i1 : i0, l1 = fl ? i0 : i1;
+      const double x0r = re[l0], x0i = im[l0], x1r = re[l1], x1i = im[l1];
+      if ((kind & 3u) == SLOT_REAL) {
+        re[l0] = m[0] * x0r + m[1] * x1r;
+        im[l0] = m[0] * x0i + m[1] * x1i;
+        re[l1] = m[2] * x0r + m[3] * x1r;
+        im[l1] = m[2] * x0i + m[3] * x1i;
+      } else {
+        re[l0] = m[0] * x0r - m[1] * x0i + m[2] * x1r - m[3] * x1i;
+        im[l0] = m[0] * x0i + m[1] * x0r + m[2] * x1i + m[3] * x1r;
+        re[l1] = m[4] * x0r - m[5] * x0i + m[6] * x1r - m[7] * x1i;
+        im[l1] = m[4] * x0i + m[5] * x0r + m[6] * x1i + m[7] * x1r;
+      }
     }
   }
   for (uint32_t k = 0; k < S.ntog; ++k) {

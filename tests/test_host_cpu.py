@@ -98,11 +98,12 @@ def test_emulated_lite_passes_rotations_and_cx(emul, opts):
     n = 13
     ops = random_layers(n, 6, seed=77, lam0=True)
     txt = capi.plan_describe(n, ops, opts)
-    if opts not in ("rot=0", "lite=0"):
-        assert "lite=1" in txt and "lite=0" not in txt
-        assert all(int(m) > 0 for m in re.findall(r"lite=1 steps=(\d+)", txt))
+    if opts != "lite=0":  # (rot=0: the same gates as real-class slots -> the all-class step kernel, lite=2)
+        want = "lite=2" if opts == "rot=0" else "lite=1"
+        assert want in txt and "lite=0" not in txt
+        assert all(int(m) > 0 for m in re.findall(r"lite=[12] steps=(\d+)", txt))
     else:
-        assert "lite=1" not in txt
+        assert "lite=1" not in txt and "lite=2" not in txt
     rng = np.random.default_rng(5)
     v = S.gen_state(n, rng)
     ref = S.run_ops(n, ops, v)

@@ -28,6 +28,8 @@ enum GateType : uint32_t {
   G_SWAP = 3,     // [[0,1],[1,0]]: pure permutation           0
   G_ROT = 4,      // rotation [[c,-s],[s,c]], c >= 0 (a scale / sign is pulled into the deferred
                   // scalar): three in-place shears            3
+  G_GENERAL1 = 5, // complex 2x2 scaled to m00 = 1 (the scale goes to the deferred scalar): 6 where no
+                  // flip can be pending; everywhere else it is just a G_GENERAL matrix
 };
 
 // One gate as the fused-pass kernel sees it (per round: register/thread/external split).
@@ -71,9 +73,9 @@ static_assert(sizeof(DevGate) == 112, "DevGate layout");
 // fetch, no dispatch tree, no jump table: per step ONE header read, per gate two constants.
 constexpr int kStepToggles = 4;
 constexpr int kMaxSteps = 72;  // steps per pass (kernel parameter space: 72 * 416 B + header < 32 KB)
-// slot kinds (4 bits per register bit in DevStep::kinds): class in bits 0-1, bit 2 = a flip may
+// slot kinds (4 bits per register bit in DevStep::kinds): class in bits 0-2, bit 3 = a flip may
 // be pending on that register bit (flip-aware flavour)
-enum : uint32_t { SLOT_NONE = 0, SLOT_ROT = 1, SLOT_REAL = 2, SLOT_GENERAL = 3, SLOT_FLIP = 4 };
+enum : uint32_t { SLOT_NONE = 0, SLOT_ROT = 1, SLOT_REAL = 2, SLOT_GENERAL = 3, SLOT_GENERAL1 = 4, SLOT_CLASS = 7, SLOT_FLIP = 8 };
 struct alignas(16) DevStep {
   double slot[kMaxRegBits][8];  // the 1-qubit gate on register bit J: ROT (t, s); REAL a b c d; GENERAL = DevGate::m
   uint32_t kinds;              // slot kind of register bit J in bits 4J .. 4J+3

@@ -99,6 +99,30 @@ __device__ __forceinline__ void gate_general(double (&re)[1 << R], double (&im)[
   gate_general_m<R, J, FL>(re, im, g.m, g.creg, ok_thr, f);
 }
 
+// general complex 2x2 scaled to m00 = 1 (uncontrolled, no flip pending): 12 instead of 16 FP64
+// operations per pair
+template <int R, int J>
+__device__ __forceinline__ void gate_general1_m(double (&re)[1 << R], double (&im)[1 << R], const double *m) {
+  const double Br = m[2], Bi = m[3], Cr = m[4], Ci = m[5], Dr = m[6], Di = m[7];
+#pragma unroll
+  for (int p = 0; p < (1 << (R - 1)); ++p) {
+    const int i0 = ((p >> J) << (J + 1)) | (p & ((1 << J) - 1));
+    const int i1 = i0 | (1 << J);
+    double Tr = Cr * re[i0];
+    double Ti = Cr * im[i0];
+    double P = fma(Br, re[i1], re[i0]);
+    double Q = fma(Br, im[i1], im[i0]);
+    Tr = fma(-Ci, im[i0], Tr);
+    Ti = fma(Ci, re[i0], Ti);
+    Tr = fma(-Di, im[i1], Tr);
+    Ti = fma(Di, re[i1], Ti);
+    re[i0] = fma(-Bi, im[i1], P);
+    im[i0] = fma(Bi, re[i1], Q);
+    re[i1] = fma(Dr, re[i1], Tr);
+    im[i1] = fma(Dr, im[i1], Ti);
+  }
+}
+
 template <int R, int J, int FL>
 __device__ __forceinline__ void gate_real_m(double (&re)[1 << R], double (&im)[1 << R], double a, double b, double c,
                                             double d, uint32_t creg_in, bool ok_thr, uint32_t f) {
@@ -354,9 +378,11 @@ __device__ __forceinline__ void step_slot(double (&re)[1 << R], double (&im)[1 <
   const uint32_t kind = (kinds >> (4 * J)) & 15u;
   if (kind == SLOT_NONE) return;
   const bool flip = (kind & SLOT_FLIP) != 0;
-  const uint32_t cls = kind & 3u;
+  const uint32_t cls = kind & SLOT_CLASS;
   if (ROT_ONLY || cls == SLOT_ROT) {
     step_rot<R, J>(re, im, S, f, flip);
+  } else if (cls == SLOT_GENERAL1) {
+    gate_general1_m<R, J>(re, im, S.slot[J]);
   } else if (cls == SLOT_REAL) {
     const double a = S.slot[J][0], b = S.slot[J][1], c = S.slot[J][2], d = S.slot[J][3];
     if (flip) gate_real_m<R, J, 1>(re, im, a, b, c, d, 0u, true, f);

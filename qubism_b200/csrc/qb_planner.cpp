@@ -159,6 +159,26 @@ static void set_rotation(Classified &c, double k, double cs, double sn) {
   c.phase[1] *= k;
 }
 
+// general complex 2x2 with a well-sized m00: divide by it (6 instead of 8 FP64 operations per
+// amplitude where no flip can be pending), the factor goes to the deferred scalar
+static Classified as_general1(Classified c, double bigabs) {
+  const double ar = c.m[0], ai = c.m[1], a2 = ar * ar + ai * ai;
+  if (!(a2 >= 0.25 * bigabs * bigabs) || !std::isfinite(a2)) return c;
+  const double mag = std::sqrt(a2);
+  if (mag < 0x1p-20 || mag > 0x1p20) return c;
+  for (int i = 1; i < 4; ++i) {  // x / a = x * conj(a) / |a|^2
+    const double xr = c.m[2 * i], xi = c.m[2 * i + 1];
+    c.m[2 * i] = (xr * ar + xi * ai) / a2;
+    c.m[2 * i + 1] = (xi * ar - xr * ai) / a2;
+  }
+  c.m[0] = 1.0;
+  c.m[1] = 0.0;
+  c.phase[0] = ar;
+  c.phase[1] = ai;
+  c.type = G_GENERAL1;
+  return c;
+}
+
 Classified classify_2x2(const double m[8], bool allow_phase_pull, bool allow_scale) {
   Classified c{};
   std::memcpy(c.m, m, sizeof(c.m));
@@ -205,7 +225,7 @@ Classified classify_2x2(const double m[8], bool allow_phase_pull, bool allow_sca
     const double xr = m[2 * i], xi = m[2 * i + 1];
     const double yr = xr * sr + xi * si;   // x * conj(s)
     const double yi = xi * sr - xr * si;
-    if (!(std::fabs(yi) <= tol)) return c;
+    if (!(std::fabs(yi) <= tol)) return allow_scale ? as_general1(c, bigabs) : c;
     r[i] = yr;
   }
   c.type = G_REAL;
@@ -827,7 +847,7 @@ static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &don
         const uint32_t fl = ctrl ? 2u : ((g.treg >> 8) & 1u);
         if (g.type == G_SWAP) g.op = (g.creg == 0) ? op_toggle(R) : op_swap_reg(R, J);
         else if (g.type == G_DIAG) g.op = (J < 8 && g.dreg) ? op_arith(R, C_DIAG_REG, fl, J) : op_diag_thr(R);
-        else g.op = op_arith(R, g.type == G_GENERAL ? C_GENERAL : (g.type == G_ROT ? C_ROT : C_REAL), fl, J);
+        else g.op = op_arith(R, (g.type == G_GENERAL || g.type == G_GENERAL1) ? C_GENERAL : (g.type == G_ROT ? C_ROT : C_REAL), fl, J);
         if (g.type == G_ROT) {  // shear coefficients from (cos, sin), cos >= 0 by classification
           const double cs = op.m[0], sn = op.m[4];
           std::memset(g.m, 0, sizeof(g.m));
@@ -846,7 +866,9 @@ static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &don
     for (uint32_t gi = 0; gi < gcount && lite; ++gi) {
       const DevGate &g = G[gi];
       const bool ctrl = (g.creg | g.cthr) != 0 || g.cext != 0;
-      if (!(g.type == G_SWAP || ((g.type == G_ROT || g.type == G_REAL || g.type == G_GENERAL) && !ctrl))) lite = false;
+      if (!(g.type == G_SWAP ||
+            ((g.type == G_ROT || g.type == G_REAL || g.type == G_GENERAL || g.type == G_GENERAL1) && !ctrl)))
+        lite = false;
     }
     std::vector<DevStep> steps;
     if (lite) {
@@ -887,7 +909,7 @@ static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &don
               kind = SLOT_REAL;
               for (int e = 0; e < 4; ++e) S.slot[J][e] = g.m[2 * e];
             } else {
-              kind = SLOT_GENERAL;
+              kind = (g.type == G_GENERAL1 && !((g.treg >> 8) & 1u)) ? SLOT_GENERAL1 : SLOT_GENERAL;
               std::memcpy(S.slot[J], g.m, sizeof(g.m));
             }
             if ((g.treg >> 8) & 1u) kind |= SLOT_FLIP;
@@ -924,7 +946,7 @@ static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &don
       bool rot_only = true;
       for (const DevStep &st : steps)
         for (int J = 0; J < kMaxRegBits; ++J) {
-          const uint32_t cls = (st.kinds >> (4 * J)) & 3u;
+          const uint32_t cls = (st.kinds >> (4 * J)) & SLOT_CLASS;
           if (cls != SLOT_NONE && cls != SLOT_ROT) rot_only = false;
         }
       P->lite = rot_only ? 1u : 2u;  // which step-kernel instantiation (qb_kernels.cu)
@@ -995,10 +1017,10 @@ std::string describe_plan(const PlanResult &r) {
         else if ((d.treg >> 8) & 1) kinds[3]++;                    // uncontrolled, flip-aware
         else kinds[4]++;                                           // plain
       }
-      int types[5] = {0};
-      for (int g = 0; g < p.ngates; ++g) types[G[g].type < 5 ? G[g].type : 0]++;
-      os << " types[general,real,diag,swap,rot]=" << types[0] << "," << types[1] << "," << types[2] << "," << types[3] << ","
-         << types[4];
+      int types[6] = {0};
+      for (int g = 0; g < p.ngates; ++g) types[G[g].type < 6 ? G[g].type : 0]++;
+      os << " types[general,real,diag,swap,rot,general1]=" << types[0] << "," << types[1] << "," << types[2] << "," << types[3]
+         << "," << types[4] << "," << types[5];
       os << " kinds[toggle,regswap,ctrl,flipaware,plain]=" << kinds[0] << "," << kinds[1] << "," << kinds[2] << ","
          << kinds[3] << "," << kinds[4];
     }

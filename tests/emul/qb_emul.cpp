@@ -80,13 +80,13 @@ void apply_step_host(std::vector<double> &re, std::vector<double> &im, int R, co
   const int NR = 1 << R;
   for (int J = 0; J < R; ++J) {
     const uint32_t kind = (S.kinds >> (4 * J)) & 15u;
-    if ((kind & 3u) == SLOT_NONE) continue;
+    if ((kind & SLOT_CLASS) == SLOT_NONE) continue;
     const bool fl = (f >> J) & 1u;
     if (fl && !(kind & SLOT_FLIP)) std::fprintf(stderr, "emulator: flip pending on a slot the planner marked flip-free\n");
     const double *m = S.slot[J];
     for (int p = 0; p < NR / 2; ++p) {
       const int i0 = ((p >> J) << (J + 1)) | (p & ((1 << J) - 1)), i1 = i0 | (1 << J);
-      if ((kind & 3u) == SLOT_ROT) {
+      if ((kind & SLOT_CLASS) == SLOT_ROT) {
         const double t = fl ? -m[0] : m[0], s = fl ? -m[1] : m[1];
         re[i0] = std::fma(t, re[i1], re[i0]);
         im[i0] = std::fma(t, im[i1], im[i0]);
@@ -99,7 +99,9 @@ void apply_step_host(std::vector<double> &re, std::vector<double> &im, int R, co
       // logical pair: register i holds logical index i ^ f
       const int l0 = fl ? i1 : i0, l1 = fl ? i0 : i1;
       const double x0r = re[l0], x0i = im[l0], x1r = re[l1], x1i = im[l1];
-      if ((kind & 3u) == SLOT_REAL) {
+      if ((kind & SLOT_CLASS) == SLOT_GENERAL1 && (fl || m[0] != 1.0 || m[1] != 0.0))
+        std::fprintf(stderr, "emulator: scaled-general slot with a pending flip or m00 != 1\n");
+      if ((kind & SLOT_CLASS) == SLOT_REAL) {
         re[l0] = m[0] * x0r + m[1] * x1r;
         im[l0] = m[0] * x0i + m[1] * x1i;
         re[l1] = m[2] * x0r + m[3] * x1r;

@@ -171,6 +171,9 @@ typedef struct {
                                launching stream), accumulated while option "time_kernels"=1 */
   uint64_t fused_timed;     /* number of fused launches that were timed                    */
   uint64_t tiles;           /* tiles the fused passes visited (all-zero tiles are skipped)  */
+  uint64_t jit_compiled;    /* pass structures compiled into specialised kernels (option "jit") */
+  uint64_t jit_launches;    /* fused passes that ran as a specialised kernel                 */
+  double jit_compile_ms;    /* host time spent in NVRTC + module load                        */
 } qb_stats;
 int qb_get_stats(const qb_ctx *ctx, qb_stats *out);
 int qb_reset_stats(qb_ctx *ctx);
@@ -179,8 +182,10 @@ void *qb_ctx_stream(qb_ctx *ctx);
 /* Tuning knobs: "tile_bits", "reg_bits", "low_bits", "lane_fixed", "max_rounds",
  * "max_pass_gates", "peephole", "fuse" (0 = one pass per op), "rot" (rotations as shears),
  * "lite" (step-packed passes), "skip_dead" (skip all-zero tiles using the tracked support),
- * "time_kernels" (bracket every fused launch with CUDA events).  Returns QB_ERR_ARG for unknown
- * names / bad values. */
+ * "time_kernels" (bracket every fused launch with CUDA events), "jit" (k > 0: a pass structure
+ * seen k times is compiled with NVRTC into a straight-line kernel -- structure as literals, gate
+ * coefficients still kernel parameters -- and cached; 0 = generic kernels only).  Returns
+ * QB_ERR_ARG for unknown names / bad values. */
 int qb_set_option(qb_ctx *ctx, const char *name, int64_t value);
 int64_t qb_get_option(const qb_ctx *ctx, const char *name);
 /* Host-only planner entry point (no device needed): plan `nops` ops for an n-qubit local
@@ -188,6 +193,11 @@ int64_t qb_get_option(const qb_ctx *ctx, const char *name);
  * Returns the number of bytes the full plan needs (snprintf-style) or a negative status. */
 int64_t qb_plan_describe(int nlocal, const qb_op *ops, int64_t nops, const char *options,
                          char *buf, int64_t buflen);
+
+/* Host-only check of the specialised-kernel toolchain (no device needed): compile `src` (CUDA C++)
+ * with NVRTC for sm_100a; *cubin_bytes = size of the resulting cubin.  QB_ERR_UNSUPPORTED if
+ * libnvrtc cannot be loaded, QB_ERR_CUDA if the compilation fails (log in qb_last_error). */
+int qb_jit_compile_check(const char *src, int64_t *cubin_bytes);
 
 #ifdef __cplusplus
 }

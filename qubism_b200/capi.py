@@ -36,7 +36,8 @@ class QbStats(C.Structure):
     _fields_ = [("ops_submitted", C.c_uint64), ("ops_folded", C.c_uint64), ("ops_executed", C.c_uint64),
                 ("passes", C.c_uint64), ("rounds", C.c_uint64), ("simple_launches", C.c_uint64),
                 ("reduce_launches", C.c_uint64), ("exchange_bytes", C.c_uint64), ("exchanges", C.c_uint64),
-                ("plan_ms", C.c_double), ("fused_ms", C.c_double), ("fused_timed", C.c_uint64), ("tiles", C.c_uint64)]
+                ("plan_ms", C.c_double), ("fused_ms", C.c_double), ("fused_timed", C.c_uint64), ("tiles", C.c_uint64),
+                ("jit_compiled", C.c_uint64), ("jit_launches", C.c_uint64), ("jit_compile_ms", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -91,6 +92,7 @@ SIGNATURES = {
     "qb_set_option": (_I, [_VP, C.c_char_p, _I64]),
     "qb_get_option": (_I64, [_VP, C.c_char_p]),
     "qb_plan_describe": (_I64, [_I, C.POINTER(QbOp), _I64, C.c_char_p, C.c_char_p, _I64]),
+    "qb_jit_compile_check": (_I, [C.c_char_p, C.POINTER(_I64)]),
 }
 
 _lib = None

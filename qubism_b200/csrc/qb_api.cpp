@@ -16,6 +16,7 @@
 
 #include "qb_dist.h"
 #include "qb_internal.h"
+#include "qb_jit.h"
 #include "qb_kernels.h"
 
 using namespace qb;
@@ -82,6 +83,10 @@ struct qb_state {
   // true amplitudes = pscale * device amplitudes.  Reductions apply it arithmetically; everything
   // that exposes raw amplitudes forces it first (force_scale).
   double pscale[2] = {1.0, 0.0};
+  // real factor the structure-specialised passes of the running flush left out of the device
+  // amplitudes (their rotations defer a cosine each, qb_jit.cpp): taken by the flush's last
+  // pass, or folded into pscale when the flush ends
+  double jit_left = 1.0;
   bool all_finite = false;  // no NaN / inf can be in the amplitudes (created here, only finite gates since)
 };
 
@@ -104,7 +109,7 @@ int init_common(qb_ctx *c) {
   QB_CUDA(cudaMallocHost(&c->red_host, sizeof(double) * 4));
   QB_CUDA(cudaMalloc(&c->kq_bits_dev, sizeof(int) * 2 * QB_MAX_KQ));
   QB_CUDA(cudaMalloc(&c->kq_mat_dev, sizeof(double2) << (2 * QB_MAX_KQ)));
-  for (const char *name : {"tile_bits", "reg_bits", "low_bits", "max_rounds", "peephole", "fuse", "max_pass_gates", "l2_prefetch", "avoid_regswap", "hot_bits", "rot", "lite", "dbg_skip", "lane_fixed", "skip_dead", "support"}) {
+  for (const char *name : {"tile_bits", "reg_bits", "low_bits", "max_rounds", "peephole", "fuse", "max_pass_gates", "l2_prefetch", "avoid_regswap", "hot_bits", "rot", "lite", "dbg_skip", "lane_fixed", "skip_dead", "support", "jit"}) {
     std::string env = "QB_";
     for (const char *p = name; *p; ++p) env.push_back((char)toupper(*p));
     const char *v = getenv(env.c_str());
@@ -271,7 +276,8 @@ static bool finite8(const double *m) {
   return true;
 }
 
-int run_fused_segment(qb_state *s, std::vector<const HostOp *> seg, const double *gscale, bool *gscale_done) {
+int run_fused_segment(qb_state *s, std::vector<const HostOp *> seg, const double *gscale, bool *gscale_done,
+                      bool final_seg = false) {
   qb_ctx *c = s->ctx;
   int T, R;
   effective_tile(c->opt, s->L, T, R);
@@ -310,24 +316,94 @@ int run_fused_segment(qb_state *s, std::vector<const HostOp *> seg, const double
     auto t0 = std::chrono::steady_clock::now();
     PlanResult plan = plan_passes(pops, s->L, c->rank, opt, nullptr);
     const bool all = plan.consumed == seg.size();
-    if (all && gscale && !*gscale_done && !plan.passes.empty()) {
-      DevPass *P = reinterpret_cast<DevPass *>(plan.passes.back().blob.data());
-      P->gscale[0] = gscale[0];
-      P->gscale[1] = gscale[1];
-      P->has_gscale = 1;
+    c->stats.plan_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    // ---- which passes run as structure-specialised kernels (qb_jit.cpp).  Every rank takes the
+    // same decisions (same plans, same sighting counts): the factors those kernels leave out
+    // must be the same on every shard, because exchanges move raw device amplitudes.
+    const int jit_thr = (c->opt.jit > 0 && !c->opt.dbg_skip) ? c->opt.jit : 0;
+    const size_t npass = plan.passes.size();
+    // the flush's last pass takes the pending scalar (and whatever the specialised passes leave out)
+    const bool finish = all && final_seg && npass > 0;
+    double gfin[2] = {1.0, 0.0};
+    bool want_gfin = false;
+    if (finish && gscale && !*gscale_done) {
+      gfin[0] = gscale[0];
+      gfin[1] = gscale[1];
+      want_gfin = true;
       *gscale_done = true;
     }
-    c->stats.plan_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    for (const PassPlan &p : plan.passes) {
+    if (finish && jit_thr) want_gfin = true;  // (has_gscale is part of a pass's STRUCTURE: keep it stable)
+    if (want_gfin) reinterpret_cast<DevPass *>(plan.passes.back().blob.data())->has_gscale = 1;
+    std::vector<void *> jit_handle(npass, nullptr);
+    std::vector<JitProgram> jit_prog(npass);
+    std::vector<double> mid_scale(npass, 0.0);  // != 0: this (not last) pass applies the running factor (range guard)
+    if (jit_thr) {
+      for (size_t i = 0; i < npass; ++i) {
+        PassPlan &p = plan.passes[i];
+        std::string err;
+        if (!jit_generate(p, JIT_KEY_ONLY, jit_prog[i], nullptr)) continue;
+        DevPass *P = reinterpret_cast<DevPass *>(p.blob.data());
+        const bool last = finish && i + 1 == npass;
+        if (!last && !P->has_gscale && !(std::fabs(s->jit_left * jit_prog[i].left_out) > 0x1p-300)) {
+          // keep the stored amplitudes inside the exponent range: apply the factor here
+          P->has_gscale = 1;
+          P->gscale[0] = 1.0;
+          P->gscale[1] = 0.0;
+          if (!jit_generate(p, JIT_KEY_ONLY, jit_prog[i], nullptr)) continue;
+          mid_scale[i] = 1.0;
+        }
+        const int jr = jit_lookup(jit_prog[i], p, jit_thr, &jit_handle[i], &err);
+        if (jr < 0) {
+          if (c->nranks > 1) return fail(QB_ERR_CUDA, "specialised kernel: %s", err.c_str());
+          jit_handle[i] = nullptr;  // single GPU: the generic kernel computes the same thing
+        }
+        if (jit_handle[i]) {
+          s->jit_left *= jit_prog[i].left_out;
+          if (mid_scale[i] != 0.0) {
+            mid_scale[i] = s->jit_left;
+            s->jit_left = 1.0;
+          }
+        } else if (mid_scale[i] != 0.0) {
+          mid_scale[i] = 1.0;  // generic kernel after all: it scales by one
+        }
+      }
+    }
+    if (finish) {
+      gfin[0] *= s->jit_left;
+      gfin[1] *= s->jit_left;
+      s->jit_left = 1.0;
+      if (want_gfin) {
+        DevPass *P = reinterpret_cast<DevPass *>(plan.passes.back().blob.data());
+        P->gscale[0] = gfin[0];
+        P->gscale[1] = gfin[1];
+      }
+    }
+    for (size_t i = 0; i < npass; ++i) {
+      const PassPlan &p = plan.passes[i];
       cudaEvent_t e0 = nullptr, e1 = nullptr;
       if (c->opt.time_kernels) {
         QB_TRY(get_event(c, &e0));
         QB_TRY(get_event(c, &e1));
         QB_CUDA(cudaEventRecord(e0, c->stream));
       }
-      if (!rank_dead)
-        QB_CUDA(launch_fused_pass(s->amps, p.blob.data(), (uint32_t)p.blob.size(), p.tile_bits, p.reg_bits, p.ntiles,
-                                  c->sm_count, c->stream, nullptr));
+      if (!rank_dead) {
+        if (jit_handle[i]) {
+          const DevPass *P = reinterpret_cast<const DevPass *>(p.blob.data());
+          double gs[2] = {P->gscale[0], P->gscale[1]};
+          if (mid_scale[i] != 0.0) {
+            gs[0] = mid_scale[i];
+            gs[1] = 0.0;
+          }
+          if (!P->has_gscale) gs[0] = 1.0, gs[1] = 0.0;
+          std::string err;
+          const std::vector<uint8_t> args = jit_pack_args(jit_prog[i], gs, P->rank_bits, P->base_fixed);
+          if (jit_launch(jit_handle[i], s->amps, p.ntiles, args, c->sm_count, c->stream, &err) != 0)
+            return fail(QB_ERR_CUDA, "%s", err.c_str());
+        } else {
+          QB_CUDA(launch_fused_pass(s->amps, p.blob.data(), (uint32_t)p.blob.size(), p.tile_bits, p.reg_bits, p.ntiles,
+                                    c->sm_count, c->stream, nullptr));
+        }
+      }
       c->stats.tiles += rank_dead ? 0 : p.ntiles;
       if (e0) {
         QB_CUDA(cudaEventRecord(e1, c->stream));
@@ -435,11 +511,16 @@ int flush_ops_locked(qb_state *s) {
       }
       if (rc == QB_OK) rc = run_simple(s, op);
     }
-    if (rc == QB_OK && !seg.empty()) rc = run_fused_segment(s, seg, has_g ? g : nullptr, &g_done);
+    if (rc == QB_OK && !seg.empty()) rc = run_fused_segment(s, seg, has_g ? g : nullptr, &g_done, true);
   }
   if (rc == QB_OK && g_done) {
     s->pscale[0] = 1.0;
     s->pscale[1] = 0.0;
+  }
+  if (s->jit_left != 1.0) {  // specialised passes ran but no last pass took their factor: it stays pending
+    s->pscale[0] *= s->jit_left;
+    s->pscale[1] *= s->jit_left;
+    s->jit_left = 1.0;
   }
   support_after_ops(s);
   q.clear();
@@ -1005,6 +1086,10 @@ int qb_get_stats(const qb_ctx *cc, qb_stats *out) {
   Guard g(c);
   QB_TRY(resolve_timed(c));
   *out = c->stats;
+  const JitStats js = jit_stats();  // (process-wide: one process per GPU)
+  out->jit_compiled = js.compiled;
+  out->jit_launches = js.launches;
+  out->jit_compile_ms = js.compile_ms;
   return QB_OK;
 }
 
@@ -1028,6 +1113,18 @@ int qb_set_option(qb_ctx *c, const char *name, int64_t value) {
 int64_t qb_get_option(const qb_ctx *c, const char *name) {
   if (!c || !name) return QB_ERR_ARG;
   return get_opt(c->opt, name);
+}
+
+int qb_jit_compile_check(const char *src, int64_t *cubin_bytes) {
+  if (!src) return fail(QB_ERR_ARG, "null argument");
+  std::string why;
+  size_t nbytes = 0;
+  if (!jit_compile_only(src, &nbytes, &why)) {
+    const bool missing = why.find("libnvrtc") != std::string::npos;
+    return fail(missing ? QB_ERR_UNSUPPORTED : QB_ERR_CUDA, "%s", why.c_str());
+  }
+  if (cubin_bytes) *cubin_bytes = (int64_t)nbytes;
+  return QB_OK;
 }
 
 int64_t qb_plan_describe(int nlocal, const qb_op *ops, int64_t nops, const char *options, char *buf,

@@ -175,6 +175,8 @@ struct PlanOptions {
   uint64_t known_val = 0;   // ... and that value: tiles that contradict it are all zero and are skipped
   int lane_fixed = 0;     // low tile bits that stay on lanes in the load / store rounds (1..3)
   int lite = 1;           // passes of rotations and X / CX only use the lean kernel instantiation
+  int jit = 2;            // k > 0: a step-pass STRUCTURE seen k times is compiled (NVRTC) into a straight-line
+                          // kernel and cached (qb_jit.cpp); 0 = generic kernels only
   int hot_bits = 0;       // planner: max distinct TARGET bits per pass (0 = tile_bits).  With
                           // hot_bits <= tile_bits - warp bits every transpose can stay warp-local.
 };

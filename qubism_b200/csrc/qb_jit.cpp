@@ -1,0 +1,717 @@
+// Structure-specialised fused passes: generator (host only) + NVRTC runtime.  See qb_jit.h.
+#include "qb_jit.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <sstream>
+
+namespace qb {
+
+static const char kPrelude[] =
+#include "qb_jit_prelude.inc"
+    ;
+const char *jit_prelude() { return kPrelude; }
+
+namespace {
+
+// Every literal that shapes the generated code goes through lit(): it is appended to the
+// structural key whether or not source text is being produced, so equal keys mean equal source.
+struct Gen {
+  bool want_src = false, host = false;
+  std::string key;
+  std::ostringstream o;
+  std::ostringstream *cur = &o;  // where line() / barrier() write
+  std::vector<double> coefs;
+  double left_out = 1.0;
+
+  void k64(uint64_t v) { key.append(reinterpret_cast<const char *>(&v), sizeof(v)); }
+  std::string lit(uint64_t v, const char *suffix = "u") {
+    k64(v);
+    if (!want_src) return std::string();
+    char b[40];
+    std::snprintf(b, sizeof(b), "0x%llx%s", (unsigned long long)v, suffix);
+    return b;
+  }
+  std::string dec(int64_t v) {
+    k64((uint64_t)v);
+    if (!want_src) return std::string();
+    return std::to_string(v);
+  }
+  void tag(const char *t) {  // a structural choice without a number (which helper is called)
+    key.append(t);
+    key.push_back('\0');
+  }
+  int coef(double v) {
+    coefs.push_back(v);
+    return (int)coefs.size() - 1;
+  }
+  void line(const std::string &s) {
+    if (want_src) *cur << "    " << s << "\n";
+  }
+  // a barrier between thread phases: the host emulation runs the threads of a CTA one after the
+  // other, phase by phase
+  void barrier(bool warp_only) {
+    tag(warp_only ? "bw" : "bc");
+    if (!want_src) return;
+    if (host) *cur << "  }\n  for (u32 tid = 0; tid < QBJ_NT; ++tid) {\n    QBJ_THREAD_REFS\n";
+    else *cur << (warp_only ? "    __syncwarp();\n" : "    __syncthreads();\n");
+  }
+};
+
+std::string reg_offset_expr(Gen &g, const DevPass &P, const DevRound &rd, int R, int i, int from_bit, const char *op) {
+  // XOR / sum of the global strides of the set register bits of i (bits >= from_bit)
+  uint64_t off = 0;
+  for (int j = from_bit; j < R; ++j)
+    if ((i >> j) & 1) off |= 1ull << P.tile_pos[rd.reg_pos[j]];
+  (void)op;
+  return g.lit(off, "ull");
+}
+
+}  // namespace
+
+bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string *why) {
+  auto fail = [&](const char *m) {
+    if (why) *why = m;
+    return false;
+  };
+  if (pp.blob.size() < sizeof(DevPass)) return fail("short blob");
+  const DevPass &P = *reinterpret_cast<const DevPass *>(pp.blob.data());
+  if (P.lite == 0) return fail("not a step (lite) pass");
+  if (P.dbg_skip) return fail("profiling switches set");
+  if (pp.blob.size() < sizeof(DevPass) + size_t(P.nsteps) * sizeof(DevStep)) return fail("short blob");
+  const DevStep *S = reinterpret_cast<const DevStep *>(pp.blob.data() + sizeof(DevPass));
+  const int T = (int)P.tile_bits, R = (int)P.reg_bits, NT = 1 << (T - R), NR = 1 << R;
+  const int nrounds = (int)P.nrounds;
+  if (R < 3 || R > kMaxRegBits || T > kMaxTileBits || T - R > 10 || nrounds < 1 || nrounds > kMaxRounds)
+    return fail("unsupported geometry");
+  if (!(P.tile_pos[0] == 0 && P.tile_pos[1] == 1 && P.tile_pos[2] == 2)) return fail("tile without the low line bits");
+
+  Gen g;
+  g.want_src = emit != JIT_KEY_ONLY;
+  g.host = emit == JIT_HOST_SRC;
+  g.tag("qbj1");
+  const size_t smem = (size_t(16) << T) + size_t(nrounds) * NT * sizeof(uint16_t) + size_t(2) * NT * sizeof(uint64_t) +
+                      (size_t(1) << (T - 3)) * sizeof(uint32_t);
+  int minb;
+  {
+    const int regs_wanted = 4 * NR + 64;
+    const int by_regs = 65536 / (NT * regs_wanted);
+    const int by_smem = (int)((227u * 1024u) / (smem + 1024));
+    minb = std::max(1, std::min(std::min(by_regs, by_smem), 8));
+  }
+  const std::string sT = g.dec(T), sR = g.dec(R), sNT = g.dec(NT), sMINB = g.dec(minb), sNROUNDS = g.dec(nrounds);
+  const int l2pf = (int)P.l2_prefetch;
+  const std::string sL2 = g.dec(l2pf);
+  const bool has_gs = P.has_gscale != 0;
+  g.dec(has_gs);
+  const int LPT = 1 << (R - 3);
+
+  // ---------------------------------------------------------------- fragments shared by both modes
+  auto tid_bits_expr = [&](const DevRound &rd, bool phys, const char *var) {
+    // OR of ((var >> j) & 1) << position, positions as literals
+    std::string e;
+    for (int j = 0; j < T - R; ++j) {
+      const uint64_t pos = phys ? P.tile_pos[rd.tid_pos[j]] : rd.tid_pos[j];
+      const std::string sp = g.dec((int64_t)pos);
+      if (!g.want_src) continue;
+      if (!e.empty()) e += " | ";
+      e += phys ? "((u64)((" : "(((";
+      e += var;
+      e += " >> " + std::to_string(j) + ") & 1u) << " + sp + ")";
+    }
+    return e;
+  };
+  auto deposit = [&](const char *dst, const char *id) {
+    // dst = tile id scattered into the free non-tile bit runs | A.base_fixed
+    g.line(std::string("{ u64 t_ = ") + id + "; " + dst + " = A.base_fixed;");
+    for (uint32_t k = 0; k < P.nruns; ++k) {
+      const std::string len = g.dec(P.run_len[k]), sh = g.dec(P.run_shift[k]);
+      g.line(std::string("  ") + dst + " |= (t_ & ((1ull << " + len + ") - 1ull)) << " + sh + "; t_ >>= " + len + ";");
+    }
+    g.line("}");
+  };
+  const DevRound &R0 = P.rounds[0];
+  const DevRound &RL = P.rounds[nrounds - 1];
+  auto stride_of = [&](const DevRound &rd, int j) { return 1ull << P.tile_pos[rd.reg_pos[j]]; };
+
+  auto emit_tables = [&]() {
+    for (int r = 0; r < nrounds; ++r)
+      g.line("sidx_tab[" + std::to_string(r) + " * QBJ_NT + tid] = (u16)qbj_swz(" + tid_bits_expr(P.rounds[r], false, "tid") + ");");
+    g.line("goff_tab[tid] = " + tid_bits_expr(R0, true, "tid") + ";");
+    g.line("goff_tab[QBJ_NT + tid] = " + tid_bits_expr(RL, true, "tid") + ";");
+    for (int k = 0; k < LPT; ++k) {
+      std::string e;
+      for (int j = 0; j < T - 3; ++j) {
+        const std::string sp = g.dec(P.tile_pos[3 + j]);
+        if (!g.want_src) continue;
+        if (!e.empty()) e += " | ";
+        e += "((u64)(((tid + " + std::to_string(k) + "u * QBJ_NT) >> " + std::to_string(j) + ") & 1u) << " + sp + ")";
+      }
+      g.line("line_tab[" + std::to_string(k) + " * QBJ_NT + tid] = (u32)((" + e + ") >> 3);");
+    }
+  };
+
+  auto emit_load = [&]() {
+    g.tag("ld");
+    g.line("{ const u64 src_ = base + goff_tab[tid];");
+    if (stride_of(R0, 0) == 1ull) {
+      g.tag("p");
+      for (int i = 0; i < NR; i += 2) g.line("  QBJ_LD2(src_ + " + reg_offset_expr(g, P, R0, R, i, 1, "+") + ", " + std::to_string(i) + ");");
+    } else {
+      for (int i = 0; i < NR; ++i) g.line("  QBJ_LD1(src_ + " + reg_offset_expr(g, P, R0, R, i, 0, "+") + ", " + std::to_string(i) + ");");
+    }
+    g.line("}");
+  };
+  // mf: register bits on which a flip may be pending in some thread
+  auto emit_store = [&](uint32_t mf) {
+    g.tag("st");
+    g.dec(mf);
+    g.line("{ u64 fx_ = 0;");
+    for (int j = 0; j < R; ++j)
+      if ((mf >> j) & 1u)
+        g.line("  fx_ |= ((f >> " + std::to_string(j) + ") & 1u) ? " + g.lit(stride_of(RL, j), "ull") + " : 0ull;");
+    if (stride_of(RL, 0) == 1ull) {
+      g.tag("p");
+      g.line("  const u64 at_ = (base + goff_tab[QBJ_NT + tid]) ^ (fx_ & ~1ull);");
+      const bool sw = (mf & 1u) != 0;
+      if (sw) g.line("  const bool sw_ = (f & 1u) != 0;");
+      for (int i = 0; i < NR; i += 2) {
+        const std::string a = std::to_string(i), b = std::to_string(i + 1);
+        const std::string off = reg_offset_expr(g, P, RL, R, i, 1, "^");
+        if (sw)
+          g.line("  QBJ_ST2(at_ ^ " + off + ", sw_ ? re[" + b + "] : re[" + a + "], sw_ ? im[" + b + "] : im[" + a + "], sw_ ? re[" + a +
+                 "] : re[" + b + "], sw_ ? im[" + a + "] : im[" + b + "]);");
+        else
+          g.line("  QBJ_ST2(at_ ^ " + off + ", re[" + a + "], im[" + a + "], re[" + b + "], im[" + b + "]);");
+      }
+    } else {
+      g.line("  const u64 at_ = (base + goff_tab[QBJ_NT + tid]) ^ fx_;");
+      for (int i = 0; i < NR; ++i)
+        g.line("  QBJ_ST1(at_ ^ " + reg_offset_expr(g, P, RL, R, i, 0, "^") + ", re[" + std::to_string(i) + "], im[" + std::to_string(i) + "]);");
+    }
+    g.line("}");
+  };
+  auto sx_of = [&](const DevRound &rd, int i) {
+    uint32_t c = 0;
+    for (int j = 0; j < R; ++j)
+      if ((i >> j) & 1) c ^= rd.reg_sx[j] << 4;
+    return c;
+  };
+
+  // ---------------------------------------------------------------- the rounds (both modes)
+  uint32_t mf_end = 0;  // flips possibly pending when the last round ends
+  bool bad = false;
+  auto emit_rounds = [&]() {
+    uint32_t mf = 0;
+    for (int r = 0; r < nrounds; ++r) {
+      const DevRound &RD = P.rounds[r];
+      if (r > 0) {
+        const DevRound &PR = P.rounds[r - 1];
+        const bool local = RD.warp_local != 0;
+        const std::string sr = std::to_string(r);
+        g.tag("tr");
+        g.dec(mf);
+        if (local) g.barrier(true);  // (the lanes of this warp finished reading the previous layout)
+        g.line("u32 us" + sr + " = (u32)sidx_tab[" + std::to_string(r - 1) + " * QBJ_NT + tid] << 4;");
+        for (int j = 0; j < R; ++j)
+          if ((mf >> j) & 1u)
+            g.line("us" + sr + " ^= (0u - ((f >> " + std::to_string(j) + ") & 1u)) & " + g.lit(PR.reg_sx[j] << 4) + ";");
+        g.line("f = 0;");
+        mf = 0;
+        for (int i = 0; i < NR; ++i)
+          g.line("QBJ_STS(us" + sr + " ^ " + g.lit(sx_of(PR, i)) + ", re[" + std::to_string(i) + "], im[" + std::to_string(i) + "]);");
+        g.barrier(local);
+        g.line("const u32 ul" + sr + " = (u32)sidx_tab[" + sr + " * QBJ_NT + tid] << 4;");
+        for (int i = 0; i < NR; ++i) g.line("QBJ_LDS(ul" + sr + " ^ " + g.lit(sx_of(RD, i)) + ", " + std::to_string(i) + ");");
+        // free the buffer for the next CTA-wide transpose (of this tile, or the first of the next)
+        if (P.rounds[(r + 1 < nrounds) ? r + 1 : 1].warp_local == 0) g.barrier(false);
+      }
+      for (uint32_t si = RD.step_begin; si < RD.step_end; ++si) {
+        const DevStep &st = S[si];
+        for (int J = 0; J < R; ++J) {
+          const uint32_t kind = (st.kinds >> (4 * J)) & 15u;
+          const uint32_t cls = kind & SLOT_CLASS;
+          if (cls == SLOT_NONE) continue;
+          const bool flip = ((mf >> J) & 1u) != 0;
+          if (flip && !(kind & SLOT_FLIP)) bad = true;  // the planner says no flip can be pending here
+          const std::string sJ = std::to_string(J);
+          if (cls == SLOT_ROT) {
+            const double cs = st.slot[J][2], sn = st.slot[J][3];
+            if (!(cs >= 0.0) || !std::isfinite(cs) || !std::isfinite(sn) || !(cs * cs + sn * sn > 0.5)) bad = true;
+            const bool formA = std::fabs(sn) <= cs;
+            if (formA) {
+              const int k = g.coef(sn / cs);
+              g.left_out *= cs;
+              if (flip) {
+                g.tag("raf");
+                g.line("qbj_rot_a_flip<" + g.dec(J) + ">(re, im, A.c[" + g.dec(k) + "], f);");
+              } else {
+                g.tag("ra");
+                g.line("qbj_rot_a<" + g.dec(J) + ">(re, im, A.c[" + g.dec(k) + "]);");
+              }
+            } else if (!flip) {
+              const int k = g.coef(cs / sn);
+              g.left_out *= sn;
+              g.tag("rb");
+              g.line("qbj_rot_b<" + g.dec(J) + ">(re, im, A.c[" + g.dec(k) + "]);");
+            } else {
+              const int k = g.coef(st.slot[J][0]);
+              g.coef(st.slot[J][1]);
+              g.tag("r3f");
+              g.line("qbj_rot3_flip<" + g.dec(J) + ">(re, im, A.c[" + g.dec(k) + "], A.c[" + std::to_string(k + 1) + "], f);");
+            }
+          } else if (cls == SLOT_REAL) {
+            const int k = g.coef(st.slot[J][0]);
+            for (int e = 1; e < 4; ++e) g.coef(st.slot[J][e]);
+            g.tag("re");
+            g.line("qbj_real<" + g.dec(J) + ", " + g.dec(flip ? 1 : 0) + ">(re, im, &A.c[" + g.dec(k) + "], f);");
+          } else if (cls == SLOT_GENERAL || cls == SLOT_GENERAL1) {
+            const int k = g.coef(st.slot[J][0]);
+            for (int e = 1; e < 8; ++e) g.coef(st.slot[J][e]);
+            if (cls == SLOT_GENERAL1 && !flip) {
+              g.tag("g1");
+              g.line("qbj_general1<" + g.dec(J) + ">(re, im, &A.c[" + g.dec(k) + "]);");
+            } else {
+              g.tag("ge");
+              g.line("qbj_general<" + g.dec(J) + ", " + g.dec(flip ? 1 : 0) + ">(re, im, &A.c[" + g.dec(k) + "], f);");
+            }
+          } else {
+            bad = true;
+          }
+          (void)sJ;
+        }
+        if (st.ntog > (uint32_t)kStepToggles) bad = true;
+        for (uint32_t k = 0; k < st.ntog && k < (uint32_t)kStepToggles; ++k) {
+          const auto &tg = st.tog[k];
+          if ((int)tg.bit >= R) bad = true;
+          if (tg.cthr == 0 && tg.cext == 0) {  // uncontrolled X: a renaming
+            g.tag("xa");
+            g.line("qbj_swap_all<" + g.dec(tg.bit) + ">(re, im);");
+            continue;
+          }
+          g.tag("tg");
+          std::string cond;
+          const std::string sth = g.lit(tg.cthr), sex = g.lit(tg.cext, "ull");
+          if (tg.cthr) cond = "((tid & " + sth + ") == " + sth + ")";
+          if (tg.cext) cond += std::string(cond.empty() ? "" : " && ") + "((basefull & " + sex + ") == " + sex + ")";
+          g.line("f ^= (" + cond + ") ? " + g.lit(1u << tg.bit) + " : 0u;");
+          mf |= 1u << tg.bit;
+        }
+        if (st.swap_j != 0xffu) {
+          const int J = (int)(st.swap_j & 7u);
+          if (J >= R || st.swap_creg == 0 || (st.swap_creg >> R) != 0 || ((st.swap_creg >> J) & 1u)) bad = true;
+          const bool stat = __builtin_popcount(st.swap_creg) == 1 && st.swap_cthr == 0 && st.swap_cext == 0 && !(mf & st.swap_creg);
+          if (stat) {
+            g.tag("ss");
+            g.line("qbj_swap_static<" + g.dec(J) + ", " + g.dec(__builtin_ctz(st.swap_creg)) + ">(re, im);");
+          } else {
+            g.tag("sd");
+            std::string cond = "true";
+            const std::string sth = g.lit(st.swap_cthr), sex = g.lit(st.swap_cext, "ull");
+            if (st.swap_cthr) cond = "((tid & " + sth + ") == " + sth + ")";
+            if (st.swap_cext) cond += " && ((basefull & " + sex + ") == " + sex + ")";
+            g.line("qbj_swap_dyn<" + g.dec(J) + ">(re, im, " + g.lit(st.swap_creg) + ", " + cond + ", f);");
+          }
+        }
+      }
+    }
+    mf_end = mf;
+    if (has_gs) g.line("qbj_scale(re, im, A.gs[0], A.gs[1]);");
+  };
+
+  // ---------------------------------------------------------------- assemble
+  if (!g.want_src) {
+    // key only: walk every fragment once (order irrelevant as long as it is fixed)
+    emit_tables();
+    deposit("base", "tile_id");
+    emit_load();
+    emit_rounds();
+    emit_store(mf_end);
+  } else {
+    std::ostringstream &o = g.o;
+    o << "#define QBJ_T " << sT << "\n#define QBJ_R " << sR << "\n#define QBJ_NT " << sNT << "\n";
+    if (g.host) o << "#define QB_JIT_HOST 1\n";
+    o << kPrelude << "\n";
+    // the rounds are generated first (into a side buffer): the coefficient count sizes QbjArgs
+    std::ostringstream side;
+    g.cur = &side;
+    emit_rounds();
+    g.cur = &g.o;
+    const std::string rounds_txt = side.str();
+    const size_t nc = std::max<size_t>(1, g.coefs.size());
+    o << "struct QbjArgs { double gs[2]; u64 rank_bits; u64 base_fixed; double c[" << nc << "]; };\n";
+    if (!g.host) {
+      o << "#define QBJ_LD2(p, i) qbj_ld256(amps + (p), re[i], im[i], re[(i) + 1], im[(i) + 1])\n"
+           "#define QBJ_LD1(p, i) { const double2 a_ = __ldcs(amps + (p)); re[i] = a_.x; im[i] = a_.y; }\n"
+           "#define QBJ_ST2(p, a0, a1, b0, b1) qbj_st256(amps + (p), a0, a1, b0, b1)\n"
+           "#define QBJ_ST1(p, xr, xi) __stcs(amps + (p), make_double2(xr, xi))\n"
+           "#define QBJ_STS(off, xr, xi) *reinterpret_cast<double2 *>(smem_raw + (off)) = make_double2(xr, xi)\n"
+           "#define QBJ_LDS(off, i) { const double2 a_ = *reinterpret_cast<const double2 *>(smem_raw + (off)); re[i] = a_.x; im[i] = a_.y; }\n";
+      o << "extern \"C\" __global__ void __launch_bounds__(QBJ_NT, " << sMINB
+        << ") qb_jit_pass(double2 *__restrict__ amps, u64 ntiles, const __grid_constant__ QbjArgs A) {\n"
+           "  extern __shared__ __align__(16) unsigned char smem_raw[];\n"
+           "  const u32 tid = threadIdx.x;\n"
+           "  u16 *sidx_tab = reinterpret_cast<u16 *>(smem_raw + (16u << QBJ_T));\n"
+           "  u64 *goff_tab = reinterpret_cast<u64 *>(sidx_tab + "
+        << sNROUNDS
+        << " * QBJ_NT);\n"
+           "  u32 *line_tab = reinterpret_cast<u32 *>(goff_tab + 2 * QBJ_NT);\n  {\n";
+      emit_tables();
+      o << "  }\n"
+           "  const u32 ntiles32 = (u32)ntiles, stride = gridDim.x, first = blockIdx.x;\n"
+           "  const u32 iters = (ntiles32 + stride - 1) / stride;\n"
+           "  double re[QBJ_NR], im[QBJ_NR];\n"
+           "  u32 f = 0;\n"
+           "  u64 base = 0, next_base = 0;\n"
+           "  for (u32 it = 0; it <= iters; ++it) {\n"
+           "    const u32 tile_id = first + it * stride;\n"
+           "    if (it > 0 && tile_id - stride < ntiles32) {\n";
+      // NOTE: the flips pending at the store are those of the previous tile's last round
+      // (mf_end was computed by emit_rounds above)
+      emit_store(mf_end);
+      o << "    }\n"
+           "    const bool active = it < iters && tile_id < ntiles32;\n"
+           "    if (!active) break;\n";
+      if (l2pf == 1) o << "    if (it > 0) base = next_base; else\n";
+      deposit("base", "tile_id");
+      emit_load();
+      if (l2pf > 0) {
+        o << "    { const u32 next_id = tile_id + stride * " << sL2 << "u;\n"
+             "      if (next_id < ntiles32) {\n      u64 nb_;\n";
+        deposit("nb_", "next_id");
+        o << "      next_base = nb_;\n";
+        for (int k = 0; k < LPT; ++k)
+          o << "      asm volatile(\"prefetch.global.L2 [%0];\" ::\"l\"(amps + nb_ + ((u64)line_tab[" << k << " * QBJ_NT + tid] << 3)));\n";
+        o << "      }\n    }\n";
+      }
+      o << "    const u64 basefull = base | A.rank_bits;\n    (void)basefull;\n    f = 0;\n";
+      o << rounds_txt;
+      o << "  }\n}\n";
+    } else {
+      o << "#define QBJ_LD2(p, i) { re[i] = amps[2 * (p)]; im[i] = amps[2 * (p) + 1]; re[(i) + 1] = amps[2 * (p) + 2]; im[(i) + 1] = amps[2 * (p) + 3]; }\n"
+           "#define QBJ_LD1(p, i) { re[i] = amps[2 * (p)]; im[i] = amps[2 * (p) + 1]; }\n"
+           "#define QBJ_ST2(p, a0, a1, b0, b1) { amps[2 * (p)] = a0; amps[2 * (p) + 1] = a1; amps[2 * (p) + 2] = b0; amps[2 * (p) + 3] = b1; }\n"
+           "#define QBJ_ST1(p, xr, xi) { amps[2 * (p)] = xr; amps[2 * (p) + 1] = xi; }\n"
+           "#define QBJ_STS(off, xr, xi) { SM[2 * ((off) >> 4)] = xr; SM[2 * ((off) >> 4) + 1] = xi; }\n"
+           "#define QBJ_LDS(off, i) { re[i] = SM[2 * ((off) >> 4)]; im[i] = SM[2 * ((off) >> 4) + 1]; }\n"
+           "#define QBJ_THREAD_REFS double (&re)[QBJ_NR] = RE[tid]; double (&im)[QBJ_NR] = IM[tid]; u32 &f = F[tid]; (void)re; (void)im; (void)f;\n"
+           "static double RE[QBJ_NT][QBJ_NR], IM[QBJ_NT][QBJ_NR], SM[2 << QBJ_T];\n"
+           "static u32 F[QBJ_NT];\n"
+           "static u16 sidx_tab["
+        << sNROUNDS
+        << " * QBJ_NT];\nstatic u64 goff_tab[2 * QBJ_NT];\nstatic u32 line_tab[(1 << (QBJ_T - 3))];\n"
+           "extern \"C\" int qb_jit_pass_host(double *amps, u64 ntiles, const QbjArgs *Ap, u64 args_bytes) {\n"
+           "  if (args_bytes != sizeof(QbjArgs)) return -1;\n"
+           "  const QbjArgs &A = *Ap;\n"
+           "  for (u32 tid = 0; tid < QBJ_NT; ++tid) {\n";
+      emit_tables();
+      o << "  }\n  (void)line_tab;\n"
+           "  for (u64 tile_id = 0; tile_id < ntiles; ++tile_id) {\n"
+           "  u64 base;\n";
+      deposit("base", "tile_id");
+      o << "  const u64 basefull = base | A.rank_bits;\n  (void)basefull;\n"
+           "  for (u32 tid = 0; tid < QBJ_NT; ++tid) {\n    QBJ_THREAD_REFS\n    f = 0;\n";
+      emit_load();
+      o << rounds_txt;
+      emit_store(mf_end);
+      o << "  }\n  }\n  return 0;\n}\n";
+    }
+  }
+  if (bad) return fail("step structure the generator does not accept");
+  out.key.swap(g.key);
+  out.coefs.swap(g.coefs);
+  out.left_out = g.left_out;
+  out.src = g.want_src ? g.o.str() : std::string();
+  out.T = T;
+  out.R = R;
+  out.minb = minb;
+  out.nrounds = nrounds;
+  out.smem = smem;
+  out.args_bytes = sizeof(JitArgsHead) + sizeof(double) * std::max<size_t>(1, out.coefs.size());
+  if (!std::isfinite(out.left_out) || out.left_out == 0.0) return fail("deferred factor out of range");
+  return true;
+}
+
+std::vector<uint8_t> jit_pack_args(const JitProgram &p, const double gs[2], uint64_t rank_bits, uint64_t base_fixed) {
+  std::vector<uint8_t> a(p.args_bytes, 0);
+  JitArgsHead h;
+  h.gs[0] = gs[0];
+  h.gs[1] = gs[1];
+  h.rank_bits = rank_bits;
+  h.base_fixed = base_fixed;
+  std::memcpy(a.data(), &h, sizeof(h));
+  if (!p.coefs.empty()) std::memcpy(a.data() + sizeof(h), p.coefs.data(), sizeof(double) * p.coefs.size());
+  return a;
+}
+
+}  // namespace qb
+
+// =================================================================== runtime (libqubism_sv.so only)
+#ifndef QB_JIT_NO_RUNTIME
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <chrono>
+#include <mutex>
+#include <unordered_map>
+
+namespace qb {
+namespace {
+
+// ---- NVRTC, resolved at run time: the library must load (and the generic kernels run) on a box
+// without it
+typedef struct _nvrtcProgram *nvrtcProgram_t;
+struct Nvrtc {
+  void *lib = nullptr;
+  int (*CreateProgram)(nvrtcProgram_t *, const char *, const char *, int, const char *const *, const char *const *) = nullptr;
+  int (*CompileProgram)(nvrtcProgram_t, int, const char *const *) = nullptr;
+  int (*GetCUBINSize)(nvrtcProgram_t, size_t *) = nullptr;
+  int (*GetCUBIN)(nvrtcProgram_t, char *) = nullptr;
+  int (*GetProgramLogSize)(nvrtcProgram_t, size_t *) = nullptr;
+  int (*GetProgramLog)(nvrtcProgram_t, char *) = nullptr;
+  int (*DestroyProgram)(nvrtcProgram_t *) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+  int (*Version)(int *, int *) = nullptr;
+  bool wide_ldst = false;  // ld / st .v4.f64 (256 bits): PTX ISA 8.8 = CUDA 12.9
+  std::string why;
+  bool ok = false;
+};
+
+Nvrtc &nvrtc() {
+  static Nvrtc n;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    // the toolkit's own NVRTC first: a Python process that imported torch already holds torch's
+    // bundled libnvrtc.so.12 (CUDA 12.8), whose ptxas rejects the 256-bit ld / st of sm_100a
+    const char *names[] = {"/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so", "libnvrtc.so.12",
+                           "libnvrtc.so"};
+    for (const char *nm : names) {
+      n.lib = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
+      if (n.lib) break;
+    }
+    if (!n.lib) {
+      n.why = "libnvrtc not found";
+      return;
+    }
+#define QB_SYM(field, name)                                   \
+  *reinterpret_cast<void **>(&n.field) = dlsym(n.lib, name);  \
+  if (!n.field) {                                             \
+    n.why = std::string("libnvrtc lacks ") + name;            \
+    return;                                                   \
+  }
+    QB_SYM(CreateProgram, "nvrtcCreateProgram")
+    QB_SYM(CompileProgram, "nvrtcCompileProgram")
+    QB_SYM(GetCUBINSize, "nvrtcGetCUBINSize")
+    QB_SYM(GetCUBIN, "nvrtcGetCUBIN")
+    QB_SYM(GetProgramLogSize, "nvrtcGetProgramLogSize")
+    QB_SYM(GetProgramLog, "nvrtcGetProgramLog")
+    QB_SYM(DestroyProgram, "nvrtcDestroyProgram")
+    QB_SYM(GetErrorString, "nvrtcGetErrorString")
+    QB_SYM(Version, "nvrtcVersion")
+#undef QB_SYM
+    int major = 0, minor = 0;
+    if (n.Version(&major, &minor) == 0) n.wide_ldst = major > 12 || (major == 12 && minor >= 9);
+    n.ok = true;
+  });
+  return n;
+}
+
+// ---- the driver entry points, through the runtime (no link against libcuda)
+struct Driver {
+  CUresult (*ModuleLoadData)(CUmodule *, const void *) = nullptr;
+  CUresult (*ModuleGetFunction)(CUfunction *, CUmodule, const char *) = nullptr;
+  CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
+  CUresult (*OccupancyMaxActiveBlocksPerMultiprocessor)(int *, CUfunction, int, size_t) = nullptr;
+  CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void **,
+                           void **) = nullptr;
+  CUresult (*GetErrorString)(CUresult, const char **) = nullptr;
+  std::string why;
+  bool ok = false;
+};
+
+Driver &driver() {
+  static Driver d;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    auto get = [&](const char *name, void **fn) {
+      cudaDriverEntryPointQueryResult q;
+      const cudaError_t e = cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q);
+      if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !*fn) {
+        d.why = std::string("driver entry point ") + name + " unavailable";
+        (void)cudaGetLastError();
+        return false;
+      }
+      return true;
+    };
+    if (!get("cuModuleLoadData", reinterpret_cast<void **>(&d.ModuleLoadData))) return;
+    if (!get("cuModuleGetFunction", reinterpret_cast<void **>(&d.ModuleGetFunction))) return;
+    if (!get("cuFuncSetAttribute", reinterpret_cast<void **>(&d.FuncSetAttribute))) return;
+    if (!get("cuOccupancyMaxActiveBlocksPerMultiprocessor",
+             reinterpret_cast<void **>(&d.OccupancyMaxActiveBlocksPerMultiprocessor)))
+      return;
+    if (!get("cuLaunchKernel", reinterpret_cast<void **>(&d.LaunchKernel))) return;
+    if (!get("cuGetErrorString", reinterpret_cast<void **>(&d.GetErrorString))) return;
+    d.ok = true;
+  });
+  return d;
+}
+
+std::string cu_err(CUresult r) {
+  const char *s = nullptr;
+  if (driver().GetErrorString) driver().GetErrorString(r, &s);
+  return s ? std::string(s) : ("CUresult " + std::to_string((int)r));
+}
+
+struct Entry {
+  int seen = 0;
+  int state = 0;  // 0 not compiled, 1 ready, -1 failed (stay on the generic kernel)
+  CUmodule mod = nullptr;
+  CUfunction fn = nullptr;
+  int occ = 0, threads = 0;
+  size_t smem = 0;
+};
+std::mutex g_mu;
+std::unordered_map<std::string, Entry> g_cache;
+JitStats g_stats;
+
+bool compile_cubin(const std::string &src, std::vector<char> &cubin, std::string *err) {
+  Nvrtc &n = nvrtc();
+  nvrtcProgram_t prog = nullptr;
+  int rc = n.CreateProgram(&prog, src.c_str(), "qb_jit_pass.cu", 0, nullptr, nullptr);
+  if (rc != 0) {
+    if (err) *err = std::string("nvrtcCreateProgram: ") + n.GetErrorString(rc);
+    return false;
+  }
+  const char *opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "-DQBJ_NO_LD256=1"};
+  rc = n.CompileProgram(prog, n.wide_ldst ? 3 : 4, opts);
+  if (rc != 0) {
+    size_t ls = 0;
+    n.GetProgramLogSize(prog, &ls);
+    std::string log(ls, '\0');
+    if (ls) n.GetProgramLog(prog, &log[0]);
+    if (err) *err = std::string("nvrtcCompileProgram: ") + n.GetErrorString(rc) + "\n" + log.substr(0, 2000);
+    n.DestroyProgram(&prog);
+    return false;
+  }
+  size_t cs = 0;
+  rc = n.GetCUBINSize(prog, &cs);
+  if (rc == 0 && cs) {
+    cubin.resize(cs);
+    rc = n.GetCUBIN(prog, cubin.data());
+  }
+  n.DestroyProgram(&prog);
+  if (rc != 0 || cubin.empty()) {
+    if (err) *err = "nvrtcGetCUBIN failed";
+    return false;
+  }
+  return true;
+}
+
+}  // namespace
+
+bool jit_available(std::string *why) {
+  if (!nvrtc().ok) {
+    if (why) *why = nvrtc().why;
+    return false;
+  }
+  if (!driver().ok) {
+    if (why) *why = driver().why;
+    return false;
+  }
+  return true;
+}
+
+// test hook: source -> cubin without touching a device
+bool jit_compile_only(const std::string &src, size_t *cubin_bytes, std::string *err) {
+  if (!nvrtc().ok) {
+    if (err) *err = nvrtc().why;
+    return false;
+  }
+  std::vector<char> cubin;
+  if (!compile_cubin(src, cubin, err)) return false;
+  if (cubin_bytes) *cubin_bytes = cubin.size();
+  return true;
+}
+
+int jit_lookup(const JitProgram &kp, const PassPlan &pp, int threshold, void **handle, std::string *err) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  std::string key = std::to_string(dev) + ":" + kp.key;
+  std::lock_guard<std::mutex> lock(g_mu);
+  Entry &e = g_cache[key];
+  if (e.state == 1) {
+    *handle = &e;
+    return 1;
+  }
+  if (e.state < 0) return 0;
+  if (++e.seen < threshold) return 0;
+  if (!jit_available(err)) {
+    e.state = -1;
+    g_stats.failed++;
+    return -1;
+  }
+  const auto t0 = std::chrono::steady_clock::now();
+  JitProgram full;
+  std::string why;
+  if (!jit_generate(pp, JIT_DEVICE_SRC, full, &why)) {
+    e.state = -1;
+    g_stats.failed++;
+    if (err) *err = "generator: " + why;
+    return -1;
+  }
+  std::vector<char> cubin;
+  if (!compile_cubin(full.src, cubin, err)) {
+    e.state = -1;
+    g_stats.failed++;
+    return -1;
+  }
+  Driver &d = driver();
+  CUresult r = d.ModuleLoadData(&e.mod, cubin.data());
+  if (r == CUDA_SUCCESS) r = d.ModuleGetFunction(&e.fn, e.mod, "qb_jit_pass");
+  if (r == CUDA_SUCCESS) r = d.FuncSetAttribute(e.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)full.smem);
+  e.threads = 1 << (full.T - full.R);
+  e.smem = full.smem;
+  if (r == CUDA_SUCCESS) r = d.OccupancyMaxActiveBlocksPerMultiprocessor(&e.occ, e.fn, e.threads, e.smem);
+  if (r != CUDA_SUCCESS || e.occ < 1) {
+    e.state = -1;
+    g_stats.failed++;
+    if (err) *err = "loading the specialised kernel: " + (r != CUDA_SUCCESS ? cu_err(r) : std::string("occupancy 0"));
+    return -1;
+  }
+  e.state = 1;
+  g_stats.compiled++;
+  g_stats.compile_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  *handle = &e;
+  return 1;
+}
+
+int jit_launch(void *handle, void *amps, uint64_t ntiles, const std::vector<uint8_t> &args, int sm_count, void *stream,
+               std::string *err) {
+  Entry &e = *static_cast<Entry *>(handle);
+  uint64_t grid = uint64_t(sm_count) * uint64_t(e.occ);
+  if (grid > ntiles) grid = ntiles;
+  if (grid == 0) return 0;
+  unsigned long long nt = ntiles;
+  void *params[] = {&amps, &nt, const_cast<uint8_t *>(args.data())};
+  const CUresult r = driver().LaunchKernel(e.fn, (unsigned)grid, 1, 1, (unsigned)e.threads, 1, 1, (unsigned)e.smem,
+                                           static_cast<CUstream>(stream), params, nullptr);
+  if (r != CUDA_SUCCESS) {
+    if (err) *err = "launching the specialised kernel: " + cu_err(r);
+    return -1;
+  }
+  {
+    std::lock_guard<std::mutex> lock(g_mu);
+    g_stats.launches++;
+  }
+  return 0;
+}
+
+JitStats jit_stats() {
+  std::lock_guard<std::mutex> lock(g_mu);
+  return g_stats;
+}
+
+}  // namespace qb
+#endif  // QB_JIT_NO_RUNTIME

@@ -726,7 +726,9 @@ __global__ void __launch_bounds__(1 << (T - R), MINB)
         }
       }
     }
-    if (P.has_gscale) {  // deferred global scalar (folded u1-type phases, qb_scale)
+    // deferred global scalar (folded u1-type phases, qb_scale); exactly 1 is skipped: it is the
+    // identity, and 0 * inf must not turn an infinite amplitude into NaN
+    if (P.has_gscale && !(P.gscale[0] == 1.0 && P.gscale[1] == 0.0)) {
       const double sr = P.gscale[0], si = P.gscale[1];
 #pragma unroll
       for (int i = 0; i < NR; ++i) {

@@ -53,6 +53,9 @@ bool set_opt(PlanOptions &o, const std::string &name, int64_t v) {
   } else if (name == "hot_bits") {
     if (v < 0 || v > kMaxTileBits) return false;
     o.hot_bits = (int)v;
+  } else if (name == "jit") {
+    if (v < 0 || v > 1000000) return false;
+    o.jit = (int)v;
   } else if (name == "rot") {
     o.rot = v ? 1 : 0;
   } else if (name == "lite") {
@@ -95,6 +98,7 @@ int64_t get_opt(const PlanOptions &o, const std::string &name) {
   if (name == "avoid_regswap") return o.avoid_regswap;
   if (name == "hot_bits") return o.hot_bits;
   if (name == "rot") return o.rot;
+  if (name == "jit") return o.jit;
   if (name == "lite") return o.lite;
   if (name == "lane_fixed") return o.lane_fixed;
   if (name == "skip_dead") return o.skip_dead;
@@ -905,6 +909,8 @@ static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &don
               kind = SLOT_ROT;
               S.slot[J][0] = g.m[0];
               S.slot[J][1] = g.m[1];
+              S.slot[J][2] = op.m[0];  // (cos, sin) for the structure-specialised kernels (qb_jit.cpp)
+              S.slot[J][3] = op.m[4];
             } else if (g.type == G_REAL) {
               kind = SLOT_REAL;
               for (int e = 0; e < 4; ++e) S.slot[J][e] = g.m[2 * e];

@@ -12,7 +12,11 @@
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
+#include <unistd.h>
+
 #include "../../qubism_b200/csrc/qb_internal.h"
+#include "../../qubism_b200/csrc/qb_jit.h"
 
 using namespace qb;
 
@@ -344,6 +348,125 @@ int qbe_run(int nlocal, const qb_op *ops, int64_t nops, const char *options, dou
   }
   return 0;
 }
+
+// The structure-specialised kernels (qb_jit.cpp) on the CPU: plan as qbe_run does, then run every
+// pass the generator accepts through the HOST emulation of its generated source (compiled with
+// g++ into `workdir`, loaded with dlopen), every other pass through the emulator above.  The
+// factors the specialised passes leave out are applied at the end, as the state's deferred
+// scalar would be.  stats_out[0] = passes, [1] = specialised passes, [2] = distinct structures.
+// If dev_src_out is not null, the DEVICE source of specialised pass number `dev_src_index` is
+// copied there (for an NVRTC compile check that needs no GPU).
+int qbe_run_jit(int nlocal, const qb_op *ops, int64_t nops, const char *options, double *amps, int64_t *stats_out,
+                const char *workdir, int dev_src_index, char *dev_src_out, int64_t dev_src_cap) {
+  PlanOptions opt;
+  if (options) {
+    std::string o(options);
+    size_t pos = 0;
+    while (pos < o.size()) {
+      size_t e = o.find(',', pos);
+      if (e == std::string::npos) e = o.size();
+      std::string kv = o.substr(pos, e - pos);
+      size_t eq = kv.find('=');
+      if (eq != std::string::npos && !set_opt(opt, kv.substr(0, eq), strtoll(kv.c_str() + eq + 1, nullptr, 10)))
+        return -1;
+      pos = e + 1;
+    }
+  }
+  OpQueue q;
+  q.reset(nlocal, opt.peephole != 0, opt.rot != 0);
+  static const double X[8] = {0, 0, 1, 0, 1, 0, 0, 0};
+  for (int64_t i = 0; i < nops; ++i) {
+    const qb_op &o = ops[i];
+    uint64_t cm = 0;
+    const int nc = o.kind == 1 ? 1 : o.nctrl;
+    for (int k = 0; k < nc; ++k) cm |= 1ull << (nlocal - 1 - o.ctrl[k]);
+    q.push_1q(nlocal - 1 - o.target, cm, o.kind == 1 ? X : reinterpret_cast<const double *>(o.m));
+  }
+  int T, R;
+  effective_tile(opt, nlocal, T, R);
+  if (T == 0) return -2;
+  opt.tile_bits = T;
+  opt.reg_bits = R;
+  std::vector<PhysOp> pops;
+  for (const auto &h : q.ops) {
+    if (h.dead) continue;
+    PhysOp p;
+    p.type = h.type;
+    p.target = h.target;
+    p.ctrl = h.ctrl;
+    std::memcpy(p.m, h.m, sizeof(h.m));
+    pops.push_back(p);
+  }
+  PlanResult plan = plan_passes(pops, nlocal, 0, opt, q.gscale);
+  if (plan.consumed != pops.size()) return -3;
+  std::vector<double> a(amps, amps + (size_t(2) << nlocal));
+  EmuStats st;
+  double pending = 1.0;
+  int njit = 0;
+  static int nlibs = 0;  // (file names must never repeat inside a process: dlopen caches by path)
+  std::vector<std::pair<std::string, void *>> libs;  // structural key -> host function
+  for (const auto &p : plan.passes) {
+    const DevPass &P = *reinterpret_cast<const DevPass *>(p.blob.data());
+    JitProgram kp;
+    std::string why;
+    if (!jit_generate(p, JIT_KEY_ONLY, kp, &why)) {
+      run_pass(p, nlocal, a, st);
+      continue;
+    }
+    if (dev_src_out && njit == dev_src_index) {
+      JitProgram dp;
+      if (!jit_generate(p, JIT_DEVICE_SRC, dp, &why)) return -6;
+      if ((int64_t)dp.src.size() + 1 > dev_src_cap) return -7;
+      std::memcpy(dev_src_out, dp.src.c_str(), dp.src.size() + 1);
+      if (dp.key.size() == 0 || dp.coefs != kp.coefs) return -8;
+    }
+    void *fn = nullptr;
+    for (auto &pr : libs)
+      if (pr.first == kp.key) fn = pr.second;
+    if (!fn) {
+      JitProgram hp;
+      if (!jit_generate(p, JIT_HOST_SRC, hp, &why)) return -6;
+      const std::string base = std::string(workdir) + "/qbj_" + std::to_string((long)getpid()) + "_" + std::to_string(nlibs++);
+      FILE *f = std::fopen((base + ".cpp").c_str(), "w");
+      if (!f) return -9;
+      std::fwrite(hp.src.data(), 1, hp.src.size(), f);
+      std::fclose(f);
+      const std::string cmd = "g++ -std=c++17 -O1 -fPIC -shared -Wno-unknown-pragmas -o " + base + ".so " + base + ".cpp 2> " + base + ".log";
+      if (std::system(cmd.c_str()) != 0) return -10;
+      void *lib = dlopen((base + ".so").c_str(), RTLD_NOW | RTLD_LOCAL);
+      if (!lib) return -11;
+      fn = dlsym(lib, "qb_jit_pass_host");
+      if (!fn) return -12;
+      libs.emplace_back(kp.key, fn);
+    }
+    const double one[2] = {1.0, 0.0};
+    const std::vector<uint8_t> args = jit_pack_args(kp, P.has_gscale ? P.gscale : one, P.rank_bits, P.base_fixed);
+    typedef int (*host_fn)(double *, uint64_t, const void *, uint64_t);
+    if (reinterpret_cast<host_fn>(fn)(a.data(), p.ntiles, args.data(), (uint64_t)args.size()) != 0) return -13;
+    pending *= kp.left_out;
+    ++njit;
+    st.passes++;
+  }
+  const bool qg = plan.passes.empty() && !(q.gscale[0] == 1.0 && q.gscale[1] == 0.0);
+  for (size_t i = 0; i < (size_t(1) << nlocal); ++i) {
+    double xr = a[2 * i] * pending, xi = a[2 * i + 1] * pending;
+    if (qg) {
+      const double yr = q.gscale[0] * xr - q.gscale[1] * xi;
+      xi = q.gscale[0] * xi + q.gscale[1] * xr;
+      xr = yr;
+    }
+    a[2 * i] = xr;
+    a[2 * i + 1] = xi;
+  }
+  std::memcpy(amps, a.data(), sizeof(double) * a.size());
+  if (stats_out) {
+    stats_out[0] = st.passes;
+    stats_out[1] = njit;
+    stats_out[2] = (int64_t)libs.size();
+  }
+  return 0;
+}
+
 
 // Distributed flush of ONE rank, emulated on the host.  `amps` is this rank's shard (2 * 2^L
 // doubles).  Whenever the planner is stuck on gates that target global qubits, the same

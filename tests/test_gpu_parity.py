@@ -152,6 +152,86 @@ def test_lite_steps_and_interpreter_vs_oracle_20q(default_opts, lane_fixed, lite
     assert ctx.stats()["simple_launches"] == 0
 
 
+@pytest.mark.parametrize("T,R,lane_fixed", [(12, 4, 0), (12, 4, 1), (12, 5, 0), (11, 4, 3), (10, 3, 0), (12, 3, 2), (13, 4, 0)])
+def test_specialised_kernels_vs_oracle(default_opts, T, R, lane_fixed):
+    """Option jit = 1: every step pass is compiled with NVRTC at first sight (structure as
+    literals, 2-FMA rotations with deferred cosines, register swaps as renamings) and must
+    reproduce the oracle; the factor the rotations leave out rides on the flush's last pass or
+    stays in the state's deferred scalar (reductions see it arithmetically)."""
+    ctx = default_opts
+    ctx.set_option("tile_bits", T)
+    ctx.set_option("reg_bits", R)
+    ctx.set_option("lane_fixed", lane_fixed)
+    ctx.set_option("jit", 1)
+    n = 18
+    rng = np.random.default_rng(T * 10 + R)
+    v = S.gen_state(n, rng)
+    ops = random_layers(n, 4, seed=T + R, lam0=True) + qft_ops(n) + random_layers(n, 1, seed=4, lam0=False)
+    ref = S.run_ops(n, ops, v)
+    sv = Q.StateVec.from_host(v)
+    before = ctx.stats()["jit_launches"]
+    sv.submit(ops)
+    s0, s1 = sv.sumsq(3)  # (pending scalar applied arithmetically)
+    r0, r1 = S.sumsq(n, 3, ref)
+    assert abs(s0 - r0) < 1e-12 and abs(s1 - r1) < 1e-12
+    assert close(sv.to_host(), ref)
+    st = ctx.stats()
+    assert st["jit_launches"] > before, "no specialised kernel ran"
+    # the same structure again: served from the cache, new angles are only new coefficients
+    compiled = st["jit_compiled"]
+    sv2 = Q.StateVec.from_host(v)
+    sv2.submit(ops)
+    assert close(sv2.to_host(), ref)
+    assert ctx.stats()["jit_compiled"] == compiled
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_specialised_kernels_random_mixes(default_opts, seed):
+    """Random mixes (rotations, general / real gates, Paulis, dense CX, controlled gates),
+    mid-circuit measurements on a tracked support, every pass that can be specialised is."""
+    from qubism_b200.circuits import random_mixed
+    ctx = default_opts
+    ctx.set_option("jit", 1)
+    rng = np.random.default_rng(900 + seed)
+    n = int(rng.integers(12, 19))
+    ops = random_mixed(n, int(rng.integers(30, 100)), 1700 + seed)
+    ctx.set_option("lane_fixed", int(rng.integers(0, 4)))
+    if rng.integers(0, 2):
+        v = np.zeros(1 << n, complex)
+        v[0] = 1
+        sv = Q.mkStateVec(n)
+        mid = [("MEASURE", int(rng.integers(0, n)), float(rng.uniform(0, 1))) for _ in range(2)]
+        ops = ops[: len(ops) // 2] + mid + ops[len(ops) // 2:]
+    else:
+        v = S.gen_state(n, rng)
+        sv = Q.StateVec.from_host(v)
+    rec_ref = []
+    ref = S.run_ops(n, ops, v, record=rec_ref)
+    rec = sv.run_ops(ops)
+    assert [(q, b) for q, b, _ in rec] == [(q, b) for q, b, _ in rec_ref]
+    assert close(sv.to_host(), ref, 1e-11)
+
+
+def test_specialised_kernels_second_sighting_default(default_opts):
+    """Default policy (jit = 2): the first run of a structure uses the generic kernels, the second
+    compiles, both give the oracle's amplitudes."""
+    ctx = default_opts
+    assert ctx.get_option("jit") == 2
+    n = 16
+    v = S.gen_state(n, np.random.default_rng(7))
+    ops = random_layers(n, 3, seed=123, lam0=True)
+    ref = S.run_ops(n, ops, v)
+    c0 = ctx.stats()["jit_compiled"]
+    a = Q.StateVec.from_host(v)
+    a.submit(ops)
+    assert close(a.to_host(), ref)
+    assert ctx.stats()["jit_compiled"] == c0
+    b = Q.StateVec.from_host(v)
+    b.submit(ops)
+    assert close(b.to_host(), ref)
+    assert ctx.stats()["jit_compiled"] > c0
+
+
 @pytest.mark.parametrize("seed", range(10))
 def test_random_mixed_circuits_random_knobs(default_opts, seed):
     """Randomised sweep through the real kernels: every op kind, random planner knobs, with and
@@ -463,6 +543,7 @@ def test_full_size_round_trip_and_norm(ctx, n):
     preserved by a norm-preserving circuit, S0 + S1 equals it for every probed qubit."""
     ops = qft_ops(n) + random_layers(n, 4, seed=1000)
     sv = Q.mkStateVec(n)
+    ctx.set_option("jit", 1)  # specialised kernels at full size
     sv.submit(ops)
     tot = sv.norm2() ** 2
     assert abs(tot - 1.0) < 1e-11
@@ -475,3 +556,4 @@ def test_full_size_round_trip_and_norm(ctx, n):
     head = sv.to_host(0, 4096)
     assert abs(head[0] - 1.0) < 1e-11 and np.abs(head[1:]).max() < 1e-12
     assert abs(sv.norm2() - 1.0) < 1e-11
+    ctx.set_option("jit", 2)

@@ -120,7 +120,9 @@ struct DevPass {
   uint32_t lite;                      // 0: rounds index DevGates (interpreter); 1 / 2: DevSteps (1 = every slot is a
                                       // rotation, 2 = rotation / real / general slots)
   uint32_t nsteps;
-  uint32_t _pad3[2];
+  uint32_t jit_group;                 // specialised kernels: a CTA takes this many CONSECUTIVE tiles in a row and
+                                      // prefetches the next such group with one bulk request per chunk
+  uint32_t jit_pf_last;               // ... issued while the LAST (1) or the FIRST (0) tile of the running group computes
   uint64_t base_fixed;                // known non-tile bits at their known value: OR-ed into every live tile's base
   uint64_t _pad4;
   DevRound rounds[kMaxRounds];
@@ -177,6 +179,10 @@ struct PlanOptions {
   int lite = 1;           // passes of rotations and X / CX only use the lean kernel instantiation
   int jit = 2;            // k > 0: a step-pass STRUCTURE seen k times is compiled (NVRTC) into a straight-line
                           // kernel and cached (qb_jit.cpp); 0 = generic kernels only
+  int jit_group = 2;      // specialised kernels: tiles a CTA takes in a row (1, 2, 4).  Consecutive tiles are
+                          // neighbours in memory, so a group is prefetched as runs of group x chunk bytes:
+                          // DRAM sees 256-512 contiguous bytes per row activation instead of 128
+  int jit_pf_last = 1;    // prefetch the next group during the last (1) / first (0) tile of the running one
   int hot_bits = 0;       // planner: max distinct TARGET bits per pass (0 = tile_bits).  With
                           // hot_bits <= tile_bits - warp bits every transpose can stay warp-local.
 };

@@ -91,8 +91,18 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
   g.want_src = emit != JIT_KEY_ONLY;
   g.host = emit == JIT_HOST_SRC;
   g.tag("qbj1");
+  const int l2pf = (int)P.l2_prefetch;
+  // contiguous low part of the tile (a "chunk": 2^cbits amplitudes) and how many consecutive tile
+  // ids are neighbours in memory (the lowest run of free bits starts right above the chunk)
+  int cbits = 3;
+  while (cbits < T && P.tile_pos[cbits] == cbits) ++cbits;
+  int group = 1;
+  if (l2pf > 0 && P.nruns > 0 && (int)P.run_shift[0] == cbits) {
+    const int want = P.jit_group ? (int)P.jit_group : 1;
+    while (group * 2 <= want && group * 2 <= (1 << std::min<uint32_t>(P.run_len[0], 8))) group *= 2;
+  }
   const size_t smem = (size_t(16) << T) + size_t(nrounds) * NT * sizeof(uint16_t) + size_t(2) * NT * sizeof(uint64_t) +
-                      (size_t(1) << (T - 3)) * sizeof(uint32_t);
+                      (size_t(group) << (T - 3)) * sizeof(uint32_t);
   int minb;
   {
     const int regs_wanted = 4 * NR + 64;
@@ -101,11 +111,12 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
     minb = std::max(1, std::min(std::min(by_regs, by_smem), 8));
   }
   const std::string sT = g.dec(T), sR = g.dec(R), sNT = g.dec(NT), sMINB = g.dec(minb), sNROUNDS = g.dec(nrounds);
-  const int l2pf = (int)P.l2_prefetch;
   const std::string sL2 = g.dec(l2pf);
   const bool has_gs = P.has_gscale != 0;
   g.dec(has_gs);
   const int LPT = 1 << (R - 3);
+  const std::string sG = g.dec(group), sCB = g.dec(cbits);
+  const std::string sPFK = g.dec((group > 1 && P.jit_pf_last) ? group - 1 : 0);  // prefetch while this tile of the group computes
 
   // ---------------------------------------------------------------- fragments shared by both modes
   auto tid_bits_expr = [&](const DevRound &rd, bool phys, const char *var) {
@@ -358,8 +369,9 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
         << " * QBJ_NT);\n"
            "  u32 *line_tab = reinterpret_cast<u32 *>(goff_tab + 2 * QBJ_NT);\n  {\n";
       emit_tables();
-      o << "  }\n"
-           "  const u32 ntiles32 = (u32)ntiles, stride = gridDim.x, first = blockIdx.x;\n"
+      o << "  }\n";
+      if (group == 1) {
+      o << "  const u32 ntiles32 = (u32)ntiles, stride = gridDim.x, first = blockIdx.x;\n"
            "  const u32 iters = (ntiles32 + stride - 1) / stride;\n"
            "  double re[QBJ_NR], im[QBJ_NR];\n"
            "  u32 f = 0;\n"
@@ -388,6 +400,52 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
       o << "    const u64 basefull = base | A.rank_bits;\n    (void)basefull;\n    f = 0;\n";
       o << rounds_txt;
       o << "  }\n}\n";
+      } else {
+      // ---- grouped order: this CTA takes `group` consecutive tiles in a row (neighbours in memory:
+      // together they cover group x chunk contiguous bytes per chunk) and, while it works on a
+      // group, pulls the NEXT group into L2 with one bulk request per chunk.
+      // group line table: the 128-byte lines of a whole GROUP, enumerated so that consecutive
+      // q (= consecutive lanes) walk the contiguous run of group x chunk bytes first:
+      //   q = tid + k * NT;  low bits of q = line inside the run, high bits = which chunk
+      o << "  {\n";
+      const int run_lines_log2 = (cbits - 3) + __builtin_ctz((unsigned)group);  // lines per contiguous run
+      const int glpt = group * LPT;                                           // group lines per thread
+      for (int k = 0; k < glpt; ++k) {
+        std::string e = "(u64)(q_ & " + std::to_string((1 << run_lines_log2) - 1) + "u) << 3";
+        for (int j = 0; j < T - cbits; ++j)
+          e += " | ((u64)((q_ >> " + std::to_string(run_lines_log2 + j) + ") & 1u) << " + g.dec(P.tile_pos[cbits + j]) + ")";
+        o << "    { const u32 q_ = tid + " << k << "u * QBJ_NT; line_tab[" << k << " * QBJ_NT + tid] = (u32)((" << e << ") >> 3); }\n";
+      }
+      o << "  }\n"
+           "  const u32 ntiles32 = (u32)ntiles, stride = gridDim.x;\n"
+           "  const u32 ngroups = (ntiles32 + " << sG << "u - 1u) / " << sG << "u;\n"
+           "  double re[QBJ_NR], im[QBJ_NR];\n"
+           "  u32 f = 0;\n"
+           "  u64 base = 0;\n"
+           "  u32 grp = blockIdx.x, k_in = 0;\n"
+           "  bool have_prev = false;\n"
+           "  while (true) {\n"
+           "    const u32 tile_id = grp * " << sG << "u + k_in;\n"
+           "    if (have_prev) {\n";
+      emit_store(mf_end);
+      o << "    }\n"
+           "    if (!(grp < ngroups && tile_id < ntiles32)) break;\n";
+      deposit("base", "tile_id");
+      emit_load();
+      o << "    if (k_in == " << sPFK << "u) {\n"
+           "      const u32 ng_ = grp + stride;\n"
+           "      if (ng_ < ngroups) {\n      u64 nb_;\n"
+           "      const u32 nt0_ = ng_ * " << sG << "u;\n";
+      deposit("nb_", "nt0_");
+      for (int k = 0; k < glpt; ++k)
+        o << "      asm volatile(\"prefetch.global.L2 [%0];\" ::\"l\"(amps + nb_ + ((u64)line_tab[" << k << " * QBJ_NT + tid] << 3)));\n";
+      o << "      }\n    }\n";
+      o << "    const u64 basefull = base | A.rank_bits;\n    (void)basefull;\n    f = 0;\n";
+      o << rounds_txt;
+      o << "    have_prev = true;\n"
+           "    if (++k_in == " << sG << "u) { k_in = 0; grp += stride; }\n"
+           "  }\n}\n";
+      }
     } else {
       o << "#define QBJ_LD2(p, i) { re[i] = amps[2 * (p)]; im[i] = amps[2 * (p) + 1]; re[(i) + 1] = amps[2 * (p) + 2]; im[(i) + 1] = amps[2 * (p) + 3]; }\n"
            "#define QBJ_LD1(p, i) { re[i] = amps[2 * (p)]; im[i] = amps[2 * (p) + 1]; }\n"

@@ -53,6 +53,11 @@ bool set_opt(PlanOptions &o, const std::string &name, int64_t v) {
   } else if (name == "hot_bits") {
     if (v < 0 || v > kMaxTileBits) return false;
     o.hot_bits = (int)v;
+  } else if (name == "jit_group") {
+    if (v != 1 && v != 2 && v != 4 && v != 8) return false;
+    o.jit_group = (int)v;
+  } else if (name == "jit_pf_last") {
+    o.jit_pf_last = v ? 1 : 0;
   } else if (name == "jit") {
     if (v < 0 || v > 1000000) return false;
     o.jit = (int)v;
@@ -99,6 +104,8 @@ int64_t get_opt(const PlanOptions &o, const std::string &name) {
   if (name == "hot_bits") return o.hot_bits;
   if (name == "rot") return o.rot;
   if (name == "jit") return o.jit;
+  if (name == "jit_pf_last") return o.jit_pf_last;
+  if (name == "jit_group") return o.jit_group;
   if (name == "lite") return o.lite;
   if (name == "lane_fixed") return o.lane_fixed;
   if (name == "skip_dead") return o.skip_dead;
@@ -746,6 +753,8 @@ static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &don
   P->gscale[1] = 0.0;
   P->has_gscale = 0;
   P->l2_prefetch = (uint32_t)opt.l2_prefetch;
+  P->jit_group = (uint32_t)opt.jit_group;
+  P->jit_pf_last = (uint32_t)opt.jit_pf_last;
   P->dbg_skip = (uint32_t)opt.dbg_skip;
   P->sm_count = 148;
   for (int i = 0; i < T; ++i) P->tile_pos[i] = (uint8_t)tile_bits[i];

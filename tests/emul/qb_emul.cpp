@@ -468,6 +468,70 @@ int qbe_run_jit(int nlocal, const qb_op *ops, int64_t nops, const char *options,
 }
 
 
+// Plan only (any nlocal, no amplitudes): write the DEVICE source of every pass the generator
+// accepts to `outdir`/pass_<i>.cu.  Returns the number of passes planned, or a negative error;
+// stats_out[0] = specialised passes, [1] = rotations counted from the coefficient vectors.
+int qbe_jit_dump(int nlocal, const qb_op *ops, int64_t nops, const char *options, const char *outdir, int64_t *stats_out) {
+  PlanOptions opt;
+  if (options) {
+    std::string o(options);
+    size_t pos = 0;
+    while (pos < o.size()) {
+      size_t e = o.find(',', pos);
+      if (e == std::string::npos) e = o.size();
+      std::string kv = o.substr(pos, e - pos);
+      size_t eq = kv.find('=');
+      if (eq != std::string::npos && !set_opt(opt, kv.substr(0, eq), strtoll(kv.c_str() + eq + 1, nullptr, 10)))
+        return -1;
+      pos = e + 1;
+    }
+  }
+  OpQueue q;
+  q.reset(nlocal, opt.peephole != 0, opt.rot != 0);
+  static const double X[8] = {0, 0, 1, 0, 1, 0, 0, 0};
+  for (int64_t i = 0; i < nops; ++i) {
+    const qb_op &o = ops[i];
+    uint64_t cm = 0;
+    const int nc = o.kind == 1 ? 1 : o.nctrl;
+    for (int k = 0; k < nc; ++k) cm |= 1ull << (nlocal - 1 - o.ctrl[k]);
+    q.push_1q(nlocal - 1 - o.target, cm, o.kind == 1 ? X : reinterpret_cast<const double *>(o.m));
+  }
+  int T, R;
+  effective_tile(opt, nlocal, T, R);
+  if (T == 0) return -2;
+  opt.tile_bits = T;
+  opt.reg_bits = R;
+  std::vector<PhysOp> pops;
+  for (const auto &h : q.ops) {
+    if (h.dead) continue;
+    PhysOp p;
+    p.type = h.type;
+    p.target = h.target;
+    p.ctrl = h.ctrl;
+    std::memcpy(p.m, h.m, sizeof(h.m));
+    pops.push_back(p);
+  }
+  PlanResult plan = plan_passes(pops, nlocal, 0, opt, q.gscale);
+  if (plan.consumed != pops.size()) return -3;
+  int njit = 0, idx = 0;
+  for (const auto &p : plan.passes) {
+    JitProgram dp;
+    std::string why;
+    if (jit_generate(p, JIT_DEVICE_SRC, dp, &why)) {
+      const std::string path = std::string(outdir) + "/pass_" + std::to_string(idx) + ".cu";
+      FILE *f = std::fopen(path.c_str(), "w");
+      if (!f) return -9;
+      std::fwrite(dp.src.data(), 1, dp.src.size(), f);
+      std::fclose(f);
+      ++njit;
+    }
+    ++idx;
+  }
+  if (stats_out) stats_out[0] = njit;
+  return idx;
+}
+
+
 // Distributed flush of ONE rank, emulated on the host.  `amps` is this rank's shard (2 * 2^L
 // doubles).  Whenever the planner is stuck on gates that target global qubits, the same
 // choose_swaps / swap_schedule code the NCCL path uses decides the exchange, and `xchg` moves

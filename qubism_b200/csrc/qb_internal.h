@@ -124,7 +124,8 @@ struct DevPass {
                                       // prefetches the next such group with one bulk request per chunk
   uint32_t jit_pf_last;               // ... issued while the LAST (1) or the FIRST (0) tile of the running group computes
   uint64_t base_fixed;                // known non-tile bits at their known value: OR-ed into every live tile's base
-  uint64_t _pad4;
+  uint32_t jit_minb;                  // specialised kernels: resident CTAs per SM to compile for (0 = automatic)
+  uint32_t _pad4;
   DevRound rounds[kMaxRounds];
   // followed in memory by ngates DevGate records (lite: by nsteps DevStep records)
 };
@@ -179,9 +180,10 @@ struct PlanOptions {
   int lite = 1;           // passes of rotations and X / CX only use the lean kernel instantiation
   int jit = 2;            // k > 0: a step-pass STRUCTURE seen k times is compiled (NVRTC) into a straight-line
                           // kernel and cached (qb_jit.cpp); 0 = generic kernels only
-  int jit_group = 2;      // specialised kernels: tiles a CTA takes in a row (1, 2, 4).  Consecutive tiles are
+  int jit_group = 1;      // specialised kernels: tiles a CTA takes in a row (1, 2, 4).  Consecutive tiles are
                           // neighbours in memory, so a group is prefetched as runs of group x chunk bytes:
                           // DRAM sees 256-512 contiguous bytes per row activation instead of 128
+  int jit_minb = 0;       // specialised kernels: CTAs per SM to compile for (0 = automatic)
   int jit_pf_last = 1;    // prefetch the next group during the last (1) / first (0) tile of the running one
   int hot_bits = 0;       // planner: max distinct TARGET bits per pass (0 = tile_bits).  With
                           // hot_bits <= tile_bits - warp bits every transpose can stay warp-local.

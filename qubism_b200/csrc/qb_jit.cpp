@@ -4,6 +4,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
+#include <array>
 #include <sstream>
 
 namespace qb {
@@ -101,7 +103,7 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
     const int want = P.jit_group ? (int)P.jit_group : 1;
     while (group * 2 <= want && group * 2 <= (1 << std::min<uint32_t>(P.run_len[0], 8))) group *= 2;
   }
-  const size_t smem = (size_t(16) << T) + size_t(nrounds) * NT * sizeof(uint16_t) + size_t(2) * NT * sizeof(uint64_t) +
+  const size_t smem = (size_t(16) << T) + size_t(std::max(1, 2 * (nrounds - 1))) * NT * sizeof(uint16_t) + size_t(2) * NT * sizeof(uint64_t) +
                       (size_t(group) << (T - 3)) * sizeof(uint32_t);
   int minb;
   {
@@ -109,12 +111,102 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
     const int by_regs = 65536 / (NT * regs_wanted);
     const int by_smem = (int)((227u * 1024u) / (smem + 1024));
     minb = std::max(1, std::min(std::min(by_regs, by_smem), 8));
+    if (P.jit_minb) minb = std::max(1, std::min((int)P.jit_minb, by_smem));
   }
   const std::string sT = g.dec(T), sR = g.dec(R), sNT = g.dec(NT), sMINB = g.dec(minb), sNROUNDS = g.dec(nrounds);
   const std::string sL2 = g.dec(l2pf);
   const bool has_gs = P.has_gscale != 0;
   g.dec(has_gs);
   const int LPT = 1 << (R - 3);
+  // ---- one shared-memory swizzle PER TRANSPOSE.  The slot of tile-local index u is
+  // u ^ (XOR over the set bits p >= 3 of u of col[p]), col[p] in 1..7: a bijection for any choice.
+  // A 128-bit access of a quarter warp is conflict-free iff the three lowest lane bits move the
+  // 16-byte bank group independently: the vectors v(p) = (p < 3 ? 1 << p : col[p]) of their tile
+  // positions must be linearly independent over GF(2) -- on the store side (previous round's
+  // layout) AND on the load side (this round's).  The fixed swizzle of the generic kernels
+  // (col[p] = 1 << (p % 3)) leaves 2-way conflicts where the planner kept lane bits whose
+  // positions share a residue (ncu: ~1/3 of all shared-store wavefronts); here the columns of
+  // the six positions involved are simply searched.
+  const int ntab = std::max(1, 2 * (nrounds - 1));
+  std::vector<std::array<uint8_t, 16>> swz_col(nrounds);
+  int swz_conflicts = 0, swz_fixed = 0;
+  for (int r = 1; r < nrounds; ++r) {
+    std::array<uint8_t, 16> col{};
+    for (int p = 0; p < 16; ++p) col[p] = (uint8_t)(1u << (p % 3));
+    swz_col[r] = col;
+    if (T - R < 3) continue;
+    const DevRound &PR = P.rounds[r - 1], &RD = P.rounds[r];
+    // the flip-mask toggles of the previous round: a pending flip XORs the register bit's
+    // contribution into the STORE address of the threads that hold it, and which threads do
+    // depends on thread-id bits -- possibly on the three lowest lane bits
+    struct Tg { uint32_t cthr, bit; bool ext; };
+    std::vector<Tg> togs;
+    for (uint32_t si = PR.step_begin; si < PR.step_end; ++si)
+      for (uint32_t k = 0; k < S[si].ntog && k < (uint32_t)kStepToggles; ++k)
+        if (S[si].tog[k].cthr || S[si].tog[k].cext) togs.push_back({S[si].tog[k].cthr, S[si].tog[k].bit, S[si].tog[k].cext != 0});
+    auto vec = [&](int pos) { return pos < 3 ? (uint8_t)(1u << pos) : col[pos]; };
+    auto collisions = [&]() {
+      int bad = 0;
+      for (int scen = 0; scen < 4; ++scen) {  // the other thread-id bits all 0 / all 1, external controls unmet / met
+        const uint32_t others = (scen & 1) ? (uint32_t)(NT - 1) & ~7u : 0u;
+        const bool ext_ok = (scen & 2) != 0;
+        uint32_t seen_st = 0, seen_ld = 0;
+        for (uint32_t l = 0; l < 8; ++l) {
+          const uint32_t tid = l | others;
+          uint32_t f = 0;
+          for (const Tg &t : togs)
+            if ((tid & t.cthr) == t.cthr && (!t.ext || ext_ok)) f ^= 1u << t.bit;
+          uint8_t a = 0, b = 0;
+          for (int k = 0; k < 3; ++k)
+            if ((l >> k) & 1u) {
+              a ^= vec(PR.tid_pos[k]);
+              b ^= vec(RD.tid_pos[k]);
+            }
+          for (int j = 0; j < R; ++j)
+            if ((f >> j) & 1u) a ^= vec(PR.reg_pos[j]);
+          if (seen_st & (1u << a)) ++bad;
+          if (seen_ld & (1u << b)) ++bad;
+          seen_st |= 1u << a;
+          seen_ld |= 1u << b;
+        }
+      }
+      return bad;
+    };
+    int best = collisions();
+    if (best > 0) {
+      std::vector<int> freep;  // positions >= 3 whose column matters: the six lane positions, the toggled register bits
+      auto add = [&](int pos) {
+        if (pos >= 3 && std::find(freep.begin(), freep.end(), pos) == freep.end()) freep.push_back(pos);
+      };
+      for (int k = 0; k < 3; ++k) {
+        add(PR.tid_pos[k]);
+        add(RD.tid_pos[k]);
+      }
+      for (const Tg &t : togs) add(PR.reg_pos[t.bit]);
+      std::array<uint8_t, 16> bestcol = col;
+      uint64_t rng = 0x9E3779B97F4A7C15ull + (uint64_t)r;
+      for (int tries = 0; tries < 4000 && best > 0; ++tries) {
+        for (int pos : freep) {
+          rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+          col[pos] = (uint8_t)(1 + (rng >> 33) % 7);
+        }
+        const int c = collisions();
+        if (c < best) {
+          best = c;
+          bestcol = col;
+        }
+      }
+      col = bestcol;
+      if (best > 0) ++swz_conflicts; else ++swz_fixed;
+    }
+    swz_col[r] = col;
+  }
+  auto swz_of = [&](int r, uint32_t u) {  // swizzle of transpose r (linear over XOR)
+    uint32_t x = u;
+    for (int p = 3; p < T; ++p)
+      if ((u >> p) & 1u) x ^= swz_col[r][p];
+    return x;
+  };
   const std::string sG = g.dec(group), sCB = g.dec(cbits);
   const std::string sPFK = g.dec((group > 1 && P.jit_pf_last) ? group - 1 : 0);  // prefetch while this tile of the group computes
 
@@ -147,8 +239,16 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
   auto stride_of = [&](const DevRound &rd, int j) { return 1ull << P.tile_pos[rd.reg_pos[j]]; };
 
   auto emit_tables = [&]() {
-    for (int r = 0; r < nrounds; ++r)
-      g.line("sidx_tab[" + std::to_string(r) + " * QBJ_NT + tid] = (u16)qbj_swz(" + tid_bits_expr(P.rounds[r], false, "tid") + ");");
+    // per transpose: this thread's swizzled slot in the STORE layout (table 2(r-1)) and in the
+    // LOAD layout (table 2(r-1)+1); the swizzle is linear, so each thread-id bit XORs a literal
+    for (int r = 1; r < nrounds; ++r)
+      for (int side = 0; side < 2; ++side) {
+        const DevRound &rd = P.rounds[side ? r : r - 1];
+        std::string e = "0u";
+        for (int j = 0; j < T - R; ++j)
+          e += " ^ ((0u - ((tid >> " + std::to_string(j) + ") & 1u)) & " + g.lit(swz_of(r, 1u << rd.tid_pos[j])) + ")";
+        g.line("sidx_tab[" + std::to_string(2 * (r - 1) + side) + " * QBJ_NT + tid] = (u16)(" + e + ");");
+      }
     g.line("goff_tab[tid] = " + tid_bits_expr(R0, true, "tid") + ";");
     g.line("goff_tab[QBJ_NT + tid] = " + tid_bits_expr(RL, true, "tid") + ";");
     for (int k = 0; k < LPT; ++k) {
@@ -203,11 +303,11 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
     }
     g.line("}");
   };
-  auto sx_of = [&](const DevRound &rd, int i) {
-    uint32_t c = 0;
+  auto sx_of = [&](int r, const DevRound &rd, int i) {  // byte offset contribution of register index i in transpose r
+    uint32_t u = 0;
     for (int j = 0; j < R; ++j)
-      if ((i >> j) & 1) c ^= rd.reg_sx[j] << 4;
-    return c;
+      if ((i >> j) & 1) u |= 1u << rd.reg_pos[j];
+    return swz_of(r, u) << 4;
   };
 
   // ---------------------------------------------------------------- the rounds (both modes)
@@ -224,17 +324,17 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
         g.tag("tr");
         g.dec(mf);
         if (local) g.barrier(true);  // (the lanes of this warp finished reading the previous layout)
-        g.line("u32 us" + sr + " = (u32)sidx_tab[" + std::to_string(r - 1) + " * QBJ_NT + tid] << 4;");
+        g.line("u32 us" + sr + " = (u32)sidx_tab[" + std::to_string(2 * (r - 1)) + " * QBJ_NT + tid] << 4;");
         for (int j = 0; j < R; ++j)
           if ((mf >> j) & 1u)
-            g.line("us" + sr + " ^= (0u - ((f >> " + std::to_string(j) + ") & 1u)) & " + g.lit(PR.reg_sx[j] << 4) + ";");
+            g.line("us" + sr + " ^= (0u - ((f >> " + std::to_string(j) + ") & 1u)) & " + g.lit(swz_of(r, 1u << PR.reg_pos[j]) << 4) + ";");
         g.line("f = 0;");
         mf = 0;
         for (int i = 0; i < NR; ++i)
-          g.line("QBJ_STS(us" + sr + " ^ " + g.lit(sx_of(PR, i)) + ", re[" + std::to_string(i) + "], im[" + std::to_string(i) + "]);");
+          g.line("QBJ_STS(us" + sr + " ^ " + g.lit(sx_of(r, PR, i)) + ", re[" + std::to_string(i) + "], im[" + std::to_string(i) + "]);");
         g.barrier(local);
-        g.line("const u32 ul" + sr + " = (u32)sidx_tab[" + sr + " * QBJ_NT + tid] << 4;");
-        for (int i = 0; i < NR; ++i) g.line("QBJ_LDS(ul" + sr + " ^ " + g.lit(sx_of(RD, i)) + ", " + std::to_string(i) + ");");
+        g.line("const u32 ul" + sr + " = (u32)sidx_tab[" + std::to_string(2 * (r - 1) + 1) + " * QBJ_NT + tid] << 4;");
+        for (int i = 0; i < NR; ++i) g.line("QBJ_LDS(ul" + sr + " ^ " + g.lit(sx_of(r, RD, i)) + ", " + std::to_string(i) + ");");
         // free the buffer for the next CTA-wide transpose (of this tile, or the first of the next)
         if (P.rounds[(r + 1 < nrounds) ? r + 1 : 1].warp_local == 0) g.barrier(false);
       }
@@ -365,7 +465,7 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
            "  const u32 tid = threadIdx.x;\n"
            "  u16 *sidx_tab = reinterpret_cast<u16 *>(smem_raw + (16u << QBJ_T));\n"
            "  u64 *goff_tab = reinterpret_cast<u64 *>(sidx_tab + "
-        << sNROUNDS
+        << ntab
         << " * QBJ_NT);\n"
            "  u32 *line_tab = reinterpret_cast<u32 *>(goff_tab + 2 * QBJ_NT);\n  {\n";
       emit_tables();
@@ -457,7 +557,7 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
            "static double RE[QBJ_NT][QBJ_NR], IM[QBJ_NT][QBJ_NR], SM[2 << QBJ_T];\n"
            "static u32 F[QBJ_NT];\n"
            "static u16 sidx_tab["
-        << sNROUNDS
+        << ntab
         << " * QBJ_NT];\nstatic u64 goff_tab[2 * QBJ_NT];\nstatic u32 line_tab[(1 << (QBJ_T - 3))];\n"
            "extern \"C\" int qb_jit_pass_host(double *amps, u64 ntiles, const QbjArgs *Ap, u64 args_bytes) {\n"
            "  if (args_bytes != sizeof(QbjArgs)) return -1;\n"
@@ -485,6 +585,8 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
   out.R = R;
   out.minb = minb;
   out.nrounds = nrounds;
+  out.swz_fixed = swz_fixed;
+  out.swz_conflicts = swz_conflicts;
   out.smem = smem;
   out.args_bytes = sizeof(JitArgsHead) + sizeof(double) * std::max<size_t>(1, out.coefs.size());
   if (!std::isfinite(out.left_out) || out.left_out == 0.0) return fail("deferred factor out of range");

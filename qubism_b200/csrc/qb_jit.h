@@ -23,6 +23,8 @@ struct JitProgram {
   double left_out = 1.0;       // true amplitudes = left_out * what the kernel writes
   std::string src;             // only if requested
   int T = 0, R = 0, minb = 2, nrounds = 0;
+  int swz_fixed = 0;           // transposes whose swizzle columns were re-chosen to remove a bank conflict
+  int swz_conflicts = 0;       // transposes left with a 2-way conflict (no assignment found)
   size_t smem = 0;             // dynamic shared memory of the device kernel
   size_t args_bytes = 0;       // sizeof(QbjArgs)
 };

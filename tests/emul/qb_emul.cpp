@@ -514,6 +514,7 @@ int qbe_jit_dump(int nlocal, const qb_op *ops, int64_t nops, const char *options
   PlanResult plan = plan_passes(pops, nlocal, 0, opt, q.gscale);
   if (plan.consumed != pops.size()) return -3;
   int njit = 0, idx = 0;
+  int64_t nfixed = 0, nconf = 0, ntrans = 0;
   for (const auto &p : plan.passes) {
     JitProgram dp;
     std::string why;
@@ -524,10 +525,18 @@ int qbe_jit_dump(int nlocal, const qb_op *ops, int64_t nops, const char *options
       std::fwrite(dp.src.data(), 1, dp.src.size(), f);
       std::fclose(f);
       ++njit;
+      nfixed += dp.swz_fixed;
+      nconf += dp.swz_conflicts;
+      ntrans += dp.nrounds - 1;
     }
     ++idx;
   }
-  if (stats_out) stats_out[0] = njit;
+  if (stats_out) {
+    stats_out[0] = njit;
+    stats_out[1] = ntrans;
+    stats_out[2] = nfixed;
+    stats_out[3] = nconf;
+  }
   return idx;
 }
 

@@ -125,7 +125,7 @@ struct DevPass {
   uint32_t jit_pf_last;               // ... issued while the LAST (1) or the FIRST (0) tile of the running group computes
   uint64_t base_fixed;                // known non-tile bits at their known value: OR-ed into every live tile's base
   uint32_t jit_minb;                  // specialised kernels: resident CTAs per SM to compile for (0 = automatic)
-  uint32_t _pad4;
+  uint32_t jit_mem;                   // specialised kernels: cache policy of the global accesses (QBJ_MEM, qb_jit_prelude.cuh)
   DevRound rounds[kMaxRounds];
   // followed in memory by ngates DevGate records (lite: by nsteps DevStep records)
 };
@@ -184,6 +184,7 @@ struct PlanOptions {
                           // neighbours in memory, so a group is prefetched as runs of group x chunk bytes:
                           // DRAM sees 256-512 contiguous bytes per row activation instead of 128
   int jit_minb = 0;       // specialised kernels: CTAs per SM to compile for (0 = automatic)
+  int jit_mem = 0;        // specialised kernels: cache policy of the global loads / stores (QBJ_MEM)
   int jit_pf_last = 1;    // prefetch the next group during the last (1) / first (0) tile of the running one
   int hot_bits = 0;       // planner: max distinct TARGET bits per pass (0 = tile_bits).  With
                           // hot_bits <= tile_bits - warp bits every transpose can stay warp-local.

@@ -207,7 +207,7 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
       if ((u >> p) & 1u) x ^= swz_col[r][p];
     return x;
   };
-  const std::string sG = g.dec(group), sCB = g.dec(cbits);
+  const std::string sG = g.dec(group), sCB = g.dec(cbits), sMEM = g.dec(P.jit_mem);
   const std::string sPFK = g.dec((group > 1 && P.jit_pf_last) ? group - 1 : 0);  // prefetch while this tile of the group computes
 
   // ---------------------------------------------------------------- fragments shared by both modes
@@ -441,7 +441,7 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
     emit_store(mf_end);
   } else {
     std::ostringstream &o = g.o;
-    o << "#define QBJ_T " << sT << "\n#define QBJ_R " << sR << "\n#define QBJ_NT " << sNT << "\n";
+    o << "#define QBJ_T " << sT << "\n#define QBJ_R " << sR << "\n#define QBJ_NT " << sNT << "\n#define QBJ_MEM " << sMEM << "\n";
     if (g.host) o << "#define QB_JIT_HOST 1\n";
     o << kPrelude << "\n";
     // the rounds are generated first (into a side buffer): the coefficient count sizes QbjArgs
@@ -454,9 +454,9 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
     o << "struct QbjArgs { double gs[2]; u64 rank_bits; u64 base_fixed; double c[" << nc << "]; };\n";
     if (!g.host) {
       o << "#define QBJ_LD2(p, i) qbj_ld256(amps + (p), re[i], im[i], re[(i) + 1], im[(i) + 1])\n"
-           "#define QBJ_LD1(p, i) { const double2 a_ = __ldcs(amps + (p)); re[i] = a_.x; im[i] = a_.y; }\n"
+           "#define QBJ_LD1(p, i) qbj_ld128(amps + (p), re[i], im[i])\n"
            "#define QBJ_ST2(p, a0, a1, b0, b1) qbj_st256(amps + (p), a0, a1, b0, b1)\n"
-           "#define QBJ_ST1(p, xr, xi) __stcs(amps + (p), make_double2(xr, xi))\n"
+           "#define QBJ_ST1(p, xr, xi) qbj_st128(amps + (p), xr, xi)\n"
            "#define QBJ_STS(off, xr, xi) *reinterpret_cast<double2 *>(smem_raw + (off)) = make_double2(xr, xi)\n"
            "#define QBJ_LDS(off, i) { const double2 a_ = *reinterpret_cast<const double2 *>(smem_raw + (off)); re[i] = a_.x; im[i] = a_.y; }\n";
       o << "extern \"C\" __global__ void __launch_bounds__(QBJ_NT, " << sMINB

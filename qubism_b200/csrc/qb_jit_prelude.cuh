@@ -54,21 +54,88 @@ QBJ_DEV void qbj_cswap(double &a, double &b, bool ok) {
   a = __longlong_as_double(__double_as_longlong(a) ^ x);
   b = __longlong_as_double(__double_as_longlong(b) ^ x);
 }
+// global accesses: cache policy selected by QBJ_MEM (option jit_mem; measured in profiles/)
+//   0 ld.cs / st.cs   1 ld.cs / st.wb   2 ld.ca-default / st.cs   3 ld.cs / st.cg   4 ld.lu / st.cs
+//   5 L2 evict_first on both   6 ld.cs / st with L2 evict_last   7 ld.cs / st with L2 evict_first
+#ifndef QBJ_MEM
+#define QBJ_MEM 0
+#endif
+#if QBJ_MEM == 1
+#define QBJ_LDQ "ld.global.cs"
+#define QBJ_STQ "st.global.wb"
+#elif QBJ_MEM == 2
+#define QBJ_LDQ "ld.global"
+#define QBJ_STQ "st.global.cs"
+#elif QBJ_MEM == 3
+#define QBJ_LDQ "ld.global.cs"
+#define QBJ_STQ "st.global.cg"
+#elif QBJ_MEM == 4
+#define QBJ_LDQ "ld.global.lu"
+#define QBJ_STQ "st.global.cs"
+#else
+#define QBJ_LDQ "ld.global.cs"
+#define QBJ_STQ "st.global.cs"
+#endif
+#if QBJ_MEM >= 5
+#define QBJ_HINT 1
+QBJ_DEV u64 qbj_policy_first() {
+  u64 p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+QBJ_DEV u64 qbj_policy_last() {
+  u64 p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+#endif
+QBJ_DEV void qbj_ld128(const double2 *p, double &a0, double &a1) {
+#if QBJ_MEM == 5
+  asm volatile("ld.global.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(a0), "=d"(a1) : "l"(p), "l"(qbj_policy_first()));
+#else
+  asm volatile(QBJ_LDQ ".v2.f64 {%0,%1}, [%2];" : "=d"(a0), "=d"(a1) : "l"(p));
+#endif
+}
+QBJ_DEV void qbj_st128(double2 *p, double a0, double a1) {
+#if QBJ_MEM == 5 || QBJ_MEM == 7
+  asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1,%2}, %3;" ::"l"(p), "d"(a0), "d"(a1), "l"(qbj_policy_first()) : "memory");
+#elif QBJ_MEM == 6
+  asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1,%2}, %3;" ::"l"(p), "d"(a0), "d"(a1), "l"(qbj_policy_last()) : "memory");
+#else
+  asm volatile(QBJ_STQ ".v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(a0), "d"(a1) : "memory");
+#endif
+}
 #ifndef QBJ_NO_LD256
 QBJ_DEV void qbj_ld256(const double2 *p, double &a0, double &a1, double &b0, double &b1) {
-  asm volatile("ld.global.cs.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a0), "=d"(a1), "=d"(b0), "=d"(b1) : "l"(p));
+#if QBJ_MEM == 5
+  asm volatile("ld.global.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;"
+               : "=d"(a0), "=d"(a1), "=d"(b0), "=d"(b1)
+               : "l"(p), "l"(qbj_policy_first()));
+#else
+  asm volatile(QBJ_LDQ ".v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a0), "=d"(a1), "=d"(b0), "=d"(b1) : "l"(p));
+#endif
 }
 QBJ_DEV void qbj_st256(double2 *p, double a0, double a1, double b0, double b1) {
-  asm volatile("st.global.cs.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a0), "d"(a1), "d"(b0), "d"(b1) : "memory");
+#if QBJ_MEM == 5 || QBJ_MEM == 7
+  asm volatile("st.global.L2::cache_hint.v4.f64 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "d"(a0), "d"(a1), "d"(b0), "d"(b1),
+               "l"(qbj_policy_first())
+               : "memory");
+#elif QBJ_MEM == 6
+  asm volatile("st.global.L2::cache_hint.v4.f64 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "d"(a0), "d"(a1), "d"(b0), "d"(b1),
+               "l"(qbj_policy_last())
+               : "memory");
+#else
+  asm volatile(QBJ_STQ ".v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a0), "d"(a1), "d"(b0), "d"(b1) : "memory");
+#endif
 }
 #else  // an NVRTC older than CUDA 12.9: two 128-bit accesses
 QBJ_DEV void qbj_ld256(const double2 *p, double &a0, double &a1, double &b0, double &b1) {
-  const double2 x = __ldcs(p), y = __ldcs(p + 1);
-  a0 = x.x; a1 = x.y; b0 = y.x; b1 = y.y;
+  qbj_ld128(p, a0, a1);
+  qbj_ld128(p + 1, b0, b1);
 }
 QBJ_DEV void qbj_st256(double2 *p, double a0, double a1, double b0, double b1) {
-  __stcs(p, make_double2(a0, a1));
-  __stcs(p + 1, make_double2(b0, b1));
+  qbj_st128(p, a0, a1);
+  qbj_st128(p + 1, b0, b1);
 }
 #endif
 #endif

@@ -59,6 +59,9 @@ bool set_opt(PlanOptions &o, const std::string &name, int64_t v) {
   } else if (name == "jit_minb") {
     if (v < 0 || v > 8) return false;
     o.jit_minb = (int)v;
+  } else if (name == "jit_mem") {
+    if (v < 0 || v > 7) return false;
+    o.jit_mem = (int)v;
   } else if (name == "jit_pf_last") {
     o.jit_pf_last = v ? 1 : 0;
   } else if (name == "jit") {
@@ -109,6 +112,7 @@ int64_t get_opt(const PlanOptions &o, const std::string &name) {
   if (name == "jit") return o.jit;
   if (name == "jit_pf_last") return o.jit_pf_last;
   if (name == "jit_minb") return o.jit_minb;
+  if (name == "jit_mem") return o.jit_mem;
   if (name == "jit_group") return o.jit_group;
   if (name == "lite") return o.lite;
   if (name == "lane_fixed") return o.lane_fixed;
@@ -760,6 +764,7 @@ static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &don
   P->jit_group = (uint32_t)opt.jit_group;
   P->jit_pf_last = (uint32_t)opt.jit_pf_last;
   P->jit_minb = (uint32_t)opt.jit_minb;
+  P->jit_mem = (uint32_t)opt.jit_mem;
   P->dbg_skip = (uint32_t)opt.dbg_skip;
   P->sm_count = 148;
   for (int i = 0; i < T; ++i) P->tile_pos[i] = (uint8_t)tile_bits[i];

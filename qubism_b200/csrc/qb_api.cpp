@@ -57,6 +57,8 @@ struct qb_ctx {
   double *red_partials = nullptr;  // device, 2 * max blocks
   double *red_out = nullptr;       // device, 2 doubles (+2 spare)
   double *red_host = nullptr;      // pinned, 4 doubles
+  uint64_t jit_base_compiled = 0, jit_base_launches = 0;  // qb_reset_stats baselines of the process-wide counters
+  double jit_base_ms = 0.0;
   int *kq_bits_dev = nullptr;      // 2 * QB_MAX_KQ ints
   double2 *kq_mat_dev = nullptr;   // 4^QB_MAX_KQ
   PlanOptions opt;
@@ -1086,10 +1088,10 @@ int qb_get_stats(const qb_ctx *cc, qb_stats *out) {
   Guard g(c);
   QB_TRY(resolve_timed(c));
   *out = c->stats;
-  const JitStats js = jit_stats();  // (process-wide: one process per GPU)
-  out->jit_compiled = js.compiled;
-  out->jit_launches = js.launches;
-  out->jit_compile_ms = js.compile_ms;
+  const JitStats js = jit_stats();  // (process-wide counters: one process per GPU; reset = new baseline)
+  out->jit_compiled = js.compiled - c->jit_base_compiled;
+  out->jit_launches = js.launches - c->jit_base_launches;
+  out->jit_compile_ms = js.compile_ms - c->jit_base_ms;
   return QB_OK;
 }
 
@@ -1098,6 +1100,10 @@ int qb_reset_stats(qb_ctx *c) {
   Guard g(c);
   QB_TRY(resolve_timed(c));
   c->stats = qb_stats{};
+  const JitStats js = jit_stats();
+  c->jit_base_compiled = js.compiled;
+  c->jit_base_launches = js.launches;
+  c->jit_base_ms = js.compile_ms;
   return QB_OK;
 }
 

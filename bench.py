@@ -229,6 +229,12 @@ def run_ours(args):
         clocks.start()  # nvidia-smi takes a moment to start: launch it before the warm-up
     for _ in range(args.warmup):
         step()
+    # pass structures that came back during the warm-up are being compiled into specialised
+    # kernels on background threads: let that finish, and give the next sighting (which loads
+    # the modules) its own untimed steps -- the timed region measures the steady state
+    for _ in range(2):
+        ctx.jit_wait()
+        step()
     barrier()
     ctx.reset_stats()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -293,6 +299,8 @@ def run_ours(args):
         w = sv.local_to_host(0, win)
         return red, w
 
+    e2e_step()
+    ctx.jit_wait()
     e2e_step()
     barrier()
     t0 = time.perf_counter()
@@ -360,8 +368,8 @@ def run_ours(args):
                    "planner": {k: ctx.get_option(k) for k in ("tile_bits", "reg_bits", "low_bits", "lane_fixed", "max_rounds", "peephole", "rot", "lite", "jit")},
                    "specialised_kernels": {"compiled": st["jit_compiled"], "compile_ms_total": st["jit_compile_ms"],
                                            "launches_in_timed_region": st["jit_launches"],
-                                           "note": "pass structures seen twice are compiled with NVRTC during the warm-up steps; "
-                                                   "the timed steps hit the cache"},
+                                           "note": "pass structures seen twice are compiled with NVRTC on background threads during "
+                                                   "the warm-up steps (W + 2 untimed steps); the timed steps hit the cache"},
                    "ops_executed_per_step": st["ops_executed"] / args.steps,
                    "ops_folded_per_step": st["ops_folded"] / args.steps,
                    "passes_per_step": passes, "rounds_per_step": st["rounds"] / args.steps,

@@ -184,7 +184,9 @@ void *qb_ctx_stream(qb_ctx *ctx);
  * "lite" (step-packed passes), "skip_dead" (skip all-zero tiles using the tracked support),
  * "time_kernels" (bracket every fused launch with CUDA events), "jit" (k > 0: a pass structure
  * seen k times is compiled with NVRTC into a straight-line kernel -- structure as literals, gate
- * coefficients still kernel parameters -- and cached; 0 = generic kernels only).  Returns
+ * coefficients still kernel parameters -- and cached; k = 1 compiles at first sight in the
+ * calling thread, k >= 2 in background threads while the generic kernel keeps running;
+ * 0 = generic kernels only).  Returns
  * QB_ERR_ARG for unknown names / bad values. */
 int qb_set_option(qb_ctx *ctx, const char *name, int64_t value);
 int64_t qb_get_option(const qb_ctx *ctx, const char *name);
@@ -194,6 +196,10 @@ int64_t qb_get_option(const qb_ctx *ctx, const char *name);
 int64_t qb_plan_describe(int nlocal, const qb_op *ops, int64_t nops, const char *options,
                          char *buf, int64_t buflen);
 
+/* Block until no background compilation of a specialised kernel is pending (option "jit" >= 2
+ * compiles on worker threads while the generic kernels keep running).  Benchmarks call it after
+ * their warm-up; nothing else needs it. */
+int qb_jit_sync(qb_ctx *ctx);
 /* Host-only check of the specialised-kernel toolchain (no device needed): compile `src` (CUDA C++)
  * with NVRTC for sm_100a; *cubin_bytes = size of the resulting cubin.  QB_ERR_UNSUPPORTED if
  * libnvrtc cannot be loaded, QB_ERR_CUDA if the compilation fails (log in qb_last_error). */

@@ -339,6 +339,8 @@ int run_fused_segment(qb_state *s, std::vector<const HostOp *> seg, const double
     std::vector<void *> jit_handle(npass, nullptr);
     std::vector<JitProgram> jit_prog(npass);
     std::vector<double> mid_scale(npass, 0.0);  // != 0: this (not last) pass applies the running factor (range guard)
+    std::vector<double> generic_undo(npass, 0.0);  // != 0: a GENERIC kernel runs a pass that is defined to leave
+                                                   // this factor out: it divides by it on the way out
     if (jit_thr) {
       for (size_t i = 0; i < npass; ++i) {
         PassPlan &p = plan.passes[i];
@@ -355,18 +357,21 @@ int run_fused_segment(qb_state *s, std::vector<const HostOp *> seg, const double
           mid_scale[i] = 1.0;
         }
         const int jr = jit_lookup(jit_prog[i], p, jit_thr, &jit_handle[i], &err);
-        if (jr < 0) {
-          if (c->nranks > 1) return fail(QB_ERR_CUDA, "specialised kernel: %s", err.c_str());
-          jit_handle[i] = nullptr;  // single GPU: the generic kernel computes the same thing
-        }
-        if (jit_handle[i]) {
+        if (jr < 0) jit_handle[i] = nullptr;  // the generic kernel computes the same thing
+        // Sharded states: WHICH kernel runs may differ between ranks (background compilation
+        // finishes at different times), so there the pass is DEFINED to leave its factor out
+        // whichever kernel runs -- exchanges move raw device amplitudes, every shard must carry
+        // the same pending factor.  On one GPU only a specialised kernel leaves anything out.
+        const bool leaves_out = jit_handle[i] != nullptr || c->nranks > 1;
+        if (leaves_out) {
           s->jit_left *= jit_prog[i].left_out;
+          if (!jit_handle[i]) generic_undo[i] = jit_prog[i].left_out;
           if (mid_scale[i] != 0.0) {
             mid_scale[i] = s->jit_left;
             s->jit_left = 1.0;
           }
         } else if (mid_scale[i] != 0.0) {
-          mid_scale[i] = 1.0;  // generic kernel after all: it scales by one
+          mid_scale[i] = 1.0;  // generic kernel, nothing left out: it scales by one
         }
       }
     }
@@ -378,6 +383,22 @@ int run_fused_segment(qb_state *s, std::vector<const HostOp *> seg, const double
         DevPass *P = reinterpret_cast<DevPass *>(plan.passes.back().blob.data());
         P->gscale[0] = gfin[0];
         P->gscale[1] = gfin[1];
+      }
+    }
+    for (size_t i = 0; i < npass; ++i) {  // the scalar each pass applies on its way out
+      DevPass *P = reinterpret_cast<DevPass *>(plan.passes[i].blob.data());
+      if (mid_scale[i] != 0.0) {
+        P->gscale[0] = mid_scale[i];
+        P->gscale[1] = 0.0;
+      }
+      if (generic_undo[i] != 0.0) {
+        if (!P->has_gscale) {
+          P->has_gscale = 1;
+          P->gscale[0] = 1.0;
+          P->gscale[1] = 0.0;
+        }
+        P->gscale[0] /= generic_undo[i];
+        P->gscale[1] /= generic_undo[i];
       }
     }
     for (size_t i = 0; i < npass; ++i) {
@@ -392,10 +413,6 @@ int run_fused_segment(qb_state *s, std::vector<const HostOp *> seg, const double
         if (jit_handle[i]) {
           const DevPass *P = reinterpret_cast<const DevPass *>(p.blob.data());
           double gs[2] = {P->gscale[0], P->gscale[1]};
-          if (mid_scale[i] != 0.0) {
-            gs[0] = mid_scale[i];
-            gs[1] = 0.0;
-          }
           if (!P->has_gscale) gs[0] = 1.0, gs[1] = 0.0;
           std::string err;
           const std::vector<uint8_t> args = jit_pack_args(jit_prog[i], gs, P->rank_bits, P->base_fixed);
@@ -1119,6 +1136,12 @@ int qb_set_option(qb_ctx *c, const char *name, int64_t value) {
 int64_t qb_get_option(const qb_ctx *c, const char *name) {
   if (!c || !name) return QB_ERR_ARG;
   return get_opt(c->opt, name);
+}
+
+int qb_jit_sync(qb_ctx *c) {
+  if (!c) return fail(QB_ERR_ARG, "null ctx");
+  jit_wait();
+  return QB_OK;
 }
 
 int qb_jit_compile_check(const char *src, int64_t *cubin_bytes) {

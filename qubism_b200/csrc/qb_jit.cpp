@@ -614,7 +614,10 @@ std::vector<uint8_t> jit_pack_args(const JitProgram &p, const double gs[2], uint
 #include <dlfcn.h>
 
 #include <chrono>
+#include <condition_variable>
+#include <deque>
 #include <mutex>
+#include <thread>
 #include <unordered_map>
 
 namespace qb {
@@ -726,7 +729,9 @@ std::string cu_err(CUresult r) {
 
 struct Entry {
   int seen = 0;
-  int state = 0;  // 0 not compiled, 1 ready, -1 failed (stay on the generic kernel)
+  int state = 0;  // 0 not compiled, 1 ready, -1 failed (stay on the generic kernel), 2 compiling, 3 cubin ready
+  std::vector<char> cubin;
+  std::string err;
   CUmodule mod = nullptr;
   CUfunction fn = nullptr;
   int occ = 0, threads = 0;
@@ -795,56 +800,153 @@ bool jit_compile_only(const std::string &src, size_t *cubin_bytes, std::string *
   return true;
 }
 
+namespace {
+
+// ---- background compilation: NVRTC runs on worker threads (it is CPU work and thread-safe);
+// every CUDA driver call stays on the caller's thread (module load at the next sighting)
+struct Job {
+  Entry *e;
+  PassPlan pp;  // blob only
+};
+struct Pool {
+  std::mutex mu;
+  std::condition_variable cv, idle;
+  std::deque<Job> jobs;
+  int inflight = 0;
+  int nworkers = 0;
+};
+Pool &pool() {
+  static Pool *p = new Pool;  // never destroyed: workers may outlive static destruction
+  return *p;
+}
+
+bool build_cubin(const PassPlan &pp, std::vector<char> &cubin, JitProgram &full, std::string *err) {
+  std::string why;
+  if (!jit_generate(pp, JIT_DEVICE_SRC, full, &why)) {
+    if (err) *err = "generator: " + why;
+    return false;
+  }
+  return compile_cubin(full.src, cubin, err);
+}
+
+void worker_main() {
+  Pool &P = pool();
+  for (;;) {
+    Job job;
+    {
+      std::unique_lock<std::mutex> lk(P.mu);
+      P.cv.wait(lk, [&] { return !P.jobs.empty(); });
+      job = std::move(P.jobs.front());
+      P.jobs.pop_front();
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    std::vector<char> cubin;
+    JitProgram full;
+    std::string err;
+    const bool ok = build_cubin(job.pp, cubin, full, &err);
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    {
+      std::lock_guard<std::mutex> lock(g_mu);
+      if (ok) {
+        job.e->cubin.swap(cubin);
+        job.e->smem = full.smem;
+        job.e->threads = 1 << (full.T - full.R);
+        job.e->state = 3;
+      } else {
+        job.e->state = -1;
+        job.e->err = err;
+        g_stats.failed++;
+      }
+      g_stats.compile_ms += ms;
+    }
+    {
+      std::lock_guard<std::mutex> lk(P.mu);
+      --P.inflight;
+    }
+    P.idle.notify_all();
+  }
+}
+
+// g_mu held.  cubin -> module -> function; state 1 or -1
+bool load_entry(Entry &e, std::string *err) {
+  Driver &d = driver();
+  CUresult r = d.ModuleLoadData(&e.mod, e.cubin.data());
+  if (r == CUDA_SUCCESS) r = d.ModuleGetFunction(&e.fn, e.mod, "qb_jit_pass");
+  if (r == CUDA_SUCCESS) r = d.FuncSetAttribute(e.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)e.smem);
+  if (r == CUDA_SUCCESS) r = d.OccupancyMaxActiveBlocksPerMultiprocessor(&e.occ, e.fn, e.threads, e.smem);
+  std::vector<char>().swap(e.cubin);
+  if (r != CUDA_SUCCESS || e.occ < 1) {
+    e.state = -1;
+    g_stats.failed++;
+    if (err) *err = "loading the specialised kernel: " + (r != CUDA_SUCCESS ? cu_err(r) : std::string("occupancy 0"));
+    return false;
+  }
+  e.state = 1;
+  g_stats.compiled++;
+  return true;
+}
+
+}  // namespace
+
 int jit_lookup(const JitProgram &kp, const PassPlan &pp, int threshold, void **handle, std::string *err) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
   std::string key = std::to_string(dev) + ":" + kp.key;
   std::lock_guard<std::mutex> lock(g_mu);
   Entry &e = g_cache[key];
+  if (e.state == 3 && !load_entry(e, err)) return -1;
   if (e.state == 1) {
     *handle = &e;
     return 1;
   }
-  if (e.state < 0) return 0;
+  if (e.state != 0) return 0;  // failed before, or still compiling: the generic kernel runs
   if (++e.seen < threshold) return 0;
   if (!jit_available(err)) {
     e.state = -1;
     g_stats.failed++;
     return -1;
   }
-  const auto t0 = std::chrono::steady_clock::now();
-  JitProgram full;
-  std::string why;
-  if (!jit_generate(pp, JIT_DEVICE_SRC, full, &why)) {
-    e.state = -1;
-    g_stats.failed++;
-    if (err) *err = "generator: " + why;
-    return -1;
+  if (threshold <= 1) {  // "specialise at first sight": compile here and now
+    const auto t0 = std::chrono::steady_clock::now();
+    JitProgram full;
+    if (!build_cubin(pp, e.cubin, full, err)) {
+      e.state = -1;
+      g_stats.failed++;
+      return -1;
+    }
+    e.smem = full.smem;
+    e.threads = 1 << (full.T - full.R);
+    const bool ok = load_entry(e, err);
+    g_stats.compile_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (!ok) return -1;
+    *handle = &e;
+    return 1;
   }
-  std::vector<char> cubin;
-  if (!compile_cubin(full.src, cubin, err)) {
-    e.state = -1;
-    g_stats.failed++;
-    return -1;
+  // a structure that came back: compile it in the background, keep running the generic kernel
+  e.state = 2;
+  Pool &P = pool();
+  {
+    std::lock_guard<std::mutex> lk(P.mu);
+    Job j;
+    j.e = &e;
+    j.pp.blob = pp.blob;
+    P.jobs.push_back(std::move(j));
+    ++P.inflight;
+    unsigned hw = std::thread::hardware_concurrency();
+    const int want = (int)std::max(1u, std::min(8u, hw ? hw / 2 : 2u));
+    while (P.nworkers < want && P.nworkers < (int)P.jobs.size()) {
+      std::thread(worker_main).detach();
+      ++P.nworkers;
+    }
   }
-  Driver &d = driver();
-  CUresult r = d.ModuleLoadData(&e.mod, cubin.data());
-  if (r == CUDA_SUCCESS) r = d.ModuleGetFunction(&e.fn, e.mod, "qb_jit_pass");
-  if (r == CUDA_SUCCESS) r = d.FuncSetAttribute(e.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)full.smem);
-  e.threads = 1 << (full.T - full.R);
-  e.smem = full.smem;
-  if (r == CUDA_SUCCESS) r = d.OccupancyMaxActiveBlocksPerMultiprocessor(&e.occ, e.fn, e.threads, e.smem);
-  if (r != CUDA_SUCCESS || e.occ < 1) {
-    e.state = -1;
-    g_stats.failed++;
-    if (err) *err = "loading the specialised kernel: " + (r != CUDA_SUCCESS ? cu_err(r) : std::string("occupancy 0"));
-    return -1;
-  }
-  e.state = 1;
-  g_stats.compiled++;
-  g_stats.compile_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-  *handle = &e;
-  return 1;
+  P.cv.notify_one();
+  return 0;
+}
+
+void jit_wait() {
+  Pool &P = pool();
+  std::unique_lock<std::mutex> lk(P.mu);
+  P.idle.wait(lk, [&] { return P.inflight == 0; });
 }
 
 int jit_launch(void *handle, void *amps, uint64_t ntiles, const std::vector<uint8_t> &args, int sm_count, void *stream,

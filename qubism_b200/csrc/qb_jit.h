@@ -48,14 +48,17 @@ struct JitStats {
   uint64_t compiled = 0, launches = 0, failed = 0;
   double compile_ms = 0.0;
 };
-// Looks the structure up; compiles it when it has been seen `threshold` times.  Returns 1 when a
-// kernel is ready (*handle set), 0 when the caller should use the generic kernel, < 0 on a
-// compile / load error (message in *err).
+// Looks the structure up.  threshold <= 1: compile at first sight, synchronously.  Otherwise a
+// structure seen `threshold` times is handed to background threads (NVRTC is CPU work) and the
+// generic kernel keeps running until the cubin is there.  Returns 1 when a kernel is ready
+// (*handle set), 0 when the caller should use the generic kernel, < 0 on a compile / load error
+// (message in *err).
 int jit_lookup(const JitProgram &key_only, const PassPlan &pp, int threshold, void **handle, std::string *err);
 // launch on `stream`; grid = SMs x resident CTAs (capped at ntiles)
 int jit_launch(void *handle, void *amps, uint64_t ntiles, const std::vector<uint8_t> &args, int sm_count, void *stream,
                std::string *err);
 bool jit_available(std::string *why);
+void jit_wait();  // block until no background compilation is pending
 // test hook: source -> cubin with NVRTC, no device needed
 bool jit_compile_only(const std::string &src, size_t *cubin_bytes, std::string *err);
 JitStats jit_stats();

@@ -59,6 +59,10 @@ class Context:
     def sync(self):
         capi.check(self.L.qb_sync(self.h))
 
+    def jit_wait(self):
+        """Block until no specialised kernel is being compiled in the background."""
+        capi.check(self.L.qb_jit_sync(self.h))
+
     def barrier(self):
         capi.check(self.L.qb_barrier(self.h))
 

@@ -29,6 +29,10 @@ for cfg in configs:
     for _ in range(3):
         sv.submit(ops)
         sv.flush()
+    for _ in range(2):
+        ctx.jit_wait()
+        sv.submit(ops)
+        sv.flush()
     ctx.sync()
     warm = time.perf_counter() - t0
     ctx.reset_stats()

@@ -336,7 +336,10 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
         g.line("const u32 ul" + sr + " = (u32)sidx_tab[" + std::to_string(2 * (r - 1) + 1) + " * QBJ_NT + tid] << 4;");
         for (int i = 0; i < NR; ++i) g.line("QBJ_LDS(ul" + sr + " ^ " + g.lit(sx_of(r, RD, i)) + ", " + std::to_string(i) + ");");
         // free the buffer for the next CTA-wide transpose (of this tile, or the first of the next)
-        if (P.rounds[(r + 1 < nrounds) ? r + 1 : 1].warp_local == 0) g.barrier(false);
+        // (wrapping to the next tile: also when the warps' slot regions differ between the last and
+        //  the first round, see qb_planner.cpp on rounds[0].warp_local)
+        if (r + 1 < nrounds ? P.rounds[r + 1].warp_local == 0 : (P.rounds[1].warp_local == 0 || P.rounds[0].warp_local == 0))
+          g.barrier(false);
       }
       for (uint32_t si = RD.step_begin; si < RD.step_end; ++si) {
         const DevStep &st = S[si];

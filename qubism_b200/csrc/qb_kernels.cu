@@ -714,7 +714,12 @@ __global__ void __launch_bounds__(1 << (T - R), MINB)
           }
           // free the buffer for the next CTA-wide transpose (of this tile, or the first one of the
           // next tile) now
-          if (P.rounds[(r + 1 < nrounds) ? r + 1 : 1].warp_local == 0) __syncthreads();
+          // (wrapping to the next tile: also when the warps' slot regions change between the last
+          //  and the first round -- rounds[0].warp_local == 0 -- or a fast warp's first local
+          //  transpose of the next tile would overwrite slots a slow warp is still reading here)
+          if (r + 1 < nrounds ? P.rounds[r + 1].warp_local == 0
+                              : (P.rounds[1].warp_local == 0 || P.rounds[0].warp_local == 0))
+            __syncthreads();
         }
       }
       const uint32_t wb = LITE != 0 ? RD.step_begin : RD.gate_begin, we = LITE != 0 ? RD.step_end : RD.gate_end;

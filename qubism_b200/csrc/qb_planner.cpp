@@ -813,7 +813,11 @@ static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &don
       order.insert(order.end(), rest.begin(), rest.end());
       order.insert(order.end(), warp_bits[r].begin(), warp_bits[r].end());
     }
-    RD.warp_local = (r > 0 && warp_bits[r] == warp_bits[r - 1]) ? 1u : 0u;
+    // round 0 has no transpose into it: its flag says whether the LAST round's warp bits equal the
+    // first round's, i.e. whether the first (warp-local) transpose of the NEXT tile only touches
+    // slots this warp itself read in the last transpose of this tile.  If not, the kernel must
+    // take a CTA barrier after the last transpose's loads even when the next transpose is local.
+    RD.warp_local = (r > 0 ? warp_bits[r] == warp_bits[r - 1] : warp_bits[0] == warp_bits[nrounds - 1]) ? 1u : 0u;
     for (int j = 0; j < T - R; ++j) RD.tid_pos[j] = (uint8_t)order[j];
     for (int j = 0; j < R; ++j) {
       RD.reg_pos[j] = (uint8_t)regs[j];

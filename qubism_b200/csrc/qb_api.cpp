@@ -356,13 +356,16 @@ int run_fused_segment(qb_state *s, std::vector<const HostOp *> seg, const double
           if (!jit_generate(p, JIT_KEY_ONLY, jit_prog[i], nullptr)) continue;
           mid_scale[i] = 1.0;
         }
-        const int jr = jit_lookup(jit_prog[i], p, jit_thr, &jit_handle[i], &err);
+        bool requested = false;
+        const int jr = jit_lookup(jit_prog[i], p, jit_thr, &jit_handle[i], &err, &requested);
         if (jr < 0) jit_handle[i] = nullptr;  // the generic kernel computes the same thing
         // Sharded states: WHICH kernel runs may differ between ranks (background compilation
-        // finishes at different times), so there the pass is DEFINED to leave its factor out
-        // whichever kernel runs -- exchanges move raw device amplitudes, every shard must carry
-        // the same pending factor.  On one GPU only a specialised kernel leaves anything out.
-        const bool leaves_out = jit_handle[i] != nullptr || c->nranks > 1;
+        // finishes at different times), so there a pass whose structure has reached the
+        // threshold -- the same on every rank -- is DEFINED to leave its factor out whichever
+        // kernel runs: exchanges move raw device amplitudes, every shard must carry the same
+        // pending factor.  On one GPU only a specialised kernel leaves anything out.
+        const bool leaves_out = c->nranks > 1 ? requested : jit_handle[i] != nullptr;
+        if (!leaves_out) jit_handle[i] = nullptr;
         if (leaves_out) {
           s->jit_left *= jit_prog[i].left_out;
           if (!jit_handle[i]) generic_undo[i] = jit_prog[i].left_out;

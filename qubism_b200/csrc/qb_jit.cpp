@@ -891,12 +891,17 @@ bool load_entry(Entry &e, std::string *err) {
 
 }  // namespace
 
-int jit_lookup(const JitProgram &kp, const PassPlan &pp, int threshold, void **handle, std::string *err) {
+int jit_lookup(const JitProgram &kp, const PassPlan &pp, int threshold, void **handle, std::string *err, bool *requested) {
   int dev = 0;
+  if (requested) *requested = false;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
   std::string key = std::to_string(dev) + ":" + kp.key;
   std::lock_guard<std::mutex> lock(g_mu);
   Entry &e = g_cache[key];
+  // `requested` depends only on how often this structure was looked up: every rank of a sharded
+  // state sees the same sequence of structures, so it is the same on all of them -- unlike the
+  // moment a background compilation finishes
+  if (requested) *requested = e.state != 0 || e.seen + 1 >= threshold;
   if (e.state == 3 && !load_entry(e, err)) return -1;
   if (e.state == 1) {
     *handle = &e;

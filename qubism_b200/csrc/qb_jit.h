@@ -53,7 +53,10 @@ struct JitStats {
 // generic kernel keeps running until the cubin is there.  Returns 1 when a kernel is ready
 // (*handle set), 0 when the caller should use the generic kernel, < 0 on a compile / load error
 // (message in *err).
-int jit_lookup(const JitProgram &key_only, const PassPlan &pp, int threshold, void **handle, std::string *err);
+// *requested (may be null): this structure has reached the threshold (now or earlier) -- a
+// function of the lookup sequence only, hence identical on every rank of a sharded state.
+int jit_lookup(const JitProgram &key_only, const PassPlan &pp, int threshold, void **handle, std::string *err,
+               bool *requested = nullptr);
 // launch on `stream`; grid = SMs x resident CTAs (capped at ntiles)
 int jit_launch(void *handle, void *amps, uint64_t ntiles, const std::vector<uint8_t> &args, int sm_count, void *stream,
                std::string *err);

@@ -232,7 +232,9 @@ def run_ours(args):
     # pass structures that came back during the warm-up are being compiled into specialised
     # kernels on background threads: let that finish, and give the next sighting (which loads
     # the modules) its own untimed steps -- the timed region measures the steady state
-    for _ in range(2):
+    # (sharded: the layout of the state cycles with a period of a few steps, a structure has to come
+    #  round twice before it is compiled)
+    for _ in range(2 if world == 1 else 6):
         ctx.jit_wait()
         step()
     barrier()

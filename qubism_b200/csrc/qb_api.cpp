@@ -242,7 +242,15 @@ int run_gscale_simple(qb_state *s, const double g[2]) {
 int make_local(qb_state *s, const std::vector<const HostOp *> &pending) {
   qb_ctx *c = s->ctx;
   if (c->nranks == 1) return fail(QB_ERR_UNSUPPORTED, "internal: planner stuck on a single GPU");
-  int rc = dist_make_local(c->dist, s->amps, s->peers, s->n, s->L, s->perm, pending, c->sm_count, c->stream, &c->stats);
+  // what comes after `pending`: assume the flush's op stream again (an iterated circuit).  Only
+  // consulted to order the qubits this flush never touches again, which would otherwise tie: the
+  // layout then settles into a short cycle (period 2 at 2 GPUs, 3 at 4 on the benchmark circuit)
+  // and the specialised kernels find their structures again
+  std::vector<const HostOp *> future;
+  for (const auto &op : s->q.ops)
+    if (!op.dead && op.kind == 0) future.push_back(&op);
+  int rc = dist_make_local(c->dist, s->amps, s->peers, s->n, s->L, s->perm, pending, c->sm_count, c->stream, &c->stats,
+                           &future);
   if (rc != QB_OK) return fail(rc, "global<->local swap failed: %s", dist_last_error());
   return QB_OK;
 }

@@ -253,10 +253,10 @@ static int ensure_bounce(DistState *d, size_t amps) {
 
 int dist_make_local(DistState *d, double2 *amps, const std::vector<double2 *> &peers, int n, int L,
                     std::vector<int> &perm, const std::vector<const HostOp *> &pending, int sm_count,
-                    cudaStream_t stream, qb_stats *stats) {
+                    cudaStream_t stream, qb_stats *stats, const std::vector<const HostOp *> *future) {
   NcclApi *a = nccl();
   const bool peer_path = (int)peers.size() == d->nranks;
-  std::vector<SwapPair> sw = choose_swaps(n, L, perm, pending, peer_path);
+  std::vector<SwapPair> sw = choose_swaps(n, L, perm, pending, peer_path, future);
   if (sw.empty()) {
     g_dist_err = "planner stuck but no global target pending";
     return QB_ERR_UNSUPPORTED;

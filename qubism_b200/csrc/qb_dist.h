@@ -34,7 +34,7 @@ int dist_unregister(DistState *d, std::vector<double2 *> &peers, cudaStream_t st
 // local bits through bounce buffers.
 int dist_make_local(DistState *d, double2 *amps, const std::vector<double2 *> &peers, int n, int L,
                     std::vector<int> &perm, const std::vector<const HostOp *> &pending, int sm_count,
-                    cudaStream_t stream, qb_stats *stats);
+                    cudaStream_t stream, qb_stats *stats, const std::vector<const HostOp *> *future = nullptr);
 
 // Collective read of logical amplitudes [first, first + count) into `out` on every rank.
 int dist_read_logical(DistState *d, const double2 *amps, int n, int L, const std::vector<int> &perm, uint64_t first,

@@ -277,8 +277,11 @@ struct SwapStep {
 // local bits they evict.  any_local = false: the TOP k local bits (contiguous blocks: what a
 // plain send/recv needs).  any_local = true: Belady -- the local bits (>= 5, so that warps still
 // see 512 contiguous bytes) whose qubits are needed furthest in the future (peer-memory kernel).
+// future (may be null): the ops expected AFTER `pending` (an iterated circuit: the same stream again);
+// only consulted for the next use of qubits that `pending` never touches again.
 std::vector<SwapPair> choose_swaps(int n, int L, const std::vector<int> &perm,
-                                   const std::vector<const HostOp *> &pending, bool any_local);
+                                   const std::vector<const HostOp *> &pending, bool any_local,
+                                   const std::vector<const HostOp *> *future = nullptr);
 // the pairwise exchanges rank `rank` performs, XOR-ordered so all ranks' steps match up
 std::vector<SwapStep> swap_schedule(int rank, int L, const std::vector<SwapPair> &pairs);
 void apply_swaps_to_perm(std::vector<int> &perm, const std::vector<SwapPair> &pairs);

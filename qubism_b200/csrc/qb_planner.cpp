@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <sstream>
@@ -406,7 +407,8 @@ void OpQueue::push_kq(const int *bits, int k, const double *m, uint64_t ctrl_mas
 
 // --------------------------------------------------------------------- multi-GPU swap logic
 std::vector<SwapPair> choose_swaps(int n, int L, const std::vector<int> &perm,
-                                   const std::vector<const HostOp *> &pending, bool any_local) {
+                                   const std::vector<const HostOp *> &pending, bool any_local,
+                                   const std::vector<const HostOp *> *future) {
   // global physical bits that pending non-diagonal gates target, within a lookahead window
   std::vector<int> need;
   uint64_t seen = 0;
@@ -442,6 +444,17 @@ std::vector<SwapPair> choose_swaps(int n, int L, const std::vector<int> &perm,
           for (int j = 0; j < h.k; ++j)
             if (h.kq_bits[j] == logical_of[b]) next = std::min(next, (long)i);
       }
+      // not needed again in this flush: if the caller knows what comes after it (the same op
+      // stream again, for an iterated circuit), look there -- the qubits that end a step on the
+      // rank bits are then the ones the NEXT step needs last, and the layout settles into a cycle
+      if (next == (1L << 40) && future)
+        for (size_t i = 0; i < future->size(); ++i) {
+          const HostOp &h = *(*future)[i];
+          if (h.kind == 0 && h.type != G_DIAG && h.target == logical_of[b]) {
+            next = (long)(pending.size() + i);
+            break;
+          }
+        }
       cand.emplace_back(-next, -b);
     }
     std::sort(cand.begin(), cand.end());

@@ -5,6 +5,7 @@
 // transposes, gate predicates), so that planner and program-encoding bugs are caught on a
 // CPU-only box, and so that the shared-memory bank behaviour of every transpose can be
 // counted.  It is NOT part of libqubism_sv.so and nothing in qubism_b200 can reach it.
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -538,6 +539,95 @@ int qbe_jit_dump(int nlocal, const qb_op *ops, int64_t nops, const char *options
     stats_out[3] = nconf;
   }
   return idx;
+}
+
+
+// Layout dynamics of a sharded state under a REPEATED op stream (host only, no amplitudes): plan
+// and choose swaps exactly as a flush would, `nsteps` times in a row; out_perm receives the
+// logical->physical map after every step (nsteps x n ints), out_counts per step
+// (passes, swaps, structures not seen in any earlier step).
+int qbe_layout_trace(int n, int nranks, const qb_op *ops, int64_t nops, const char *options, int nsteps, int any_local,
+                     int *out_perm, int64_t *out_counts) {
+  PlanOptions opt;
+  if (options) {
+    std::string o(options);
+    size_t pos = 0;
+    while (pos < o.size()) {
+      size_t e = o.find(',', pos);
+      if (e == std::string::npos) e = o.size();
+      std::string kv = o.substr(pos, e - pos);
+      size_t eq = kv.find('=');
+      if (eq != std::string::npos && !set_opt(opt, kv.substr(0, eq), strtoll(kv.c_str() + eq + 1, nullptr, 10)))
+        return -1;
+      pos = e + 1;
+    }
+  }
+  int pbits = 0;
+  while ((1 << pbits) < nranks) ++pbits;
+  const int L = n - pbits;
+  int T, R;
+  effective_tile(opt, L, T, R);
+  if (T == 0) return -2;
+  opt.tile_bits = T;
+  opt.reg_bits = R;
+  std::vector<int> perm(n);
+  for (int i = 0; i < n; ++i) perm[i] = i;
+  std::vector<std::string> seen_keys;
+  static const double X[8] = {0, 0, 1, 0, 1, 0, 0, 0};
+  for (int step = 0; step < nsteps; ++step) {
+    OpQueue q;
+    q.reset(n, opt.peephole != 0, opt.rot != 0);
+    for (int64_t i = 0; i < nops; ++i) {
+      const qb_op &o = ops[i];
+      uint64_t cm = 0;
+      const int nc = o.kind == 1 ? 1 : o.nctrl;
+      for (int k = 0; k < nc; ++k) cm |= 1ull << (n - 1 - o.ctrl[k]);
+      q.push_1q(n - 1 - o.target, cm, o.kind == 1 ? X : reinterpret_cast<const double *>(o.m));
+    }
+    std::vector<const HostOp *> seg;
+    for (const auto &h : q.ops)
+      if (!h.dead) seg.push_back(&h);
+    int64_t npass = 0, nswap = 0, nnew = 0;
+    std::vector<std::string> step_keys;
+    while (!seg.empty()) {
+      std::vector<PhysOp> pops(seg.size());
+      for (size_t i = 0; i < seg.size(); ++i) {
+        const HostOp &h = *seg[i];
+        pops[i].type = h.type;
+        pops[i].target = perm[h.target];
+        uint64_t cm = 0;
+        for (uint64_t b = h.ctrl; b; b &= b - 1) cm |= 1ull << perm[__builtin_ctzll(b)];
+        pops[i].ctrl = cm;
+        std::memcpy(pops[i].m, h.m, sizeof(h.m));
+      }
+      PlanResult plan = plan_passes(pops, L, 0, opt, nullptr);
+      for (const auto &p : plan.passes) {
+        ++npass;
+        JitProgram kp;
+        if (jit_generate(p, JIT_KEY_ONLY, kp, nullptr)) step_keys.push_back(kp.key);
+      }
+      if (plan.consumed == seg.size()) break;
+      std::vector<const HostOp *> rest;
+      for (size_t i = 0; i < seg.size(); ++i)
+        if (!plan.done[i]) rest.push_back(seg[i]);
+      std::vector<const HostOp *> all;
+      for (const auto &h : q.ops)
+        if (!h.dead) all.push_back(&h);
+      std::vector<SwapPair> sw = choose_swaps(n, L, perm, rest, (any_local & 1) != 0, (any_local & 2) ? &all : nullptr);
+      if (sw.empty()) return -4;
+      apply_swaps_to_perm(perm, sw);
+      ++nswap;
+      seg.swap(rest);
+    }
+    for (const auto &k : step_keys)
+      if (std::find(seen_keys.begin(), seen_keys.end(), k) == seen_keys.end()) ++nnew;
+    for (auto &k : step_keys) seen_keys.push_back(std::move(k));
+    for (int i = 0; i < n; ++i) out_perm[step * n + i] = perm[i];
+    out_counts[step * 3 + 0] = npass;
+    out_counts[step * 3 + 1] = nswap;
+    out_counts[step * 3 + 2] = nnew;
+  }
+  return 0;
 }
 
 

@@ -891,12 +891,36 @@ bool load_entry(Entry &e, std::string *err) {
 
 }  // namespace
 
+// The cache is keyed by a 128-bit digest of (device, structural key): a long run over ever new
+// structures (an interpreter session, a sharded state whose layout never comes back) must not
+// keep ~10 KB of key per pass it has ever planned.
+static std::string digest_of(int dev, const std::string &key) {
+  uint64_t h1 = 1469598103934665603ull ^ (uint64_t)dev, h2 = 0x9E3779B97F4A7C15ull + (uint64_t)dev;
+  for (unsigned char ch : key) {
+    h1 = (h1 ^ ch) * 1099511628211ull;                               // FNV-1a
+    h2 = (h2 + ch) * 0xFF51AFD7ED558CCDull;                          // an independent multiply-xorshift walk
+    h2 ^= h2 >> 29;
+  }
+  const uint64_t len = key.size();
+  std::string d(24, '\0');
+  std::memcpy(&d[0], &h1, 8);
+  std::memcpy(&d[8], &h2, 8);
+  std::memcpy(&d[16], &len, 8);
+  return d;
+}
+constexpr size_t kMaxSightings = 1u << 16;  // sighting records kept before the never-compiled ones are dropped
+constexpr uint64_t kMaxCompiled = 4096;     // specialised kernels per process
+
 int jit_lookup(const JitProgram &kp, const PassPlan &pp, int threshold, void **handle, std::string *err, bool *requested) {
   int dev = 0;
   if (requested) *requested = false;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-  std::string key = std::to_string(dev) + ":" + kp.key;
+  const std::string key = digest_of(dev, kp.key);
   std::lock_guard<std::mutex> lock(g_mu);
+  if (g_cache.size() >= kMaxSightings && g_cache.find(key) == g_cache.end()) {
+    for (auto it = g_cache.begin(); it != g_cache.end();)
+      it = (it->second.state == 0) ? g_cache.erase(it) : std::next(it);  // (entries being compiled / loaded stay: workers hold pointers)
+  }
   Entry &e = g_cache[key];
   // `requested` depends only on how often this structure was looked up: every rank of a sharded
   // state sees the same sequence of structures, so it is the same on all of them -- unlike the
@@ -909,6 +933,10 @@ int jit_lookup(const JitProgram &kp, const PassPlan &pp, int threshold, void **h
   }
   if (e.state != 0) return 0;  // failed before, or still compiling: the generic kernel runs
   if (++e.seen < threshold) return 0;
+  if (g_stats.compiled + g_stats.failed >= kMaxCompiled) {
+    e.seen = threshold;  // (stays "requested": sharded ranks must agree on it)
+    return 0;
+  }
   if (!jit_available(err)) {
     e.state = -1;
     g_stats.failed++;

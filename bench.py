@@ -351,7 +351,21 @@ def run_ours(args):
                 "specialised_share_of_launches": jit_share,
                 "launches_per_step": passes, "avg_launch_ms": fused_ms,
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                "kernel_share_of_step": (st["fused_ms"] / 1e3) / elapsed if elapsed > 0 else None}
+                "kernel_share_of_step": (st["fused_ms"] / 1e3) / elapsed if elapsed > 0 else None,
+                # what the same op stream would move one sweep per primitive op: may
+                # exceed the HBM peak, which is the point of fusing
+                "unfused_equivalent_gbs": value / world * 32.0 / 1e9}
+    if world > 1:
+        # T_roof(P) = passes x 32 B x 2^L / HBM  +  bytes sent per GPU / NVLink per direction
+        nvl = 770.0  # GB/s per direction, measured peer copy on this pool (900 nominal)
+        xb = st["exchange_bytes"] / args.steps
+        t_roof = passes * alg_bytes / (peak * 1e9) + xb / (nvl * 1e9)
+        roofline["sharded"] = {"t_roof_ms": t_roof * 1e3, "t_measured_ms": elapsed / args.steps * 1e3,
+                               "efficiency": t_roof / (elapsed / args.steps),
+                               "hbm_term_ms": passes * alg_bytes / (peak * 1e9) * 1e3, "nvlink_term_ms": xb / (nvl * 1e9) * 1e3,
+                               "nvlink_gbs_per_direction": nvl,
+                               "what": "SURVEY.md 8d: sum of the passes at the HBM peak plus the exchanged bytes at the "
+                                       "measured NVLink rate, over the measured step"}
 
     # ---------------- CPU baseline (rank 0, N = 1 only): the oracle's C port, bounded sample
     cpu = None

@@ -359,36 +359,36 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
               g.left_out *= cs;
               if (flip) {
                 g.tag("raf");
-                g.line("qbj_rot_a_flip<" + g.dec(J) + ">(re, im, A.c[" + g.dec(k) + "], f);");
+                g.line("qbj_rot_a_flip<" + g.dec(J) + ">(re, im, QBJ_C(" + g.dec(k) + "), f);");
               } else {
                 g.tag("ra");
-                g.line("qbj_rot_a<" + g.dec(J) + ">(re, im, A.c[" + g.dec(k) + "]);");
+                g.line("qbj_rot_a<" + g.dec(J) + ">(re, im, QBJ_C(" + g.dec(k) + "));");
               }
             } else if (!flip) {
               const int k = g.coef(cs / sn);
               g.left_out *= sn;
               g.tag("rb");
-              g.line("qbj_rot_b<" + g.dec(J) + ">(re, im, A.c[" + g.dec(k) + "]);");
+              g.line("qbj_rot_b<" + g.dec(J) + ">(re, im, QBJ_C(" + g.dec(k) + "));");
             } else {
               const int k = g.coef(st.slot[J][0]);
               g.coef(st.slot[J][1]);
               g.tag("r3f");
-              g.line("qbj_rot3_flip<" + g.dec(J) + ">(re, im, A.c[" + g.dec(k) + "], A.c[" + std::to_string(k + 1) + "], f);");
+              g.line("qbj_rot3_flip<" + g.dec(J) + ">(re, im, QBJ_C(" + g.dec(k) + "), QBJ_C(" + std::to_string(k + 1) + "), f);");
             }
           } else if (cls == SLOT_REAL) {
             const int k = g.coef(st.slot[J][0]);
             for (int e = 1; e < 4; ++e) g.coef(st.slot[J][e]);
             g.tag("re");
-            g.line("qbj_real<" + g.dec(J) + ", " + g.dec(flip ? 1 : 0) + ">(re, im, &A.c[" + g.dec(k) + "], f);");
+            g.line("qbj_real<" + g.dec(J) + ", " + g.dec(flip ? 1 : 0) + ">(re, im, &QBJ_C(" + g.dec(k) + "), f);");
           } else if (cls == SLOT_GENERAL || cls == SLOT_GENERAL1) {
             const int k = g.coef(st.slot[J][0]);
             for (int e = 1; e < 8; ++e) g.coef(st.slot[J][e]);
             if (cls == SLOT_GENERAL1 && !flip) {
               g.tag("g1");
-              g.line("qbj_general1<" + g.dec(J) + ">(re, im, &A.c[" + g.dec(k) + "]);");
+              g.line("qbj_general1<" + g.dec(J) + ">(re, im, &QBJ_C(" + g.dec(k) + "));");
             } else {
               g.tag("ge");
-              g.line("qbj_general<" + g.dec(J) + ", " + g.dec(flip ? 1 : 0) + ">(re, im, &A.c[" + g.dec(k) + "], f);");
+              g.line("qbj_general<" + g.dec(J) + ", " + g.dec(flip ? 1 : 0) + ">(re, im, &QBJ_C(" + g.dec(k) + "), f);");
             }
           } else {
             bad = true;
@@ -455,6 +455,15 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
     const std::string rounds_txt = side.str();
     const size_t nc = std::max<size_t>(1, g.coefs.size());
     o << "struct QbjArgs { double gs[2]; u64 rank_bits; u64 base_fixed; double c[" << nc << "]; };\n";
+    // Coefficients are loop-invariant kernel parameters.  Up to ~30 of them the compiler keeps them
+    // in uniform registers across the tile loop; beyond that it hoists them into ordinary
+    // registers and spills those (the general-class passes of the benchmark: 200-300 bytes per
+    // thread re-read through L1 for every tile).  There the index gets a zero the compiler cannot
+    // see through and that is re-made every tile (tile_id >> 31), so each use is one indexed
+    // constant-bank load and nothing is hoisted.
+    const bool coef_reload = !g.host && g.coefs.size() > 30;  // (63 uniform registers = 31 doubles)
+    g.dec(coef_reload);
+    o << (coef_reload ? "#define QBJ_C(k) A.c[(k) + cz_]\n" : "#define QBJ_C(k) A.c[k]\n");
     if (!g.host) {
       o << "#define QBJ_LD2(p, i) qbj_ld256(amps + (p), re[i], im[i], re[(i) + 1], im[(i) + 1])\n"
            "#define QBJ_LD1(p, i) qbj_ld128(amps + (p), re[i], im[i])\n"
@@ -501,6 +510,7 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
         o << "      }\n    }\n";
       }
       o << "    const u64 basefull = base | A.rank_bits;\n    (void)basefull;\n    f = 0;\n";
+      if (coef_reload) o << "    const u32 cz_ = tile_id >> 31;  // always 0 (tile ids are < 2^31), but not to the compiler\n";
       o << rounds_txt;
       o << "  }\n}\n";
       } else {
@@ -544,6 +554,7 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
         o << "      asm volatile(\"prefetch.global.L2 [%0];\" ::\"l\"(amps + nb_ + ((u64)line_tab[" << k << " * QBJ_NT + tid] << 3)));\n";
       o << "      }\n    }\n";
       o << "    const u64 basefull = base | A.rank_bits;\n    (void)basefull;\n    f = 0;\n";
+      if (coef_reload) o << "    const u32 cz_ = tile_id >> 31;  // always 0 (tile ids are < 2^31), but not to the compiler\n";
       o << rounds_txt;
       o << "    have_prev = true;\n"
            "    if (++k_in == " << sG << "u) { k_in = 0; grp += stride; }\n"

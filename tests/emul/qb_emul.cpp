@@ -604,7 +604,25 @@ int qbe_layout_trace(int n, int nranks, const qb_op *ops, int64_t nops, const ch
       for (const auto &p : plan.passes) {
         ++npass;
         JitProgram kp;
-        if (jit_generate(p, JIT_KEY_ONLY, kp, nullptr)) step_keys.push_back(kp.key);
+        if (any_local & 4) {
+          // LOGICAL signature (experiment): rounds and gates with physical positions replaced by the
+          // logical qubits sitting there -- does the plan recur up to a relabelling of positions?
+          std::vector<int> logical_of(n, -1);
+          for (int qq = 0; qq < n; ++qq) logical_of[perm[qq]] = qq;
+          const DevPass &P = *reinterpret_cast<const DevPass *>(p.blob.data());
+          std::string sig;
+          for (uint32_t r = 0; r < P.nrounds; ++r) {
+            sig += "R";
+            for (int j = 0; j < (int)P.reg_bits; ++j) sig += std::to_string(logical_of[P.tile_pos[P.rounds[r].reg_pos[j]]]) + ",";
+            sig += "T";
+            for (int j = 0; j < (int)(P.tile_bits - P.reg_bits); ++j)
+              sig += std::to_string(logical_of[P.tile_pos[P.rounds[r].tid_pos[j]]]) + ",";
+          }
+          for (int oi : p.op_index) sig += "g" + std::to_string(oi) + ",";
+          step_keys.push_back(sig);
+        } else if (jit_generate(p, JIT_KEY_ONLY, kp, nullptr)) {
+          step_keys.push_back(kp.key);
+        }
       }
       if (plan.consumed == seg.size()) break;
       std::vector<const HostOp *> rest;

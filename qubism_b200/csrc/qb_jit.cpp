@@ -973,6 +973,19 @@ int jit_lookup(const JitProgram &kp, const PassPlan &pp, int threshold, void **h
   e.state = 2;
   Pool &P = pool();
   {
+    // Process exit must not tear libnvrtc down under a worker that is still compiling.  This
+    // handler is registered after libnvrtc was loaded (jit_available above), so exit() runs it
+    // BEFORE libnvrtc's own destructors: it simply waits for the queue to drain (bounded).
+    static std::once_flag at_exit_once;
+    std::call_once(at_exit_once, [] {
+      std::atexit([] {
+        Pool &Q = pool();
+        std::unique_lock<std::mutex> lk(Q.mu);
+        Q.idle.wait_for(lk, std::chrono::seconds(30), [&] { return Q.inflight == 0; });
+      });
+    });
+  }
+  {
     std::lock_guard<std::mutex> lk(P.mu);
     Job j;
     j.e = &e;

@@ -18,6 +18,7 @@ from qubism_b200.circuits import adder_ops, proper_unitary_layers, qft_ops, rand
 pytestmark = pytest.mark.gpu
 TOL = 1e-12
 GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden.json")))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def close(a, b, tol=TOL):
@@ -594,3 +595,14 @@ def test_full_size_round_trip_and_norm(ctx, n):
     assert abs(head[0] - 1.0) < 1e-11 and np.abs(head[1:]).max() < 1e-12
     assert abs(sv.norm2() - 1.0) < 1e-11
     ctx.set_option("jit", 2)
+
+
+def test_exit_with_compilations_in_flight(ctx):
+    """A process that exits while specialised kernels are still being compiled in the background
+    must leave with status 0: the library drains its compile queue before libnvrtc goes away."""
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "exit_check.py")], capture_output=True, text=True,
+                         timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "compilations in flight" in out.stdout

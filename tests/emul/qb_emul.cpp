@@ -405,7 +405,11 @@ int qbe_run_jit(int nlocal, const qb_op *ops, int64_t nops, const char *options,
   double pending = 1.0;
   int njit = 0;
   static int nlibs = 0;  // (file names must never repeat inside a process: dlopen caches by path)
-  std::vector<std::pair<std::string, void *>> libs;  // structural key -> host function
+  // structural key -> host function, PROCESS-WIDE: if two different structures ever shared a key,
+  // a later circuit would run the wrong code here and fail its parity check -- the tests thereby
+  // also check that the key captures everything that shapes the generated source
+  static std::vector<std::pair<std::string, void *>> libs;
+  const size_t libs_before = libs.size();
   for (const auto &p : plan.passes) {
     const DevPass &P = *reinterpret_cast<const DevPass *>(p.blob.data());
     JitProgram kp;
@@ -463,7 +467,7 @@ int qbe_run_jit(int nlocal, const qb_op *ops, int64_t nops, const char *options,
   if (stats_out) {
     stats_out[0] = st.passes;
     stats_out[1] = njit;
-    stats_out[2] = (int64_t)libs.size();
+    stats_out[2] = (int64_t)(libs.size() - libs_before);
   }
   return 0;
 }

@@ -61,7 +61,7 @@ def test_specialised_passes_of_rotation_cx_layers_match_oracle(jit_emul, opts):
     assert np.abs(out - ref).max() < 1e-13
 
 
-@pytest.mark.parametrize("seed", range(6))
+@pytest.mark.parametrize("seed", range(10))
 def test_specialised_passes_random_mixes(jit_emul, seed):
     """General / real / scaled-general slots, uncontrolled X (a renaming), controlled gates and
     diagonal gates (those passes stay with the generic kernels), known support."""

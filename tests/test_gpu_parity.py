@@ -606,3 +606,21 @@ def test_exit_with_compilations_in_flight(ctx):
                          timeout=300)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "compilations in flight" in out.stdout
+
+
+def test_specialised_kernels_range_guard_on_a_long_flush(default_opts):
+    """(last in the file on purpose: written after the round's GPU budget was spent, it has not run
+    on a GPU yet)  A single flush of ~2,800 rotations through the specialised kernels: the product of the
+    cosines their 2-FMA rotations leave out falls below 2^-300 on the way, so a pass in the
+    middle has to apply the running factor (run_fused_segment's range guard) -- the amplitudes
+    must still be the oracle's."""
+    ctx = default_opts
+    ctx.set_option("jit", 1)
+    n = 14
+    ops = random_layers(n, 200, seed=77, lam0=True)  # 2,800 rotations: the product of their deferred factors is ~2^-440
+    v = S.gen_state(n, np.random.default_rng(77))
+    ref = S.run_ops(n, ops, v)
+    sv = Q.StateVec.from_host(v)
+    sv.submit(ops)
+    assert close(sv.to_host(), ref, 1e-11)
+    assert abs(sv.norm2() - np.linalg.norm(ref)) < 1e-11

@@ -47,7 +47,8 @@ def jit_emul(tmp_path_factory):
 
 
 @pytest.mark.parametrize("opts", ["", "reg_bits=3", "reg_bits=5", "tile_bits=10,reg_bits=4", "low_bits=5", "rot=0",
-                                  "lane_fixed=1", "lane_fixed=2,reg_bits=5", "max_pass_gates=7", "tile_bits=11,reg_bits=3"])
+                                  "lane_fixed=1", "lane_fixed=2,reg_bits=5", "max_pass_gates=7", "tile_bits=11,reg_bits=3",
+                                  "tile_bits=13,reg_bits=4", "tile_bits=13,reg_bits=5,low_bits=6", "max_rounds=3", "lane_fixed=3"])
 def test_specialised_passes_of_rotation_cx_layers_match_oracle(jit_emul, opts):
     """U(theta, phi, 0) + CX layers: every pass is a step pass, every one is specialised: 2-FMA
     rotations with deferred cosines (forms A and B), flip-aware flavours after toggles, static
@@ -140,7 +141,8 @@ def test_equal_structure_gives_one_kernel_and_new_angles_only_new_coefficients(j
     assert src_a == src_b, "angles leaked into the generated source"
 
 
-@pytest.mark.parametrize("opts", ["", "reg_bits=5", "tile_bits=10,reg_bits=3", "rot=0"])
+@pytest.mark.parametrize("opts", ["", "reg_bits=5", "tile_bits=10,reg_bits=3", "rot=0", "jit_group=4,jit_pf_last=0",
+                                  "jit_mem=5", "jit_mem=6,jit_minb=3", "tile_bits=13,reg_bits=4", "l2_prefetch=0"])
 def test_device_source_compiles_with_nvrtc(jit_emul, opts):
     """NVRTC needs no GPU: the CUDA flavour of the generated source must compile for sm_100a."""
     n = 13

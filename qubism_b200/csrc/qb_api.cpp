@@ -353,7 +353,7 @@ int run_fused_segment(qb_state *s, std::vector<const HostOp *> seg, const double
       for (size_t i = 0; i < npass; ++i) {
         PassPlan &p = plan.passes[i];
         std::string err;
-        if (!jit_generate(p, JIT_KEY_ONLY, jit_prog[i], nullptr)) continue;
+        if (!jit_quick(p, jit_prog[i], nullptr)) continue;
         DevPass *P = reinterpret_cast<DevPass *>(p.blob.data());
         const bool last = finish && i + 1 == npass;
         if (!last && !P->has_gscale && !(std::fabs(s->jit_left * jit_prog[i].left_out) > 0x1p-300)) {
@@ -361,7 +361,7 @@ int run_fused_segment(qb_state *s, std::vector<const HostOp *> seg, const double
           P->has_gscale = 1;
           P->gscale[0] = 1.0;
           P->gscale[1] = 0.0;
-          if (!jit_generate(p, JIT_KEY_ONLY, jit_prog[i], nullptr)) continue;
+          if (!jit_quick(p, jit_prog[i], nullptr)) continue;
           mid_scale[i] = 1.0;
         }
         bool requested = false;

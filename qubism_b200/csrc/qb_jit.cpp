@@ -607,6 +607,111 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
   return true;
 }
 
+bool jit_quick(const PassPlan &pp, JitProgram &out, std::string *why) {
+  auto fail = [&](const char *m) {
+    if (why) *why = m;
+    return false;
+  };
+  // ---- the same eligibility rules as jit_generate
+  if (pp.blob.size() < sizeof(DevPass)) return fail("short blob");
+  const DevPass &P = *reinterpret_cast<const DevPass *>(pp.blob.data());
+  if (P.lite == 0) return fail("not a step (lite) pass");
+  if (P.dbg_skip) return fail("profiling switches set");
+  if (pp.blob.size() < sizeof(DevPass) + size_t(P.nsteps) * sizeof(DevStep)) return fail("short blob");
+  const DevStep *S = reinterpret_cast<const DevStep *>(pp.blob.data() + sizeof(DevPass));
+  const int T = (int)P.tile_bits, R = (int)P.reg_bits;
+  const int nrounds = (int)P.nrounds;
+  if (R < 3 || R > kMaxRegBits || T > kMaxTileBits || T - R > 10 || nrounds < 1 || nrounds > kMaxRounds)
+    return fail("unsupported geometry");
+  if (!(P.tile_pos[0] == 0 && P.tile_pos[1] == 1 && P.tile_pos[2] == 2)) return fail("tile without the low line bits");
+  // ---- digest: two independent 64-bit walks over every field the generator reads
+  uint64_t h1 = 1469598103934665603ull, h2 = 0x9E3779B97F4A7C15ull;
+  auto mix = [&](uint64_t v) {
+    h1 = (h1 ^ v) * 1099511628211ull;
+    h1 ^= h1 >> 32;
+    h2 = (h2 + v) * 0xFF51AFD7ED558CCDull;
+    h2 ^= h2 >> 29;
+  };
+  mix(0x716a6231);  // format tag
+  mix(P.tile_bits); mix(P.reg_bits); mix(P.nrounds); mix(P.l2_prefetch); mix(P.has_gscale != 0);
+  mix(P.nruns);
+  for (uint32_t k = 0; k < P.nruns && k < (uint32_t)kMaxRuns; ++k) { mix(P.run_shift[k]); mix(P.run_len[k]); }
+  for (int i = 0; i < T; ++i) mix(P.tile_pos[i]);
+  mix(P.jit_group); mix(P.jit_pf_last); mix(P.jit_minb); mix(P.jit_mem); mix(P.nsteps);
+  out.coefs.clear();
+  double left = 1.0;
+  bool bad = false;
+  uint32_t mf = 0;
+  for (int r = 0; r < nrounds; ++r) {
+    const DevRound &RD = P.rounds[r];
+    for (int j = 0; j < T - R; ++j) mix(RD.tid_pos[j]);
+    for (int j = 0; j < R; ++j) mix(RD.reg_pos[j]);
+    mix(RD.warp_local); mix(RD.step_begin); mix(RD.step_end);
+    if (r > 0) mf = 0;  // flips are folded into the transpose
+    if (RD.step_end > P.nsteps || RD.step_begin > RD.step_end) return fail("step range");
+    for (uint32_t si = RD.step_begin; si < RD.step_end; ++si) {
+      const DevStep &st = S[si];
+      mix(st.kinds); mix(st.ntog); mix(st.swap_j);
+      for (int J = 0; J < R; ++J) {
+        const uint32_t kind = (st.kinds >> (4 * J)) & 15u;
+        const uint32_t cls = kind & SLOT_CLASS;
+        if (cls == SLOT_NONE) continue;
+        const bool flip = ((mf >> J) & 1u) != 0;
+        if (flip && !(kind & SLOT_FLIP)) bad = true;
+        if (cls == SLOT_ROT) {
+          const double cs = st.slot[J][2], sn = st.slot[J][3];
+          if (!(cs >= 0.0) || !std::isfinite(cs) || !std::isfinite(sn) || !(cs * cs + sn * sn > 0.5)) bad = true;
+          const bool formA = std::fabs(sn) <= cs;
+          mix(formA);
+          if (formA) {
+            out.coefs.push_back(sn / cs);
+            left *= cs;
+          } else if (!flip) {
+            out.coefs.push_back(cs / sn);
+            left *= sn;
+          } else {
+            out.coefs.push_back(st.slot[J][0]);
+            out.coefs.push_back(st.slot[J][1]);
+          }
+        } else if (cls == SLOT_REAL) {
+          for (int e = 0; e < 4; ++e) out.coefs.push_back(st.slot[J][e]);
+        } else if (cls == SLOT_GENERAL || cls == SLOT_GENERAL1) {
+          for (int e = 0; e < 8; ++e) out.coefs.push_back(st.slot[J][e]);
+        } else {
+          bad = true;
+        }
+      }
+      if (st.ntog > (uint32_t)kStepToggles) bad = true;
+      for (uint32_t k = 0; k < st.ntog && k < (uint32_t)kStepToggles; ++k) {
+        const auto &tg = st.tog[k];
+        mix(tg.cthr); mix(tg.bit); mix(tg.cext);
+        if ((int)tg.bit >= R) bad = true;
+        if (tg.cthr == 0 && tg.cext == 0) continue;  // uncontrolled X: a renaming, no flip
+        mf |= 1u << tg.bit;
+      }
+      if (st.swap_j != 0xffu) {
+        const int J = (int)(st.swap_j & 7u);
+        mix(st.swap_creg); mix(st.swap_cthr); mix(st.swap_cext);
+        if (J >= R || st.swap_creg == 0 || (st.swap_creg >> R) != 0 || ((st.swap_creg >> J) & 1u)) bad = true;
+      }
+    }
+  }
+  if (bad) return fail("step structure the generator does not accept");
+  if (!std::isfinite(left) || left == 0.0) return fail("deferred factor out of range");
+  const uint64_t nco = out.coefs.size();
+  out.key.assign(24, '\0');
+  std::memcpy(&out.key[0], &h1, 8);
+  std::memcpy(&out.key[8], &h2, 8);
+  std::memcpy(&out.key[16], &nco, 8);
+  out.left_out = left;
+  out.src.clear();
+  out.T = T;
+  out.R = R;
+  out.nrounds = nrounds;
+  out.args_bytes = sizeof(JitArgsHead) + sizeof(double) * std::max<size_t>(1, out.coefs.size());
+  return true;
+}
+
 std::vector<uint8_t> jit_pack_args(const JitProgram &p, const double gs[2], uint64_t rank_bits, uint64_t base_fixed) {
   std::vector<uint8_t> a(p.args_bytes, 0);
   JitArgsHead h;

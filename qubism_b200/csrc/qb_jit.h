@@ -32,6 +32,11 @@ enum JitEmit { JIT_KEY_ONLY = 0, JIT_DEVICE_SRC = 1, JIT_HOST_SRC = 2 };
 
 // false: this pass cannot be specialised (not a lite pass, inconsistent flip tracking, ...).
 bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string *why);
+// What a flush needs per pass and per launch, without building a single string: a 128-bit digest of
+// the structure (the same inputs jit_generate reads), the coefficient vector in the generator's
+// order and the factor left out.  ~2 us per pass where the full key walk costs ~80 (a 20-qubit
+// pass runs in 10 us).  tests/emul cross-checks it against jit_generate on every pass it plans.
+bool jit_quick(const PassPlan &pp, JitProgram &out, std::string *why);
 // the prelude text (qb_jit_prelude.cuh, embedded at build time)
 const char *jit_prelude();
 

@@ -6,9 +6,11 @@
 // CPU-only box, and so that the shared-memory bank behaviour of every transpose can be
 // counted.  It is NOT part of libqubism_sv.so and nothing in qubism_b200 can reach it.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -412,9 +414,15 @@ int qbe_run_jit(int nlocal, const qb_op *ops, int64_t nops, const char *options,
   const size_t libs_before = libs.size();
   for (const auto &p : plan.passes) {
     const DevPass &P = *reinterpret_cast<const DevPass *>(p.blob.data());
-    JitProgram kp;
+    JitProgram kp, full_key;
     std::string why;
-    if (!jit_generate(p, JIT_KEY_ONLY, kp, &why)) {
+    // the flush uses jit_quick (digest + coefficients, no strings); check it against the full walk
+    const bool ok_quick = jit_quick(p, kp, &why);
+    const bool ok_full = jit_generate(p, JIT_KEY_ONLY, full_key, &why);
+    if (ok_quick != ok_full) return -20;
+    if (ok_quick && (kp.coefs != full_key.coefs || kp.left_out != full_key.left_out || kp.args_bytes != full_key.args_bytes))
+      return -21;
+    if (!ok_quick) {
       run_pass(p, nlocal, a, st);
       continue;
     }
@@ -520,6 +528,26 @@ int qbe_jit_dump(int nlocal, const qb_op *ops, int64_t nops, const char *options
   if (plan.consumed != pops.size()) return -3;
   int njit = 0, idx = 0;
   int64_t nfixed = 0, nconf = 0, ntrans = 0;
+  if (std::getenv("QBE_TIME_KEYS")) {  // host cost of the structural key (what every flush pays per pass)
+    const auto t0 = std::chrono::steady_clock::now();
+    size_t bytes = 0;
+    for (int rep = 0; rep < 50; ++rep)
+      for (const auto &p : plan.passes) {
+        JitProgram kp;
+        if (jit_generate(p, JIT_KEY_ONLY, kp, nullptr)) bytes += kp.key.size();
+      }
+    const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+    std::fprintf(stderr, "key-only generation: %.1f us per pass, %.0f bytes per key\n", us / (50.0 * plan.passes.size()),
+                 double(bytes) / (50.0 * plan.passes.size()));
+    const auto t1 = std::chrono::steady_clock::now();
+    for (int rep = 0; rep < 50; ++rep)
+      for (const auto &p : plan.passes) {
+        JitProgram kp;
+        if (jit_quick(p, kp, nullptr)) bytes += kp.key.size();
+      }
+    const double us2 = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t1).count();
+    std::fprintf(stderr, "jit_quick: %.2f us per pass\n", us2 / (50.0 * plan.passes.size()));
+  }
   for (const auto &p : plan.passes) {
     JitProgram dp;
     std::string why;

@@ -756,7 +756,12 @@ int qbe_run_rank(int n, int nranks, int rank, const qb_op *ops, int64_t nops, co
     std::vector<const HostOp *> rest;
     for (size_t i = 0; i < seg.size(); ++i)
       if (!plan.done[i]) rest.push_back(seg[i]);
-    std::vector<SwapPair> sw = choose_swaps(n, L, perm, rest, any_local != 0);
+    // any_local: bit 0 = Belady over any local bit (peer-memory path), bit 1 = cyclic tie-break
+    // (the flush's own op stream as the future, as qb_api.cpp's make_local passes it)
+    std::vector<const HostOp *> all_ops;
+    for (const auto &h : q.ops)
+      if (!h.dead) all_ops.push_back(&h);
+    std::vector<SwapPair> sw = choose_swaps(n, L, perm, rest, (any_local & 1) != 0, (any_local & 2) ? &all_ops : nullptr);
     if (sw.empty()) return -4;
     const int k = (int)sw.size();
     const uint64_t block = 1ull << (L - k);

@@ -87,7 +87,7 @@ def _worker(rank, world, port, n, seed, out_dir, any_local):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("any_local", [0, 1], ids=["top_bits_nccl_style", "belady_peer_style"])
+@pytest.mark.parametrize("any_local", [0, 1, 3], ids=["top_bits_nccl_style", "belady_peer_style", "belady_cyclic_tiebreak"])
 @pytest.mark.parametrize("world,n", [(2, 13), (4, 13)])
 def test_sharded_exchange_over_gloo(tmp_path, emul, world, n, any_local):
     """any_local = 0: the top local bits are evicted (contiguous blocks, what the NCCL send/recv

@@ -412,8 +412,22 @@ int qbe_run_jit(int nlocal, const qb_op *ops, int64_t nops, const char *options,
   // also check that the key captures everything that shapes the generated source
   static std::vector<std::pair<std::string, void *>> libs;
   const size_t libs_before = libs.size();
-  for (const auto &p : plan.passes) {
-    const DevPass &P = *reinterpret_cast<const DevPass *>(p.blob.data());
+  int nguard = 0;
+  for (auto &p : plan.passes) {
+    DevPass &P = *reinterpret_cast<DevPass *>(p.blob.data());
+    {
+      // the flush's range guard (qb_api.cpp run_fused_segment): when the factor the specialised
+      // passes have left out so far would fall below 2^-300 with this pass, the pass applies the
+      // running factor on its way out (has_gscale is structural: a different kernel)
+      JitProgram probe;
+      if (!P.has_gscale && jit_quick(p, probe, nullptr) && !(std::fabs(pending * probe.left_out) > 0x1p-300)) {
+        P.has_gscale = 1;
+        P.gscale[0] = pending * probe.left_out;
+        P.gscale[1] = 0.0;
+        pending = 1.0 / probe.left_out;  // (multiplied by left_out again below: 1 after this pass)
+        ++nguard;
+      }
+    }
     JitProgram kp, full_key;
     std::string why;
     // the flush uses jit_quick (digest + coefficients, no strings); check it against the full walk
@@ -476,6 +490,7 @@ int qbe_run_jit(int nlocal, const qb_op *ops, int64_t nops, const char *options,
     stats_out[0] = st.passes;
     stats_out[1] = njit;
     stats_out[2] = (int64_t)(libs.size() - libs_before);
+    stats_out[3] = nguard;
   }
   return 0;
 }

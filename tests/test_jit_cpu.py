@@ -41,7 +41,7 @@ def jit_emul(tmp_path_factory):
         rc = E.qbe_run_jit(n, arr, len(arr), options.encode(), a.ctypes.data_as(C.c_void_p), st, work.encode(),
                            src_index, buf, cap)
         assert rc == 0, f"qbe_run_jit rc={rc} (see {work}/*.log)"
-        return a, dict(passes=st[0], jit=st[1], structures=st[2]), (buf.value.decode() if buf else None)
+        return a, dict(passes=st[0], jit=st[1], structures=st[2], guards=st[3]), (buf.value.decode() if buf else None)
 
     return run
 
@@ -156,3 +156,22 @@ def test_device_source_compiles_with_nvrtc(jit_emul, opts):
         pytest.skip("libnvrtc not available: " + capi.lib().qb_last_error().decode())
     assert rc == 0, capi.lib().qb_last_error().decode()[:2000]
     assert nbytes.value > 1000
+
+
+def test_range_guard_applies_the_running_factor_mid_flush(jit_emul):
+    """~1,100 rotations near 90 degrees in one flush: the product of the factors their 2-FMA forms
+    leave out drops below 2^-300, so a pass in the middle must apply the running factor (its
+    kernel is the has_gscale flavour) and the bookkeeping restarts at 1."""
+    n = 12
+    rng = np.random.default_rng(314)
+    ops = []
+    for layer in range(90):
+        for q in range(n):
+            ops.append(("U", q, D.unitary(float(rng.uniform(1.2, 1.9)), float(rng.uniform(0, 6)), 0.0)))
+        perm = rng.permutation(n)
+        for k in range(0, n - 1, 2):
+            ops.append(("CX", int(perm[k]), int(perm[k + 1])))
+    v = S.gen_state(n, rng)
+    out, st, _ = jit_emul(n, ops, v)
+    assert st["guards"] >= 1, "the circuit was meant to trip the range guard"
+    assert np.abs(out - S.run_ops(n, ops, v)).max() < 1e-12

@@ -61,6 +61,16 @@ int qb_init(int device, qb_ctx **out);
  * caller (torch.distributed, MPI, a file ...). */
 int qb_dist_unique_id(void *id128);
 int qb_init_dist(int device, int rank, int nranks, const void *nccl_id, qb_ctx **out);
+/* Rank group inside ONE process (no NCCL): out[r] becomes rank r of nranks (a power of two) on
+ * CUDA device devices[r].  Distinct devices = P GPUs driven from one process (peer access is
+ * enabled; global<->local swaps run over NVLink through the peers' shard pointers); the SAME
+ * device repeated = P virtual ranks on one GPU, which is how the sharded path -- swap selection,
+ * fused passes with rank-bit predicates, the pairwise swap kernel -- is parity-tested for
+ * P = 2 / 4 / 8 on a single-GPU box.  Collective calls (everything that touches a state) must be
+ * issued for every rank, each rank from its own host thread. */
+int qb_init_group(const int *devices, int nranks, qb_ctx **out);
+/* Frees every device resource of the context.  States that are still alive turn invalid (their
+ * calls return QB_ERR_STATE); their handles may be freed afterwards. */
 int qb_shutdown(qb_ctx *ctx);
 int qb_ctx_rank(const qb_ctx *ctx);
 int qb_ctx_nranks(const qb_ctx *ctx);
@@ -70,6 +80,16 @@ const char *qb_last_error(void);
 /* Library build identification ("qubism_sv <version> sm_100a ..."). */
 const char *qb_version(void);
 
+/* One primitive op of a batch (qb_submit, qb_state_apply_pure). */
+typedef struct {
+  int32_t kind;      /* 0 = (controlled) 1q gate, 1 = cnot */
+  int32_t target;
+  int32_t nctrl;
+  int32_t ctrl[4];
+  int32_t _pad;
+  qb_c64 m[4];
+} qb_op;
+
 /* ---- state creation / lifetime ------------------------------------------------------- */
 /* mkStateVec / mkStateVec' (StateVec.hs:78-85): basis != 0 -> |0...0>;
  * zero (StateVec.hs:52): basis == 0 -> all-zero vector. */
@@ -78,9 +98,23 @@ int qb_state_create(qb_ctx *ctx, int nqubits, int basis, qb_state **out);
  * amplitudes.  In a distributed context every rank passes its own shard
  * (2^n / nranks amplitudes, the ones it owns). */
 int qb_state_from_host(qb_ctx *ctx, int nqubits, const qb_c64 *amps, qb_state **out);
-/* Value semantics of the pure (#>) (QGate.hs:78-80). */
+/* Value semantics of the pure (#>) (QGate.hs:78-80; the interpreter builds sv' = g #> sv once per
+ * primitive op and writes sv' back, QASM/Simulation.hs:94-122).  LAZY: the clone is a second
+ * handle on the same device shard -- no flush, no copy, no allocation -- and gates queued on the
+ * source stay queued for both.  Gates applied to either handle extend a shared log; the ops
+ * between two observations fuse exactly as for in-place calls, however they were sliced into
+ * handles.  Data is copied only when a handle is observed (or changed in place) while another
+ * live handle still denotes an OLDER value of the same shard, and then the copy rides on the
+ * first fused pass (it reads the old shard and writes the new one).  Option "linear" = 1 declares
+ * that values are used linearly (the interpreter's pattern): the older handles are then CONSUMED
+ * instead -- any later call on them fails with QB_ERR_STATE, nothing is ever copied. */
 int qb_state_clone(qb_state *src, qb_state **out);
-/* ForeignPtr finalizer; callable from any thread. */
+/* g #> sv in one crossing: *out = a new state holding `ops` applied to src's value (clone +
+ * qb_submit); src stays valid. */
+int qb_state_apply_pure(qb_state *src, const qb_op *ops, int64_t nops, qb_state **out);
+/* ForeignPtr finalizer; callable from any thread, at any time, also after qb_shutdown.  Never a
+ * collective: on a sharded context the shard is only marked released and is retired (reused or
+ * freed) at a later collective call once every rank has released it. */
 void qb_state_free(qb_state *s);
 /* dimension (StateVec.hs:74-75). */
 int qb_state_nqubits(const qb_state *s);
@@ -93,8 +127,11 @@ int qb_state_read(qb_state *s, uint64_t first, uint64_t count, qb_c64 *out);
 /* Copy this rank's raw shard (physical order) to the host: bench/e2e only. */
 int qb_state_read_local(qb_state *s, uint64_t first, uint64_t count, qb_c64 *out);
 /* Overwrite amplitudes [first, first+count) of this rank's shard from a host buffer (pinned
- * memory makes the copy asynchronous to the host); queued gates are dropped and the qubit
- * layout returns to the identity map.  The upload counterpart of qb_state_read_local. */
+ * memory makes the copy asynchronous to the host).  An upload STARTS at first = 0: queued gates,
+ * the deferred scalar and the qubit layout of the old contents are dropped.  A call with
+ * first > 0 continues it: the amplitudes it does not touch keep their meaning (anything pending
+ * on them is applied first; QB_ERR_STATE if the layout is no longer the identity).  The upload
+ * counterpart of qb_state_read_local. */
 int qb_state_write_local(qb_state *s, uint64_t first, uint64_t count, const qb_c64 *amps);
 
 /* ---- gates (enqueue) ------------------------------------------------------------------ */
@@ -112,14 +149,6 @@ int qb_apply_cnot(qb_state *s, int c, int t);
 int qb_apply_kq(qb_state *s, const int *qs, int k, const qb_c64 *m, const int *ctrls, int nctrl);
 
 /* Batch submission: one FFI crossing for a whole op list. */
-typedef struct {
-  int32_t kind;      /* 0 = (controlled) 1q gate, 1 = cnot */
-  int32_t target;
-  int32_t nctrl;
-  int32_t ctrl[4];
-  int32_t _pad;
-  qb_c64 m[4];
-} qb_op;
 int qb_submit(qb_state *s, const qb_op *ops, int64_t nops);
 
 /* Plan and run every queued gate.  Returns after the work is ENQUEUED on the stream;
@@ -174,6 +203,9 @@ typedef struct {
   uint64_t jit_compiled;    /* pass structures compiled into specialised kernels (option "jit") */
   uint64_t jit_launches;    /* fused passes that ran as a specialised kernel                 */
   double jit_compile_ms;    /* host time spent in NVRTC + module load                        */
+  uint64_t clones;          /* qb_state_clone calls (all lazy)                               */
+  uint64_t cow_fused;       /* copy-on-write copies that rode on a fused pass (no extra traffic) */
+  uint64_t cow_copies;      /* copy-on-write / fork copies done as a separate device copy     */
 } qb_stats;
 int qb_get_stats(const qb_ctx *ctx, qb_stats *out);
 int qb_reset_stats(qb_ctx *ctx);
@@ -186,7 +218,7 @@ void *qb_ctx_stream(qb_ctx *ctx);
  * seen k times is compiled with NVRTC into a straight-line kernel -- structure as literals, gate
  * coefficients still kernel parameters -- and cached; k = 1 compiles at first sight in the
  * calling thread, k >= 2 in background threads while the generic kernel keeps running;
- * 0 = generic kernels only).  Returns
+ * 0 = generic kernels only), "linear" (see qb_state_clone), "pool" (spare shards kept for reuse).  Returns
  * QB_ERR_ARG for unknown names / bad values. */
 int qb_set_option(qb_ctx *ctx, const char *name, int64_t value);
 int64_t qb_get_option(const qb_ctx *ctx, const char *name);

@@ -37,7 +37,8 @@ class QbStats(C.Structure):
                 ("passes", C.c_uint64), ("rounds", C.c_uint64), ("simple_launches", C.c_uint64),
                 ("reduce_launches", C.c_uint64), ("exchange_bytes", C.c_uint64), ("exchanges", C.c_uint64),
                 ("plan_ms", C.c_double), ("fused_ms", C.c_double), ("fused_timed", C.c_uint64), ("tiles", C.c_uint64),
-                ("jit_compiled", C.c_uint64), ("jit_launches", C.c_uint64), ("jit_compile_ms", C.c_double)]
+                ("jit_compiled", C.c_uint64), ("jit_launches", C.c_uint64), ("jit_compile_ms", C.c_double),
+                ("clones", C.c_uint64), ("cow_fused", C.c_uint64), ("cow_copies", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -50,6 +51,7 @@ SIGNATURES = {
     "qb_init": (_I, [_I, C.POINTER(_VP)]),
     "qb_dist_unique_id": (_I, [_VP]),
     "qb_init_dist": (_I, [_I, _I, _I, _VP, C.POINTER(_VP)]),
+    "qb_init_group": (_I, [C.POINTER(_I), _I, C.POINTER(_VP)]),
     "qb_shutdown": (_I, [_VP]),
     "qb_ctx_rank": (_I, [_VP]),
     "qb_ctx_nranks": (_I, [_VP]),
@@ -59,6 +61,7 @@ SIGNATURES = {
     "qb_state_create": (_I, [_VP, _I, _I, C.POINTER(_VP)]),
     "qb_state_from_host": (_I, [_VP, _I, _VP, C.POINTER(_VP)]),
     "qb_state_clone": (_I, [_VP, C.POINTER(_VP)]),
+    "qb_state_apply_pure": (_I, [_VP, C.POINTER(QbOp), _I64, C.POINTER(_VP)]),
     "qb_state_free": (None, [_VP]),
     "qb_state_nqubits": (_I, [_VP]),
     "qb_state_local_len": (_U64, [_VP]),

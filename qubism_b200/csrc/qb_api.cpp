@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -49,6 +50,8 @@ static int fail(int code, const char *fmt, ...) {
   } while (0)
 
 // ------------------------------------------------------------------------- objects
+struct Buffer;
+
 struct qb_ctx {
   int device = 0;
   int sm_count = 148;
@@ -61,22 +64,51 @@ struct qb_ctx {
   double jit_base_ms = 0.0;
   int *kq_bits_dev = nullptr;      // 2 * QB_MAX_KQ ints
   double2 *kq_mat_dev = nullptr;   // 4^QB_MAX_KQ
+  double2 **peer_tab_dev = nullptr;  // nranks device pointers (sharded tensor)
   PlanOptions opt;
+  int linear = 0;                  // option "linear": 1 = a pure application CONSUMES the older handles of its
+                                   // lineage (they turn stale and fail loudly) instead of copying on write
+  int pool_max = 1;                // option "pool": spare shards kept for the next clone / copy-on-write
   qb_stats stats{};
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;  // pending (start, stop) pairs
   std::vector<cudaEvent_t> event_pool;
   std::recursive_mutex mu;
   DistState *dist = nullptr;
+  // device shards: in use (creation order), spare (registered with the peers, ready for reuse), and
+  // released by their last handle but not yet agreed dead by every rank (sharded contexts: a
+  // finalizer may run at a different time on every rank, so nothing collective happens in it)
+  std::vector<Buffer *> in_use, pool, graveyard;
+  uint64_t next_buffer_id = 0;
+  long handles = 0;                // live qb_state handles (a finalizer may run after qb_shutdown)
+  bool closed = false;
 };
 
-struct qb_state {
+// One entry of a lineage log: what a handle did after the position its buffer stands at.
+enum LogKind : int { LOG_1Q = 0, LOG_KQ = 2, LOG_SCALE = 3, LOG_COLLAPSE = 4 };
+struct LogOp {
+  int kind = LOG_1Q;
+  int target = -1;    // 1Q: logical target bit.  COLLAPSE: the logical bit
+  uint64_t ctrl = 0;  // 1Q / KQ: logical control mask.  COLLAPSE: the outcome (0 / 1)
+  double m[8] = {0};  // 1Q: the matrix.  SCALE: (re, im).  COLLAPSE: m[0] = weight of the outcome
+  int k = 0;
+  int kq_bits[QB_MAX_KQ] = {0};
+  std::shared_ptr<const std::vector<double>> kq_m;
+};
+
+// A device shard plus everything that describes what its amplitudes MEAN, shared by the handles
+// of one lineage.  The device data stands at log position `mat`; a handle at position p denotes
+// the state "data advanced by log[mat .. p)".  Value semantics of the reference's pure (#>)
+// (QGate.hs:78-80; the interpreter builds sv' = g #> sv once per primitive op,
+// QASM/Simulation.hs:94-122) therefore cost nothing per op: a clone is a new handle at the same
+// position, an apply appends to the log, and the ops between two observations still fuse.
+struct Buffer {
   qb_ctx *ctx = nullptr;
-  int n = 0;           // total qubits
-  int L = 0;           // local bits (n - pbits)
+  int n = 0, L = 0;
+  uint64_t id = 0;
   double2 *amps = nullptr;
+  std::vector<double2 *> peers;  // distributed: every rank's shard (IPC / same process); empty: NCCL swaps
+  const double2 *cow_src = nullptr;  // copy-on-write in progress: the first full pass reads its tiles here
   std::vector<int> perm;  // logical bit -> physical bit (bits >= L are rank bits)
-  std::vector<double2 *> peers;  // distributed: every rank's shard through CUDA IPC (empty: NCCL swaps)
-  OpQueue q;
   // SUPPORT of the amplitudes on the device: every non-zero amplitude has
   // (logical index & zmask) == zval.  |0...0> knows every bit, a collapse learns one, a
   // non-diagonal gate forgets its target.  Measurement works on the live sub-cube only.
@@ -90,6 +122,24 @@ struct qb_state {
   // pass, or folded into pscale when the flush ends
   double jit_left = 1.0;
   bool all_finite = false;  // no NaN / inf can be in the amplitudes (created here, only finite gates since)
+  std::vector<LogOp> log;   // positions log_base .. log_base + log.size()
+  size_t log_base = 0, mat = 0;
+  std::vector<qb_state *> handles;
+  bool broken = false;      // a flush failed half way: the data matches no position any more
+  std::string broken_why;
+  bool released = false;    // in the graveyard
+  bool ever_shared = false; // a second handle has existed on this shard (clone): liveness questions need the ranks' agreement
+  OpQueue q;                // scratch of exec_log
+
+  size_t tip() const { return log_base + log.size(); }
+};
+
+struct qb_state {
+  qb_ctx *ctx = nullptr;
+  Buffer *b = nullptr;
+  size_t pos = 0;
+  int n = 0;
+  bool stale = false;  // option "linear": a later pure application consumed this value
 };
 
 namespace {
@@ -111,42 +161,191 @@ int init_common(qb_ctx *c) {
   QB_CUDA(cudaMallocHost(&c->red_host, sizeof(double) * 4));
   QB_CUDA(cudaMalloc(&c->kq_bits_dev, sizeof(int) * 2 * QB_MAX_KQ));
   QB_CUDA(cudaMalloc(&c->kq_mat_dev, sizeof(double2) << (2 * QB_MAX_KQ)));
-  for (const char *name : {"tile_bits", "reg_bits", "low_bits", "max_rounds", "peephole", "fuse", "max_pass_gates", "l2_prefetch", "avoid_regswap", "hot_bits", "rot", "lite", "dbg_skip", "lane_fixed", "skip_dead", "support", "jit", "jit_group", "jit_pf_last", "jit_minb", "jit_mem"}) {
+  for (const char *name : {"tile_bits", "reg_bits", "low_bits", "max_rounds", "peephole", "fuse", "max_pass_gates", "l2_prefetch", "avoid_regswap", "hot_bits", "rot", "lite", "dbg_skip", "lane_fixed", "skip_dead", "support", "jit", "jit_group", "jit_pf_last", "jit_minb", "jit_mem", "tma"}) {
     std::string env = "QB_";
     for (const char *p = name; *p; ++p) env.push_back((char)toupper(*p));
     const char *v = getenv(env.c_str());
     if (v && *v) set_opt(c->opt, name, strtoll(v, nullptr, 10));
   }
+  if (const char *v = getenv("QB_LINEAR")) c->linear = atoi(v) ? 1 : 0;
+  if (const char *v = getenv("QB_POOL")) c->pool_max = std::max(0, atoi(v));
   return QB_OK;
 }
 
-int alloc_state(qb_ctx *ctx, int n, qb_state **out) {
-  if (!ctx || !out) return fail(QB_ERR_ARG, "null argument");
-  if (n < 1 || n > 62) return fail(QB_ERR_ARG, "nqubits %d out of range", n);
-  if (n < ctx->pbits) return fail(QB_ERR_ARG, "nqubits %d smaller than log2(nranks) = %d", n, ctx->pbits);
-  qb_state *s = new qb_state();
-  s->ctx = ctx;
-  s->n = n;
-  s->L = n - ctx->pbits;
-  s->perm.resize(n);
-  for (int i = 0; i < n; ++i) s->perm[i] = i;
-  s->q.reset(n, ctx->opt.peephole != 0, ctx->opt.rot != 0);
-  const size_t bytes = sizeof(double2) << s->L;
-  cudaError_t e = cudaMalloc(&s->amps, bytes);
-  if (e != cudaSuccess) {
-    delete s;
-    return fail(e == cudaErrorMemoryAllocation ? QB_ERR_OOM : QB_ERR_CUDA, "cudaMalloc(%zu bytes): %s", bytes,
-                cudaGetErrorString(e));
+// ---- device shards: allocation, the spare pool, release without collectives --------------------
+void free_buffer_memory(Buffer *b) {
+  if (b->amps) cudaFree(b->amps);
+  b->amps = nullptr;
+}
+
+// Sharded contexts: which released shards are released on EVERY rank?  Handles die in finalizers,
+// at a different moment on every rank; a shard exported to the peers can only be reused or freed
+// once all of them are done with it.  Collective; called where every rank is anyway (allocation,
+// qb_barrier, qb_shutdown): one all-reduce over the first 64 shards in use, in creation order --
+// the same list on every rank, because shards are created and retired collectively.
+int drain_graveyard(qb_ctx *c) {
+  if (c->nranks == 1) {
+    for (Buffer *b : c->graveyard) {
+      if ((int)c->pool.size() < c->pool_max) {
+        c->pool.push_back(b);
+      } else {
+        free_buffer_memory(b);
+        delete b;
+      }
+    }
+    c->graveyard.clear();
+    return QB_OK;
   }
-  if (ctx->nranks > 1) {  // collective: map every peer's shard for the NVLink swap kernel
-    int rc = dist_register(ctx->dist, s->amps, s->peers, ctx->stream);
-    if (rc != QB_OK) {
-      cudaFree(s->amps);
-      delete s;
-      return fail(rc, "peer registration failed: %s", dist_last_error());
+  if (c->in_use.empty()) return QB_OK;
+  const int w = (int)std::min<size_t>(64, c->in_use.size());
+  double v[64];
+  for (int i = 0; i < w; ++i) v[i] = c->in_use[i]->released ? 1.0 : 0.0;
+  int rc = dist_allreduce_sum(c->dist, v, w, c->stream);
+  if (rc != QB_OK) return fail(rc, "shard release agreement failed: %s", dist_last_error());
+  std::vector<Buffer *> keep, gone;
+  for (int i = 0; i < (int)c->in_use.size(); ++i)
+    (i < w && v[i] == (double)c->nranks ? gone : keep).push_back(c->in_use[i]);
+  c->in_use.swap(keep);
+  bool any_free = false;
+  for (Buffer *b : gone) {
+    c->graveyard.erase(std::find(c->graveyard.begin(), c->graveyard.end(), b));
+    if ((int)c->pool.size() < c->pool_max) {
+      c->pool.push_back(b);  // stays mapped by the peers: reuse needs no collective
+    } else {
+      any_free = true;
+      if (!b->peers.empty()) dist_unregister(c->dist, b->peers, c->stream);  // collective (same `gone` on every rank)
     }
   }
-  *out = s;
+  if (any_free)
+    for (Buffer *b : gone)
+      if (std::find(c->pool.begin(), c->pool.end(), b) == c->pool.end()) {
+        free_buffer_memory(b);
+        delete b;
+      }
+  return QB_OK;
+}
+
+int new_buffer(qb_ctx *ctx, int n, Buffer **out) {
+  if (!ctx || !out) return fail(QB_ERR_ARG, "null argument");
+  if (ctx->closed) return fail(QB_ERR_STATE, "context was shut down");
+  if (n < 1 || n > 62) return fail(QB_ERR_ARG, "nqubits %d out of range", n);
+  if (n < ctx->pbits) return fail(QB_ERR_ARG, "nqubits %d smaller than log2(nranks) = %d", n, ctx->pbits);
+  const int L = n - ctx->pbits;
+  if (L > 58) return fail(QB_ERR_OOM, "2^%d amplitudes per shard do not fit a size_t", L);
+  QB_TRY(drain_graveyard(ctx));
+  Buffer *b = nullptr;
+  for (size_t i = 0; i < ctx->pool.size(); ++i)
+    if (ctx->pool[i]->L == L) {
+      b = ctx->pool[i];
+      ctx->pool.erase(ctx->pool.begin() + i);
+      break;
+    }
+  if (!b) {
+    // (the pool holds other sizes: give their memory back first)
+    const size_t bytes = sizeof(double2) << L;
+    b = new Buffer();
+    b->ctx = ctx;
+    cudaError_t e = cudaMalloc(&b->amps, bytes);
+    if (e != cudaSuccess && !ctx->pool.empty() && ctx->nranks == 1) {
+      (void)cudaGetLastError();
+      for (Buffer *p : ctx->pool) {
+        free_buffer_memory(p);
+        delete p;
+      }
+      ctx->pool.clear();
+      e = cudaMalloc(&b->amps, bytes);
+    }
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      delete b;
+      return fail(e == cudaErrorMemoryAllocation ? QB_ERR_OOM : QB_ERR_CUDA, "cudaMalloc(%zu bytes): %s", bytes,
+                  cudaGetErrorString(e));
+    }
+    b->id = ctx->next_buffer_id++;
+    if (ctx->nranks > 1) {  // collective: map every peer's shard for the NVLink swap kernel
+      int rc = dist_register(ctx->dist, b->amps, b->peers, ctx->stream);
+      if (rc != QB_OK) {
+        free_buffer_memory(b);
+        delete b;
+        return fail(rc, "peer registration failed: %s", dist_last_error());
+      }
+    }
+  }
+  b->n = n;
+  b->L = L;
+  b->cow_src = nullptr;
+  b->perm.resize(n);
+  for (int i = 0; i < n; ++i) b->perm[i] = i;
+  b->zmask = b->zval = 0;
+  b->pscale[0] = 1.0;
+  b->pscale[1] = 0.0;
+  b->jit_left = 1.0;
+  b->all_finite = false;
+  b->log.clear();
+  b->log_base = b->mat = 0;
+  b->handles.clear();
+  b->broken = false;
+  b->released = false;
+  b->ever_shared = false;
+  ctx->in_use.push_back(b);
+  *out = b;
+  return QB_OK;
+}
+
+// the last handle of a shard went away (possibly inside a finalizer): nothing collective here
+void release_buffer(Buffer *b) {
+  qb_ctx *c = b->ctx;
+  b->log.clear();
+  b->released = true;
+  c->graveyard.push_back(b);
+  if (c->nranks == 1) {
+    c->in_use.erase(std::find(c->in_use.begin(), c->in_use.end(), b));
+    drain_graveyard(c);
+  }
+}
+
+void attach(qb_state *h, Buffer *b, size_t pos) {
+  h->b = b;
+  h->pos = pos;
+  b->handles.push_back(h);
+}
+
+void detach(qb_state *h) {
+  Buffer *b = h->b;
+  if (!b) return;
+  b->handles.erase(std::find(b->handles.begin(), b->handles.end(), h));
+  h->b = nullptr;
+  if (b->handles.empty()) release_buffer(b);
+}
+
+int new_handle(qb_ctx *ctx, Buffer *b, size_t pos, qb_state **out) {
+  qb_state *h = new qb_state();
+  h->ctx = ctx;
+  h->n = b->n;
+  attach(h, b, pos);
+  ++ctx->handles;
+  *out = h;
+  return QB_OK;
+}
+
+// Sharded contexts: handles die in finalizers, at a different moment on every rank, but whether a
+// shard has to be copied (a collective allocation) must be decided alike everywhere: "does ANY
+// rank still hold such a handle?".  Only asked for shards that were ever cloned.
+int agree_any(qb_ctx *c, const Buffer *b, bool *flag) {
+  if (c->nranks == 1 || !b->ever_shared) return QB_OK;
+  double v = *flag ? 1.0 : 0.0;
+  int rc = dist_allreduce_sum(c->dist, &v, 1, c->stream);
+  if (rc != QB_OK) return fail(rc, "handle agreement failed: %s", dist_last_error());
+  *flag = v != 0.0;
+  return QB_OK;
+}
+
+int check_state(const qb_state *s) {
+  if (!s) return fail(QB_ERR_ARG, "null state");
+  if (s->ctx->closed) return fail(QB_ERR_STATE, "the context of this state was shut down");
+  if (s->stale || !s->b)
+    return fail(QB_ERR_STATE, "stale handle: a later pure application consumed this value (option \"linear\" = 1)");
+  if (s->b->broken) return fail(QB_ERR_STATE, "state lost by an earlier failure: %s", s->b->broken_why.c_str());
   return QB_OK;
 }
 
@@ -157,7 +356,7 @@ int check_qubit(const qb_state *s, int q) {
   return QB_OK;
 }
 
-uint64_t phys_mask(const qb_state *s, uint64_t logical_mask) {
+uint64_t phys_mask(const Buffer *s, uint64_t logical_mask) {
   uint64_t m = 0;
   for (uint64_t b = logical_mask; b; b &= b - 1) m |= 1ull << s->perm[__builtin_ctzll(b)];
   return m;
@@ -189,9 +388,19 @@ int resolve_timed(qb_ctx *c) {
   return QB_OK;
 }
 
+// a copy-on-write whose copy has not happened yet (no full pass has run): do it now
+int ensure_inplace(Buffer *s) {
+  if (!s->cow_src) return QB_OK;
+  QB_CUDA(cudaMemcpyAsync(s->amps, s->cow_src, sizeof(double2) << s->L, cudaMemcpyDeviceToDevice, s->ctx->stream));
+  s->cow_src = nullptr;
+  s->ctx->stats.cow_copies++;
+  return QB_OK;
+}
+
 // run one op with the unfused kernels
-int run_simple(qb_state *s, const HostOp &op) {
+int run_simple(Buffer *s, const HostOp &op) {
   qb_ctx *c = s->ctx;
+  QB_TRY(ensure_inplace(s));
   const uint64_t rank_bits = uint64_t(c->rank) << s->L;
   const uint64_t cmask = phys_mask(s, op.ctrl);
   if (op.kind == 2) {
@@ -199,7 +408,7 @@ int run_simple(qb_state *s, const HostOp &op) {
     if (op.k < 1 || op.k > QB_MAX_KQ) return fail(QB_ERR_ARG, "bad k");
     for (int j = 0; j < op.k; ++j) {
       const int pb = s->perm[op.kq_bits[op.k - 1 - j]];  // matrix index bit j (LSB first)
-      if (pb >= s->L) return fail(QB_ERR_UNSUPPORTED, "dense k-qubit block on a global qubit");
+      if (pb >= s->L) return fail(QB_ERR_UNSUPPORTED, "internal: dense k-qubit block on a global qubit");
       order[j] = pb;
       sorted[j] = pb;
     }
@@ -212,6 +421,8 @@ int run_simple(qb_state *s, const HostOp &op) {
                             c->stream));
     QB_CUDA(launch_simple_kq(s->amps, s->L, op.k, c->kq_bits_dev, c->kq_bits_dev + QB_MAX_KQ, c->kq_mat_dev, cmask,
                              rank_bits, c->sm_count, c->stream));
+    // the host vectors above are read by the copies asynchronously (pageable memory is staged at
+    // call time) -- and the NEXT dense block must not overwrite the device copies early: same stream
     c->stats.simple_launches++;
     c->stats.ops_executed++;
     return QB_OK;
@@ -230,18 +441,20 @@ int run_simple(qb_state *s, const HostOp &op) {
   return QB_OK;
 }
 
-int run_gscale_simple(qb_state *s, const double g[2]) {
+int run_gscale_simple(Buffer *s, const double g[2]) {
   qb_ctx *c = s->ctx;
+  QB_TRY(ensure_inplace(s));
   QB_CUDA(launch_simple_diag(s->amps, s->L, 0, 0, 0, g, g, c->sm_count, c->stream));
   c->stats.simple_launches++;
   return QB_OK;
 }
 
-// Make every op in `seg` (1q ops only, live) runnable locally: in a distributed context bring
-// the global targets of the not-yet-done ops into the shard with one multi-bit swap.
-int make_local(qb_state *s, const std::vector<const HostOp *> &pending) {
+// Make the global targets of `pending` (live ops, program order) local: in a distributed context
+// one multi-bit swap brings them into the shard.
+int make_local(Buffer *s, const std::vector<const HostOp *> &pending) {
   qb_ctx *c = s->ctx;
   if (c->nranks == 1) return fail(QB_ERR_UNSUPPORTED, "internal: planner stuck on a single GPU");
+  QB_TRY(ensure_inplace(s));
   // what comes after `pending`: assume the flush's op stream again (an iterated circuit).  Only
   // consulted to order the qubits this flush never touches again, which would otherwise tie: the
   // layout then settles into a short cycle (period 2 at 2 GPUs, 3 at 4 on the benchmark circuit)
@@ -258,7 +471,7 @@ int make_local(qb_state *s, const std::vector<const HostOp *> &pending) {
 // The live sub-cube of this rank's shard in PHYSICAL local bits.  Returns false if the support
 // cannot be used (nothing known, or too fragmented for the kernels); *dead = this rank holds
 // only zeros (a known global bit has the other value here).
-bool live_cube(const qb_state *s, uint64_t *mask, uint64_t *val, bool *dead) {
+bool live_cube(const Buffer *s, uint64_t *mask, uint64_t *val, bool *dead) {
   *mask = *val = 0;
   *dead = false;
   if (!s->zmask || !s->ctx->opt.support) return false;
@@ -286,7 +499,7 @@ static bool finite8(const double *m) {
   return true;
 }
 
-int run_fused_segment(qb_state *s, std::vector<const HostOp *> seg, const double *gscale, bool *gscale_done,
+int run_fused_segment(Buffer *s, std::vector<const HostOp *> seg, const double *gscale, bool *gscale_done,
                       bool final_seg = false) {
   qb_ctx *c = s->ctx;
   int T, R;
@@ -365,7 +578,7 @@ int run_fused_segment(qb_state *s, std::vector<const HostOp *> seg, const double
           mid_scale[i] = 1.0;
         }
         bool requested = false;
-        const int jr = jit_lookup(jit_prog[i], p, jit_thr, &jit_handle[i], &err, &requested);
+        const int jr = jit_lookup(jit_prog[i], p, jit_thr, &jit_handle[i], &err, &requested, c->rank);
         if (jr < 0) jit_handle[i] = nullptr;  // the generic kernel computes the same thing
         // Sharded states: WHICH kernel runs may differ between ranks (background compilation
         // finishes at different times), so there a pass whose structure has reached the
@@ -420,6 +633,18 @@ int run_fused_segment(qb_state *s, std::vector<const HostOp *> seg, const double
         QB_TRY(get_event(c, &e1));
         QB_CUDA(cudaEventRecord(e0, c->stream));
       }
+      // a pending copy-on-write rides on the first pass that visits every tile: it reads the old
+      // shard and writes the new one (no separate copy); anything else copies first
+      const double2 *src = nullptr;
+      if (s->cow_src) {
+        if (!rank_dead && p.ntiles == (1ull << (s->L - p.tile_bits))) {
+          src = s->cow_src;
+          s->cow_src = nullptr;
+          c->stats.cow_fused++;
+        } else {
+          QB_TRY(ensure_inplace(s));
+        }
+      }
       if (!rank_dead) {
         if (jit_handle[i]) {
           const DevPass *P = reinterpret_cast<const DevPass *>(p.blob.data());
@@ -427,10 +652,10 @@ int run_fused_segment(qb_state *s, std::vector<const HostOp *> seg, const double
           if (!P->has_gscale) gs[0] = 1.0, gs[1] = 0.0;
           std::string err;
           const std::vector<uint8_t> args = jit_pack_args(jit_prog[i], gs, P->rank_bits, P->base_fixed);
-          if (jit_launch(jit_handle[i], s->amps, p.ntiles, args, c->sm_count, c->stream, &err) != 0)
+          if (jit_launch(jit_handle[i], s->amps, src, p.ntiles, args, c->sm_count, c->stream, &err) != 0)
             return fail(QB_ERR_CUDA, "%s", err.c_str());
         } else {
-          QB_CUDA(launch_fused_pass(s->amps, p.blob.data(), (uint32_t)p.blob.size(), p.tile_bits, p.reg_bits, p.ntiles,
+          QB_CUDA(launch_fused_pass(s->amps, src, p.blob.data(), (uint32_t)p.blob.size(), p.tile_bits, p.reg_bits, p.ntiles,
                                     c->sm_count, c->stream, nullptr));
         }
       }
@@ -463,19 +688,17 @@ int run_fused_segment(qb_state *s, std::vector<const HostOp *> seg, const double
   return QB_OK;
 }
 
-// what the queued ops do to the support once they have run
-void support_after_ops(qb_state *s) {
-  for (const auto &op : s->q.ops) {
-    if (op.dead) continue;
-    if (op.kind == 2) {
-      for (int j = 0; j < op.k; ++j) s->zmask &= ~(1ull << op.kq_bits[j]);
-      for (double x : op.kq_m)
-        if (!std::isfinite(x)) {
-          s->zmask = 0;
-          s->all_finite = false;
-        }
-      continue;
-    }
+// what one executed op does to the support.  Applied right after the op has run: the NEXT
+// segment of the same flush plans its dead tiles from it (a dense block populates its qubits).
+void support_after_op(Buffer *s, const HostOp &op) {
+  if (op.kind == 2) {
+    for (int j = 0; j < op.k; ++j) s->zmask &= ~(1ull << op.kq_bits[j]);
+    for (double x : op.kq_m)
+      if (!std::isfinite(x)) {
+        s->zmask = 0;
+        s->all_finite = false;
+      }
+  } else {
     if (!finite8(op.m)) {  // 0 * NaN = NaN: nothing stays zero (zero-weight collapse, StateVec.hs:92)
       s->zmask = 0;
       s->all_finite = false;
@@ -487,7 +710,7 @@ void support_after_ops(qb_state *s) {
 
 // run the queued ops.  The deferred scalar rides on the last fused pass if there is one;
 // otherwise it stays pending in s->pscale (no sweep just to scale).
-int flush_ops_locked(qb_state *s) {
+int exec_queue(Buffer *s) {
   qb_ctx *c = s->ctx;
   OpQueue &q = s->q;
   c->stats.ops_submitted += q.submitted;
@@ -515,16 +738,27 @@ int flush_ops_locked(qb_state *s) {
   int T, R;
   effective_tile(c->opt, s->L, T, R);
   int rc = QB_OK;
+  // ops from index i on that are still to run (swap selection looks ahead over them)
+  auto pending_from = [&](size_t i) {
+    std::vector<const HostOp *> pend;
+    for (size_t j = i; j < q.ops.size(); ++j)
+      if (!q.ops[j].dead) pend.push_back(&q.ops[j]);
+    return pend;
+  };
+  // a dense block needs ALL its qubits inside the shard
+  auto kq_needs_swap = [&](const HostOp &op) {
+    for (int j = 0; j < op.k; ++j)
+      if (s->perm[op.kq_bits[j]] >= s->L) return true;
+    return false;
+  };
   if (T == 0) {
-    for (const auto &op : q.ops) {
+    for (size_t i = 0; i < q.ops.size(); ++i) {
+      const HostOp &op = q.ops[i];
       if (op.dead) continue;
-      if (op.kind == 0 && op.type != G_DIAG && s->perm[op.target] >= s->L) {
-        std::vector<const HostOp *> pend;
-        for (const auto &o2 : q.ops)
-          if (!o2.dead && &o2 >= &op && o2.kind == 0) pend.push_back(&o2);
-        if ((rc = make_local(s, pend)) != QB_OK) break;
-      }
+      if ((op.kind == 0 && op.type != G_DIAG && s->perm[op.target] >= s->L) || (op.kind == 2 && kq_needs_swap(op)))
+        if ((rc = make_local(s, pending_from(i))) != QB_OK) break;
       if ((rc = run_simple(s, op)) != QB_OK) break;
+      support_after_op(s, op);
     }
   } else {
     std::vector<const HostOp *> seg;
@@ -539,7 +773,9 @@ int flush_ops_locked(qb_state *s) {
         rc = run_fused_segment(s, seg, nullptr, nullptr);
         seg.clear();
       }
+      if (rc == QB_OK && kq_needs_swap(op)) rc = make_local(s, pending_from(i));
       if (rc == QB_OK) rc = run_simple(s, op);
+      if (rc == QB_OK) support_after_op(s, op);
     }
     if (rc == QB_OK && !seg.empty()) rc = run_fused_segment(s, seg, has_g ? g : nullptr, &g_done, true);
   }
@@ -552,13 +788,12 @@ int flush_ops_locked(qb_state *s) {
     s->pscale[1] *= s->jit_left;
     s->jit_left = 1.0;
   }
-  support_after_ops(s);
   q.clear();
   return rc;
 }
 
 // apply the pending scalar to the device amplitudes (live sub-cube only when the support is known)
-int force_scale(qb_state *s) {
+int force_scale(Buffer *s) {
   if (s->pscale[0] == 1.0 && s->pscale[1] == 0.0) return QB_OK;
   qb_ctx *c = s->ctx;
   uint64_t mask, val;
@@ -578,16 +813,10 @@ int force_scale(qb_state *s) {
   return QB_OK;
 }
 
-// run the queued ops AND materialise the deferred scalar: the device holds the true amplitudes
-int flush_locked(qb_state *s) {
-  QB_TRY(flush_ops_locked(s));
-  return force_scale(s);
-}
-
-// reduce (S0, S1) split by a logical bit (lb < 0: total) into host doubles; all-reduced when distributed
-int sumsq_locked(qb_state *s, int lb, double *s0, double *s1) {
+// reduce (S0, S1) split by a logical bit (lb < 0: total) into host doubles; all-reduced when
+// distributed.  The buffer stands at the position to be measured (materialise() first).
+int sumsq_buffer(Buffer *s, int lb, double *s0, double *s1) {
   qb_ctx *c = s->ctx;
-  QB_TRY(flush_ops_locked(s));
   if (!(std::isfinite(s->pscale[0]) && std::isfinite(s->pscale[1]))) QB_TRY(force_scale(s));  // NaN / inf must reach the data
   const int pb = lb < 0 ? -1 : s->perm[lb];
   const bool known = lb >= 0 && ((s->zmask >> lb) & 1ull);
@@ -622,7 +851,7 @@ int sumsq_locked(qb_state *s, int lb, double *s0, double *s1) {
   if (c->nranks > 1) {
     double v[2] = {a0, a1};
     int rc = dist_allreduce_sum(c->dist, v, 2, c->stream);
-    if (rc != QB_OK) return fail(rc, "allreduce failed");
+    if (rc != QB_OK) return fail(rc, "allreduce failed: %s", dist_last_error());
     a0 = v[0];
     a1 = v[1];
   }
@@ -636,9 +865,10 @@ int sumsq_locked(qb_state *s, int lb, double *s0, double *s1) {
   return QB_OK;
 }
 
-// collapse (StateVec.hs:104-114) right after sumsq_locked (queue empty): zero-fill the half of
-// the live sub-cube that dies, learn the bit, defer the normalisation.  No read, no full pass.
-int collapse_with(qb_state *s, int lb, int bit, double weight) {
+// collapse (StateVec.hs:104-114) as a log entry being executed (everything before it has run, the
+// queue is empty): zero-fill the half of the live sub-cube that dies, learn the bit, defer the
+// normalisation.  No read, no full pass.  `weight` = the reduction taken when the entry was logged.
+int collapse_exec(Buffer *s, int lb, int bit, double weight) {
   qb_ctx *c = s->ctx;
   if (weight == 0.0 || !std::isfinite(weight)) {
     // the reference divides by norm_2 = 0: every amplitude becomes NaN (StateVec.hs:92,107)
@@ -656,6 +886,7 @@ int collapse_with(qb_state *s, int lb, int bit, double weight) {
   }
   const bool known = (s->zmask >> lb) & 1ull;  // then the other value has weight 0 and was handled above
   if (!known) {
+    QB_TRY(ensure_inplace(s));
     uint64_t mask, val;
     bool dead;
     const bool cube = live_cube(s, &mask, &val, &dead);
@@ -684,6 +915,218 @@ int collapse_with(qb_state *s, int lb, int bit, double weight) {
   return QB_OK;
 }
 
+// ---- lineage: execute log[mat .. upto) on the buffer's device data ------------------------------
+// The peephole (qb_planner.cpp, OpQueue) runs here, over the whole stretch between two
+// observations, however the caller sliced it into handles.
+int exec_log(Buffer *b, size_t upto) {
+  qb_ctx *c = b->ctx;
+  int rc = QB_OK;
+  b->q.reset(b->n, c->opt.peephole != 0, c->opt.rot != 0);
+  for (size_t p = b->mat; p < upto && rc == QB_OK; ++p) {
+    const LogOp &o = b->log[p - b->log_base];
+    switch (o.kind) {
+      case LOG_1Q: b->q.push_1q(o.target, o.ctrl, o.m); break;
+      case LOG_KQ: b->q.push_kq(o.kq_bits, o.k, o.kq_m->data(), o.ctrl); break;
+      case LOG_SCALE: b->q.mul_gscale(o.m[0], o.m[1]); break;
+      case LOG_COLLAPSE:
+        rc = exec_queue(b);
+        if (rc == QB_OK) rc = collapse_exec(b, o.target, (int)o.ctrl, o.m[0]);
+        break;
+      default: rc = fail(QB_ERR_ARG, "internal: bad log entry"); break;
+    }
+  }
+  if (rc == QB_OK) rc = exec_queue(b);
+  if (rc == QB_OK) rc = ensure_inplace(b);  // (a copy-on-write no pass took along)
+  if (rc != QB_OK) {
+    b->broken = true;
+    b->broken_why = g_last_error;
+    b->cow_src = nullptr;
+    return rc;
+  }
+  b->mat = upto;
+  return QB_OK;
+}
+
+// drop the log entries nobody can ask for any more
+void trim_log(Buffer *b) {
+  size_t keep = b->mat;
+  for (const qb_state *h : b->handles)
+    if (!h->stale) keep = std::min(keep, h->pos);
+  if (keep > b->log_base) {
+    b->log.erase(b->log.begin(), b->log.begin() + (keep - b->log_base));
+    b->log_base = keep;
+  }
+}
+
+void copy_meta(Buffer *dst, const Buffer *src) {
+  dst->perm = src->perm;
+  dst->zmask = src->zmask;
+  dst->zval = src->zval;
+  dst->pscale[0] = src->pscale[0];
+  dst->pscale[1] = src->pscale[1];
+  dst->all_finite = src->all_finite;
+}
+
+// Give handle h a shard of its own that stands where h's old shard stands, carrying the log
+// entries h still needs.  lazy: the copy itself may ride on the first pass of the caller's exec_log.
+int split_off(qb_state *h, bool lazy_copy) {
+  Buffer *b = h->b;
+  qb_ctx *c = h->ctx;
+  Buffer *nb = nullptr;
+  QB_TRY(new_buffer(c, b->n, &nb));
+  copy_meta(nb, b);
+  nb->log.assign(b->log.begin() + (b->mat - b->log_base), b->log.begin() + (h->pos - b->log_base));
+  nb->log_base = nb->mat = 0;
+  if (lazy_copy) {
+    nb->cow_src = b->amps;
+  } else {
+    cudaError_t e = cudaMemcpyAsync(nb->amps, b->amps, sizeof(double2) << b->L, cudaMemcpyDeviceToDevice, c->stream);
+    if (e != cudaSuccess) {
+      nb->handles.clear();
+      release_buffer(nb);
+      return fail(QB_ERR_CUDA, "clone: %s", cudaGetErrorString(e));
+    }
+    c->stats.cow_copies++;
+  }
+  const size_t npos = nb->log.size();
+  b->handles.erase(std::find(b->handles.begin(), b->handles.end(), h));
+  attach(h, nb, npos);
+  if (b->handles.empty()) release_buffer(b);  // (cannot happen: a split is only needed while others share b)
+  else trim_log(b);
+  return QB_OK;
+}
+
+// Bring the device data to h's position so that it can be observed.  In place when no live handle
+// needs the older data; otherwise h moves to a shard of its own (copy-on-write, the copy riding on
+// the first fused pass), or -- option "linear" -- the older handles are consumed.
+int materialise(qb_state *h) {
+  QB_TRY(check_state(h));
+  Buffer *b = h->b;
+  if (b->mat == h->pos) return QB_OK;
+  bool older = false;
+  for (const qb_state *g : b->handles)
+    if (g != h && !g->stale && g->pos < h->pos) older = true;
+  QB_TRY(agree_any(h->ctx, b, &older));
+  if (older && h->ctx->linear) {
+    for (qb_state *g : b->handles)
+      if (g != h && g->pos < h->pos) g->stale = true;
+    older = false;
+  }
+  if (older) {
+    QB_TRY(split_off(h, true));
+    b = h->b;
+  }
+  QB_TRY(exec_log(b, h->pos));
+  trim_log(b);
+  return QB_OK;
+}
+
+// h is about to be changed in place (upload, axpy target): nobody else may see its shard
+int make_unique(qb_state *h) {
+  QB_TRY(materialise(h));
+  Buffer *b = h->b;
+  bool shared = false;
+  for (const qb_state *g : b->handles)
+    if (g != h && !g->stale) shared = true;
+  QB_TRY(agree_any(h->ctx, b, &shared));
+  if (!shared) return QB_OK;
+  if (h->ctx->linear) {
+    for (qb_state *g : b->handles)
+      if (g != h) g->stale = true;
+    return QB_OK;
+  }
+  return split_off(h, false);
+}
+
+// Change the qubit layout of a buffer (logical bit q moves to physical bit want[q]) without
+// changing what it means: operands of <.>, +: and tensor must agree on where each qubit lives,
+// and independent global<->local swaps make layouts diverge (StateVec.hs:51-58,98-100).  A
+// sequence of position swaps: local/local = one in-place kernel over half the shard, global/local
+// = one pairwise exchange, global/global = three of those through the top local bit.  Collective
+// on a sharded context (every rank holds the same perm and takes the same steps).
+int relayout(Buffer *b, const std::vector<int> &want) {
+  qb_ctx *c = b->ctx;
+  QB_TRY(ensure_inplace(b));
+  const int L = b->L;
+  const bool peer_path = c->nranks > 1 && dist_has_peers(c->dist, b->peers);
+  auto swap_positions = [&](int p1, int p2) -> int {  // physical positions
+    if (p1 == p2) return QB_OK;
+    if (p1 < p2) std::swap(p1, p2);  // p1 > p2
+    if (p1 < L) {
+      QB_CUDA(launch_swap_bits(b->amps, L, p1, p2, c->sm_count, c->stream));
+      c->stats.simple_launches++;
+      for (int &x : b->perm) x = (x == p1) ? p2 : (x == p2 ? p1 : x);
+      return QB_OK;
+    }
+    if (p2 < L) {  // global p1 <-> local p2
+      int lb = p2;
+      if (!peer_path && lb != L - 1) {  // send/recv moves contiguous blocks: go through the top local bit
+        QB_CUDA(launch_swap_bits(b->amps, L, lb, L - 1, c->sm_count, c->stream));
+        for (int &x : b->perm) x = (x == lb) ? L - 1 : (x == L - 1 ? lb : x);
+        lb = L - 1;
+      }
+      std::vector<SwapPair> sw{{p1, lb}};
+      int rc = dist_swap_pairs(c->dist, b->amps, b->peers, L, b->perm, sw, c->sm_count, c->stream, &c->stats);
+      if (rc != QB_OK) return fail(rc, "layout exchange failed: %s", dist_last_error());
+      if (lb != p2) {
+        QB_CUDA(launch_swap_bits(b->amps, L, p2, L - 1, c->sm_count, c->stream));
+        for (int &x : b->perm) x = (x == p2) ? L - 1 : (x == L - 1 ? p2 : x);
+      }
+      return QB_OK;
+    }
+    // both global: through the top local bit t: (p1 t)(p2 t)(p1 t)
+    const int t = L - 1;
+    for (int g : {p1, p2, p1}) {
+      std::vector<SwapPair> sw{{g, t}};
+      int rc = dist_swap_pairs(c->dist, b->amps, b->peers, L, b->perm, sw, c->sm_count, c->stream, &c->stats);
+      if (rc != QB_OK) return fail(rc, "layout exchange failed: %s", dist_last_error());
+    }
+    return QB_OK;
+  };
+  for (int q = 0; q < b->n; ++q) {
+    // each swap puts at least qubit q where it belongs (the qubit that sat there takes q's old place)
+    if (b->perm[q] != want[q]) QB_TRY(swap_positions(b->perm[q], want[q]));
+  }
+  for (int q = 0; q < b->n; ++q)
+    if (b->perm[q] != want[q]) return fail(QB_ERR_STATE, "internal: relayout did not converge");
+  return QB_OK;
+}
+
+// the device holds the TRUE amplitudes of h (deferred scalar applied)
+int flush_locked(qb_state *h) {
+  QB_TRY(materialise(h));
+  return force_scale(h->b);
+}
+
+constexpr size_t kMaxLog = size_t(1) << 20;  // entries a lineage may queue before it is flushed on its own
+
+// append an op to h's lineage.  A handle that is not at the tip of its log (another handle of the
+// lineage went on from the same value) starts a lineage of its own first.
+int append(qb_state *h, LogOp &&op) {
+  QB_TRY(check_state(h));
+  Buffer *b = h->b;
+  if (h->pos != b->tip()) {
+    QB_TRY(split_off(h, false));
+    b = h->b;
+  }
+  b->log.push_back(std::move(op));
+  h->pos = b->tip();
+  if (b->log.size() > kMaxLog) QB_TRY(materialise(h));
+  return QB_OK;
+}
+
+void drop_handle(qb_state *s) {
+  qb_ctx *c = s->ctx;
+  bool last_of_closed;
+  {
+    Guard g(c);
+    if (!c->closed) detach(s);
+    last_of_closed = (--c->handles == 0) && c->closed;
+  }
+  delete s;
+  if (last_of_closed) delete c;
+}
+
 }  // namespace
 
 // ============================================================================ C ABI
@@ -691,7 +1134,7 @@ extern "C" {
 
 const char *qb_last_error(void) { return g_last_error.c_str(); }
 
-const char *qb_version(void) { return "qubism_sv 0.1 sm_100a fused-pass"; }
+const char *qb_version(void) { return "qubism_sv 0.2 sm_100a fused-pass"; }
 
 int qb_init(int device, qb_ctx **out) {
   if (!out) return fail(QB_ERR_ARG, "null out");
@@ -736,26 +1179,94 @@ int qb_init_dist(int device, int rank, int nranks, const void *nccl_id, qb_ctx *
     *out = nullptr;
     return fail(rc, "distributed init failed: %s", msg.c_str());
   }
+  QB_CUDA(cudaMalloc(&c->peer_tab_dev, sizeof(double2 *) * nranks));
   return QB_OK;
+}
+
+int qb_init_group(const int *devices, int nranks, qb_ctx **out) {
+  if (!devices || !out) return fail(QB_ERR_ARG, "null argument");
+  if (nranks < 1 || nranks > 64 || (nranks & (nranks - 1))) return fail(QB_ERR_ARG, "nranks must be a power of two <= 64");
+  for (int r = 0; r < nranks; ++r) out[r] = nullptr;
+  DistGroup *grp = nranks > 1 ? dist_group_create(nranks) : nullptr;
+  int rc = QB_OK;
+  for (int r = 0; r < nranks && rc == QB_OK; ++r) {
+    rc = qb_init(devices[r], &out[r]);
+    if (rc != QB_OK || nranks == 1) continue;
+    qb_ctx *c = out[r];
+    c->rank = r;
+    c->nranks = nranks;
+    c->pbits = __builtin_ctz((unsigned)nranks);
+    rc = dist_create_group(&c->dist, devices[r], r, grp);
+    if (rc != QB_OK) {
+      fail(rc, "rank group init failed: %s", dist_last_error());
+      continue;
+    }
+    if (cudaMalloc(&c->peer_tab_dev, sizeof(double2 *) * nranks) != cudaSuccess) rc = fail(QB_ERR_OOM, "cudaMalloc");
+    // distinct devices: the swap kernel dereferences the peers' shards directly
+    for (int q = 0; q < nranks && rc == QB_OK; ++q) {
+      if (devices[q] == devices[r]) continue;
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, devices[r], devices[q]);
+      if (!can) {
+        rc = fail(QB_ERR_UNSUPPORTED, "device %d cannot access device %d", devices[r], devices[q]);
+        break;
+      }
+      cudaSetDevice(devices[r]);
+      const cudaError_t e = cudaDeviceEnablePeerAccess(devices[q], 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) rc = fail(QB_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+      (void)cudaGetLastError();
+    }
+  }
+  if (rc != QB_OK) {
+    const std::string msg = g_last_error;
+    for (int r = 0; r < nranks; ++r) {
+      if (out[r]) qb_shutdown(out[r]);
+      out[r] = nullptr;
+    }
+    g_last_error = msg;
+  }
+  return rc;
 }
 
 int qb_shutdown(qb_ctx *c) {
   if (!c) return QB_OK;
-  cudaSetDevice(c->device);
-  if (c->stream) cudaStreamSynchronize(c->stream);
-  if (c->dist) dist_destroy(c->dist);
-  for (auto &pr : c->timed) {
-    cudaEventDestroy(pr.first);
-    cudaEventDestroy(pr.second);
+  bool del;
+  {
+    std::lock_guard<std::recursive_mutex> lk(c->mu);
+    if (c->closed) return QB_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    // every shard goes, whoever still holds a handle (those handles fail with QB_ERR_STATE from now on)
+    for (auto *list : {&c->in_use, &c->pool})
+      for (Buffer *b : *list) {
+        for (qb_state *h : b->handles) h->b = nullptr;
+        free_buffer_memory(b);
+        delete b;
+      }
+    c->in_use.clear();
+    c->pool.clear();
+    c->graveyard.clear();
+    if (c->dist) dist_destroy(c->dist);
+    c->dist = nullptr;
+    for (auto &pr : c->timed) {
+      cudaEventDestroy(pr.first);
+      cudaEventDestroy(pr.second);
+    }
+    for (auto e : c->event_pool) cudaEventDestroy(e);
+    c->timed.clear();
+    c->event_pool.clear();
+    cudaFree(c->red_partials);
+    cudaFree(c->red_out);
+    cudaFreeHost(c->red_host);
+    cudaFree(c->kq_bits_dev);
+    cudaFree(c->kq_mat_dev);
+    cudaFree(c->peer_tab_dev);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    c->stream = nullptr;
+    c->closed = true;
+    del = c->handles == 0;  // otherwise the last qb_state_free deletes the context object
   }
-  for (auto e : c->event_pool) cudaEventDestroy(e);
-  cudaFree(c->red_partials);
-  cudaFree(c->red_out);
-  cudaFreeHost(c->red_host);
-  cudaFree(c->kq_bits_dev);
-  cudaFree(c->kq_mat_dev);
-  if (c->stream) cudaStreamDestroy(c->stream);
-  delete c;
+  if (del) delete c;
   return QB_OK;
 }
 
@@ -770,19 +1281,20 @@ int qb_barrier(qb_ctx *c) {
     double v = 0.0;
     int rc = dist_allreduce_sum(c->dist, &v, 1, c->stream);
     if (rc != QB_OK) return fail(rc, "barrier failed: %s", dist_last_error());
+    QB_TRY(drain_graveyard(c));
   }
   return QB_OK;
 }
 
 int qb_state_create(qb_ctx *ctx, int nqubits, int basis, qb_state **out) {
-  if (!ctx) return fail(QB_ERR_ARG, "null ctx");
+  if (!ctx || !out) return fail(QB_ERR_ARG, "null argument");
   Guard g(ctx);
-  qb_state *s = nullptr;
-  QB_TRY(alloc_state(ctx, nqubits, &s));
+  Buffer *s = nullptr;
+  QB_TRY(new_buffer(ctx, nqubits, &s));
   cudaError_t e = cudaMemsetAsync(s->amps, 0, sizeof(double2) << s->L, ctx->stream);
   if (e == cudaSuccess && basis && ctx->rank == 0) e = launch_set_amp(s->amps, 0, 1.0, 0.0, ctx->stream);
   if (e != cudaSuccess) {
-    qb_state_free(s);
+    release_buffer(s);
     return fail(QB_ERR_CUDA, "state init: %s", cudaGetErrorString(e));
   }
   if (basis) {  // |0...0>: every index bit of the one non-zero amplitude is known
@@ -790,97 +1302,119 @@ int qb_state_create(qb_ctx *ctx, int nqubits, int basis, qb_state **out) {
     s->zval = 0;
   }
   s->all_finite = true;
-  *out = s;
-  return QB_OK;
+  return new_handle(ctx, s, 0, out);
 }
 
 int qb_state_from_host(qb_ctx *ctx, int nqubits, const qb_c64 *amps, qb_state **out) {
-  if (!ctx || !amps) return fail(QB_ERR_ARG, "null argument");
+  if (!ctx || !amps || !out) return fail(QB_ERR_ARG, "null argument");
   Guard g(ctx);
-  qb_state *s = nullptr;
-  QB_TRY(alloc_state(ctx, nqubits, &s));
+  Buffer *s = nullptr;
+  QB_TRY(new_buffer(ctx, nqubits, &s));
   cudaError_t e = cudaMemcpyAsync(s->amps, amps, sizeof(double2) << s->L, cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) {
-    qb_state_free(s);
+    release_buffer(s);
     return fail(QB_ERR_CUDA, "upload: %s", cudaGetErrorString(e));
   }
-  *out = s;
-  return QB_OK;
+  return new_handle(ctx, s, 0, out);
 }
 
+// Lazy: the clone is a second handle on the same shard at the same log position.  No flush, no
+// copy, no allocation; the queued gates of the source stay queued -- for both.  Data is copied
+// only if one of the two is later observed or changed while the other still needs the old value.
 int qb_state_clone(qb_state *src, qb_state **out) {
   if (!src || !out) return fail(QB_ERR_ARG, "null argument");
   Guard g(src->ctx);
-  QB_TRY(flush_ops_locked(src));
-  qb_state *s = nullptr;
-  QB_TRY(alloc_state(src->ctx, src->n, &s));
-  s->perm = src->perm;
-  s->zmask = src->zmask;
-  s->zval = src->zval;
-  s->all_finite = src->all_finite;
-  s->pscale[0] = src->pscale[0];
-  s->pscale[1] = src->pscale[1];
-  cudaError_t e =
-      cudaMemcpyAsync(s->amps, src->amps, sizeof(double2) << s->L, cudaMemcpyDeviceToDevice, src->ctx->stream);
-  if (e != cudaSuccess) {
-    qb_state_free(s);
-    return fail(QB_ERR_CUDA, "clone: %s", cudaGetErrorString(e));
+  QB_TRY(check_state(src));
+  src->ctx->stats.clones++;
+  src->b->ever_shared = true;
+  return new_handle(src->ctx, src->b, src->pos, out);
+}
+
+// g #> sv in ONE call (QGate.hs:78-80): *out = a new handle holding `ops` applied to src's value;
+// src stays valid (option "linear" = 1: src is consumed).
+int qb_state_apply_pure(qb_state *src, const qb_op *ops, int64_t nops, qb_state **out) {
+  if (!src || !out || (!ops && nops)) return fail(QB_ERR_ARG, "null argument");
+  qb_state *h = nullptr;
+  QB_TRY(qb_state_clone(src, &h));
+  int rc = qb_submit(h, ops, nops);
+  if (rc != QB_OK) {
+    qb_state_free(h);
+    return rc;
   }
-  *out = s;
+  *out = h;
   return QB_OK;
 }
 
+// ForeignPtr finalizer: any thread, any time, also after qb_shutdown.  Never collective: in a
+// sharded context the shard is only marked released here and retired when every rank has done so.
 void qb_state_free(qb_state *s) {
   if (!s) return;
-  {
-    Guard g(s->ctx);
-    cudaStreamSynchronize(s->ctx->stream);
-    if (s->ctx->nranks > 1 && !s->peers.empty()) dist_unregister(s->ctx->dist, s->peers, s->ctx->stream);  // collective
-    cudaFree(s->amps);
-  }
-  delete s;
+  drop_handle(s);
 }
 
 int qb_state_nqubits(const qb_state *s) { return s ? s->n : QB_ERR_ARG; }
-uint64_t qb_state_local_len(const qb_state *s) { return s ? (1ull << s->L) : 0; }
+uint64_t qb_state_local_len(const qb_state *s) { return s ? (1ull << (s->n - s->ctx->pbits)) : 0; }
 
 int qb_state_read_local(qb_state *s, uint64_t first, uint64_t count, qb_c64 *out) {
   if (!s || !out) return fail(QB_ERR_ARG, "null argument");
   Guard g(s->ctx);
   QB_TRY(flush_locked(s));
-  if (first + count > (1ull << s->L)) return fail(QB_ERR_ARG, "range beyond the local shard");
-  QB_CUDA(cudaMemcpyAsync(out, s->amps + first, count * sizeof(double2), cudaMemcpyDeviceToHost, s->ctx->stream));
+  const uint64_t len = 1ull << s->b->L;
+  if (first > len || count > len - first) return fail(QB_ERR_ARG, "range beyond the local shard");
+  QB_CUDA(cudaMemcpyAsync(out, s->b->amps + first, count * sizeof(double2), cudaMemcpyDeviceToHost, s->ctx->stream));
   QB_CUDA(cudaStreamSynchronize(s->ctx->stream));
   return QB_OK;
 }
 
 int qb_state_write_local(qb_state *s, uint64_t first, uint64_t count, const qb_c64 *amps) {
   if (!s || !amps) return fail(QB_ERR_ARG, "null argument");
-  if (first + count > (1ull << s->L)) return fail(QB_ERR_ARG, "range beyond the local shard");
   Guard g(s->ctx);
-  s->q.clear();
-  s->zmask = s->zval = 0;
-  s->all_finite = false;
-  s->pscale[0] = 1.0;
-  s->pscale[1] = 0.0;
-  for (int i = 0; i < s->n; ++i) s->perm[i] = i;
-  QB_CUDA(cudaMemcpyAsync(s->amps + first, amps, count * sizeof(double2), cudaMemcpyHostToDevice, s->ctx->stream));
+  QB_TRY(check_state(s));
+  const uint64_t len = 1ull << (s->n - s->ctx->pbits);
+  if (first > len || count > len - first) return fail(QB_ERR_ARG, "range beyond the local shard");
+  Buffer *b = s->b;
+  bool shared = false;
+  for (const qb_state *h : b->handles)
+    if (h != s && !h->stale) shared = true;
+  QB_TRY(agree_any(s->ctx, b, &shared));
+  if (first == 0 && !shared) {
+    // an upload starts at offset 0: whatever the state held (queued gates, layout, deferred
+    // scalar, support) is being replaced
+    b->log.clear();
+    b->log_base = b->mat = s->pos = 0;
+    for (int i = 0; i < b->n; ++i) b->perm[i] = i;
+    b->pscale[0] = 1.0;
+    b->pscale[1] = 0.0;
+  } else {
+    // continuing an upload (or writing into a state others share): the untouched amplitudes keep
+    // their meaning, so they must be the true ones, in the identity layout
+    QB_TRY(make_unique(s));
+    b = s->b;
+    QB_TRY(force_scale(b));
+    for (int i = 0; i < b->n; ++i)
+      if (b->perm[i] != i) return fail(QB_ERR_STATE, "partial upload into a state whose qubit layout has changed");
+  }
+  b->zmask = b->zval = 0;
+  b->all_finite = false;
+  QB_CUDA(cudaMemcpyAsync(b->amps + first, amps, count * sizeof(double2), cudaMemcpyHostToDevice, s->ctx->stream));
   return QB_OK;
 }
 
 int qb_state_read(qb_state *s, uint64_t first, uint64_t count, qb_c64 *out) {
   if (!s || (!out && count)) return fail(QB_ERR_ARG, "null argument");
-  if (first + count > (1ull << s->n)) return fail(QB_ERR_ARG, "range beyond 2^n");
+  const uint64_t len = 1ull << s->n;
+  if (first > len || count > len - first) return fail(QB_ERR_ARG, "range beyond 2^n");
   qb_ctx *c = s->ctx;
   Guard g(c);
   QB_TRY(flush_locked(s));
+  Buffer *b = s->b;
   if (c->nranks == 1) {
-    QB_CUDA(cudaMemcpyAsync(out, s->amps + first, count * sizeof(double2), cudaMemcpyDeviceToHost, c->stream));
+    QB_CUDA(cudaMemcpyAsync(out, b->amps + first, count * sizeof(double2), cudaMemcpyDeviceToHost, c->stream));
     QB_CUDA(cudaStreamSynchronize(c->stream));
     return QB_OK;
   }
-  int rc = dist_read_logical(c->dist, s->amps, s->n, s->L, s->perm, first, count, out, c->stream);
+  int rc = dist_read_logical(c->dist, b->amps, b->n, b->L, b->perm, first, count, out, c->stream);
   if (rc != QB_OK) return fail(rc, "distributed read failed: %s", dist_last_error());
   return QB_OK;
 }
@@ -895,11 +1429,13 @@ int qb_apply_ctrl_1q(qb_state *s, const int *ctrls, int nctrl, int t, const qb_c
     if (ctrls[i] == t) return fail(QB_ERR_ARG, "control %d equals target", t);
     cm |= 1ull << logical_bit(s, ctrls[i]);
   }
-  std::lock_guard<std::recursive_mutex> lk(s->ctx->mu);
-  s->q.peephole = s->ctx->opt.peephole != 0;
-  s->q.use_rot = s->ctx->opt.rot != 0;
-  s->q.push_1q(logical_bit(s, t), cm, reinterpret_cast<const double *>(m));
-  return QB_OK;
+  Guard g(s->ctx);
+  LogOp o;
+  o.kind = LOG_1Q;
+  o.target = logical_bit(s, t);
+  o.ctrl = cm;
+  memcpy(o.m, m, sizeof(o.m));
+  return append(s, std::move(o));
 }
 
 int qb_apply_1q(qb_state *s, int q, const qb_c64 m[4]) { return qb_apply_ctrl_1q(s, nullptr, 0, q, m); }
@@ -923,13 +1459,16 @@ int qb_apply_kq(qb_state *s, const int *qs, int k, const qb_c64 *m, const int *c
   if (!s || !qs || !m || (nctrl > 0 && !ctrls)) return fail(QB_ERR_ARG, "null argument");
   if (k < 1 || k > QB_MAX_KQ) return fail(QB_ERR_UNSUPPORTED, "dense blocks support 1 <= k <= %d", QB_MAX_KQ);
   if (k == 1) return qb_apply_ctrl_1q(s, ctrls, nctrl, qs[0], m);
+  if (k > s->n - s->ctx->pbits) return fail(QB_ERR_UNSUPPORTED, "a %d-qubit block does not fit a shard of %d local qubits", k, s->n - s->ctx->pbits);
   uint64_t seen = 0, cm = 0;
-  int bits[QB_MAX_KQ];
+  LogOp o;
+  o.kind = LOG_KQ;
+  o.k = k;
   for (int i = 0; i < k; ++i) {
     QB_TRY(check_qubit(s, qs[i]));
-    bits[i] = logical_bit(s, qs[i]);
-    if (seen & (1ull << bits[i])) return fail(QB_ERR_ARG, "repeated qubit %d", qs[i]);
-    seen |= 1ull << bits[i];
+    o.kq_bits[i] = logical_bit(s, qs[i]);
+    if (seen & (1ull << o.kq_bits[i])) return fail(QB_ERR_ARG, "repeated qubit %d", qs[i]);
+    seen |= 1ull << o.kq_bits[i];
   }
   for (int i = 0; i < nctrl; ++i) {
     QB_TRY(check_qubit(s, ctrls[i]));
@@ -937,13 +1476,17 @@ int qb_apply_kq(qb_state *s, const int *qs, int k, const qb_c64 *m, const int *c
     if (seen & b) return fail(QB_ERR_ARG, "control %d is also a target", ctrls[i]);
     cm |= b;
   }
-  std::lock_guard<std::recursive_mutex> lk(s->ctx->mu);
-  s->q.push_kq(bits, k, reinterpret_cast<const double *>(m), cm);
-  return QB_OK;
+  o.ctrl = cm;
+  o.target = o.kq_bits[0];
+  const double *md = reinterpret_cast<const double *>(m);
+  o.kq_m = std::make_shared<const std::vector<double>>(md, md + (size_t(2) << (2 * k)));
+  Guard g(s->ctx);
+  return append(s, std::move(o));
 }
 
 int qb_submit(qb_state *s, const qb_op *ops, int64_t nops) {
   if (!s || (!ops && nops)) return fail(QB_ERR_ARG, "null argument");
+  Guard g(s->ctx);
   for (int64_t i = 0; i < nops; ++i) {
     const qb_op &o = ops[i];
     if (o.kind == 1) {
@@ -976,7 +1519,19 @@ int qb_sumsq(qb_state *s, int q, double *s0, double *s1) {
   if (!s) return fail(QB_ERR_ARG, "null state");
   QB_TRY(check_qubit(s, q));
   Guard g(s->ctx);
-  return sumsq_locked(s, logical_bit(s, q), s0, s1);
+  QB_TRY(materialise(s));
+  return sumsq_buffer(s->b, logical_bit(s, q), s0, s1);
+}
+
+// the collapse itself is a log entry (it carries the weight just reduced): executed in place at the
+// next observation, or fused away as a queued diagonal gate -- never a reason to copy a shared shard
+static int log_collapse(qb_state *s, int lb, int bit, double weight) {
+  LogOp o;
+  o.kind = LOG_COLLAPSE;
+  o.target = lb;
+  o.ctrl = (uint64_t)bit;
+  o.m[0] = weight;
+  return append(s, std::move(o));
 }
 
 int qb_collapse(qb_state *s, int q, int bit) {
@@ -985,8 +1540,9 @@ int qb_collapse(qb_state *s, int q, int bit) {
   if (bit != 0 && bit != 1) return fail(QB_ERR_ARG, "bit must be 0 or 1");
   Guard g(s->ctx);
   double s0, s1;
-  QB_TRY(sumsq_locked(s, logical_bit(s, q), &s0, &s1));
-  return collapse_with(s, logical_bit(s, q), bit, bit ? s1 : s0);
+  QB_TRY(materialise(s));
+  QB_TRY(sumsq_buffer(s->b, logical_bit(s, q), &s0, &s1));
+  return log_collapse(s, logical_bit(s, q), bit, bit ? s1 : s0);
 }
 
 int qb_measure_qubit(qb_state *s, int q, double r, int *bit, double *pone) {
@@ -994,14 +1550,15 @@ int qb_measure_qubit(qb_state *s, int q, double r, int *bit, double *pone) {
   QB_TRY(check_qubit(s, q));
   Guard g(s->ctx);
   double s0, s1;
-  QB_TRY(sumsq_locked(s, logical_bit(s, q), &s0, &s1));
+  QB_TRY(materialise(s));
+  QB_TRY(sumsq_buffer(s->b, logical_bit(s, q), &s0, &s1));
   // the reference's pOne = sqrt(s1); when s1 == 0 it is NaN there (0/0 in collapse) and
   // `r < NaN` is False for EVERY r, so the outcome is Zero even for an out-of-range draw
   const double p = std::sqrt(s1);
   const int b = (s1 > 0.0 && r < p) ? 1 : 0;
   *bit = b;
   if (pone) *pone = p;
-  return collapse_with(s, logical_bit(s, q), b, b ? s1 : s0);
+  return log_collapse(s, logical_bit(s, q), b, b ? s1 : s0);
 }
 
 int qb_measure_all(qb_state *s, const double *rs, int *bits) {
@@ -1013,9 +1570,12 @@ int qb_measure_all(qb_state *s, const double *rs, int *bits) {
 // ---- vector space
 int qb_scale(qb_state *s, qb_c64 z) {
   if (!s) return fail(QB_ERR_ARG, "null state");
-  std::lock_guard<std::recursive_mutex> lk(s->ctx->mu);
-  s->q.mul_gscale(z.re, z.im);
-  return QB_OK;
+  Guard g(s->ctx);
+  LogOp o;
+  o.kind = LOG_SCALE;
+  o.m[0] = z.re;
+  o.m[1] = z.im;
+  return append(s, std::move(o));
 }
 
 int qb_neg(qb_state *s) { return qb_scale(s, qb_c64{-1.0, 0.0}); }
@@ -1032,16 +1592,19 @@ int qb_axpy(qb_state *y, qb_c64 z, qb_state *x) {
   QB_TRY(same_shape(y, x));
   qb_ctx *c = y->ctx;
   Guard g(c);
-  QB_TRY(flush_locked(y));
   QB_TRY(flush_locked(x));
-  if (y->perm != x->perm) return fail(QB_ERR_UNSUPPORTED, "operands have different qubit layouts");
+  QB_TRY(make_unique(y));   // (x == y, or a clone of it: y moves to its own shard, x keeps the old one)
+  QB_TRY(flush_locked(x));  // (no-op unless the split moved things)
+  QB_TRY(force_scale(y->b));
+  Buffer *yb = y->b, *xb = x->b;
+  if (yb->perm != xb->perm) QB_TRY(relayout(xb, yb->perm));
   const double zz[2] = {z.re, z.im};
-  QB_CUDA(launch_axpy(y->amps, x->amps, 1ull << y->L, zz, c->sm_count, c->stream));
+  QB_CUDA(launch_axpy(yb->amps, xb->amps, 1ull << yb->L, zz, c->sm_count, c->stream));
   // the sum is non-zero only where one of the operands is: keep the bits both know with the same value
-  y->zmask = y->zmask & x->zmask & ~(y->zval ^ x->zval);
-  y->zval &= y->zmask;
-  y->all_finite = y->all_finite && x->all_finite && std::isfinite(z.re) && std::isfinite(z.im);
-  if (!y->all_finite) y->zmask = y->zval = 0;
+  yb->zmask = yb->zmask & xb->zmask & ~(yb->zval ^ xb->zval);
+  yb->zval &= yb->zmask;
+  yb->all_finite = yb->all_finite && xb->all_finite && std::isfinite(z.re) && std::isfinite(z.im);
+  if (!yb->all_finite) yb->zmask = yb->zval = 0;
   return QB_OK;
 }
 
@@ -1054,8 +1617,10 @@ int qb_dotc(qb_state *a, qb_state *b, qb_c64 *out) {
   Guard g(c);
   QB_TRY(flush_locked(a));
   QB_TRY(flush_locked(b));
-  if (a->perm != b->perm) return fail(QB_ERR_UNSUPPORTED, "operands have different qubit layouts");
-  QB_CUDA(launch_dotc(a->amps, b->amps, 1ull << a->L, c->red_partials, c->red_out, c->sm_count, c->stream));
+  QB_TRY(flush_locked(a));  // (b's flush may have split a lineage the two share; idempotent)
+  Buffer *ab = a->b, *bb = b->b;
+  if (ab->perm != bb->perm) QB_TRY(relayout(bb, ab->perm));
+  QB_CUDA(launch_dotc(ab->amps, bb->amps, 1ull << ab->L, c->red_partials, c->red_out, c->sm_count, c->stream));
   c->stats.reduce_launches += 2;
   QB_CUDA(cudaMemcpyAsync(c->red_host, c->red_out, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   QB_CUDA(cudaStreamSynchronize(c->stream));
@@ -1073,7 +1638,8 @@ int qb_norm2(qb_state *s, double *out) {
   if (!s || !out) return fail(QB_ERR_ARG, "null argument");
   Guard g(s->ctx);
   double s0 = 0, s1 = 0;
-  QB_TRY(sumsq_locked(s, -1, &s0, &s1));
+  QB_TRY(materialise(s));
+  QB_TRY(sumsq_buffer(s->b, -1, &s0, &s1));
   *out = std::sqrt(s0 + s1);
   return QB_OK;
 }
@@ -1088,25 +1654,48 @@ int qb_tensor(qb_state *a, qb_state *b, qb_state **out) {
   if (!a || !b || !out) return fail(QB_ERR_ARG, "null argument");
   if (a->ctx != b->ctx) return fail(QB_ERR_STATE, "states live on different contexts");
   qb_ctx *c = a->ctx;
-  if (c->nranks > 1) return fail(QB_ERR_UNSUPPORTED, "tensor of distributed states");
   Guard g(c);
   QB_TRY(flush_locked(a));
   QB_TRY(flush_locked(b));
-  qb_state *s = nullptr;
-  QB_TRY(alloc_state(c, a->n + b->n, &s));
-  cudaError_t e = launch_tensor(s->amps, a->amps, b->amps, a->n, b->n, c->sm_count, c->stream);
+  QB_TRY(flush_locked(a));
+  Buffer *ab = a->b, *bb = b->b;
+  if (c->nranks > 1) {
+    // sharded: a's qubits are the high ones (StateVec.hs:98-100), so with both operands in the
+    // identity layout rank r's shard of the product is (r's shard of a) x (ALL of b): b is read
+    // through the peers' mapped shards, a local fill otherwise
+    std::vector<int> ident(ab->n);
+    for (int i = 0; i < ab->n; ++i) ident[i] = i;
+    if (ab->perm != ident) QB_TRY(relayout(ab, ident));
+    ident.resize(bb->n);
+    for (int i = 0; i < bb->n; ++i) ident[i] = i;
+    if (bb->perm != ident) QB_TRY(relayout(bb, ident));
+    if ((int)bb->peers.size() != c->nranks)
+      return fail(QB_ERR_UNSUPPORTED, "tensor of distributed states needs peer-mapped shards (CUDA IPC or a rank group)");
+  }
+  Buffer *s = nullptr;
+  QB_TRY(new_buffer(c, ab->n + bb->n, &s));
+  cudaError_t e;
+  if (c->nranks > 1) {
+    e = cudaMemcpyAsync(c->peer_tab_dev, bb->peers.data(), sizeof(double2 *) * c->nranks, cudaMemcpyHostToDevice, c->stream);
+    // every rank's b must be final before anyone reads it, and nobody may change b before all are done
+    if (e == cudaSuccess && qb_barrier(c) != QB_OK) e = cudaErrorUnknown;
+    if (e == cudaSuccess)
+      e = launch_tensor_sharded(s->amps, ab->amps, c->peer_tab_dev, ab->L, bb->n, bb->L, c->sm_count, c->stream);
+    if (e == cudaSuccess && qb_barrier(c) != QB_OK) e = cudaErrorUnknown;
+  } else {
+    e = launch_tensor(s->amps, ab->amps, bb->amps, ab->n, bb->n, c->sm_count, c->stream);
+  }
   if (e != cudaSuccess) {
-    qb_state_free(s);
+    release_buffer(s);
     return fail(QB_ERR_CUDA, "tensor: %s", cudaGetErrorString(e));
   }
   // a's bits are the high ones (StateVec.hs:98-100); a known zero stays zero only against finite factors
-  s->all_finite = a->all_finite && b->all_finite;
+  s->all_finite = ab->all_finite && bb->all_finite;
   if (s->all_finite) {
-    s->zmask = (a->zmask << b->n) | b->zmask;
-    s->zval = (a->zval << b->n) | b->zval;
+    s->zmask = (ab->zmask << bb->n) | bb->zmask;
+    s->zval = (ab->zval << bb->n) | bb->zval;
   }
-  *out = s;
-  return QB_OK;
+  return new_handle(c, s, 0, out);
 }
 
 // ---- introspection
@@ -1140,12 +1729,23 @@ void *qb_ctx_stream(qb_ctx *c) { return c ? (void *)c->stream : nullptr; }
 int qb_set_option(qb_ctx *c, const char *name, int64_t value) {
   if (!c || !name) return fail(QB_ERR_ARG, "null argument");
   std::lock_guard<std::recursive_mutex> lk(c->mu);
+  if (!strcmp(name, "linear")) {
+    c->linear = value ? 1 : 0;
+    return QB_OK;
+  }
+  if (!strcmp(name, "pool")) {
+    if (value < 0 || value > 8) return fail(QB_ERR_ARG, "bad option pool=%lld", (long long)value);
+    c->pool_max = (int)value;
+    return QB_OK;
+  }
   if (!set_opt(c->opt, name, value)) return fail(QB_ERR_ARG, "bad option %s=%lld", name, (long long)value);
   return QB_OK;
 }
 
 int64_t qb_get_option(const qb_ctx *c, const char *name) {
   if (!c || !name) return QB_ERR_ARG;
+  if (!strcmp(name, "linear")) return c->linear;
+  if (!strcmp(name, "pool")) return c->pool_max;
   return get_opt(c->opt, name);
 }
 

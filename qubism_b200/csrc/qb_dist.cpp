@@ -14,9 +14,12 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 
 namespace qb {
@@ -77,8 +80,57 @@ NcclApi *nccl() {
 
 }  // namespace
 
+// In-process rank group (qb_init_group): the P ranks are P contexts of ONE process, each driven by
+// its own host thread -- P GPUs without NCCL, or P "virtual ranks" on one GPU (tests: the sharded
+// planner, the fused passes with rank bits and the peer swap kernel all run for P = 2 / 4 / 8 on a
+// 1-GPU box).  Collectives are host-side: a generation barrier plus shared slots.  Shards are
+// plain device pointers of the same process (peer access enabled between distinct devices).
+struct DistGroup {
+  int nranks = 1;
+  std::mutex mu;
+  std::condition_variable cv;
+  int arrived = 0, refs = 0;
+  uint64_t generation = 0;
+  bool broken = false;                 // a rank timed out: every later collective fails at once
+  std::vector<double> slots;           // nranks x 64 doubles
+  std::vector<void *> ptrs;            // nranks
+  std::vector<qb_c64> gather;          // dist_read_logical staging
+  int timeout_s = 300;
+};
+
+DistGroup *dist_group_create(int nranks) {
+  DistGroup *g = new DistGroup();
+  g->nranks = nranks;
+  g->slots.assign(size_t(nranks) * 64, 0.0);
+  g->ptrs.assign(nranks, nullptr);
+  if (const char *e = getenv("QB_GROUP_TIMEOUT"))
+    if (atoi(e) > 0) g->timeout_s = atoi(e);
+  return g;
+}
+
+// generation barrier over the group's host threads; false = a rank never arrived
+static bool group_barrier(DistGroup *g) {
+  std::unique_lock<std::mutex> lk(g->mu);
+  if (g->broken) return false;
+  const uint64_t gen = g->generation;
+  if (++g->arrived == g->nranks) {
+    g->arrived = 0;
+    ++g->generation;
+    g->cv.notify_all();
+    return true;
+  }
+  const bool ok = g->cv.wait_for(lk, std::chrono::seconds(g->timeout_s), [&] { return g->generation != gen || g->broken; });
+  if (!ok || g->broken) {
+    g->broken = true;
+    g->cv.notify_all();
+    return false;
+  }
+  return true;
+}
+
 struct DistState {
   int device = 0, rank = 0, nranks = 1, pbits = 0;
+  DistGroup *grp = nullptr;          // in-process group (no NCCL) when set
   ncclComm_t comm = nullptr;
   double *scratch_dev = nullptr;   // 64 doubles
   unsigned char *ipc_dev = nullptr;  // nranks IPC handles
@@ -143,9 +195,37 @@ int dist_create(DistState **out, int device, int rank, int nranks, const void *i
   return QB_OK;
 }
 
+int dist_create_group(DistState **out, int device, int rank, DistGroup *grp) {
+  DistState *d = new DistState();
+  d->device = device;
+  d->rank = rank;
+  d->nranks = grp->nranks;
+  d->pbits = __builtin_ctz((unsigned)grp->nranks);
+  d->grp = grp;
+  QB_DCUDA(cudaSetDevice(device));
+  QB_DCUDA(cudaMalloc(&d->scratch_dev, 64 * sizeof(double)));
+  {
+    std::lock_guard<std::mutex> lk(grp->mu);
+    ++grp->refs;
+  }
+  *out = d;
+  return QB_OK;
+}
+
 void dist_destroy(DistState *d) {
   if (!d) return;
   cudaSetDevice(d->device);
+  if (d->grp) {
+    bool last;
+    {
+      std::lock_guard<std::mutex> lk(d->grp->mu);
+      last = --d->grp->refs == 0;
+    }
+    if (last) delete d->grp;
+    cudaFree(d->scratch_dev);
+    delete d;
+    return;
+  }
   if (d->comm && nccl()) nccl()->CommDestroy(d->comm);
   cudaFree(d->scratch_dev);
   cudaFree(d->ipc_dev);
@@ -158,8 +238,29 @@ void dist_destroy(DistState *d) {
   delete d;
 }
 
+#define QB_GROUP_BARRIER(d)                                                        \
+  do {                                                                             \
+    if (!group_barrier((d)->grp)) {                                                \
+      g_dist_err = "rank group barrier timed out (a rank failed or never arrived)"; \
+      return QB_ERR_NCCL;                                                          \
+    }                                                                              \
+  } while (0)
+
 int dist_allreduce_sum(DistState *d, double *vals, int n, cudaStream_t stream) {
   if (n > 64) return QB_ERR_ARG;
+  if (d->grp) {  // host-side: every rank's earlier stream work is complete, sums in rank order
+    QB_DCUDA(cudaStreamSynchronize(stream));
+    DistGroup *g = d->grp;
+    memcpy(&g->slots[size_t(d->rank) * 64], vals, n * sizeof(double));
+    QB_GROUP_BARRIER(d);
+    for (int i = 0; i < n; ++i) {
+      double s = 0.0;
+      for (int r = 0; r < d->nranks; ++r) s += g->slots[size_t(r) * 64 + i];
+      vals[i] = s;
+    }
+    QB_GROUP_BARRIER(d);  // nobody overwrites a slot another rank is still reading
+    return QB_OK;
+  }
   NcclApi *a = nccl();
   QB_DCUDA(cudaMemcpyAsync(d->scratch_dev, vals, n * sizeof(double), cudaMemcpyHostToDevice, stream));
   QB_NCCL(a->AllReduce(d->scratch_dev, d->scratch_dev, n, ncclDouble, ncclSum, d->comm, stream));
@@ -171,14 +272,31 @@ int dist_allreduce_sum(DistState *d, double *vals, int n, cudaStream_t stream) {
 // stream-ordered barrier over all ranks: every rank's earlier work on its stream is complete
 // before anything enqueued after it starts on any rank
 static int stream_barrier(DistState *d, cudaStream_t stream) {
+  if (d->grp) {
+    QB_DCUDA(cudaStreamSynchronize(stream));
+    QB_GROUP_BARRIER(d);
+    return QB_OK;
+  }
   NcclApi *a = nccl();
   QB_NCCL(a->AllReduce(d->scratch_dev + 32, d->scratch_dev + 32, 1, ncclDouble, ncclSum, d->comm, stream));
   return QB_OK;
 }
 
 int dist_register(DistState *d, double2 *ptr, std::vector<double2 *> &peers, cudaStream_t stream) {
-  NcclApi *a = nccl();
   peers.clear();
+  if (d->grp) {  // same process: the peers' shards are plain device pointers
+    DistGroup *g = d->grp;
+    g->ptrs[d->rank] = ptr;
+    QB_GROUP_BARRIER(d);
+    if (d->ipc_ok) {
+      peers.resize(d->nranks);
+      for (int r = 0; r < d->nranks; ++r) peers[r] = static_cast<double2 *>(g->ptrs[r]);
+    }
+    QB_GROUP_BARRIER(d);
+    (void)stream;
+    return QB_OK;
+  }
+  NcclApi *a = nccl();
   // every rank takes part in the handle exchange even if IPC is switched off, so that the
   // collective call sequence stays identical on all ranks
   cudaIpcMemHandle_t mine;
@@ -231,6 +349,11 @@ int dist_register(DistState *d, double2 *ptr, std::vector<double2 *> &peers, cud
 
 int dist_unregister(DistState *d, std::vector<double2 *> &peers, cudaStream_t stream) {
   QB_DCUDA(cudaStreamSynchronize(stream));
+  if (d->grp) {
+    peers.clear();
+    QB_GROUP_BARRIER(d);  // nobody frees a shard a peer's kernel may still touch
+    return QB_OK;
+  }
   for (int r = 0; r < (int)peers.size(); ++r)
     if (r != d->rank && peers[r]) cudaIpcCloseMemHandle(peers[r]);
   peers.clear();
@@ -254,13 +377,23 @@ static int ensure_bounce(DistState *d, size_t amps) {
 int dist_make_local(DistState *d, double2 *amps, const std::vector<double2 *> &peers, int n, int L,
                     std::vector<int> &perm, const std::vector<const HostOp *> &pending, int sm_count,
                     cudaStream_t stream, qb_stats *stats, const std::vector<const HostOp *> *future) {
-  NcclApi *a = nccl();
   const bool peer_path = (int)peers.size() == d->nranks;
   std::vector<SwapPair> sw = choose_swaps(n, L, perm, pending, peer_path, future);
   if (sw.empty()) {
     g_dist_err = "planner stuck but no global target pending";
     return QB_ERR_UNSUPPORTED;
   }
+  return dist_swap_pairs(d, amps, peers, L, perm, sw, sm_count, stream, stats);
+}
+
+bool dist_has_peers(const DistState *d, const std::vector<double2 *> &peers) { return (int)peers.size() == d->nranks; }
+
+// Execute one all-to-all swap step: the global physical bits sw[i].gbit trade places with the local
+// bits sw[i].lbit (without peer mappings the local bits must be the TOP k local bits, descending).
+int dist_swap_pairs(DistState *d, double2 *amps, const std::vector<double2 *> &peers, int L, std::vector<int> &perm,
+                    const std::vector<SwapPair> &sw, int sm_count, cudaStream_t stream, qb_stats *stats) {
+  NcclApi *a = d->grp ? nullptr : nccl();
+  const bool peer_path = (int)peers.size() == d->nranks;
   const int k = (int)sw.size();
   if (k > L) {
     g_dist_err = "shard too small for the swap";
@@ -288,6 +421,10 @@ int dist_make_local(DistState *d, double2 *amps, const std::vector<double2 *> &p
     if (stats) stats->exchanges++;
     apply_swaps_to_perm(perm, sw);
     return QB_OK;
+  }
+  if (d->grp) {
+    g_dist_err = "in-process rank groups exchange through peer pointers only (QB_PEER_EXCHANGE=0 needs NCCL)";
+    return QB_ERR_UNSUPPORTED;
   }
   // NCCL path: every peer at once (one group = an all-to-all over the 2^k - 1 partners), in
   // pieces of <= 2^22 amplitudes (64 MiB) per peer, double-buffered: while the copy-back of
@@ -325,15 +462,17 @@ int dist_make_local(DistState *d, double2 *amps, const std::vector<double2 *> &p
   return QB_OK;
 }
 
-int dist_read_logical(DistState *d, const double2 *amps, int n, int L, const std::vector<int> &perm, uint64_t first,
+// one piece (<= 2^22 amplitudes) of dist_read_logical
+static int read_piece(DistState *d, const double2 *amps, int n, int L, const std::vector<int> &perm, uint64_t first,
                       uint64_t count, qb_c64 *out, cudaStream_t stream) {
-  NcclApi *a = nccl();
-  if (count == 0) return QB_OK;
-  if (count > (1ull << 22)) {
-    g_dist_err = "distributed qb_state_read is limited to 2^22 amplitudes per call";
-    return QB_ERR_UNSUPPORTED;
-  }
-  std::vector<qb_c64> host(count, qb_c64{0.0, 0.0});
+  // Amplitudes this rank does not own start as -0.0: x + (-0.0) == x for EVERY x (including +0.0
+  // and -0.0 themselves), so the sum over ranks returns the owner's bits unchanged.
+  DistGroup *g = d->grp;
+  std::vector<qb_c64> local;
+  if (!g) local.assign(count, qb_c64{-0.0, -0.0});
+  if (g && d->rank == 0) g->gather.assign(count, qb_c64{0.0, 0.0});
+  if (g) QB_GROUP_BARRIER(d);
+  qb_c64 *host = g ? g->gather.data() : local.data();  // group: ranks fill disjoint entries of one shared buffer
   QB_DCUDA(cudaStreamSynchronize(stream));
   // gather the elements this rank owns, merging contiguous runs into single copies
   uint64_t run_start = 0, run_len = 0, run_phys = 0;
@@ -353,14 +492,14 @@ int dist_read_logical(DistState *d, const double2 *amps, int n, int L, const std
       if (rc != QB_OK) return rc;
       continue;
     }
-    const uint64_t local = phys & ((1ull << L) - 1);
-    if (run_len && local == run_phys + run_len) {
+    const uint64_t local_idx = phys & ((1ull << L) - 1);
+    if (run_len && local_idx == run_phys + run_len) {
       ++run_len;
     } else {
       int rc = flush_run();
       if (rc != QB_OK) return rc;
       run_start = i;
-      run_phys = local;
+      run_phys = local_idx;
       run_len = 1;
     }
   }
@@ -369,9 +508,16 @@ int dist_read_logical(DistState *d, const double2 *amps, int n, int L, const std
     if (rc != QB_OK) return rc;
   }
   QB_DCUDA(cudaStreamSynchronize(stream));
+  if (g) {
+    QB_GROUP_BARRIER(d);
+    memcpy(out, g->gather.data(), count * sizeof(qb_c64));
+    QB_GROUP_BARRIER(d);
+    return QB_OK;
+  }
+  NcclApi *a = nccl();
   double *tmp = nullptr;
   QB_DCUDA(cudaMalloc(&tmp, count * sizeof(double2)));
-  cudaError_t e = cudaMemcpyAsync(tmp, host.data(), count * sizeof(double2), cudaMemcpyHostToDevice, stream);
+  cudaError_t e = cudaMemcpyAsync(tmp, host, count * sizeof(double2), cudaMemcpyHostToDevice, stream);
   ncclResult_t r = ncclSuccess;
   if (e == cudaSuccess) r = a->AllReduce(tmp, tmp, count * 2, ncclDouble, ncclSum, d->comm, stream);
   if (e == cudaSuccess && r == ncclSuccess)
@@ -385,6 +531,18 @@ int dist_read_logical(DistState *d, const double2 *amps, int n, int L, const std
   if (e != cudaSuccess) {
     g_dist_err = std::string("distributed read: ") + cudaGetErrorString(e);
     return QB_ERR_CUDA;
+  }
+  return QB_OK;
+}
+
+int dist_read_logical(DistState *d, const double2 *amps, int n, int L, const std::vector<int> &perm, uint64_t first,
+                      uint64_t count, qb_c64 *out, cudaStream_t stream) {
+  // any range: pieces of 2^22 amplitudes (64 MiB of staging per piece)
+  const uint64_t piece = 1ull << 22;
+  for (uint64_t off = 0; off < count; off += piece) {
+    const uint64_t c = std::min(piece, count - off);
+    int rc = read_piece(d, amps, n, L, perm, first + off, c, out + off, stream);
+    if (rc != QB_OK) return rc;
   }
   return QB_OK;
 }

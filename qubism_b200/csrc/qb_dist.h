@@ -12,6 +12,9 @@
 namespace qb {
 
 struct DistState;
+struct DistGroup;  // in-process rank group: P contexts of one process, one host thread each (no NCCL)
+DistGroup *dist_group_create(int nranks);
+int dist_create_group(DistState **out, int device, int rank, DistGroup *grp);
 
 const char *dist_last_error();
 int dist_unique_id(void *id128);
@@ -35,6 +38,12 @@ int dist_unregister(DistState *d, std::vector<double2 *> &peers, cudaStream_t st
 int dist_make_local(DistState *d, double2 *amps, const std::vector<double2 *> &peers, int n, int L,
                     std::vector<int> &perm, const std::vector<const HostOp *> &pending, int sm_count,
                     cudaStream_t stream, qb_stats *stats, const std::vector<const HostOp *> *future = nullptr);
+
+// The same exchange for an explicit list of (global bit, local bit) pairs (layout changes that no
+// gate asked for: operands of <.> / +: / tensor whose layouts diverged).
+int dist_swap_pairs(DistState *d, double2 *amps, const std::vector<double2 *> &peers, int L, std::vector<int> &perm,
+                    const std::vector<SwapPair> &sw, int sm_count, cudaStream_t stream, qb_stats *stats);
+bool dist_has_peers(const DistState *d, const std::vector<double2 *> &peers);
 
 // Collective read of logical amplitudes [first, first + count) into `out` on every rank.
 int dist_read_logical(DistState *d, const double2 *amps, int n, int L, const std::vector<int> &perm, uint64_t first,

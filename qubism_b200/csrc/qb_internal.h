@@ -186,6 +186,7 @@ struct PlanOptions {
   int jit_minb = 0;       // specialised kernels: CTAs per SM to compile for (0 = automatic)
   int jit_mem = 0;        // specialised kernels: cache policy of the global loads / stores (QBJ_MEM)
   int jit_pf_last = 1;    // prefetch the next group during the last (1) / first (0) tile of the running one
+  int tma = 0;            // specialised kernels: tile loads / stores as asynchronous bulk copies (cp.async.bulk)
   int hot_bits = 0;       // planner: max distinct TARGET bits per pass (0 = tile_bits).  With
                           // hot_bits <= tile_bits - warp bits every transpose can stay warp-local.
 };

@@ -465,14 +465,14 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
     g.dec(coef_reload);
     o << (coef_reload ? "#define QBJ_C(k) A.c[(k) + cz_]\n" : "#define QBJ_C(k) A.c[k]\n");
     if (!g.host) {
-      o << "#define QBJ_LD2(p, i) qbj_ld256(amps + (p), re[i], im[i], re[(i) + 1], im[(i) + 1])\n"
-           "#define QBJ_LD1(p, i) qbj_ld128(amps + (p), re[i], im[i])\n"
+      o << "#define QBJ_LD2(p, i) qbj_ld256(src + (p), re[i], im[i], re[(i) + 1], im[(i) + 1])\n"
+           "#define QBJ_LD1(p, i) qbj_ld128(src + (p), re[i], im[i])\n"
            "#define QBJ_ST2(p, a0, a1, b0, b1) qbj_st256(amps + (p), a0, a1, b0, b1)\n"
            "#define QBJ_ST1(p, xr, xi) qbj_st128(amps + (p), xr, xi)\n"
            "#define QBJ_STS(off, xr, xi) *reinterpret_cast<double2 *>(smem_raw + (off)) = make_double2(xr, xi)\n"
            "#define QBJ_LDS(off, i) { const double2 a_ = *reinterpret_cast<const double2 *>(smem_raw + (off)); re[i] = a_.x; im[i] = a_.y; }\n";
       o << "extern \"C\" __global__ void __launch_bounds__(QBJ_NT, " << sMINB
-        << ") qb_jit_pass(double2 *__restrict__ amps, u64 ntiles, const __grid_constant__ QbjArgs A) {\n"
+        << ") qb_jit_pass(double2 *amps, const double2 *src, u64 ntiles, const __grid_constant__ QbjArgs A) {\n"
            "  extern __shared__ __align__(16) unsigned char smem_raw[];\n"
            "  const u32 tid = threadIdx.x;\n"
            "  u16 *sidx_tab = reinterpret_cast<u16 *>(smem_raw + (16u << QBJ_T));\n"
@@ -506,7 +506,7 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
         deposit("nb_", "next_id");
         o << "      next_base = nb_;\n";
         for (int k = 0; k < LPT; ++k)
-          o << "      asm volatile(\"prefetch.global.L2 [%0];\" ::\"l\"(amps + nb_ + ((u64)line_tab[" << k << " * QBJ_NT + tid] << 3)));\n";
+          o << "      asm volatile(\"prefetch.global.L2 [%0];\" ::\"l\"(src + nb_ + ((u64)line_tab[" << k << " * QBJ_NT + tid] << 3)));\n";
         o << "      }\n    }\n";
       }
       o << "    const u64 basefull = base | A.rank_bits;\n    (void)basefull;\n    f = 0;\n";
@@ -551,7 +551,7 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
            "      const u32 nt0_ = ng_ * " << sG << "u;\n";
       deposit("nb_", "nt0_");
       for (int k = 0; k < glpt; ++k)
-        o << "      asm volatile(\"prefetch.global.L2 [%0];\" ::\"l\"(amps + nb_ + ((u64)line_tab[" << k << " * QBJ_NT + tid] << 3)));\n";
+        o << "      asm volatile(\"prefetch.global.L2 [%0];\" ::\"l\"(src + nb_ + ((u64)line_tab[" << k << " * QBJ_NT + tid] << 3)));\n";
       o << "      }\n    }\n";
       o << "    const u64 basefull = base | A.rank_bits;\n    (void)basefull;\n    f = 0;\n";
       if (coef_reload) o << "    const u32 cz_ = tile_id >> 31;  // always 0 (tile ids are < 2^31), but not to the compiler\n";
@@ -602,6 +602,7 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
   out.swz_fixed = swz_fixed;
   out.swz_conflicts = swz_conflicts;
   out.smem = smem;
+  out.threads = NT;
   out.args_bytes = sizeof(JitArgsHead) + sizeof(double) * std::max<size_t>(1, out.coefs.size());
   if (!std::isfinite(out.left_out) || out.left_out == 0.0) return fail("deferred factor out of range");
   return true;
@@ -969,7 +970,7 @@ void worker_main() {
       if (ok) {
         job.e->cubin.swap(cubin);
         job.e->smem = full.smem;
-        job.e->threads = 1 << (full.T - full.R);
+        job.e->threads = full.threads;
         job.e->state = 3;
       } else {
         job.e->state = -1;
@@ -1027,7 +1028,18 @@ static std::string digest_of(int dev, const std::string &key) {
 constexpr size_t kMaxSightings = 1u << 16;  // sighting records kept before the never-compiled ones are dropped
 constexpr uint64_t kMaxCompiled = 4096;     // specialised kernels per process
 
-int jit_lookup(const JitProgram &kp, const PassPlan &pp, int threshold, void **handle, std::string *err, bool *requested) {
+// Sighting counts are kept per (device, salt, structure): the salt is the rank of an in-process rank
+// group, where P ranks share this cache -- each of them must see the sequence of counts a rank
+// process of its own would see (`requested` has to come out the same on every rank).  Compiled
+// kernels are shared by all ranks of the device.
+struct Sighting {
+  int seen = 0;
+  bool requested = false;
+};
+static std::unordered_map<std::string, Sighting> g_seen;
+
+int jit_lookup(const JitProgram &kp, const PassPlan &pp, int threshold, void **handle, std::string *err, bool *requested,
+               int salt) {
   int dev = 0;
   if (requested) *requested = false;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
@@ -1037,22 +1049,26 @@ int jit_lookup(const JitProgram &kp, const PassPlan &pp, int threshold, void **h
     for (auto it = g_cache.begin(); it != g_cache.end();)
       it = (it->second.state == 0) ? g_cache.erase(it) : std::next(it);  // (entries being compiled / loaded stay: workers hold pointers)
   }
+  if (g_seen.size() >= kMaxSightings) {
+    for (auto it = g_seen.begin(); it != g_seen.end();) it = it->second.requested ? std::next(it) : g_seen.erase(it);
+  }
   Entry &e = g_cache[key];
-  // `requested` depends only on how often this structure was looked up: every rank of a sharded
-  // state sees the same sequence of structures, so it is the same on all of them -- unlike the
-  // moment a background compilation finishes
-  if (requested) *requested = e.state != 0 || e.seen + 1 >= threshold;
+  std::string skey = key;
+  skey.append(reinterpret_cast<const char *>(&salt), sizeof salt);
+  Sighting &sg = g_seen[skey];
+  // `requested` depends only on how often THIS rank looked this structure up: every rank of a
+  // sharded state sees the same sequence of structures, so it is the same on all of them -- unlike
+  // the moment a background compilation finishes
+  if (!sg.requested && ++sg.seen >= threshold) sg.requested = true;
+  if (requested) *requested = sg.requested;
   if (e.state == 3 && !load_entry(e, err)) return -1;
+  if (!sg.requested) return 0;
   if (e.state == 1) {
     *handle = &e;
     return 1;
   }
   if (e.state != 0) return 0;  // failed before, or still compiling: the generic kernel runs
-  if (++e.seen < threshold) return 0;
-  if (g_stats.compiled + g_stats.failed >= kMaxCompiled) {
-    e.seen = threshold;  // (stays "requested": sharded ranks must agree on it)
-    return 0;
-  }
+  if (g_stats.compiled + g_stats.failed >= kMaxCompiled) return 0;
   if (!jit_available(err)) {
     e.state = -1;
     g_stats.failed++;
@@ -1067,7 +1083,7 @@ int jit_lookup(const JitProgram &kp, const PassPlan &pp, int threshold, void **h
       return -1;
     }
     e.smem = full.smem;
-    e.threads = 1 << (full.T - full.R);
+    e.threads = full.threads;
     const bool ok = load_entry(e, err);
     g_stats.compile_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     if (!ok) return -1;
@@ -1114,14 +1130,15 @@ void jit_wait() {
   P.idle.wait(lk, [&] { return P.inflight == 0; });
 }
 
-int jit_launch(void *handle, void *amps, uint64_t ntiles, const std::vector<uint8_t> &args, int sm_count, void *stream,
-               std::string *err) {
+int jit_launch(void *handle, void *amps, const void *src, uint64_t ntiles, const std::vector<uint8_t> &args, int sm_count,
+               void *stream, std::string *err) {
   Entry &e = *static_cast<Entry *>(handle);
   uint64_t grid = uint64_t(sm_count) * uint64_t(e.occ);
   if (grid > ntiles) grid = ntiles;
   if (grid == 0) return 0;
   unsigned long long nt = ntiles;
-  void *params[] = {&amps, &nt, const_cast<uint8_t *>(args.data())};
+  if (!src) src = amps;
+  void *params[] = {&amps, &src, &nt, const_cast<uint8_t *>(args.data())};
   const CUresult r = driver().LaunchKernel(e.fn, (unsigned)grid, 1, 1, (unsigned)e.threads, 1, 1, (unsigned)e.smem,
                                            static_cast<CUstream>(stream), params, nullptr);
   if (r != CUDA_SUCCESS) {

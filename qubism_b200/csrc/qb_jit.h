@@ -26,6 +26,7 @@ struct JitProgram {
   int swz_fixed = 0;           // transposes whose swizzle columns were re-chosen to remove a bank conflict
   int swz_conflicts = 0;       // transposes left with a 2-way conflict (no assignment found)
   size_t smem = 0;             // dynamic shared memory of the device kernel
+  int threads = 0;             // threads per CTA of the device kernel
   size_t args_bytes = 0;       // sizeof(QbjArgs)
 };
 enum JitEmit { JIT_KEY_ONLY = 0, JIT_DEVICE_SRC = 1, JIT_HOST_SRC = 2 };
@@ -60,11 +61,13 @@ struct JitStats {
 // (message in *err).
 // *requested (may be null): this structure has reached the threshold (now or earlier) -- a
 // function of the lookup sequence only, hence identical on every rank of a sharded state.
+// salt: the rank inside an in-process rank group (0 otherwise): sightings are counted per rank.
 int jit_lookup(const JitProgram &key_only, const PassPlan &pp, int threshold, void **handle, std::string *err,
-               bool *requested = nullptr);
+               bool *requested = nullptr, int salt = 0);
 // launch on `stream`; grid = SMs x resident CTAs (capped at ntiles)
-int jit_launch(void *handle, void *amps, uint64_t ntiles, const std::vector<uint8_t> &args, int sm_count, void *stream,
-               std::string *err);
+// src: where the tiles are read (null / == amps: in place)
+int jit_launch(void *handle, void *amps, const void *src, uint64_t ntiles, const std::vector<uint8_t> &args, int sm_count,
+               void *stream, std::string *err);
 bool jit_available(std::string *why);
 void jit_wait();  // block until no background compilation is pending
 // test hook: source -> cubin with NVRTC, no device needed

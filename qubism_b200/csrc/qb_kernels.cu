@@ -524,7 +524,9 @@ __host__ __device__ constexpr size_t fused_smem_bytes() {
 
 template <int T, int R, int MINB, int LITE>
 __global__ void __launch_bounds__(1 << (T - R), MINB)
-    k_fused_pass(double2 *__restrict__ amps, unsigned long long ntiles, const __grid_constant__ PassProgram prog) {
+    k_fused_pass(double2 *amps, const double2 *src_amps, unsigned long long ntiles, const __grid_constant__ PassProgram prog) {
+  // src_amps == amps: in place (the normal case).  Otherwise the pass reads the tiles of src_amps
+  // and writes amps: the copy-on-write of a lazily cloned state rides on its first pass.
   constexpr int NR = 1 << R;
   constexpr int NT = 1 << (T - R);
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -618,7 +620,7 @@ __global__ void __launch_bounds__(1 << (T - R), MINB)
       }
       // coalesced load: lanes walk the low tile bits, registers stride over the round-0 bits
       const uint64_t goff_ld = goff_tab[tid];
-      const double2 *src = amps + base + goff_ld;
+      const double2 *src = src_amps + base + goff_ld;
       uint64_t st[R];
 #pragma unroll
       for (int j = 0; j < R; ++j) st[j] = 1ull << P.tile_pos[P.rounds[0].reg_pos[j]];
@@ -662,7 +664,7 @@ __global__ void __launch_bounds__(1 << (T - R), MINB)
         next_base = nbase;
 #pragma unroll
         for (int k = 0; k < LPT; ++k)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(amps + nbase + (uint64_t(line_tab[k * NT + tid]) << 3)));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(src_amps + nbase + (uint64_t(line_tab[k * NT + tid]) << 3)));
       }
     }
     if (!active) break;
@@ -782,8 +784,8 @@ bool fused_variant_supported(int tile_bits, int reg_bits) { return find_variant(
 static_assert(sizeof(kVariants) / sizeof(kVariants[0]) == sizeof(kFusedVariants) / sizeof(kFusedVariants[0]), "variant tables out of sync");
 #endif
 
-cudaError_t launch_fused_pass(double2 *amps, const uint8_t *blob, uint32_t blob_bytes, int tile_bits, int reg_bits,
-                              uint64_t ntiles, int sm_count, cudaStream_t stream, int *grid_out) {
+cudaError_t launch_fused_pass(double2 *amps, const double2 *src, const uint8_t *blob, uint32_t blob_bytes, int tile_bits,
+                              int reg_bits, uint64_t ntiles, int sm_count, cudaStream_t stream, int *grid_out) {
   const FusedVariant *v = find_variant(tile_bits, reg_bits);
   if (!v) return cudaErrorInvalidValue;
   if (blob_bytes > sizeof(PassProgram) || blob_bytes < sizeof(DevPass)) return cudaErrorInvalidValue;
@@ -802,7 +804,8 @@ cudaError_t launch_fused_pass(double2 *amps, const uint8_t *blob, uint32_t blob_
   if (grid > ntiles) grid = ntiles;
   if (grid_out) *grid_out = (int)grid;
   unsigned long long nt = ntiles;
-  void *args[] = {(void *)&amps, (void *)&nt, (void *)&prog};
+  if (!src) src = amps;
+  void *args[] = {(void *)&amps, (void *)&src, (void *)&nt, (void *)&prog};
   return cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(threads), args, smem, stream);
 }
 
@@ -1231,6 +1234,33 @@ __global__ void __launch_bounds__(256) k_tensor(double2 *__restrict__ out, const
 
 __global__ void k_set_amp(double2 *amps, uint64_t idx, double re, double im) { amps[idx] = make_double2(re, im); }
 
+// exchange two index bits in place (a change of qubit LAYOUT, no gate): every element whose bits
+// (hi, lo) read (1, 0) trades places with its partner (0, 1).  Half of the shard moves.
+__global__ void __launch_bounds__(256) k_swap_bits(double2 *__restrict__ amps, uint64_t nquads, int lo, int hi) {
+  for (uint64_t p = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; p < nquads; p += uint64_t(gridDim.x) * blockDim.x) {
+    uint64_t i = ((p >> lo) << (lo + 1)) | (p & ((1ull << lo) - 1));   // insert a 0 at `lo`
+    i = ((i >> hi) << (hi + 1)) | (i & ((1ull << hi) - 1));            // ... and at `hi` (hi > lo)
+    const uint64_t ia = i | (1ull << hi), ib = i | (1ull << lo);
+    const double2 a = amps[ia], b = amps[ib];
+    amps[ia] = b;
+    amps[ib] = a;
+  }
+}
+
+// out[i * 2^nb + j] = a[i] * b[j] on a sharded context, both operands in the identity layout: this
+// rank's shard of `out` is (this rank's shard of a) x (ALL of b); b[j] lives on rank j >> Lb and is
+// read through that rank's mapped shard (StateVec.hs:98-100; ProgState.hs:137-166 fuses registers
+// this way)
+__global__ void __launch_bounds__(256) k_tensor_sharded(double2 *__restrict__ out, const double2 *__restrict__ a,
+                                                        double2 *const *__restrict__ b_shards, uint64_t n, int nb, int Lb) {
+  const uint64_t bmask = (1ull << nb) - 1, lmask = (1ull << Lb) - 1;
+  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x) {
+    const uint64_t j = i & bmask;
+    const double2 x = a[i >> nb], y = b_shards[j >> Lb][j & lmask];
+    out[i] = make_double2(x.x * y.x - x.y * y.y, x.x * y.y + x.y * y.x);
+  }
+}
+
 cudaError_t launch_axpy(double2 *y, const double2 *x, uint64_t n, const double z[2], int sm_count,
                         cudaStream_t stream) {
   k_axpy<<<grid_for(n, 256, sm_count, 8), 256, 0, stream>>>(y, x, n, z[0], z[1]);
@@ -1241,6 +1271,21 @@ cudaError_t launch_tensor(double2 *out, const double2 *a, const double2 *b, int 
                           cudaStream_t stream) {
   const uint64_t n = 1ull << (abits + bbits);
   k_tensor<<<grid_for(n, 256, sm_count, 8), 256, 0, stream>>>(out, a, b, n, bbits);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_swap_bits(double2 *amps, int local_bits, int b1, int b2, int sm_count, cudaStream_t stream) {
+  if (b1 == b2) return cudaSuccess;
+  if (local_bits < 2) return cudaErrorInvalidValue;
+  const uint64_t nquads = 1ull << (local_bits - 2);
+  k_swap_bits<<<grid_for(nquads, 256, sm_count, 8), 256, 0, stream>>>(amps, nquads, std::min(b1, b2), std::max(b1, b2));
+  return cudaGetLastError();
+}
+
+cudaError_t launch_tensor_sharded(double2 *out, const double2 *a, double2 *const *b_shards_dev, int a_local_bits, int bbits,
+                                  int b_local_bits, int sm_count, cudaStream_t stream) {
+  const uint64_t n = 1ull << (a_local_bits + bbits);
+  k_tensor_sharded<<<grid_for(n, 256, sm_count, 8), 256, 0, stream>>>(out, a, b_shards_dev, n, bbits, b_local_bits);
   return cudaGetLastError();
 }
 

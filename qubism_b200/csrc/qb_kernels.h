@@ -11,8 +11,10 @@ bool fused_variant_supported(int tile_bits, int reg_bits);
 // One fused pass: `blob` is the planner's HOST DevPass blob (header + gates); it is passed to
 // the kernel by value as a __grid_constant__ parameter.  Persistent grid = SMs x resident
 // CTAs/SM (capped at ntiles).
-cudaError_t launch_fused_pass(double2 *amps, const uint8_t *blob, uint32_t blob_bytes, int tile_bits, int reg_bits,
-                              uint64_t ntiles, int sm_count, cudaStream_t stream, int *grid_out);
+// src: where the tiles are READ (null / == amps: in place; else the pass doubles as the copy of
+// a copy-on-write: every tile must be visited).
+cudaError_t launch_fused_pass(double2 *amps, const double2 *src, const uint8_t *blob, uint32_t blob_bytes, int tile_bits,
+                              int reg_bits, uint64_t ntiles, int sm_count, cudaStream_t stream, int *grid_out);
 
 cudaError_t launch_simple_gate(double2 *amps, int local_bits, int tbit, uint64_t cmask, uint64_t rank_bits,
                                uint32_t type, const double m[8], int sm_count, cudaStream_t stream);
@@ -48,6 +50,11 @@ cudaError_t launch_axpy(double2 *y, const double2 *x, uint64_t n, const double z
                         cudaStream_t stream);
 cudaError_t launch_tensor(double2 *out, const double2 *a, const double2 *b, int abits, int bbits, int sm_count,
                           cudaStream_t stream);
+// exchange local index bits b1 and b2 in place (layout change)
+cudaError_t launch_swap_bits(double2 *amps, int local_bits, int b1, int b2, int sm_count, cudaStream_t stream);
+// sharded a `tensor` b: out shard = (a shard) x (all of b, read through the ranks' mapped shards)
+cudaError_t launch_tensor_sharded(double2 *out, const double2 *a, double2 *const *b_shards_dev, int a_local_bits, int bbits,
+                                  int b_local_bits, int sm_count, cudaStream_t stream);
 cudaError_t launch_set_amp(double2 *amps, uint64_t idx, double re, double im, cudaStream_t stream);
 
 }  // namespace qb

@@ -65,6 +65,9 @@ bool set_opt(PlanOptions &o, const std::string &name, int64_t v) {
     o.jit_mem = (int)v;
   } else if (name == "jit_pf_last") {
     o.jit_pf_last = v ? 1 : 0;
+  } else if (name == "tma") {
+    if (v < 0 || v > 3) return false;
+    o.tma = (int)v;
   } else if (name == "jit") {
     if (v < 0 || v > 1000000) return false;
     o.jit = (int)v;
@@ -112,6 +115,7 @@ int64_t get_opt(const PlanOptions &o, const std::string &name) {
   if (name == "rot") return o.rot;
   if (name == "jit") return o.jit;
   if (name == "jit_pf_last") return o.jit_pf_last;
+  if (name == "tma") return o.tma;
   if (name == "jit_minb") return o.jit_minb;
   if (name == "jit_mem") return o.jit_mem;
   if (name == "jit_group") return o.jit_group;
@@ -415,6 +419,16 @@ std::vector<SwapPair> choose_swaps(int n, int L, const std::vector<int> &perm,
   const size_t window = std::max<size_t>(64, size_t(4) * n);
   for (size_t i = 0; i < pending.size() && i < window; ++i) {
     const HostOp &h = *pending[i];
+    if (h.kind == 2) {  // a dense block runs unfused and needs ALL its qubits inside the shard
+      for (int j = 0; j < h.k; ++j) {
+        const int pb = perm[h.kq_bits[j]];
+        if (pb >= L && !(seen & (1ull << pb))) {
+          seen |= 1ull << pb;
+          need.push_back(pb);
+        }
+      }
+      continue;
+    }
     if (h.kind != 0 || h.type == G_DIAG) continue;
     const int pb = perm[h.target];
     if (pb >= L && !(seen & (1ull << pb))) {

@@ -36,6 +36,22 @@ class Context:
             cls._default = Context(0)
         return cls._default
 
+    @classmethod
+    def group(cls, devices) -> list:
+        """Rank group inside this process (qb_init_group): one Context per entry of ``devices``; the
+        same device repeated gives virtual ranks on one GPU.  Drive each rank from its own thread."""
+        L = capi.lib()
+        n = len(devices)
+        arr = (C.c_int * n)(*devices)
+        hs = (C.c_void_p * n)()
+        capi.check(L.qb_init_group(arr, n, hs))
+        out = []
+        for r in range(n):
+            c = cls.__new__(cls)
+            c.L, c.h, c.device, c.rank, c.nranks = L, C.c_void_p(hs[r]), devices[r], r, n
+            out.append(c)
+        return out
+
     @staticmethod
     def unique_id() -> bytes:
         buf = C.create_string_buffer(128)
@@ -115,6 +131,19 @@ class StateVec:
         h = C.c_void_p()
         capi.check(self.ctx.L.qb_state_clone(self._h, C.byref(h)))
         return StateVec(h, self.ctx)
+
+    def apply_pure(self, ops) -> "StateVec":
+        """``g #> sv`` in one crossing (qb_state_apply_pure): a NEW state, ``self`` stays valid."""
+        arr = ops if isinstance(ops, C.Array) else capi.pack_ops(ops)
+        h = C.c_void_p()
+        capi.check(self.ctx.L.qb_state_apply_pure(self._h, arr, len(arr), C.byref(h)))
+        return StateVec(h, self.ctx)
+
+    def free(self):
+        """Release the handle now (what the ForeignPtr finalizer does at some later GC)."""
+        if self._h:
+            self.ctx.L.qb_state_free(self._h)
+            self._h = None
 
     # -- observation -------------------------------------------------------------------
     @property

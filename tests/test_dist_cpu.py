@@ -1,4 +1,4 @@
-"""Multi-rank host logic on the CPU: world_size 2 and 4 over the gloo backend.
+"""Multi-rank host logic on the CPU: world_size 2, 4 and 8 over the gloo backend.
 
 Each rank owns a shard (numpy), runs the SAME planner / swap-selection / exchange-schedule
 code as the NCCL path (choose_swaps, swap_schedule, apply_swaps_to_perm in qb_planner.cpp)
@@ -87,8 +87,9 @@ def _worker(rank, world, port, n, seed, out_dir, any_local):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("any_local", [0, 1, 3], ids=["top_bits_nccl_style", "belady_peer_style", "belady_cyclic_tiebreak"])
-@pytest.mark.parametrize("world,n", [(2, 13), (4, 13)])
+@pytest.mark.parametrize("world,n,any_local", [(2, 13, 0), (2, 13, 1), (2, 13, 3), (4, 13, 0), (4, 13, 1), (4, 13, 3),
+                                               (8, 14, 0), (8, 14, 3)],
+                         ids=lambda v: str(v))
 def test_sharded_exchange_over_gloo(tmp_path, emul, world, n, any_local):
     """any_local = 0: the top local bits are evicted (contiguous blocks, what the NCCL send/recv
     fallback moves); 1: the bits needed furthest in the future (what the peer-memory kernel moves)."""

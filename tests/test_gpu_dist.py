@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.parametrize("jit", [2, 1])
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_sharded_parity_over_nccl(world, jit):
     """jit = 1: every step pass runs as a structure-specialised kernel on every rank; the factors
     those kernels leave out must agree across shards (exchanges move raw device amplitudes)."""

@@ -126,6 +126,9 @@ struct DevPass {
   uint64_t base_fixed;                // known non-tile bits at their known value: OR-ed into every live tile's base
   uint32_t jit_minb;                  // specialised kernels: resident CTAs per SM to compile for (0 = automatic)
   uint32_t jit_mem;                   // specialised kernels: cache policy of the global accesses (QBJ_MEM, qb_jit_prelude.cuh)
+  uint32_t tma;                       // specialised kernels: 1 = the tile is LOADED with asynchronous bulk copies
+                                      // (cp.async.bulk -> shared memory, mbarrier) issued one tile ahead
+  uint32_t _pad_tma[3];
   DevRound rounds[kMaxRounds];
   // followed in memory by ngates DevGate records (lite: by nsteps DevStep records)
 };

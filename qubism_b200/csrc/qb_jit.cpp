@@ -103,8 +103,23 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
     const int want = P.jit_group ? (int)P.jit_group : 1;
     while (group * 2 <= want && group * 2 <= (1 << std::min<uint32_t>(P.run_len[0], 8))) group *= 2;
   }
+  // Bulk-asynchronous tile load (option "tma"): every 128-byte line of the NEXT tile is copied
+  // global -> shared by the copy engine (cp.async.bulk, completion counted on an mbarrier) into
+  // the transpose buffer as soon as the last transpose of the running tile has been read back, i.e.
+  // while the last round's gates and the stores of the running tile execute; round 0 then takes
+  // its registers from shared memory (tile-local index u at byte 16 u).  No load holds registers
+  // or scoreboard slots while DRAM answers, and the LSU sees 128-byte shared wavefronts instead of
+  // 64-byte global ones.  Needs tile bits 0..2 on the three lowest lanes in round 0 (one whole
+  // line per quarter warp: conflict-free without a swizzle, which a plain bulk copy cannot apply).
+  bool tma = P.tma != 0 && T - R >= 3 && l2pf <= 1;
+  if (tma) {
+    uint32_t low = 0;
+    for (int k = 0; k < 3; ++k) low |= 1u << P.rounds[0].tid_pos[k];
+    if (low != 7u) tma = false;
+  }
+  if (tma) group = 1;
   const size_t smem = (size_t(16) << T) + size_t(std::max(1, 2 * (nrounds - 1))) * NT * sizeof(uint16_t) + size_t(2) * NT * sizeof(uint64_t) +
-                      (size_t(group) << (T - 3)) * sizeof(uint32_t);
+                      (size_t(group) << (T - 3)) * sizeof(uint32_t) + (tma ? NT * sizeof(uint16_t) + 16 : 0);
   int minb;
   {
     const int regs_wanted = 4 * NR + 64;
@@ -208,6 +223,7 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
     return x;
   };
   const std::string sG = g.dec(group), sCB = g.dec(cbits), sMEM = g.dec(P.jit_mem);
+  g.dec(tma);
   const std::string sPFK = g.dec((group > 1 && P.jit_pf_last) ? group - 1 : 0);  // prefetch while this tile of the group computes
 
   // ---------------------------------------------------------------- fragments shared by both modes
@@ -249,6 +265,7 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
           e += " ^ ((0u - ((tid >> " + std::to_string(j) + ") & 1u)) & " + g.lit(swz_of(r, 1u << rd.tid_pos[j])) + ")";
         g.line("sidx_tab[" + std::to_string(2 * (r - 1) + side) + " * QBJ_NT + tid] = (u16)(" + e + ");");
       }
+    if (tma) g.line("lin_tab[tid] = (u16)(" + tid_bits_expr(R0, false, "tid") + ");");
     g.line("goff_tab[tid] = " + tid_bits_expr(R0, true, "tid") + ";");
     g.line("goff_tab[QBJ_NT + tid] = " + tid_bits_expr(RL, true, "tid") + ";");
     for (int k = 0; k < LPT; ++k) {
@@ -273,6 +290,19 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
       for (int i = 0; i < NR; ++i) g.line("  QBJ_LD1(src_ + " + reg_offset_expr(g, P, R0, R, i, 0, "+") + ", " + std::to_string(i) + ");");
     }
     g.line("}");
+  };
+  // round 0 takes its registers from the bulk-copied tile: tile-local index u at byte 16 u
+  auto emit_load_smem = [&]() {
+    g.tag("lds0");
+    g.line("{ const u32 ul0_ = (u32)lin_tab[tid] << 4;");
+    for (int i = 0; i < NR; ++i) {
+      uint32_t u = 0;
+      for (int j = 0; j < R; ++j)
+        if ((i >> j) & 1) u |= 1u << R0.reg_pos[j];
+      g.line("  QBJ_LDS(ul0_ | " + g.lit(u << 4) + ", " + std::to_string(i) + ");");
+    }
+    g.line("}");
+    g.barrier(false);  // every thread holds its registers: the buffer is free for the transposes
   };
   // mf: register bits on which a flip may be pending in some thread
   auto emit_store = [&](uint32_t mf) {
@@ -313,8 +343,21 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
   // ---------------------------------------------------------------- the rounds (both modes)
   uint32_t mf_end = 0;  // flips possibly pending when the last round ends
   bool bad = false;
+  // tma: the transpose buffer is free from here to the end of the tile -- start the NEXT tile's bulk copies
+  auto issue_next = [&]() {
+    g.tag("tmaissue");
+    if (g.host) return;  // (the host emulation copies the tile at the top of its tile loop)
+    g.line("if (have_next_) {");
+    g.line("  qbj_fence_proxy_async();  // generic-proxy reads of the buffer happen before the async-proxy writes");
+    g.line("  if (tid == 0) qbj_mbar_expect_tx(bar_a_, 16u << QBJ_T);");
+    for (int k = 0; k < LPT; ++k)
+      g.line("  qbj_bulk_load(smem_a_ + ((tid + " + std::to_string(k) + "u * QBJ_NT) << 7), src + next_base + ((u64)line_tab[" + std::to_string(k) +
+             " * QBJ_NT + tid] << 3), 128u, bar_a_);");
+    g.line("}");
+  };
   auto emit_rounds = [&]() {
     uint32_t mf = 0;
+    if (tma && nrounds == 1) issue_next();
     for (int r = 0; r < nrounds; ++r) {
       const DevRound &RD = P.rounds[r];
       if (r > 0) {
@@ -338,7 +381,10 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
         // free the buffer for the next CTA-wide transpose (of this tile, or the first of the next)
         // (wrapping to the next tile: also when the warps' slot regions differ between the last and
         //  the first round, see qb_planner.cpp on rounds[0].warp_local)
-        if (r + 1 < nrounds ? P.rounds[r + 1].warp_local == 0 : (P.rounds[1].warp_local == 0 || P.rounds[0].warp_local == 0))
+        if (tma && r + 1 == nrounds) {  // the copy engine overwrites the whole buffer next: everybody must be done with it
+          g.barrier(false);
+          issue_next();
+        } else if (r + 1 < nrounds ? P.rounds[r + 1].warp_local == 0 : (P.rounds[1].warp_local == 0 || P.rounds[0].warp_local == 0))
           g.barrier(false);
       }
       for (uint32_t si = RD.step_begin; si < RD.step_end; ++si) {
@@ -439,7 +485,7 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
     // key only: walk every fragment once (order irrelevant as long as it is fixed)
     emit_tables();
     deposit("base", "tile_id");
-    emit_load();
+    if (tma) emit_load_smem(); else emit_load();
     emit_rounds();
     emit_store(mf_end);
   } else {
@@ -479,10 +525,65 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
            "  u64 *goff_tab = reinterpret_cast<u64 *>(sidx_tab + "
         << ntab
         << " * QBJ_NT);\n"
-           "  u32 *line_tab = reinterpret_cast<u32 *>(goff_tab + 2 * QBJ_NT);\n  {\n";
+           "  u32 *line_tab = reinterpret_cast<u32 *>(goff_tab + 2 * QBJ_NT);\n";
+      if (tma)
+        o << "  u16 *lin_tab = reinterpret_cast<u16 *>(line_tab + (1 << (QBJ_T - 3)));\n"
+             "  const u32 smem_a_ = (u32)__cvta_generic_to_shared(smem_raw);\n"
+             "  const u32 bar_a_ = (u32)__cvta_generic_to_shared(lin_tab + QBJ_NT);\n";
+      o << "  {\n";
       emit_tables();
       o << "  }\n";
-      if (group == 1) {
+      if (tma) {
+      // ---- bulk-asynchronous loads: the copy engine fills the transpose buffer one tile ahead
+      o << "  if (tid == 0) qbj_mbar_init(bar_a_, 1u);\n"
+           "  qbj_fence_mbar_init();\n"
+           "  __syncthreads();\n"
+           "  const u32 ntiles32 = (u32)ntiles, stride = gridDim.x, first = blockIdx.x;\n"
+           "  const u32 iters = (ntiles32 + stride - 1) / stride;\n"
+           "  double re[QBJ_NR], im[QBJ_NR];\n"
+           "  u32 f = 0, phase_ = 0;\n"
+           "  u64 base = 0, next_base = 0;\n"
+           "  bool have_next_ = first < ntiles32;\n"
+           "  if (have_next_) {\n";
+      deposit("next_base", "first");
+      {
+        std::ostringstream side2;
+        std::ostringstream *keep = g.cur;
+        g.cur = &side2;
+        issue_next();
+        g.cur = keep;
+        o << side2.str();
+      }
+      o << "  }\n"
+           "  for (u32 it = 0; it < iters; ++it) {\n"
+           "    const u32 tile_id = first + it * stride;\n"
+           "    if (tile_id >= ntiles32) break;\n"
+           "    base = next_base;\n"
+           "    { const u32 next_id = tile_id + stride;\n"
+           "      have_next_ = next_id < ntiles32;\n"
+           "      if (have_next_) {\n      u64 nb_;\n";
+      deposit("nb_", "next_id");
+      o << "      next_base = nb_;\n";
+      if (l2pf > 0)
+        for (int k = 0; k < LPT; ++k)
+          o << "      asm volatile(\"prefetch.global.L2 [%0];\" ::\"l\"(src + nb_ + ((u64)line_tab[" << k << " * QBJ_NT + tid] << 3)));\n";
+      o << "      }\n    }\n"
+           "    qbj_mbar_wait(bar_a_, phase_);\n"
+           "    phase_ ^= 1u;\n"
+           "    const u64 basefull = base | A.rank_bits;\n    (void)basefull;\n    f = 0;\n";
+      if (coef_reload) o << "    const u32 cz_ = tile_id >> 31;  // always 0 (tile ids are < 2^31), but not to the compiler\n";
+      {
+        std::ostringstream side2;
+        std::ostringstream *keep = g.cur;
+        g.cur = &side2;
+        emit_load_smem();
+        g.cur = keep;
+        o << side2.str();
+      }
+      o << rounds_txt;
+      emit_store(mf_end);
+      o << "  }\n}\n";
+      } else if (group == 1) {
       o << "  const u32 ntiles32 = (u32)ntiles, stride = gridDim.x, first = blockIdx.x;\n"
            "  const u32 iters = (ntiles32 + stride - 1) / stride;\n"
            "  double re[QBJ_NR], im[QBJ_NR];\n"
@@ -572,19 +673,22 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
            "static u32 F[QBJ_NT];\n"
            "static u16 sidx_tab["
         << ntab
-        << " * QBJ_NT];\nstatic u64 goff_tab[2 * QBJ_NT];\nstatic u32 line_tab[(1 << (QBJ_T - 3))];\n"
+        << " * QBJ_NT];\nstatic u64 goff_tab[2 * QBJ_NT];\nstatic u32 line_tab[(1 << (QBJ_T - 3))];\nstatic u16 lin_tab[QBJ_NT];\n"
            "extern \"C\" int qb_jit_pass_host(double *amps, u64 ntiles, const QbjArgs *Ap, u64 args_bytes) {\n"
            "  if (args_bytes != sizeof(QbjArgs)) return -1;\n"
            "  const QbjArgs &A = *Ap;\n"
            "  for (u32 tid = 0; tid < QBJ_NT; ++tid) {\n";
       emit_tables();
-      o << "  }\n  (void)line_tab;\n"
+      o << "  }\n  (void)line_tab;\n  (void)lin_tab;\n"
            "  for (u64 tile_id = 0; tile_id < ntiles; ++tile_id) {\n"
            "  u64 base;\n";
       deposit("base", "tile_id");
-      o << "  const u64 basefull = base | A.rank_bits;\n  (void)basefull;\n"
-           "  for (u32 tid = 0; tid < QBJ_NT; ++tid) {\n    QBJ_THREAD_REFS\n    f = 0;\n";
-      emit_load();
+      o << "  const u64 basefull = base | A.rank_bits;\n  (void)basefull;\n";
+      if (tma)  // what the copy engine does: line c of the tile lands at byte 128 c of the buffer
+        o << "  for (u32 c_ = 0; c_ < (1u << (QBJ_T - 3)); ++c_)\n"
+             "    for (u32 e_ = 0; e_ < 16; ++e_) SM[16 * c_ + e_] = amps[2 * (base + ((u64)line_tab[c_] << 3)) + e_];\n";
+      o << "  for (u32 tid = 0; tid < QBJ_NT; ++tid) {\n    QBJ_THREAD_REFS\n    f = 0;\n";
+      if (tma) emit_load_smem(); else emit_load();
       o << rounds_txt;
       emit_store(mf_end);
       o << "  }\n  }\n  return 0;\n}\n";
@@ -638,7 +742,7 @@ bool jit_quick(const PassPlan &pp, JitProgram &out, std::string *why) {
   mix(P.nruns);
   for (uint32_t k = 0; k < P.nruns && k < (uint32_t)kMaxRuns; ++k) { mix(P.run_shift[k]); mix(P.run_len[k]); }
   for (int i = 0; i < T; ++i) mix(P.tile_pos[i]);
-  mix(P.jit_group); mix(P.jit_pf_last); mix(P.jit_minb); mix(P.jit_mem); mix(P.nsteps);
+  mix(P.jit_group); mix(P.jit_pf_last); mix(P.jit_minb); mix(P.jit_mem); mix(P.nsteps); mix(P.tma);
   out.coefs.clear();
   double left = 1.0;
   bool bad = false;

@@ -140,6 +140,33 @@ QBJ_DEV void qbj_st256(double2 *p, double a0, double a1, double b0, double b1) {
 #endif
 #endif
 
+#ifndef QB_JIT_HOST
+// ---- bulk-asynchronous copies (the TMA engine without a tensor map: cp.async.bulk) + mbarrier ----
+QBJ_DEV void qbj_mbar_init(u32 bar, u32 count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+QBJ_DEV void qbj_fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+QBJ_DEV void qbj_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// one arrival that also announces `bytes` of copy traffic: the phase completes when they have landed
+QBJ_DEV void qbj_mbar_expect_tx(u32 bar, u32 bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+QBJ_DEV void qbj_mbar_wait(u32 bar, u32 parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "QBJ_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra QBJ_DONE;\n"
+      "bra QBJ_WAIT;\n"
+      "QBJ_DONE:\n"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+// global -> shared, `bytes` (multiple of 16) contiguous, completion counted on the mbarrier
+QBJ_DEV void qbj_bulk_load(u32 dst, const void *src, u32 bytes, u32 bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+#endif
+
 #define QBJ_NR (1 << QBJ_R)
 #define QBJ_PAIRS(J)                                                              \
   _Pragma("unroll") for (int p = 0; p < (QBJ_NR >> 1); ++p)                       \

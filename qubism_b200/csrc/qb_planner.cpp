@@ -792,6 +792,7 @@ static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &don
   P->jit_pf_last = (uint32_t)opt.jit_pf_last;
   P->jit_minb = (uint32_t)opt.jit_minb;
   P->jit_mem = (uint32_t)opt.jit_mem;
+  P->tma = (uint32_t)opt.tma;
   P->dbg_skip = (uint32_t)opt.dbg_skip;
   P->sm_count = 148;
   for (int i = 0; i < T; ++i) P->tile_pos[i] = (uint8_t)tile_bits[i];

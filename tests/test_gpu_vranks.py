@@ -86,7 +86,7 @@ def test_virtual_ranks_match_the_oracle(groups, P, n, jit):
     # every rank read the same logical amplitudes, bit for bit
     assert all(np.array_equal(res[0][0], x[0]) for x in res[1:])
     if P == 8:  # all three rank bits were needed at once somewhere: a 3-bit all-to-all swap moves 7/8 of a shard
-        assert res[0][6]["exchange_bytes"] >= (7 * (16 << L)) // 8 * 2
+        assert res[0][6]["exchange_bytes"] >= (7 * (16 << L)) // 8
 
 
 @pytest.mark.parametrize("P", [2, 4, 8])

@@ -48,7 +48,9 @@ def jit_emul(tmp_path_factory):
 
 @pytest.mark.parametrize("opts", ["", "reg_bits=3", "reg_bits=5", "tile_bits=10,reg_bits=4", "low_bits=5", "rot=0",
                                   "lane_fixed=1", "lane_fixed=2,reg_bits=5", "max_pass_gates=7", "tile_bits=11,reg_bits=3",
-                                  "tile_bits=13,reg_bits=4", "tile_bits=13,reg_bits=5,low_bits=6", "max_rounds=3", "lane_fixed=3"])
+                                  "tile_bits=13,reg_bits=4", "tile_bits=13,reg_bits=5,low_bits=6", "max_rounds=3", "lane_fixed=3",
+                                  "tma=1", "tma=1,reg_bits=5", "tma=1,tile_bits=11,reg_bits=3", "tma=1,lane_fixed=3",
+                                  "tma=1,max_pass_gates=5", "tma=1,low_bits=5"])
 def test_specialised_passes_of_rotation_cx_layers_match_oracle(jit_emul, opts):
     """U(theta, phi, 0) + CX layers: every pass is a step pass, every one is specialised: 2-FMA
     rotations with deferred cosines (forms A and B), flip-aware flavours after toggles, static
@@ -91,6 +93,7 @@ def test_specialised_passes_random_mixes(jit_emul, seed):
     if rng.integers(0, 2): knobs.append(f"lane_fixed={int(rng.integers(0, 3))}")
     if rng.integers(0, 2): knobs.append(f"low_bits={int(rng.integers(3, 6))}")
     if rng.integers(0, 3) == 0: knobs.append(f"max_pass_gates={int(rng.integers(4, 20))}")
+    if rng.integers(0, 2): knobs.append("tma=1")
     v = S.gen_state(n, rng)
     if rng.integers(0, 2):
         qa = int(rng.integers(0, n))
@@ -142,7 +145,8 @@ def test_equal_structure_gives_one_kernel_and_new_angles_only_new_coefficients(j
 
 
 @pytest.mark.parametrize("opts", ["", "reg_bits=5", "tile_bits=10,reg_bits=3", "rot=0", "jit_group=4,jit_pf_last=0",
-                                  "jit_mem=5", "jit_mem=6,jit_minb=3", "tile_bits=13,reg_bits=4", "l2_prefetch=0"])
+                                  "jit_mem=5", "jit_mem=6,jit_minb=3", "tile_bits=13,reg_bits=4", "l2_prefetch=0",
+                                  "tma=1", "tma=1,reg_bits=5", "tma=1,l2_prefetch=0", "tma=1,max_pass_gates=3"])
 def test_device_source_compiles_with_nvrtc(jit_emul, opts):
     """NVRTC needs no GPU: the CUDA flavour of the generated source must compile for sm_100a."""
     n = 13
@@ -150,6 +154,8 @@ def test_device_source_compiles_with_nvrtc(jit_emul, opts):
     v = S.gen_state(n, np.random.default_rng(0))
     _, st, src = jit_emul(n, ops, v, opts, 0)
     assert src and "qb_jit_pass" in src and "__launch_bounds__" in src
+    if "tma=1" in opts:
+        assert "qbj_bulk_load(" in src.split("qb_jit_pass(")[1], "the bulk-asynchronous load path was not generated"
     nbytes = C.c_int64(0)
     rc = capi.lib().qb_jit_compile_check(src.encode(), C.byref(nbytes))
     if rc == capi.QB_ERR_UNSUPPORTED:

@@ -2,6 +2,7 @@
 """bench.py -- amplitude-updates/s of the qubism state-vector hot path on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload qft_rand|adder32|general] [--qubits n]
 
 One STEP = one pass of the hot path over one batch of synthetic input: the whole primitive
 op stream of the workload circuit applied to an n-qubit device-resident state through the C
@@ -15,8 +16,15 @@ followed by 20 random layers (30 U + 15 CX each, 900 ops).  N > 1: the same fami
 n = 31 + log2(N) qubits (32 GiB of amplitudes per GPU; N = 8 is the 34-qubit configuration),
 sharded one rank per GPU with global<->local qubit swaps over NCCL/NVLink.
 
+Other workloads (profiles/ keeps their lines): --workload adder32 = examples/rippleCarryAdder.qasm
+widened to 32 qubits (BASELINE.json config 4, meant for 2 and 4 GPUs); --workload general = 20
+layers of true SU(2) matrices (the general complex gate class); --qubits overrides n (36 = the
+capacity stretch point on 8 GPUs).
+
 The JSON line carries: value (device-timed, inputs resident in HBM), e2e (through the C ABI
-from HOST buffers: pinned state upload + one FFI call per gate + result readback inside the
+from HOST buffers the way the reference interpreter drives it: pinned state upload, then per
+primitive op one PURE application sv' = g #> sv -- qb_state_apply_pure on the current value, the
+old value freed, QASM/Simulation.hs:94-122 -- then reductions and a readback, all inside the
 timed region), roofline (HBM, for the fused-pass kernel, measured live with CUDA events on
 the launching stream), cpu_baseline (the oracle's C/OpenMP port on the host cores, bounded
 sample), clocks (nvidia-smi during the timed region).
@@ -47,13 +55,28 @@ UNIT = "amplitude-updates/s"
 CPU_SAMPLE_N = 24
 
 
-def workload(n: int):
-    from qubism_b200.circuits import qft_ops, random_layers
+def workload(n: int, kind: str = "qft_rand"):
+    from qubism_b200.circuits import adder_ops, proper_unitary_layers, qft_ops, random_layers
+    if kind == "adder32":
+        return adder_ops((n - 2) // 2)
+    if kind == "general":
+        return proper_unitary_layers(n, 20, seed=3000)
     return qft_ops(n) + random_layers(n, 20, seed=1000)
 
 
-def workload_name(n: int) -> str:
+def workload_name(n: int, kind: str = "qft_rand") -> str:
+    if kind == "adder32":
+        return (f"adder{n}: examples/rippleCarryAdder.qasm widened to {(n - 2) // 2}-bit operands on one qreg q[{n}] "
+                "(ccx = 9 U + 6 CX through qelib1.inc)")
+    if kind == "general":
+        return f"general20x{n}: 20 layers of true SU(2) matrices (general complex class) + CX pairs ({20 * (n + n // 2)} ops)"
     return f"qft{n}+rand20x{n}: QFT-{n} ({n + 5 * n * (n - 1) // 2 + 2} ops) + 20 random U/CX layers ({20 * (n + n // 2)} ops)"
+
+
+def inverse_ops(ops):
+    """C^-1 for a stream of (near-)unitary U and CX ops: reversed, matrices conjugate-transposed."""
+    import numpy as np
+    return [op if op[0] == "CX" else ("U", op[1], np.asarray(op[2]).conj().T) for op in reversed(ops)]
 
 
 # ------------------------------------------------------------------------------ clocks
@@ -117,28 +140,53 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------ CPU arm
-def cpu_run(n: int, steps: int, warmup: int):
-    """Times the oracle's C/OpenMP port (one sweep per primitive op, no fusion) on the host."""
+def cpu_threads() -> int:
+    """All host threads the process may use.  torch.distributed.run exports OMP_NUM_THREADS=1 to its
+    workers; the CPU arm overrides that explicitly."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_sample_ops(n: int):
+    from qubism_b200.circuits import qft_ops, random_layers
+    return qft_ops(n) + random_layers(n, 2, seed=1000)
+
+
+def cpu_run(n: int, steps: int, warmup: int, budget_s: float = 150.0, keep_first: bool = False):
+    """Times the oracle's C/OpenMP port (one sweep per primitive op, no fusion) on the host.
+    Bounded: stops after `budget_s` seconds of timed work (at least one step)."""
     import numpy as np
     from oracle import cport
-    ops = workload(n) if n < CPU_SAMPLE_N else None
-    if ops is None:
-        from qubism_b200.circuits import qft_ops, random_layers
-        ops = qft_ops(n) + random_layers(n, 2, seed=1000)
+    cport.lib().sv_set_threads(cpu_threads())
+    ops = cpu_sample_ops(n)
     packed = cport.pack_ops(ops)
     v = np.zeros(1 << n, dtype=np.complex128)
     v[0] = 1.0
-    for _ in range(warmup):
+    first = None
+    t_w = time.perf_counter()
+    for i in range(warmup):
         cport.run_ops_inplace(n, packed, v)
+        if keep_first and first is None:
+            first = v.copy()
+        if time.perf_counter() - t_w > budget_s / 3:
+            break
+    done = 0
     t0 = time.perf_counter()
     for _ in range(steps):
         cport.run_ops_inplace(n, packed, v)
+        done += 1
+        if keep_first and first is None:
+            first = v.copy()
+        if time.perf_counter() - t0 > budget_s:
+            break
     dt = time.perf_counter() - t0
     cores = int(cport.lib().sv_num_threads())
-    aups = len(ops) * (1 << n) * steps / dt
+    aups = len(ops) * (1 << n) * done / dt
     sample = (f"QFT-{n} + 2 random layers at n={n} ({len(ops)} primitive ops, {(16 << n) >> 20} MiB state), "
-              f"{steps} step(s), one sweep per op, OpenMP x{cores}")
-    return aups, dt / steps, cores, sample, len(ops)
+              f"{done} step(s), one sweep per op, OpenMP x{cores}")
+    return aups, dt / done, cores, sample, done, first
 
 
 def literal_dense_sample():
@@ -159,17 +207,25 @@ def literal_dense_sample():
             "what": "literal dense restatement of QGate.hs:121-154 (numpy/BLAS), 3 H + 3 CX"}
 
 
+def bench_n(args, world: int) -> int:
+    if args.qubits:
+        return args.qubits
+    if args.workload == "adder32":
+        return 32
+    return 30 if world == 1 else 31 + (world.bit_length() - 1)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    aups, step_s, cores, sample, nops = cpu_run(CPU_SAMPLE_N, args.steps, args.warmup)
+    os.environ["OMP_NUM_THREADS"] = str(cpu_threads())
+    aups, step_s, cores, sample, done, _ = cpu_run(CPU_SAMPLE_N, max(1, args.steps), args.warmup)
     line = {
-        "impl": "reference", "metric": METRIC, "value": aups, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": METRIC, "value": aups, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
         "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "complex128 (f64)", "data": "synthetic",
-        "config": {"workload": workload_name(30 if args.gpus == 1 else 31 + args.gpus.bit_length() - 1),
-                   "sample": sample},
+        "config": {"workload": workload_name(bench_n(args, args.gpus), args.workload), "sample": sample},
         "cpu_baseline": {"value": aups, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": aups, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -179,6 +235,7 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------ GPU arm
 def run_ours(args):
+    import ctypes as C
     import numpy as np
     import torch
     import qubism_b200 as Q
@@ -202,10 +259,9 @@ def run_ours(args):
         ctx = Q.Context(local_rank, rank, world, bytes(idbuf.cpu().numpy().tobytes()))
     else:
         ctx = Q.Context(local_rank)
-    n = 30 if world == 1 else 31 + (world.bit_length() - 1)
-    n = int(os.environ.get("QB_BENCH_N", n))
+    n = int(os.environ.get("QB_BENCH_N", bench_n(args, world)))
     L = n - (world.bit_length() - 1)
-    ops = workload(n)
+    ops = workload(n, args.workload)
     packed = capi.pack_ops(ops)
     nops = len(ops)
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
@@ -215,6 +271,13 @@ def run_ours(args):
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     sv = Q.StateVec.create(n, True, ctx)
     ctx.set_option("time_kernels", 1)
@@ -227,7 +290,17 @@ def run_ours(args):
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()  # nvidia-smi takes a moment to start: launch it before the warm-up
-    for _ in range(args.warmup):
+    # the very first step of the process: no pass structure has been seen, every pass runs the
+    # generic kernels (what a one-shot program -- the interpreter's usual use -- gets); from a
+    # fresh |0...0>, so the early passes also skip the all-zero tiles
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    f0.record(stream)
+    step()
+    f1.record(stream)
+    barrier()
+    first_step_ms = max_over_ranks(f0.elapsed_time(f1))
+    for _ in range(max(0, args.warmup - 1)):
         step()
     # pass structures that came back during the warm-up are being compiled into specialised
     # kernels on background threads: let that finish, and give the next sighting (which loads
@@ -257,20 +330,36 @@ def run_ours(args):
             step()
         ctx.sync()
     clk = clocks.stop() if rank == 0 else None
-    if dist is not None:
-        t = torch.tensor([elapsed], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed = float(t.item())
+    elapsed = max_over_ranks(elapsed)
     value = nops * float(1 << n) * args.steps / elapsed
     passes = st["passes"] / args.steps
     fused_ms = st["fused_ms"] / max(1, st["fused_timed"])  # average launch duration
     launches = (st["passes"] + st["simple_launches"] + st["reduce_launches"])
+    ops_exec = st["ops_executed"] / args.steps
+    ops_fold = st["ops_folded"] / args.steps
+    ctx.set_option("time_kernels", 0)
+
+    # ---------------- sharded runs: an untimed inverse-circuit round trip, C^-1 C |0...0> = |0...0>
+    round_trip = None
+    if world > 1 or args.round_trip:
+        rt = Q.StateVec.create(n, True, ctx)
+        rt.submit(packed)
+        rt.flush()
+        rt.submit(capi.pack_ops(inverse_ops(ops)))
+        head = rt.to_host(0, min(1 << n, 1 << 20))
+        nrm = rt.norm2()
+        head[0] -= 1.0
+        round_trip = {"max_abs_diff_vs_basis_state": float(np.abs(head).max()), "amplitudes_checked": int(head.size),
+                      "norm_minus_one": nrm - 1.0,
+                      "what": "fresh |0...0> -> workload -> inverse workload, first 2^20 logical amplitudes + the norm"}
+        rt.free()
+        barrier()
 
     # ---------------- end to end through the C ABI from host buffers (`e2e`)
-    # every step: upload this rank's shard from pinned host memory, one FFI call PER GATE (the way
-    # the Haskell interpreter drives the boundary), flush, read back three measurement reductions
-    # and a window of amplitudes.
-    import ctypes as C
+    # every step: upload this rank's shard from pinned host memory, then drive the boundary the way
+    # the reference interpreter does -- per primitive op ONE pure application sv' = g #> sv on the
+    # current value (qb_state_apply_pure: lazy clone + enqueue), the old value dropped
+    # (QASM/Simulation.hs:94-122) -- then flush, three measurement reductions and a window of amplitudes.
     shard = 1 << L
     chunk = min(shard, 1 << 28)  # 4 GiB of pinned host memory per rank, re-sent to fill the shard
     host = torch.empty(2 * chunk, dtype=torch.float64, pin_memory=True)
@@ -278,43 +367,44 @@ def run_ours(args):
     one = torch.zeros(2, dtype=torch.float64, pin_memory=True)
     one[0] = 1.0
     win = min(4096, shard)
-    ctx.set_option("time_kernels", 0)
-    lib, h = ctx.L, sv._h
-    calls = []  # the per-gate FFI calls, arguments marshalled once (a compiled host pays ~100 ns each)
-    for op in ops:
-        if op[0] == "U":
-            calls.append((lib.qb_apply_1q, (h, op[1], capi.mat4(op[2]))))
-        else:
-            calls.append((lib.qb_apply_cnot, (h, op[1], op[2])))
+    lib = ctx.L
+    op_ptrs = [C.cast(C.byref(packed, i * C.sizeof(capi.QbOp)), C.POINTER(capi.QbOp)) for i in range(nops)]
+    cur = {"sv": sv}
 
     def e2e_step():
+        s0 = cur["sv"]
         for off in range(0, shard, chunk):
-            sv.write_local((host.data_ptr(), chunk), first=off)
+            s0.write_local((host.data_ptr(), chunk), first=off)
         if rank == 0:
-            sv.write_local((one.data_ptr(), 1), first=0)
-        for fn, a in calls:
-            rc = fn(*a)
+            s0.write_local((one.data_ptr(), 1), first=0)
+        h = s0._h
+        for ptr in op_ptrs:
+            nh = C.c_void_p()
+            rc = lib.qb_state_apply_pure(h, ptr, 1, C.byref(nh))
             if rc != 0:
                 capi.check(rc)
-        sv.flush()
-        red = [sv.sumsq(q) for q in (0, n // 2, n - 1)]
-        w = sv.local_to_host(0, win)
+            lib.qb_state_free(h)  # the interpreter's map entry is overwritten: the old value is garbage
+            h = nh
+        s0._h = None
+        s1 = Q.StateVec(h, ctx)
+        cur["sv"] = s1
+        s1.flush()
+        red = [s1.sumsq(q) for q in (0, n // 2, n - 1)]
+        w = s1.local_to_host(0, win)
         return red, w
 
     e2e_step()
     ctx.jit_wait()
     e2e_step()
     barrier()
+    ctx.reset_stats()
     t0 = time.perf_counter()
     e2e_steps = max(1, min(args.steps, 2))
     for _ in range(e2e_steps):
         red, w = e2e_step()
     barrier()
-    e2e_dt = (time.perf_counter() - t0) / e2e_steps
-    if dist is not None:
-        t = torch.tensor([e2e_dt], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_dt = float(t.item())
+    e2e_dt = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+    st_e2e = ctx.stats()
     e2e_value = nops * float(1 << n) / e2e_dt
     h2d = 16 * shard + nops * 80
     d2h = 3 * 16 + 16 * win
@@ -335,26 +425,27 @@ def run_ours(args):
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "B200_PROFILING.md fallback 6650 GB/s (of fallback)"
     alg_bytes = 32.0 * float(1 << L)  # 16 B read + 16 B written per local amplitude per pass
     achieved = alg_bytes / (fused_ms / 1e3) / 1e9 if fused_ms > 0 else None
-    traffic = None
-    for tag in ("r01e", "r01d"):  # newest ncu --set full capture of the dominant kernel
+    traffic, traffic_src = None, None
+    for tag in ("r02", "r01e", "r01d"):  # newest ncu --set full capture of the dominant kernel
         try:
             prof = json.load(open(os.path.join(ROOT, "profiles", f"{tag}_fused_pass_summary.json")))
             traffic = prof.get("dram_bytes_per_launch_scaled_to", {}).get(str(L))
+            traffic_src = f"profiles/{tag}_fused_pass_summary.json (ncu --set full capture of an earlier run of this command, not measured in this run)"
             break
         except (OSError, ValueError):
             continue
     jit_share = st["jit_launches"] / max(1, st["passes"])
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src,
                 "kernel": ("qb_jit_pass (k_fused_pass specialised per pass structure with NVRTC)" if jit_share > 0.5
                            else "k_fused_pass"),
                 "specialised_share_of_launches": jit_share,
                 "launches_per_step": passes, "avg_launch_ms": fused_ms,
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "kernel_share_of_step": (st["fused_ms"] / 1e3) / elapsed if elapsed > 0 else None,
-                # what the same op stream would move one sweep per primitive op: may
-                # exceed the HBM peak, which is the point of fusing
-                "unfused_equivalent_gbs": value / world * 32.0 / 1e9}
+                # what the ops that REACH a kernel would move one sweep per op: may exceed
+                # the HBM peak, which is the point of fusing.  Folded ops are not counted here.
+                "unfused_equivalent_gbs_executed_ops": ops_exec * float(1 << n) / (elapsed / args.steps) / world * 32.0 / 1e9}
     if world > 1:
         # T_roof(P) = passes x 32 B x 2^L / HBM  +  bytes sent per GPU / NVLink per direction
         nvl = 770.0  # GB/s per direction, measured peer copy on this pool (900 nominal)
@@ -367,38 +458,61 @@ def run_ours(args):
                                "what": "SURVEY.md 8d: sum of the passes at the HBM peak plus the exchanged bytes at the "
                                        "measured NVLink rate, over the measured step"}
 
-    # ---------------- CPU baseline (rank 0, N = 1 only): the oracle's C port, bounded sample
+    # ---------------- CPU baseline (rank 0, N = 1 only): the oracle's C port, bounded sample, and the
+    # same sample on the GPU: max |amplitude difference|
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        aups, _, cores, sample, _ = cpu_run(CPU_SAMPLE_N, 1, 0)
+        aups, _, cores, sample, _, cpu_first = cpu_run(CPU_SAMPLE_N, 1, 0, keep_first=True)
+        g = Q.StateVec.create(CPU_SAMPLE_N, True, ctx)
+        g.submit(cpu_sample_ops(CPU_SAMPLE_N))
+        diff = float(np.abs(g.to_host() - cpu_first).max())
+        g.free()
         cpu = {"value": aups, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+               "max_abs_amplitude_diff_gpu_vs_port": diff, "diff_what": f"all 2^{CPU_SAMPLE_N} amplitudes after the sample circuit from |0...0>",
                "literal_dense": literal_dense_sample()}
 
+    step_s = elapsed / args.steps
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "complex128 (f64)", "data": "synthetic",
-        "config": {"workload": workload_name(n), "qubits": n, "local_qubits": L, "primitive_ops_per_step": nops,
+        # the same time split by what happened to the ops: `value` counts every primitive
+        # op submitted; `value_executed` only those that reached a kernel (the host peephole folds scalar
+        # u1-type gates, merges runs on one qubit and cancels CX pairs before anything is planned)
+        "by_class": {"value_executed": ops_exec * float(1 << n) / step_s, "ops_submitted_per_step": nops,
+                     "ops_executed_per_step": ops_exec, "ops_folded_per_step": ops_fold,
+                     "folded_share": ops_fold / max(1, nops)},
+        # the same step the first time the process sees it: no specialised kernel exists yet
+        "first_step": {"ms": first_step_ms, "value": nops * float(1 << n) / (first_step_ms / 1e3),
+                       "what": "step 1 of the process from a fresh |0...0>: generic kernels (nothing compiled yet), "
+                               "all-zero tiles skipped; steady state = `value`"},
+        "config": {"workload": workload_name(n, args.workload), "qubits": n, "local_qubits": L, "primitive_ops_per_step": nops,
                    "state_bytes_per_gpu": 16 << L, "l2_policy": "inputs larger than L2 (state >= 16 GiB >> 126 MB)",
                    "parallelism": f"shard{world}" if world > 1 else "single",
-                   "planner": {k: ctx.get_option(k) for k in ("tile_bits", "reg_bits", "low_bits", "lane_fixed", "max_rounds", "peephole", "rot", "lite", "jit")},
+                   "planner": {k: ctx.get_option(k) for k in ("tile_bits", "reg_bits", "low_bits", "lane_fixed", "max_rounds", "peephole", "rot", "lite", "jit", "tma")},
                    "specialised_kernels": {"compiled": st["jit_compiled"], "compile_ms_total": st["jit_compile_ms"],
                                            "launches_in_timed_region": st["jit_launches"],
+                                           "toolchain": lib.qb_jit_toolchain().decode(),
                                            "note": "pass structures seen twice are compiled with NVRTC on background threads during "
                                                    "the warm-up steps (W + 2 untimed steps); the timed steps hit the cache"},
-                   "ops_executed_per_step": st["ops_executed"] / args.steps,
-                   "ops_folded_per_step": st["ops_folded"] / args.steps,
+                   "ops_executed_per_step": ops_exec, "ops_folded_per_step": ops_fold,
                    "passes_per_step": passes, "rounds_per_step": st["rounds"] / args.steps,
                    "exchanges_per_step": st["exchanges"] / args.steps,
                    "exchange_bytes_per_gpu_per_step": st["exchange_bytes"] / args.steps,
                    "plan_ms_per_step": st["plan_ms"] / args.steps},
         "clocks": clk,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_dt * 1e3, "ffi_calls_per_step": nops + 6,
+                "ms_per_step": e2e_dt * 1e3, "ffi_calls_per_step": 2 * nops + 8,
+                "pattern": "per primitive op: qb_state_apply_pure (sv' = g #> sv) + qb_state_free (old value), "
+                           "QASM/Simulation.hs:94-122; lazy clones keep the ops fused",
+                "clones_per_step": st_e2e["clones"] / e2e_steps, "passes_per_step": st_e2e["passes"] / e2e_steps,
+                "copies_per_step": (st_e2e["cow_fused"] + st_e2e["cow_copies"]) / e2e_steps,
                 "check": {"s1_q0": red[0][1], "amp0": [float(w[0].real), float(w[0].imag)]}},
         "gpu_launches": int(launches),
         "roofline": roofline,
     }
+    if round_trip:
+        line["round_trip"] = round_trip
     if cpu:
         line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)
@@ -413,6 +527,9 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="qft_rand", choices=["qft_rand", "adder32", "general"])
+    ap.add_argument("--qubits", type=int, default=0)
+    ap.add_argument("--round-trip", action="store_true", help="also at 1 GPU: the untimed inverse-circuit check")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)

@@ -232,6 +232,9 @@ int64_t qb_plan_describe(int nlocal, const qb_op *ops, int64_t nops, const char 
  * compiles on worker threads while the generic kernels keep running).  Benchmarks call it after
  * their warm-up; nothing else needs it. */
 int qb_jit_sync(qb_ctx *ctx);
+/* Which NVRTC compiles the specialised kernels in this process and the widest global access it
+ * emits ("nvrtc 12.9, 256-bit ..."; a process that loaded an older libnvrtc first gets 128-bit). */
+const char *qb_jit_toolchain(void);
 /* Host-only check of the specialised-kernel toolchain (no device needed): compile `src` (CUDA C++)
  * with NVRTC for sm_100a; *cubin_bytes = size of the resulting cubin.  QB_ERR_UNSUPPORTED if
  * libnvrtc cannot be loaded, QB_ERR_CUDA if the compilation fails (log in qb_last_error). */

@@ -37,6 +37,7 @@ def lib():
         L = C.CDLL(path)
         dp = C.POINTER(C.c_double)
         L.sv_num_threads.restype = C.c_int
+        L.sv_set_threads.argtypes = [C.c_int]
         L.sv_apply_1q.argtypes = [dp, C.c_int, C.c_int, dp, C.POINTER(C.c_int), C.c_int]
         L.sv_apply_cnot.argtypes = [dp, C.c_int, C.c_int, C.c_int]
         L.sv_sumsq.argtypes = [dp, C.c_int, C.c_int, dp, dp]

@@ -37,6 +37,16 @@ int sv_num_threads(void) {
 #endif
 }
 
+/* torch.distributed.run exports OMP_NUM_THREADS=1 to its workers: the CPU baseline sets its thread
+ * count explicitly (bench.py --impl reference). */
+void sv_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 static inline uint64_t insert_zero(uint64_t x, int pos) {
   uint64_t lo = x & ((1ull << pos) - 1);
   return ((x >> pos) << (pos + 1)) | lo;

@@ -97,6 +97,7 @@ SIGNATURES = {
     "qb_plan_describe": (_I64, [_I, C.POINTER(QbOp), _I64, C.c_char_p, C.c_char_p, _I64]),
     "qb_jit_compile_check": (_I, [C.c_char_p, C.POINTER(_I64)]),
     "qb_jit_sync": (_I, [_VP]),
+    "qb_jit_toolchain": (C.c_char_p, []),
 }
 
 _lib = None

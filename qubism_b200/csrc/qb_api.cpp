@@ -1755,6 +1755,12 @@ int qb_jit_sync(qb_ctx *c) {
   return QB_OK;
 }
 
+const char *qb_jit_toolchain(void) {
+  static thread_local std::string s;
+  s = jit_toolchain();
+  return s.c_str();
+}
+
 int qb_jit_compile_check(const char *src, int64_t *cubin_bytes) {
   if (!src) return fail(QB_ERR_ARG, "null argument");
   std::string why;

@@ -1000,6 +1000,15 @@ bool compile_cubin(const std::string &src, std::vector<char> &cubin, std::string
 
 }  // namespace
 
+std::string jit_toolchain() {
+  Nvrtc &n = nvrtc();
+  if (!n.ok) return "nvrtc unavailable (" + n.why + "): generic kernels only";
+  int major = 0, minor = 0;
+  n.Version(&major, &minor);
+  return "nvrtc " + std::to_string(major) + "." + std::to_string(minor) +
+         (n.wide_ldst ? ", 256-bit ld/st.global.v4.f64" : ", 128-bit ld/st (PTX ISA < 8.8: no .v4.f64)");
+}
+
 bool jit_available(std::string *why) {
   if (!nvrtc().ok) {
     if (why) *why = nvrtc().why;

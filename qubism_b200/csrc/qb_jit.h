@@ -69,6 +69,7 @@ int jit_lookup(const JitProgram &key_only, const PassPlan &pp, int threshold, vo
 int jit_launch(void *handle, void *amps, const void *src, uint64_t ntiles, const std::vector<uint8_t> &args, int sm_count,
                void *stream, std::string *err);
 bool jit_available(std::string *why);
+std::string jit_toolchain();  // which NVRTC serves the specialised kernels, and the global access width it allows
 void jit_wait();  // block until no background compilation is pending
 // test hook: source -> cubin with NVRTC, no device needed
 bool jit_compile_only(const std::string &src, size_t *cubin_bytes, std::string *err);

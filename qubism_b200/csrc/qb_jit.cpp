@@ -57,7 +57,7 @@ struct Gen {
     tag(warp_only ? "bw" : "bc");
     if (!want_src) return;
     if (host) *cur << "  }\n  for (u32 tid = 0; tid < QBJ_NT; ++tid) {\n    QBJ_THREAD_REFS\n";
-    else *cur << (warp_only ? "    __syncwarp();\n" : "    __syncthreads();\n");
+    else *cur << (warp_only ? "    __syncwarp();\n" : "    QBJ_BAR();\n");
   }
 };
 
@@ -118,8 +118,15 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
     if (low != 7u) tma = false;
   }
   if (tma) group = 1;
-  const size_t smem = (size_t(16) << T) + size_t(std::max(1, 2 * (nrounds - 1))) * NT * sizeof(uint16_t) + size_t(2) * NT * sizeof(uint64_t) +
-                      (size_t(group) << (T - 3)) * sizeof(uint32_t) + (tma ? NT * sizeof(uint16_t) + 16 : 0);
+  const size_t tables_bytes = size_t(std::max(1, 2 * (nrounds - 1))) * NT * sizeof(uint16_t) + size_t(2) * NT * sizeof(uint64_t) +
+                              (size_t(group) << (T - 3)) * sizeof(uint32_t) + (tma ? NT * sizeof(uint16_t) + 16 : 0);
+  // tma = 2: ONE CTA per SM holds TWO groups of 2^(T-R) threads, each working on its own tile with a
+  // transpose buffer of its own, plus ONE input buffer the copy engine fills: the group that has
+  // just taken its registers out of the input buffer starts the copy of the next tile -- which
+  // belongs to the OTHER group -- so every group's next tile arrives while it still computes the
+  // running one (a true double buffer: 3 x 2^T x 16 bytes of shared memory, 192 KB at T = 12).
+  const bool dual = tma && P.tma >= 2 && 3 * (size_t(16) << T) + tables_bytes + 64 <= 227u * 1024u && 2 * NT <= 1024;
+  const size_t smem = (dual ? 3 : 1) * (size_t(16) << T) + tables_bytes;
   int minb;
   {
     const int regs_wanted = 4 * NR + 64;
@@ -127,6 +134,7 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
     const int by_smem = (int)((227u * 1024u) / (smem + 1024));
     minb = std::max(1, std::min(std::min(by_regs, by_smem), 8));
     if (P.jit_minb) minb = std::max(1, std::min((int)P.jit_minb, by_smem));
+    if (dual) minb = 1;
   }
   const std::string sT = g.dec(T), sR = g.dec(R), sNT = g.dec(NT), sMINB = g.dec(minb), sNROUNDS = g.dec(nrounds);
   const std::string sL2 = g.dec(l2pf);
@@ -224,6 +232,7 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
   };
   const std::string sG = g.dec(group), sCB = g.dec(cbits), sMEM = g.dec(P.jit_mem);
   g.dec(tma);
+  g.dec(dual);
   const std::string sPFK = g.dec((group > 1 && P.jit_pf_last) ? group - 1 : 0);  // prefetch while this tile of the group computes
 
   // ---------------------------------------------------------------- fragments shared by both modes
@@ -299,7 +308,7 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
       uint32_t u = 0;
       for (int j = 0; j < R; ++j)
         if ((i >> j) & 1) u |= 1u << R0.reg_pos[j];
-      g.line("  QBJ_LDS(ul0_ | " + g.lit(u << 4) + ", " + std::to_string(i) + ");");
+      g.line("  QBJ_LDSI(ul0_ | " + g.lit(u << 4) + ", " + std::to_string(i) + ");");
     }
     g.line("}");
     g.barrier(false);  // every thread holds its registers: the buffer is free for the transposes
@@ -344,20 +353,21 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
   uint32_t mf_end = 0;  // flips possibly pending when the last round ends
   bool bad = false;
   // tma: the transpose buffer is free from here to the end of the tile -- start the NEXT tile's bulk copies
-  auto issue_next = [&]() {
+  auto issue_next = [&](const char *bar = nullptr) {
     g.tag("tmaissue");
     if (g.host) return;  // (the host emulation copies the tile at the top of its tile loop)
+    const std::string b = bar ? bar : (dual ? "(bar_a_ + 8u * (grp_ ^ 1u))" : "bar_a_");
     g.line("if (have_next_) {");
     g.line("  qbj_fence_proxy_async();  // generic-proxy reads of the buffer happen before the async-proxy writes");
-    g.line("  if (tid == 0) qbj_mbar_expect_tx(bar_a_, 16u << QBJ_T);");
+    g.line("  if (tid == 0) qbj_mbar_expect_tx(" + b + ", 16u << QBJ_T);");
     for (int k = 0; k < LPT; ++k)
-      g.line("  qbj_bulk_load(smem_a_ + ((tid + " + std::to_string(k) + "u * QBJ_NT) << 7), src + next_base + ((u64)line_tab[" + std::to_string(k) +
-             " * QBJ_NT + tid] << 3), 128u, bar_a_);");
+      g.line("  qbj_bulk_load(in_a_ + ((tid + " + std::to_string(k) + "u * QBJ_NT) << 7), src + next_base + ((u64)line_tab[" + std::to_string(k) +
+             " * QBJ_NT + tid] << 3), 128u, " + b + ");");
     g.line("}");
   };
   auto emit_rounds = [&]() {
     uint32_t mf = 0;
-    if (tma && nrounds == 1) issue_next();
+    if (tma && (nrounds == 1 || dual)) issue_next();
     for (int r = 0; r < nrounds; ++r) {
       const DevRound &RD = P.rounds[r];
       if (r > 0) {
@@ -381,7 +391,11 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
         // free the buffer for the next CTA-wide transpose (of this tile, or the first of the next)
         // (wrapping to the next tile: also when the warps' slot regions differ between the last and
         //  the first round, see qb_planner.cpp on rounds[0].warp_local)
-        if (tma && r + 1 == nrounds) {  // the copy engine overwrites the whole buffer next: everybody must be done with it
+        if (dual && r + 1 == nrounds) {
+          // (nothing: the group barrier after the next tile's register fill separates this tile's
+          //  transposes from the next one's, and the input buffer is not this buffer)
+          g.tag("dualend");
+        } else if (tma && r + 1 == nrounds) {  // the copy engine overwrites the whole buffer next: everybody must be done with it
           g.barrier(false);
           issue_next();
         } else if (r + 1 < nrounds ? P.rounds[r + 1].warp_local == 0 : (P.rounds[1].warp_local == 0 || P.rounds[0].warp_local == 0))
@@ -515,25 +529,83 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
            "#define QBJ_LD1(p, i) qbj_ld128(src + (p), re[i], im[i])\n"
            "#define QBJ_ST2(p, a0, a1, b0, b1) qbj_st256(amps + (p), a0, a1, b0, b1)\n"
            "#define QBJ_ST1(p, xr, xi) qbj_st128(amps + (p), xr, xi)\n"
-           "#define QBJ_STS(off, xr, xi) *reinterpret_cast<double2 *>(smem_raw + (off)) = make_double2(xr, xi)\n"
-           "#define QBJ_LDS(off, i) { const double2 a_ = *reinterpret_cast<const double2 *>(smem_raw + (off)); re[i] = a_.x; im[i] = a_.y; }\n";
-      o << "extern \"C\" __global__ void __launch_bounds__(QBJ_NT, " << sMINB
+           "#define QBJ_STS(off, xr, xi) *reinterpret_cast<double2 *>(sm_ + (off)) = make_double2(xr, xi)\n"
+           "#define QBJ_LDS(off, i) { const double2 a_ = *reinterpret_cast<const double2 *>(sm_ + (off)); re[i] = a_.x; im[i] = a_.y; }\n"
+           "#define QBJ_LDSI(off, i) { const double2 a_ = *reinterpret_cast<const double2 *>(in_ + (off)); re[i] = a_.x; im[i] = a_.y; }\n";
+      if (dual)
+        o << "#define QBJ_BAR() asm volatile(\"bar.sync %0, %1;\" ::\"r\"(grp_ + 1u), \"r\"((u32)QBJ_NT) : \"memory\")\n";
+      else
+        o << "#define QBJ_BAR() __syncthreads()\n";
+      o << "extern \"C\" __global__ void __launch_bounds__(" << (dual ? "2 * QBJ_NT" : "QBJ_NT") << ", " << sMINB
         << ") qb_jit_pass(double2 *amps, const double2 *src, u64 ntiles, const __grid_constant__ QbjArgs A) {\n"
-           "  extern __shared__ __align__(16) unsigned char smem_raw[];\n"
-           "  const u32 tid = threadIdx.x;\n"
-           "  u16 *sidx_tab = reinterpret_cast<u16 *>(smem_raw + (16u << QBJ_T));\n"
+           "  extern __shared__ __align__(16) unsigned char smem_raw[];\n";
+      if (dual)
+        o << "  const u32 grp_ = threadIdx.x >> (QBJ_T - QBJ_R), tid = threadIdx.x & (QBJ_NT - 1u);\n"
+             "  unsigned char *const sm_ = smem_raw + ((size_t)grp_ << (QBJ_T + 4));\n"
+             "  const unsigned char *const in_ = smem_raw + ((size_t)2 << (QBJ_T + 4));\n"
+             "  u16 *sidx_tab = reinterpret_cast<u16 *>(smem_raw + ((size_t)3 << (QBJ_T + 4)));\n";
+      else
+        o << "  const u32 tid = threadIdx.x;\n"
+             "  unsigned char *const sm_ = smem_raw;\n"
+             "  const unsigned char *const in_ = smem_raw;\n  (void)in_;\n"
+             "  u16 *sidx_tab = reinterpret_cast<u16 *>(smem_raw + (16u << QBJ_T));\n";
+      o << ""
            "  u64 *goff_tab = reinterpret_cast<u64 *>(sidx_tab + "
         << ntab
         << " * QBJ_NT);\n"
            "  u32 *line_tab = reinterpret_cast<u32 *>(goff_tab + 2 * QBJ_NT);\n";
       if (tma)
         o << "  u16 *lin_tab = reinterpret_cast<u16 *>(line_tab + (1 << (QBJ_T - 3)));\n"
-             "  const u32 smem_a_ = (u32)__cvta_generic_to_shared(smem_raw);\n"
+             "  const u32 in_a_ = (u32)__cvta_generic_to_shared(in_);\n"
              "  const u32 bar_a_ = (u32)__cvta_generic_to_shared(lin_tab + QBJ_NT);\n";
       o << "  {\n";
       emit_tables();
       o << "  }\n";
-      if (tma) {
+      if (dual) {
+      // ---- two groups, one input buffer: group g takes this CTA's tiles k = g, g + 2, ...; copy k + 1 is
+      // started by the group that has just emptied the input buffer of copy k
+      o << "  if (threadIdx.x == 0) { qbj_mbar_init(bar_a_, 1u); qbj_mbar_init(bar_a_ + 8u, 1u); }\n"
+           "  qbj_fence_mbar_init();\n"
+           "  __syncthreads();  // (also: the tables above, written by both groups with the same values)\n"
+           "  const u32 ntiles32 = (u32)ntiles, stride = gridDim.x, first = blockIdx.x;\n"
+           "  const u32 my_iters = first < ntiles32 ? (ntiles32 - first + stride - 1u) / stride : 0u;\n"
+           "  double re[QBJ_NR], im[QBJ_NR];\n"
+           "  u32 f = 0;\n"
+           "  u64 base = 0, next_base = 0;\n"
+           "  bool have_next_ = grp_ == 0u && my_iters > 0u;\n"
+           "  if (have_next_) {\n";
+      deposit("next_base", "first");
+      {
+        std::ostringstream side2;
+        std::ostringstream *keep = g.cur;
+        g.cur = &side2;
+        issue_next("bar_a_");
+        g.cur = keep;
+        o << side2.str();
+      }
+      o << "  }\n"
+           "  for (u32 k_ = grp_; k_ < my_iters; k_ += 2u) {\n"
+           "    const u32 tile_id = first + k_ * stride;\n";
+      deposit("base", "tile_id");
+      o << "    have_next_ = k_ + 1u < my_iters;\n"
+           "    if (have_next_) {\n      const u32 next_id = tile_id + stride;\n      u64 nb_;\n";
+      deposit("nb_", "next_id");
+      o << "      next_base = nb_;\n    }\n"
+           "    qbj_mbar_wait(bar_a_ + 8u * grp_, (k_ >> 1) & 1u);\n"
+           "    const u64 basefull = base | A.rank_bits;\n    (void)basefull;\n    f = 0;\n";
+      if (coef_reload) o << "    const u32 cz_ = tile_id >> 31;  // always 0 (tile ids are < 2^31), but not to the compiler\n";
+      {
+        std::ostringstream side2;
+        std::ostringstream *keep = g.cur;
+        g.cur = &side2;
+        emit_load_smem();
+        g.cur = keep;
+        o << side2.str();
+      }
+      o << rounds_txt;
+      emit_store(mf_end);
+      o << "  }\n}\n";
+      } else if (tma) {
       // ---- bulk-asynchronous loads: the copy engine fills the transpose buffer one tile ahead
       o << "  if (tid == 0) qbj_mbar_init(bar_a_, 1u);\n"
            "  qbj_fence_mbar_init();\n"
@@ -668,6 +740,7 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
            "#define QBJ_ST1(p, xr, xi) { amps[2 * (p)] = xr; amps[2 * (p) + 1] = xi; }\n"
            "#define QBJ_STS(off, xr, xi) { SM[2 * ((off) >> 4)] = xr; SM[2 * ((off) >> 4) + 1] = xi; }\n"
            "#define QBJ_LDS(off, i) { re[i] = SM[2 * ((off) >> 4)]; im[i] = SM[2 * ((off) >> 4) + 1]; }\n"
+           "#define QBJ_LDSI(off, i) QBJ_LDS(off, i)\n"
            "#define QBJ_THREAD_REFS double (&re)[QBJ_NR] = RE[tid]; double (&im)[QBJ_NR] = IM[tid]; u32 &f = F[tid]; (void)re; (void)im; (void)f;\n"
            "static double RE[QBJ_NT][QBJ_NR], IM[QBJ_NT][QBJ_NR], SM[2 << QBJ_T];\n"
            "static u32 F[QBJ_NT];\n"
@@ -706,7 +779,7 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
   out.swz_fixed = swz_fixed;
   out.swz_conflicts = swz_conflicts;
   out.smem = smem;
-  out.threads = NT;
+  out.threads = dual ? 2 * NT : NT;
   out.args_bytes = sizeof(JitArgsHead) + sizeof(double) * std::max<size_t>(1, out.coefs.size());
   if (!std::isfinite(out.left_out) || out.left_out == 0.0) return fail("deferred factor out of range");
   return true;

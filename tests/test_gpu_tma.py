@@ -21,7 +21,7 @@ def test_bulk_async_loads_match_the_oracle(ctx, default_opts, n, opts):
         ctx.set_option(k, val)
     ctx.set_option("jit", 1)
     outs = {}
-    for tma in (0, 1):
+    for tma in (0, 1, 2):
         ctx.set_option("tma", tma)
         ctx.reset_stats()
         sv = Q.StateVec.from_host(v, ctx=ctx)
@@ -31,10 +31,11 @@ def test_bulk_async_loads_match_the_oracle(ctx, default_opts, n, opts):
         assert st["jit_launches"] == st["passes"] > 0
         assert np.abs(outs[tma] - ref).max() < TOL
     # the same arithmetic in the same order: only the way the tile reaches the registers differs
-    assert np.array_equal(outs[0], outs[1])
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
 
 
-def test_bulk_async_loads_through_lazy_clones_and_from_known_support(ctx, default_opts):
+@pytest.mark.parametrize("tma", [1, 2])
+def test_bulk_async_loads_through_lazy_clones_and_from_known_support(ctx, default_opts, tma):
     """Out-of-place first pass (copy-on-write) and dead-tile skipping with the bulk-copy pipeline."""
     import qubism_b200 as Q
     from oracle import structured as S
@@ -42,7 +43,7 @@ def test_bulk_async_loads_through_lazy_clones_and_from_known_support(ctx, defaul
     n = 18
     ops = random_layers(n, 4, seed=9, lam0=True)
     ctx.set_option("jit", 1)
-    ctx.set_option("tma", 1)
+    ctx.set_option("tma", tma)
     v = S.gen_state(n, np.random.default_rng(3))
     sv = Q.StateVec.from_host(v, ctx=ctx)
     ctx.reset_stats()
@@ -58,7 +59,8 @@ def test_bulk_async_loads_through_lazy_clones_and_from_known_support(ctx, defaul
     assert np.abs(sv.to_host() - S.run_ops(n, ops, z)).max() < TOL
 
 
-def test_round_trip_26_qubits_with_bulk_async_loads(ctx, default_opts):
+@pytest.mark.parametrize("tma", [1, 2])
+def test_round_trip_26_qubits_with_bulk_async_loads(ctx, default_opts, tma):
     """Size-independent property at a size the oracle cannot reach: C^-1 C |0> = |0>."""
     import qubism_b200 as Q
     from qubism_b200.circuits import random_layers
@@ -67,7 +69,7 @@ def test_round_trip_26_qubits_with_bulk_async_loads(ctx, default_opts):
     inv = []
     for op in reversed(ops):
         inv.append(op if op[0] == "CX" else ("U", op[1], np.asarray(op[2]).conj().T))
-    ctx.set_option("tma", 1)
+    ctx.set_option("tma", tma)
     ctx.set_option("jit", 1)
     sv = Q.mkStateVec(n, ctx)
     sv.apply_1q(0, np.array([[1, 1], [1, -1]]) / np.sqrt(2))  # leave the fully known support first

@@ -50,7 +50,8 @@ def jit_emul(tmp_path_factory):
                                   "lane_fixed=1", "lane_fixed=2,reg_bits=5", "max_pass_gates=7", "tile_bits=11,reg_bits=3",
                                   "tile_bits=13,reg_bits=4", "tile_bits=13,reg_bits=5,low_bits=6", "max_rounds=3", "lane_fixed=3",
                                   "tma=1", "tma=1,reg_bits=5", "tma=1,tile_bits=11,reg_bits=3", "tma=1,lane_fixed=3",
-                                  "tma=1,max_pass_gates=5", "tma=1,low_bits=5"])
+                                  "tma=1,max_pass_gates=5", "tma=1,low_bits=5", "tma=2", "tma=2,reg_bits=5",
+                                  "tma=2,tile_bits=11,reg_bits=3", "tma=2,max_pass_gates=4"])
 def test_specialised_passes_of_rotation_cx_layers_match_oracle(jit_emul, opts):
     """U(theta, phi, 0) + CX layers: every pass is a step pass, every one is specialised: 2-FMA
     rotations with deferred cosines (forms A and B), flip-aware flavours after toggles, static
@@ -146,7 +147,9 @@ def test_equal_structure_gives_one_kernel_and_new_angles_only_new_coefficients(j
 
 @pytest.mark.parametrize("opts", ["", "reg_bits=5", "tile_bits=10,reg_bits=3", "rot=0", "jit_group=4,jit_pf_last=0",
                                   "jit_mem=5", "jit_mem=6,jit_minb=3", "tile_bits=13,reg_bits=4", "l2_prefetch=0",
-                                  "tma=1", "tma=1,reg_bits=5", "tma=1,l2_prefetch=0", "tma=1,max_pass_gates=3"])
+                                  "tma=1", "tma=1,reg_bits=5", "tma=1,l2_prefetch=0", "tma=1,max_pass_gates=3",
+                                  "tma=2", "tma=2,reg_bits=5", "tma=2,tile_bits=11,reg_bits=3", "tma=2,max_pass_gates=3",
+                                  "tma=2,tile_bits=13,reg_bits=4"])
 def test_device_source_compiles_with_nvrtc(jit_emul, opts):
     """NVRTC needs no GPU: the CUDA flavour of the generated source must compile for sm_100a."""
     n = 13
@@ -154,7 +157,7 @@ def test_device_source_compiles_with_nvrtc(jit_emul, opts):
     v = S.gen_state(n, np.random.default_rng(0))
     _, st, src = jit_emul(n, ops, v, opts, 0)
     assert src and "qb_jit_pass" in src and "__launch_bounds__" in src
-    if "tma=1" in opts:
+    if "tma=" in opts:
         assert "qbj_bulk_load(" in src.split("qb_jit_pass(")[1], "the bulk-asynchronous load path was not generated"
     nbytes = C.c_int64(0)
     rc = capi.lib().qb_jit_compile_check(src.encode(), C.byref(nbytes))

@@ -4,8 +4,9 @@ Description : drop-in replacement of src/Qubism/StateVec.hs over libqubism_sv.so
 
 Same export list as the reference module (StateVec.hs:14-25).  The amplitudes live on the GPU;
 a @StateVec n@ owns one @qb_state@ through a ForeignPtr whose finalizer is @qb_state_free@.
-Pure functions (normalize, tensor, collapse) clone; the StateT ones (measureQubit, measure) mutate
-the state they own.  UNVERIFIED BY COMPILATION (no GHC in the build image).
+Pure functions (normalize, tensor, collapse) work on a lazy clone (qb_state_clone shares the device
+shard until one of the two handles is written AND the other observed); so do the StateT ones
+(measureQubit, measure), whose clone becomes the new state.  UNVERIFIED BY COMPILATION (no GHC in the build image).
 -}
 {-# LANGUAGE DataKinds, KindSignatures, ScopedTypeVariables, TypeOperators #-}
 module Qubism.StateVec
@@ -110,15 +111,20 @@ collapse i b sv = unsafePerformIO $ do
   pure r
 
 -- | StateVec.hs:118-129.  The draw stays in MonadRandom; the reduction, the rule
--- (One iff r < sqrt S1) and the collapse happen on the device, in place on the owned state.
+-- (One iff r < sqrt S1) and the collapse happen on the device.  The state read with 'get' stays
+-- valid (value semantics): the measurement runs on a lazy clone (no copy unless the old value is
+-- observed again), which becomes the new state.
 measureQubit :: (MonadRandom m, KnownNat n) => Finite n -> StateT (StateVec n) m Bit
 measureQubit i = do
   qr <- get
   r  <- getRandomR (0, 1 :: Double)
-  let bit = unsafePerformIO $ alloca $ \pb -> alloca $ \pp -> do
-        withSV qr $ \p -> check (c_qb_measure_qubit p (fromIntegral (getFinite i)) (realToFrac r) pb pp)
-        peek pb
-  bit `seq` put qr
+  let (bit, qr') = unsafePerformIO $ do
+        w <- cloneSV qr
+        b <- alloca $ \pb -> alloca $ \pp -> do
+          withSV w $ \p -> check (c_qb_measure_qubit p (fromIntegral (getFinite i)) (realToFrac r) pb pp)
+          peek pb
+        pure (b, w)
+  bit `seq` put qr'
   pure (if bit == 1 then One else Zero)
 
 measure :: forall m n . (MonadRandom m, KnownNat n) => StateT (StateVec n) m CReg   -- StateVec.hs:133-137

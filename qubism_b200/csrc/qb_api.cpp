@@ -543,7 +543,7 @@ int run_fused_segment(Buffer *s, std::vector<const HostOp *> seg, const double *
     // ---- which passes run as structure-specialised kernels (qb_jit.cpp).  Every rank takes the
     // same decisions (same plans, same sighting counts): the factors those kernels leave out
     // must be the same on every shard, because exchanges move raw device amplitudes.
-    const int jit_thr = (c->opt.jit > 0 && !c->opt.dbg_skip) ? c->opt.jit : 0;
+    const int jit_thr = (c->opt.jit > 0 && (!c->opt.dbg_skip || (c->opt.dbg_skip & 16))) ? c->opt.jit : 0;
     const size_t npass = plan.passes.size();
     // the flush's last pass takes the pending scalar (and whatever the specialised passes leave out)
     const bool finish = all && final_seg && npass > 0;

@@ -80,7 +80,11 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
   if (pp.blob.size() < sizeof(DevPass)) return fail("short blob");
   const DevPass &P = *reinterpret_cast<const DevPass *>(pp.blob.data());
   if (P.lite == 0) return fail("not a step (lite) pass");
-  if (P.dbg_skip) return fail("profiling switches set");
+  // profiling switches (results are wrong by construction): honoured here only with bit 4 set --
+  // bit 0 no global loads, 1 no global stores, 2 no transposes, 3 no gates (plain tile loop only)
+  if (P.dbg_skip && !(P.dbg_skip & 16u)) return fail("profiling switches set");
+  const uint32_t dbg = P.dbg_skip & 15u;
+  if (dbg && (P.tma != 0 || P.jit_group > 1)) return fail("profiling switches: plain tile loop only");
   if (pp.blob.size() < sizeof(DevPass) + size_t(P.nsteps) * sizeof(DevStep)) return fail("short blob");
   const DevStep *S = reinterpret_cast<const DevStep *>(pp.blob.data() + sizeof(DevPass));
   const int T = (int)P.tile_bits, R = (int)P.reg_bits, NT = 1 << (T - R), NR = 1 << R;
@@ -93,6 +97,7 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
   g.want_src = emit != JIT_KEY_ONLY;
   g.host = emit == JIT_HOST_SRC;
   g.tag("qbj1");
+  g.dec(dbg);
   const int l2pf = (int)P.l2_prefetch;
   // contiguous low part of the tile (a "chunk": 2^cbits amplitudes) and how many consecutive tile
   // ids are neighbours in memory (the lowest run of free bits starts right above the chunk)
@@ -291,7 +296,7 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
 
   auto emit_load = [&]() {
     g.tag("ld");
-    g.line("{ const u64 src_ = base + goff_tab[tid];");
+    g.line(std::string(dbg & 1u ? "if (dbg_never_) " : "") + "{ const u64 src_ = base + goff_tab[tid];");
     if (stride_of(R0, 0) == 1ull) {
       g.tag("p");
       for (int i = 0; i < NR; i += 2) g.line("  QBJ_LD2(src_ + " + reg_offset_expr(g, P, R0, R, i, 1, "+") + ", " + std::to_string(i) + ");");
@@ -317,7 +322,7 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
   auto emit_store = [&](uint32_t mf) {
     g.tag("st");
     g.dec(mf);
-    g.line("{ u64 fx_ = 0;");
+    g.line(std::string(dbg & 2u ? "if (dbg_never_) " : "") + "{ u64 fx_ = 0;");
     for (int j = 0; j < R; ++j)
       if ((mf >> j) & 1u)
         g.line("  fx_ |= ((f >> " + std::to_string(j) + ") & 1u) ? " + g.lit(stride_of(RL, j), "ull") + " : 0ull;");
@@ -370,7 +375,10 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
     if (tma && (nrounds == 1 || dual)) issue_next();
     for (int r = 0; r < nrounds; ++r) {
       const DevRound &RD = P.rounds[r];
-      if (r > 0) {
+      if (r > 0 && (dbg & 4u)) {
+        g.line("f = 0;");
+        mf = 0;
+      } else if (r > 0) {
         const DevRound &PR = P.rounds[r - 1];
         const bool local = RD.warp_local != 0;
         const std::string sr = std::to_string(r);
@@ -403,6 +411,7 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
       }
       for (uint32_t si = RD.step_begin; si < RD.step_end; ++si) {
         const DevStep &st = S[si];
+        if (dbg & 8u) continue;
         for (int J = 0; J < R; ++J) {
           const uint32_t kind = (st.kinds >> (4 * J)) & 15u;
           const uint32_t cls = kind & SLOT_CLASS;
@@ -583,15 +592,31 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
         g.cur = keep;
         o << side2.str();
       }
-      o << "  }\n"
-           "  for (u32 k_ = grp_; k_ < my_iters; k_ += 2u) {\n"
+      o << "  }\n";
+      if (l2pf > 0) {
+        o << "  if (grp_ == 1u && my_iters > 1u) {\n    const u32 pf_id = first + stride;\n    u64 pb_;\n";
+        deposit("pb_", "pf_id");
+        for (int k = 0; k < LPT; ++k)
+          o << "    asm volatile(\"prefetch.global.L2 [%0];\" ::\"l\"(src + pb_ + ((u64)line_tab[" << k << " * QBJ_NT + tid] << 3)));\n";
+        o << "  }\n";
+      }
+      o << "  for (u32 k_ = grp_; k_ < my_iters; k_ += 2u) {\n"
            "    const u32 tile_id = first + k_ * stride;\n";
       deposit("base", "tile_id");
       o << "    have_next_ = k_ + 1u < my_iters;\n"
            "    if (have_next_) {\n      const u32 next_id = tile_id + stride;\n      u64 nb_;\n";
       deposit("nb_", "next_id");
-      o << "      next_base = nb_;\n    }\n"
-           "    qbj_mbar_wait(bar_a_ + 8u * grp_, (k_ >> 1) & 1u);\n"
+      o << "      next_base = nb_;\n    }\n";
+      if (l2pf > 0) {
+        // the tile after the next one goes to L2 now: its bulk copy (issued one tile from now) must
+        // not wait for DRAM -- only ONE copy is in flight per SM, its latency is the pipeline's period
+        o << "    if (k_ + 2u < my_iters) {\n      const u32 pf_id = tile_id + 2u * stride;\n      u64 pb_;\n";
+        deposit("pb_", "pf_id");
+        for (int k = 0; k < LPT; ++k)
+          o << "      asm volatile(\"prefetch.global.L2 [%0];\" ::\"l\"(src + pb_ + ((u64)line_tab[" << k << " * QBJ_NT + tid] << 3)));\n";
+        o << "    }\n";
+      }
+      o << "    qbj_mbar_wait(bar_a_ + 8u * grp_, (k_ >> 1) & 1u);\n"
            "    const u64 basefull = base | A.rank_bits;\n    (void)basefull;\n    f = 0;\n";
       if (coef_reload) o << "    const u32 cz_ = tile_id >> 31;  // always 0 (tile ids are < 2^31), but not to the compiler\n";
       {
@@ -660,8 +685,11 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
            "  const u32 iters = (ntiles32 + stride - 1) / stride;\n"
            "  double re[QBJ_NR], im[QBJ_NR];\n"
            "  u32 f = 0;\n"
-           "  u64 base = 0, next_base = 0;\n"
-           "  for (u32 it = 0; it <= iters; ++it) {\n"
+           "  u64 base = 0, next_base = 0;\n";
+      if (dbg)
+        o << "  const bool dbg_never_ = ntiles == ~0ull;  // profiling switches: code kept, never executed\n"
+             "  for (int i = 0; i < QBJ_NR; ++i) { re[i] = 1e-3 * (double)(tid + i); im[i] = -re[i]; }\n";
+      o << "  for (u32 it = 0; it <= iters; ++it) {\n"
            "    const u32 tile_id = first + it * stride;\n"
            "    if (it > 0 && tile_id - stride < ntiles32) {\n";
       // NOTE: the flips pending at the store are those of the previous tile's last round
@@ -794,7 +822,8 @@ bool jit_quick(const PassPlan &pp, JitProgram &out, std::string *why) {
   if (pp.blob.size() < sizeof(DevPass)) return fail("short blob");
   const DevPass &P = *reinterpret_cast<const DevPass *>(pp.blob.data());
   if (P.lite == 0) return fail("not a step (lite) pass");
-  if (P.dbg_skip) return fail("profiling switches set");
+  if (P.dbg_skip && !(P.dbg_skip & 16u)) return fail("profiling switches set");
+  if ((P.dbg_skip & 15u) && (P.tma != 0 || P.jit_group > 1)) return fail("profiling switches: plain tile loop only");
   if (pp.blob.size() < sizeof(DevPass) + size_t(P.nsteps) * sizeof(DevStep)) return fail("short blob");
   const DevStep *S = reinterpret_cast<const DevStep *>(pp.blob.data() + sizeof(DevPass));
   const int T = (int)P.tile_bits, R = (int)P.reg_bits;
@@ -815,7 +844,7 @@ bool jit_quick(const PassPlan &pp, JitProgram &out, std::string *why) {
   mix(P.nruns);
   for (uint32_t k = 0; k < P.nruns && k < (uint32_t)kMaxRuns; ++k) { mix(P.run_shift[k]); mix(P.run_len[k]); }
   for (int i = 0; i < T; ++i) mix(P.tile_pos[i]);
-  mix(P.jit_group); mix(P.jit_pf_last); mix(P.jit_minb); mix(P.jit_mem); mix(P.nsteps); mix(P.tma);
+  mix(P.jit_group); mix(P.jit_pf_last); mix(P.jit_minb); mix(P.jit_mem); mix(P.nsteps); mix(P.tma); mix(P.dbg_skip);
   out.coefs.clear();
   double left = 1.0;
   bool bad = false;

@@ -91,7 +91,7 @@ bool set_opt(PlanOptions &o, const std::string &name, int64_t v) {
     if (v < 0 || v > 2) return false;
     o.avoid_regswap = (int)v;
   } else if (name == "dbg_skip") {
-    if (v < 0 || v > 15) return false;
+    if (v < 0 || v > 31) return false;  // (bit 4: the switches also apply to the specialised kernels)
     o.dbg_skip = (int)v;
   } else {
     return false;

@@ -68,7 +68,7 @@ struct qb_ctx {
   PlanOptions opt;
   int linear = 0;                  // option "linear": 1 = a pure application CONSUMES the older handles of its
                                    // lineage (they turn stale and fail loudly) instead of copying on write
-  int pool_max = 1;                // option "pool": spare shards kept for the next clone / copy-on-write
+  int pool_max = 2;                // option "pool": spare shards kept for the next clone / copy-on-write / second shard
   qb_stats stats{};
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;  // pending (start, stop) pairs
   std::vector<cudaEvent_t> event_pool;
@@ -106,6 +106,8 @@ struct Buffer {
   int n = 0, L = 0;
   uint64_t id = 0;
   double2 *amps = nullptr;
+  double2 *alt = nullptr;        // second shard of the same size (allocated on first use): out-of-place passes
+                                 // read `amps`, write `alt`, and the two trade places (option "oop")
   std::vector<double2 *> peers;  // distributed: every rank's shard (IPC / same process); empty: NCCL swaps
   const double2 *cow_src = nullptr;  // copy-on-write in progress: the first full pass reads its tiles here
   std::vector<int> perm;  // logical bit -> physical bit (bits >= L are rank bits)
@@ -161,7 +163,7 @@ int init_common(qb_ctx *c) {
   QB_CUDA(cudaMallocHost(&c->red_host, sizeof(double) * 4));
   QB_CUDA(cudaMalloc(&c->kq_bits_dev, sizeof(int) * 2 * QB_MAX_KQ));
   QB_CUDA(cudaMalloc(&c->kq_mat_dev, sizeof(double2) << (2 * QB_MAX_KQ)));
-  for (const char *name : {"tile_bits", "reg_bits", "low_bits", "max_rounds", "peephole", "fuse", "max_pass_gates", "l2_prefetch", "avoid_regswap", "hot_bits", "rot", "lite", "dbg_skip", "lane_fixed", "skip_dead", "support", "jit", "jit_group", "jit_pf_last", "jit_minb", "jit_mem", "tma"}) {
+  for (const char *name : {"tile_bits", "reg_bits", "low_bits", "max_rounds", "peephole", "fuse", "max_pass_gates", "l2_prefetch", "avoid_regswap", "hot_bits", "rot", "lite", "dbg_skip", "lane_fixed", "skip_dead", "support", "jit", "jit_group", "jit_pf_last", "jit_minb", "jit_mem", "tma", "oop", "oop_low_bits"}) {
     std::string env = "QB_";
     for (const char *p = name; *p; ++p) env.push_back((char)toupper(*p));
     const char *v = getenv(env.c_str());
@@ -175,7 +177,31 @@ int init_common(qb_ctx *c) {
 // ---- device shards: allocation, the spare pool, release without collectives --------------------
 void free_buffer_memory(Buffer *b) {
   if (b->amps) cudaFree(b->amps);
-  b->amps = nullptr;
+  if (b->alt) cudaFree(b->alt);
+  b->amps = b->alt = nullptr;
+}
+
+// the second shard of an out-of-place pass; false (and no error) if the memory is not there -- the
+// caller then stays in place
+bool ensure_alt(Buffer *b) {
+  if (b->alt) return true;
+  qb_ctx *c = b->ctx;
+  for (size_t i = 0; i < c->pool.size(); ++i)  // a spare shard of the right size is as good as a new one
+    if (c->pool[i]->L == b->L && c->pool[i]->peers.empty()) {
+      Buffer *p = c->pool[i];
+      c->pool.erase(c->pool.begin() + i);
+      b->alt = p->amps;
+      p->amps = nullptr;
+      free_buffer_memory(p);
+      delete p;
+      return true;
+    }
+  if (cudaMalloc(&b->alt, sizeof(double2) << b->L) != cudaSuccess) {
+    (void)cudaGetLastError();
+    b->alt = nullptr;
+    return false;
+  }
+  return true;
 }
 
 // Sharded contexts: which released shards are released on EVERY rank?  Handles die in finalizers,
@@ -297,6 +323,19 @@ void release_buffer(Buffer *b) {
   qb_ctx *c = b->ctx;
   b->log.clear();
   b->released = true;
+  if (b->alt) {  // (single-GPU contexts only: nothing collective about it) -> the spare pool, if there is room
+    if ((int)c->pool.size() + 1 < c->pool_max) {
+      Buffer *p = new Buffer();
+      p->ctx = c;
+      p->L = b->L;
+      p->n = b->n;
+      p->amps = b->alt;
+      c->pool.push_back(p);
+    } else {
+      cudaFree(b->alt);
+    }
+    b->alt = nullptr;
+  }
   c->graveyard.push_back(b);
   if (c->nranks == 1) {
     c->in_use.erase(std::find(c->in_use.begin(), c->in_use.end(), b));
@@ -376,14 +415,18 @@ int get_event(qb_ctx *c, cudaEvent_t *out) {
 int resolve_timed(qb_ctx *c) {
   if (c->timed.empty()) return QB_OK;
   QB_CUDA(cudaStreamSynchronize(c->stream));
+  FILE *plog = nullptr;  // developer switch: one line per fused pass (its CUDA-event time) appended to a file
+  if (const char *path = getenv("QB_PASS_LOG")) plog = fopen(path, "a");
   for (auto &pr : c->timed) {
     float ms = 0.f;
     QB_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
+    if (plog) fprintf(plog, "%.4f\n", ms);
     c->stats.fused_ms += ms;
     c->stats.fused_timed++;
     c->event_pool.push_back(pr.first);
     c->event_pool.push_back(pr.second);
   }
+  if (plog) fclose(plog);
   c->timed.clear();
   return QB_OK;
 }
@@ -508,6 +551,10 @@ int run_fused_segment(Buffer *s, std::vector<const HostOp *> seg, const double *
   opt.tile_bits = T;
   opt.reg_bits = R;
   if (!opt.fuse) opt.max_pass_gates = 1;
+  // out-of-place passes (tiles written as contiguous blocks, qubits relabelled): single-GPU states
+  // with room for a second shard
+  opt.oop = (c->opt.oop && c->nranks == 1 && T > 0 && ensure_alt(s)) ? c->opt.oop : 0;
+  if (opt.oop && opt.low_bits < c->opt.oop_low_bits) opt.low_bits = std::min(c->opt.oop_low_bits, T);
   while (!seg.empty()) {
     std::vector<PhysOp> pops(seg.size());
     for (size_t i = 0; i < seg.size(); ++i) {
@@ -537,7 +584,10 @@ int run_fused_segment(Buffer *s, std::vector<const HostOp *> seg, const double *
         if (!finite8(po.m)) rank_dead = false;
     }
     auto t0 = std::chrono::steady_clock::now();
-    PlanResult plan = plan_passes(pops, s->L, c->rank, opt, nullptr);
+    std::vector<int> labels(s->L, 0);  // the logical bit on each local physical bit (ties between qubits nothing
+    for (int q = 0; q < s->n; ++q)     // waits for: the layouts out-of-place passes produce depend on the ops only)
+      if (s->perm[q] < s->L) labels[s->perm[q]] = q;
+    PlanResult plan = plan_passes(pops, s->L, c->rank, opt, nullptr, &labels);
     const bool all = plan.consumed == seg.size();
     c->stats.plan_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     // ---- which passes run as structure-specialised kernels (qb_jit.cpp).  Every rank takes the
@@ -645,6 +695,15 @@ int run_fused_segment(Buffer *s, std::vector<const HostOp *> seg, const double *
           QB_TRY(ensure_inplace(s));
         }
       }
+      // an out-of-place pass writes the other shard (unless it already reads somebody else's: the
+      // copy-on-write source) and the two trade places
+      const bool oop_pass = reinterpret_cast<const DevPass *>(p.blob.data())->oop != 0;
+      double2 *dst = s->amps;
+      if (oop_pass && !src) {
+        if (rank_dead || !s->alt) return fail(QB_ERR_STATE, "internal: out-of-place pass without a second shard");
+        dst = s->alt;
+        src = s->amps;
+      }
       if (!rank_dead) {
         if (jit_handle[i]) {
           const DevPass *P = reinterpret_cast<const DevPass *>(p.blob.data());
@@ -652,13 +711,14 @@ int run_fused_segment(Buffer *s, std::vector<const HostOp *> seg, const double *
           if (!P->has_gscale) gs[0] = 1.0, gs[1] = 0.0;
           std::string err;
           const std::vector<uint8_t> args = jit_pack_args(jit_prog[i], gs, P->rank_bits, P->base_fixed);
-          if (jit_launch(jit_handle[i], s->amps, src, p.ntiles, args, c->sm_count, c->stream, &err) != 0)
+          if (jit_launch(jit_handle[i], dst, src, p.ntiles, args, c->sm_count, c->stream, &err) != 0)
             return fail(QB_ERR_CUDA, "%s", err.c_str());
         } else {
-          QB_CUDA(launch_fused_pass(s->amps, src, p.blob.data(), (uint32_t)p.blob.size(), p.tile_bits, p.reg_bits, p.ntiles,
+          QB_CUDA(launch_fused_pass(dst, src, p.blob.data(), (uint32_t)p.blob.size(), p.tile_bits, p.reg_bits, p.ntiles,
                                     c->sm_count, c->stream, nullptr));
         }
       }
+      if (dst != s->amps) std::swap(s->amps, s->alt);
       c->stats.tiles += rank_dead ? 0 : p.ntiles;
       if (e0) {
         QB_CUDA(cudaEventRecord(e1, c->stream));
@@ -668,6 +728,9 @@ int run_fused_segment(Buffer *s, std::vector<const HostOp *> seg, const double *
       c->stats.rounds += p.nrounds;
       c->stats.ops_executed += p.ngates;
     }
+    if (!plan.final_pos.empty())  // the out-of-place passes moved the local qubits
+      for (int &x : s->perm)
+        if (x < s->L) x = plan.final_pos[x];
     for (size_t i = 0; i < seg.size(); ++i) {  // the scheduled ops now shape the support
       if (!plan.done[i]) continue;
       const HostOp &h = *seg[i];
@@ -1048,6 +1111,24 @@ int relayout(Buffer *b, const std::vector<int> &want) {
   qb_ctx *c = b->ctx;
   QB_TRY(ensure_inplace(b));
   const int L = b->L;
+  {
+    bool local_only = true, same = true;
+    for (int q = 0; q < b->n; ++q) {
+      if (b->perm[q] != want[q]) same = false;
+      if ((b->perm[q] >= L) != (want[q] >= L) || (b->perm[q] >= L && b->perm[q] != want[q])) local_only = false;
+    }
+    if (same) return QB_OK;
+    if (local_only && c->nranks == 1 && ensure_alt(b)) {  // dst[new place of i] = src[i]
+      std::vector<int> np(L, 0);
+      for (int q = 0; q < b->n; ++q)
+        if (b->perm[q] < L) np[b->perm[q]] = want[q];
+      QB_CUDA(launch_permute_bits(b->alt, b->amps, L, np.data(), c->sm_count, c->stream));
+      c->stats.simple_launches++;
+      std::swap(b->amps, b->alt);
+      b->perm = want;
+      return QB_OK;
+    }
+  }
   const bool peer_path = c->nranks > 1 && dist_has_peers(c->dist, b->peers);
   auto swap_positions = [&](int p1, int p2) -> int {  // physical positions
     if (p1 == p2) return QB_OK;
@@ -1356,12 +1437,41 @@ void qb_state_free(qb_state *s) {
 int qb_state_nqubits(const qb_state *s) { return s ? s->n : QB_ERR_ARG; }
 uint64_t qb_state_local_len(const qb_state *s) { return s ? (1ull << (s->n - s->ctx->pbits)) : 0; }
 
+// amplitudes [first, first + count) of a single-GPU state in INDEX order, whatever its qubit layout
+static int read_in_index_order(Buffer *b, uint64_t first, uint64_t count, qb_c64 *out) {
+  qb_ctx *c = b->ctx;
+  bool ident = true;
+  for (int q = 0; q < b->n; ++q)
+    if (b->perm[q] != q) ident = false;
+  if (ident) {
+    QB_CUDA(cudaMemcpyAsync(out, b->amps + first, count * sizeof(double2), cudaMemcpyDeviceToHost, c->stream));
+    QB_CUDA(cudaStreamSynchronize(c->stream));
+    return QB_OK;
+  }
+  // gathered on the device into a staging buffer (<= 64 MiB at a time), then copied out
+  const uint64_t piece = std::min<uint64_t>(count, 1ull << 22);
+  if (piece == 0) return QB_OK;
+  double2 *stage = nullptr;
+  QB_CUDA(cudaMalloc(&stage, piece * sizeof(double2)));
+  cudaError_t e = cudaSuccess;
+  for (uint64_t off = 0; off < count && e == cudaSuccess; off += piece) {
+    const uint64_t k = std::min(piece, count - off);
+    e = launch_gather_logical(stage, b->amps, first + off, k, b->perm.data(), b->n, c->sm_count, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out + off, stage, k * sizeof(double2), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  }
+  cudaFree(stage);
+  if (e != cudaSuccess) return fail(QB_ERR_CUDA, "layout-aware read: %s", cudaGetErrorString(e));
+  return QB_OK;
+}
+
 int qb_state_read_local(qb_state *s, uint64_t first, uint64_t count, qb_c64 *out) {
   if (!s || !out) return fail(QB_ERR_ARG, "null argument");
   Guard g(s->ctx);
   QB_TRY(flush_locked(s));
   const uint64_t len = 1ull << s->b->L;
   if (first > len || count > len - first) return fail(QB_ERR_ARG, "range beyond the local shard");
+  if (s->ctx->nranks == 1) return read_in_index_order(s->b, first, count, out);  // (the shard IS the state)
   QB_CUDA(cudaMemcpyAsync(out, s->b->amps + first, count * sizeof(double2), cudaMemcpyDeviceToHost, s->ctx->stream));
   QB_CUDA(cudaStreamSynchronize(s->ctx->stream));
   return QB_OK;
@@ -1392,6 +1502,11 @@ int qb_state_write_local(qb_state *s, uint64_t first, uint64_t count, const qb_c
     QB_TRY(make_unique(s));
     b = s->b;
     QB_TRY(force_scale(b));
+    if (s->ctx->nranks == 1) {  // (out-of-place passes move qubits: back to the identity layout)
+      std::vector<int> ident(b->n);
+      for (int i = 0; i < b->n; ++i) ident[i] = i;
+      QB_TRY(relayout(b, ident));
+    }
     for (int i = 0; i < b->n; ++i)
       if (b->perm[i] != i) return fail(QB_ERR_STATE, "partial upload into a state whose qubit layout has changed");
   }
@@ -1409,11 +1524,7 @@ int qb_state_read(qb_state *s, uint64_t first, uint64_t count, qb_c64 *out) {
   Guard g(c);
   QB_TRY(flush_locked(s));
   Buffer *b = s->b;
-  if (c->nranks == 1) {
-    QB_CUDA(cudaMemcpyAsync(out, b->amps + first, count * sizeof(double2), cudaMemcpyDeviceToHost, c->stream));
-    QB_CUDA(cudaStreamSynchronize(c->stream));
-    return QB_OK;
-  }
+  if (c->nranks == 1) return read_in_index_order(b, first, count, out);
   int rc = dist_read_logical(c->dist, b->amps, b->n, b->L, b->perm, first, count, out, c->stream);
   if (rc != QB_OK) return fail(rc, "distributed read failed: %s", dist_last_error());
   return QB_OK;
@@ -1818,6 +1929,7 @@ int64_t qb_plan_describe(int nlocal, const qb_op *ops, int64_t nops, const char 
     opt.tile_bits = T;
     opt.reg_bits = R;
     if (!opt.fuse) opt.max_pass_gates = 1;
+    if (opt.oop && opt.low_bits < opt.oop_low_bits) opt.low_bits = std::min(opt.oop_low_bits, T);  // (as a flush does)
     std::vector<PhysOp> pops;
     for (const auto &h : q.ops) {
       if (h.dead) continue;

@@ -15,6 +15,7 @@ constexpr int kMaxTileBits = 13;   // 2^13 amplitudes * 16 B = 128 KB of shared 
 constexpr int kMaxRegBits = 5;     // 32 amplitudes (128 32-bit registers) per thread
 constexpr int kMaxRounds = 8;      // register-residency rounds per pass
 constexpr int kMaxRuns = 16;       // runs of non-tile bits in the tile-index deposit
+constexpr int kMaxOutRuns = 32;    // out-of-place passes: runs of tile-number bits in the block address
 constexpr int kMaxPassGates = 96;  // gates per pass (bounds the shared-memory program copy)
 constexpr int kLaneFixedBits = 3;  // bits 0..2 (one 128-B line) stay on lanes in load/store rounds
 
@@ -128,7 +129,17 @@ struct DevPass {
   uint32_t jit_mem;                   // specialised kernels: cache policy of the global accesses (QBJ_MEM, qb_jit_prelude.cuh)
   uint32_t tma;                       // specialised kernels: 1 = the tile is LOADED with asynchronous bulk copies
                                       // (cp.async.bulk -> shared memory, mbarrier) issued one tile ahead
-  uint32_t _pad_tma[3];
+  uint32_t oop;                       // 1 = OUT OF PLACE with a new qubit layout: every tile is written as ONE
+                                      // contiguous block of 2^T amplitudes of the destination shard, tile-local bit i
+                                      // at bit out_pos[i] of it (a permutation of 0..T-1); which block: onruns below.
+                                      // 0 = the tile goes back where it came from (out_pos == tile_pos).
+  uint32_t onruns;                    // oop: the block address of tile number t.  Its bits are taken from the low
+                                      // end in onruns groups of orun_len[k] bits, group k placed at bit
+                                      // orun_shift[k] (>= T): the qubits outside the tile may be re-ordered too
+  uint32_t _pad_tma;
+  uint8_t out_pos[16];                // physical bit position tile-local bit i is STORED at
+  uint8_t orun_len[kMaxOutRuns];
+  uint8_t orun_shift[kMaxOutRuns];
   DevRound rounds[kMaxRounds];
   // followed in memory by ngates DevGate records (lite: by nsteps DevStep records)
 };
@@ -192,6 +203,17 @@ struct PlanOptions {
   int tma = 0;            // specialised kernels: tile loads / stores as asynchronous bulk copies (cp.async.bulk)
   int hot_bits = 0;       // planner: max distinct TARGET bits per pass (0 = tile_bits).  With
                           // hot_bits <= tile_bits - warp bits every transpose can stay warp-local.
+  int oop = 1;            // passes run OUT OF PLACE (second shard) and write every tile as ONE contiguous block:
+                          // the tile's qubits move to the low physical bits, the others keep their order above
+                          // (measured: the scattered 128-byte STORES of the in-place pass are what holds it at
+                          // 0.65 of the HBM roofline; reads gather, writes stream).  The planner relabels the
+                          // remaining ops after every pass; the caller tracks the layout (PlanResult::final_pos).
+                          // 1: every qubit is re-sorted by its next use (the next tile is then the low bits plus
+                          // the run right above the block: 512-byte chunks inside a few 2 MB pages, and the
+                          // layout depends on the op stream only, so the structures of an iterated circuit come
+                          // back); 2: only the tile's qubits move.  Single-GPU states with room for a second shard.
+  int oop_low_bits = 5;   // low_bits while passes run out of place: the low bits hold the qubits needed next, so
+                          // a longer contiguous chunk costs no extra passes there (measured 30-31 passes either way)
 };
 
 // (tile bits, register bits, min CTAs/SM) instantiations of k_fused_pass
@@ -223,6 +245,8 @@ struct PassPlan {
   uint64_t tile_mask = 0;        // physical bits in the tile
   std::vector<int> op_index;     // indices (into the planner input) of the ops in this pass
   std::vector<uint64_t> round_regmask;  // physical-bit mask of the register bits per round
+  std::vector<int> newpos;       // out-of-place pass: physical bit b of the input layout is bit newpos[b] of the
+                                 // output layout (local bits only; empty = layout unchanged)
 };
 
 struct PlanResult {
@@ -230,14 +254,18 @@ struct PlanResult {
   size_t consumed = 0;           // number of input ops that were scheduled
   std::vector<char> done;        // per input op: scheduled?
   uint64_t known_mask = 0, known_val = 0;  // the support after the scheduled passes (PlanOptions::known_*)
+  std::vector<int> final_pos;    // out-of-place passes ran: local physical bit b (layout the plan started from)
+                                 // ends up at final_pos[b] (empty = layout unchanged)
 };
 
 // Plan fused passes for `ops` on a shard with `local_bits` local qubits.  Ops that cannot run
 // locally (non-diagonal gate on a global bit) and everything that depends on them are left
 // unscheduled: result.consumed < ops.size(), result.done says which.
 // gscale (may be null) is folded into the last pass.
+// labels (may be null): a layout-independent name for the qubit on each local physical bit (its logical
+// bit); out-of-place passes break ties by it, so that the layouts they produce depend on the op stream only.
 PlanResult plan_passes(const std::vector<PhysOp> &ops, int local_bits, int rank, const PlanOptions &opt,
-                       const double *gscale);
+                       const double *gscale, const std::vector<int> *labels = nullptr);
 
 std::string describe_plan(const PlanResult &r);
 

@@ -61,11 +61,12 @@ struct Gen {
   }
 };
 
-std::string reg_offset_expr(Gen &g, const DevPass &P, const DevRound &rd, int R, int i, int from_bit, const char *op) {
-  // XOR / sum of the global strides of the set register bits of i (bits >= from_bit)
+std::string reg_offset_expr(Gen &g, const uint8_t *pos, const DevRound &rd, int R, int i, int from_bit, const char *op) {
+  // XOR / sum of the global strides of the set register bits of i (bits >= from_bit); pos = where
+  // each tile-local bit lives (DevPass::tile_pos for loads, DevPass::out_pos for stores)
   uint64_t off = 0;
   for (int j = from_bit; j < R; ++j)
-    if ((i >> j) & 1) off |= 1ull << P.tile_pos[rd.reg_pos[j]];
+    if ((i >> j) & 1) off |= 1ull << pos[rd.reg_pos[j]];
   (void)op;
   return g.lit(off, "ull");
 }
@@ -123,6 +124,8 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
     if (low != 7u) tma = false;
   }
   if (tma) group = 1;
+  const bool oop = P.oop != 0;  // tiles are stored as contiguous blocks of the destination, bits permuted (out_pos)
+  if (oop) group = 1;
   const size_t tables_bytes = size_t(std::max(1, 2 * (nrounds - 1))) * NT * sizeof(uint16_t) + size_t(2) * NT * sizeof(uint64_t) +
                               (size_t(group) << (T - 3)) * sizeof(uint32_t) + (tma ? NT * sizeof(uint16_t) + 16 : 0);
   // tma = 2: ONE CTA per SM holds TWO groups of 2^(T-R) threads, each working on its own tile with a
@@ -238,14 +241,16 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
   const std::string sG = g.dec(group), sCB = g.dec(cbits), sMEM = g.dec(P.jit_mem);
   g.dec(tma);
   g.dec(dual);
+  g.dec(oop);
   const std::string sPFK = g.dec((group > 1 && P.jit_pf_last) ? group - 1 : 0);  // prefetch while this tile of the group computes
 
   // ---------------------------------------------------------------- fragments shared by both modes
-  auto tid_bits_expr = [&](const DevRound &rd, bool phys, const char *var) {
-    // OR of ((var >> j) & 1) << position, positions as literals
+  auto tid_bits_expr = [&](const DevRound &rd, int phys, const char *var) {
+    // OR of ((var >> j) & 1) << position, positions as literals (0 tile-local, 1 where the tile is
+    // loaded from, 2 where it is stored)
     std::string e;
     for (int j = 0; j < T - R; ++j) {
-      const uint64_t pos = phys ? P.tile_pos[rd.tid_pos[j]] : rd.tid_pos[j];
+      const uint64_t pos = phys == 2 ? P.out_pos[rd.tid_pos[j]] : (phys ? P.tile_pos[rd.tid_pos[j]] : rd.tid_pos[j]);
       const std::string sp = g.dec((int64_t)pos);
       if (!g.want_src) continue;
       if (!e.empty()) e += " | ";
@@ -267,6 +272,17 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
   const DevRound &R0 = P.rounds[0];
   const DevRound &RL = P.rounds[nrounds - 1];
   auto stride_of = [&](const DevRound &rd, int j) { return 1ull << P.tile_pos[rd.reg_pos[j]]; };
+  auto ostride_of = [&](const DevRound &rd, int j) { return 1ull << P.out_pos[rd.reg_pos[j]]; };
+  const std::string sOB = oop ? "obase_" : "base";  // (out of place: set by every tile loop before its store)
+  // out of place: the block address of tile number `id` (its bits, group by group, at their new places)
+  auto emit_obase = [&](std::ostream &os, const char *id, const char *indent) {
+    os << indent << "u64 obase_ = 0;\n" << indent << "{ u64 t_ = " << id << ";\n";
+    for (uint32_t k = 0; k < P.onruns && k < (uint32_t)kMaxOutRuns; ++k) {
+      const std::string len = g.dec(P.orun_len[k]), sh = g.dec(P.orun_shift[k]);
+      os << indent << "  obase_ |= (t_ & ((1ull << " << len << ") - 1ull)) << " << sh << "; t_ >>= " << len << ";\n";
+    }
+    os << indent << "}\n";
+  };
 
   auto emit_tables = [&]() {
     // per transpose: this thread's swizzled slot in the STORE layout (table 2(r-1)) and in the
@@ -279,9 +295,9 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
           e += " ^ ((0u - ((tid >> " + std::to_string(j) + ") & 1u)) & " + g.lit(swz_of(r, 1u << rd.tid_pos[j])) + ")";
         g.line("sidx_tab[" + std::to_string(2 * (r - 1) + side) + " * QBJ_NT + tid] = (u16)(" + e + ");");
       }
-    if (tma) g.line("lin_tab[tid] = (u16)(" + tid_bits_expr(R0, false, "tid") + ");");
-    g.line("goff_tab[tid] = " + tid_bits_expr(R0, true, "tid") + ";");
-    g.line("goff_tab[QBJ_NT + tid] = " + tid_bits_expr(RL, true, "tid") + ";");
+    if (tma) g.line("lin_tab[tid] = (u16)(" + tid_bits_expr(R0, 0, "tid") + ");");
+    g.line("goff_tab[tid] = " + tid_bits_expr(R0, 1, "tid") + ";");
+    g.line("goff_tab[QBJ_NT + tid] = " + tid_bits_expr(RL, 2, "tid") + ";");
     for (int k = 0; k < LPT; ++k) {
       std::string e;
       for (int j = 0; j < T - 3; ++j) {
@@ -299,9 +315,9 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
     g.line(std::string(dbg & 1u ? "if (dbg_never_) " : "") + "{ const u64 src_ = base + goff_tab[tid];");
     if (stride_of(R0, 0) == 1ull) {
       g.tag("p");
-      for (int i = 0; i < NR; i += 2) g.line("  QBJ_LD2(src_ + " + reg_offset_expr(g, P, R0, R, i, 1, "+") + ", " + std::to_string(i) + ");");
+      for (int i = 0; i < NR; i += 2) g.line("  QBJ_LD2(src_ + " + reg_offset_expr(g, P.tile_pos, R0, R, i, 1, "+") + ", " + std::to_string(i) + ");");
     } else {
-      for (int i = 0; i < NR; ++i) g.line("  QBJ_LD1(src_ + " + reg_offset_expr(g, P, R0, R, i, 0, "+") + ", " + std::to_string(i) + ");");
+      for (int i = 0; i < NR; ++i) g.line("  QBJ_LD1(src_ + " + reg_offset_expr(g, P.tile_pos, R0, R, i, 0, "+") + ", " + std::to_string(i) + ");");
     }
     g.line("}");
   };
@@ -325,15 +341,15 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
     g.line(std::string(dbg & 2u ? "if (dbg_never_) " : "") + "{ u64 fx_ = 0;");
     for (int j = 0; j < R; ++j)
       if ((mf >> j) & 1u)
-        g.line("  fx_ |= ((f >> " + std::to_string(j) + ") & 1u) ? " + g.lit(stride_of(RL, j), "ull") + " : 0ull;");
-    if (stride_of(RL, 0) == 1ull) {
+        g.line("  fx_ |= ((f >> " + std::to_string(j) + ") & 1u) ? " + g.lit(ostride_of(RL, j), "ull") + " : 0ull;");
+    if (ostride_of(RL, 0) == 1ull) {
       g.tag("p");
-      g.line("  const u64 at_ = (base + goff_tab[QBJ_NT + tid]) ^ (fx_ & ~1ull);");
+      g.line("  const u64 at_ = (" + sOB + " + goff_tab[QBJ_NT + tid]) ^ (fx_ & ~1ull);");
       const bool sw = (mf & 1u) != 0;
       if (sw) g.line("  const bool sw_ = (f & 1u) != 0;");
       for (int i = 0; i < NR; i += 2) {
         const std::string a = std::to_string(i), b = std::to_string(i + 1);
-        const std::string off = reg_offset_expr(g, P, RL, R, i, 1, "^");
+        const std::string off = reg_offset_expr(g, P.out_pos, RL, R, i, 1, "^");
         if (sw)
           g.line("  QBJ_ST2(at_ ^ " + off + ", sw_ ? re[" + b + "] : re[" + a + "], sw_ ? im[" + b + "] : im[" + a + "], sw_ ? re[" + a +
                  "] : re[" + b + "], sw_ ? im[" + a + "] : im[" + b + "]);");
@@ -341,9 +357,9 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
           g.line("  QBJ_ST2(at_ ^ " + off + ", re[" + a + "], im[" + a + "], re[" + b + "], im[" + b + "]);");
       }
     } else {
-      g.line("  const u64 at_ = (base + goff_tab[QBJ_NT + tid]) ^ fx_;");
+      g.line("  const u64 at_ = (" + sOB + " + goff_tab[QBJ_NT + tid]) ^ fx_;");
       for (int i = 0; i < NR; ++i)
-        g.line("  QBJ_ST1(at_ ^ " + reg_offset_expr(g, P, RL, R, i, 0, "^") + ", re[" + std::to_string(i) + "], im[" + std::to_string(i) + "]);");
+        g.line("  QBJ_ST1(at_ ^ " + reg_offset_expr(g, P.out_pos, RL, R, i, 0, "^") + ", re[" + std::to_string(i) + "], im[" + std::to_string(i) + "]);");
     }
     g.line("}");
   };
@@ -365,9 +381,17 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
     g.line("if (have_next_) {");
     g.line("  qbj_fence_proxy_async();  // generic-proxy reads of the buffer happen before the async-proxy writes");
     g.line("  if (tid == 0) qbj_mbar_expect_tx(" + b + ", 16u << QBJ_T);");
-    for (int k = 0; k < LPT; ++k)
-      g.line("  qbj_bulk_load(in_a_ + ((tid + " + std::to_string(k) + "u * QBJ_NT) << 7), src + next_base + ((u64)line_tab[" + std::to_string(k) +
-             " * QBJ_NT + tid] << 3), 128u, " + b + ");");
+    // one copy per contiguous CHUNK of the tile (2^cbits amplitudes; a line = 8): chunk c lands at byte
+    // c << (cbits + 4) of the buffer and comes from where line c << (cbits - 3) of the tile lives
+    const int nchunks = 1 << (T - cbits), cpt = std::max(1, nchunks / NT);
+    const std::string sBytes = g.lit(16u << cbits), sCb = g.dec(cbits);
+    for (int k = 0; k < cpt; ++k) {
+      const std::string c = "(tid + " + std::to_string(k) + "u * QBJ_NT)";
+      std::string ln = "  ";
+      if (nchunks < NT) ln += "if (tid < " + std::to_string(nchunks) + "u) ";
+      ln += "qbj_bulk_load(in_a_ + (" + c + " << (" + sCb + " + 4)), src + next_base + ((u64)line_tab[" + c + " << (" + sCb + " - 3)] << 3), " + sBytes + ", " + b + ");";
+      g.line(ln);
+    }
     g.line("}");
   };
   auto emit_rounds = [&]() {
@@ -511,6 +535,11 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
     if (tma) emit_load_smem(); else emit_load();
     emit_rounds();
     emit_store(mf_end);
+    g.dec(P.onruns);
+    for (uint32_t k = 0; k < P.onruns && k < (uint32_t)kMaxOutRuns; ++k) {
+      g.dec(P.orun_len[k]);
+      g.dec(P.orun_shift[k]);
+    }
   } else {
     std::ostringstream &o = g.o;
     o << "#define QBJ_T " << sT << "\n#define QBJ_R " << sR << "\n#define QBJ_NT " << sNT << "\n#define QBJ_MEM " << sMEM << "\n";
@@ -628,6 +657,7 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
         o << side2.str();
       }
       o << rounds_txt;
+      if (oop) emit_obase(o, "tile_id", "    ");
       emit_store(mf_end);
       o << "  }\n}\n";
       } else if (tma) {
@@ -678,6 +708,7 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
         o << side2.str();
       }
       o << rounds_txt;
+      if (oop) emit_obase(o, "tile_id", "    ");
       emit_store(mf_end);
       o << "  }\n}\n";
       } else if (group == 1) {
@@ -692,6 +723,7 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
       o << "  for (u32 it = 0; it <= iters; ++it) {\n"
            "    const u32 tile_id = first + it * stride;\n"
            "    if (it > 0 && tile_id - stride < ntiles32) {\n";
+      if (oop) emit_obase(o, "(tile_id - stride)", "    ");
       // NOTE: the flips pending at the store are those of the previous tile's last round
       // (mf_end was computed by emit_rounds above)
       emit_store(mf_end);
@@ -764,8 +796,8 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
     } else {
       o << "#define QBJ_LD2(p, i) { re[i] = amps[2 * (p)]; im[i] = amps[2 * (p) + 1]; re[(i) + 1] = amps[2 * (p) + 2]; im[(i) + 1] = amps[2 * (p) + 3]; }\n"
            "#define QBJ_LD1(p, i) { re[i] = amps[2 * (p)]; im[i] = amps[2 * (p) + 1]; }\n"
-           "#define QBJ_ST2(p, a0, a1, b0, b1) { amps[2 * (p)] = a0; amps[2 * (p) + 1] = a1; amps[2 * (p) + 2] = b0; amps[2 * (p) + 3] = b1; }\n"
-           "#define QBJ_ST1(p, xr, xi) { amps[2 * (p)] = xr; amps[2 * (p) + 1] = xi; }\n"
+           "#define QBJ_ST2(p, a0, a1, b0, b1) { dst[2 * (p)] = a0; dst[2 * (p) + 1] = a1; dst[2 * (p) + 2] = b0; dst[2 * (p) + 3] = b1; }\n"
+           "#define QBJ_ST1(p, xr, xi) { dst[2 * (p)] = xr; dst[2 * (p) + 1] = xi; }\n"
            "#define QBJ_STS(off, xr, xi) { SM[2 * ((off) >> 4)] = xr; SM[2 * ((off) >> 4) + 1] = xi; }\n"
            "#define QBJ_LDS(off, i) { re[i] = SM[2 * ((off) >> 4)]; im[i] = SM[2 * ((off) >> 4) + 1]; }\n"
            "#define QBJ_LDSI(off, i) QBJ_LDS(off, i)\n"
@@ -775,7 +807,7 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
            "static u16 sidx_tab["
         << ntab
         << " * QBJ_NT];\nstatic u64 goff_tab[2 * QBJ_NT];\nstatic u32 line_tab[(1 << (QBJ_T - 3))];\nstatic u16 lin_tab[QBJ_NT];\n"
-           "extern \"C\" int qb_jit_pass_host(double *amps, u64 ntiles, const QbjArgs *Ap, u64 args_bytes) {\n"
+           "extern \"C\" int qb_jit_pass_host(double *dst, const double *amps, u64 ntiles, const QbjArgs *Ap, u64 args_bytes) {\n"
            "  if (args_bytes != sizeof(QbjArgs)) return -1;\n"
            "  const QbjArgs &A = *Ap;\n"
            "  for (u32 tid = 0; tid < QBJ_NT; ++tid) {\n";
@@ -791,6 +823,7 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
       o << "  for (u32 tid = 0; tid < QBJ_NT; ++tid) {\n    QBJ_THREAD_REFS\n    f = 0;\n";
       if (tma) emit_load_smem(); else emit_load();
       o << rounds_txt;
+      if (oop) emit_obase(o, "tile_id", "    ");
       emit_store(mf_end);
       o << "  }\n  }\n  return 0;\n}\n";
     }
@@ -844,6 +877,10 @@ bool jit_quick(const PassPlan &pp, JitProgram &out, std::string *why) {
   mix(P.nruns);
   for (uint32_t k = 0; k < P.nruns && k < (uint32_t)kMaxRuns; ++k) { mix(P.run_shift[k]); mix(P.run_len[k]); }
   for (int i = 0; i < T; ++i) mix(P.tile_pos[i]);
+  mix(P.oop);
+  for (int i = 0; i < T; ++i) mix(P.out_pos[i]);
+  mix(P.onruns);
+  for (uint32_t k = 0; k < P.onruns && k < (uint32_t)kMaxOutRuns; ++k) { mix(P.orun_len[k]); mix(P.orun_shift[k]); }
   mix(P.jit_group); mix(P.jit_pf_last); mix(P.jit_minb); mix(P.jit_mem); mix(P.nsteps); mix(P.tma); mix(P.dbg_skip);
   out.coefs.clear();
   double left = 1.0;

@@ -543,7 +543,12 @@ __global__ void __launch_bounds__(1 << (T - R), MINB)
   // memory, not in four registers: the gate loop needs every register it can get)
   uint64_t *goff_tab = reinterpret_cast<uint64_t *>(sidx_tab + kMaxRounds * NT);
   goff_tab[tid] = thread_goff<T, R>(P, P.rounds[0], tid);
-  goff_tab[NT + tid] = thread_goff<T, R>(P, P.rounds[nrounds - 1], tid);
+  {  // the store layout: where the planner sends each tile bit (out_pos == tile_pos for an in-place pass)
+    uint64_t o = 0;
+#pragma unroll
+    for (int j = 0; j < T - R; ++j) o |= uint64_t((tid >> j) & 1u) << P.out_pos[P.rounds[nrounds - 1].tid_pos[j]];
+    goff_tab[NT + tid] = o;
+  }
   // ... and the 128-byte lines of a tile this thread prefetches (offsets in units of 8 elements)
   constexpr int LPT = 1 << (R - 3);  // lines per thread
   uint32_t *line_tab = reinterpret_cast<uint32_t *>(goff_tab + 2 * NT);
@@ -574,11 +579,23 @@ __global__ void __launch_bounds__(1 << (T - R), MINB)
       uint64_t fx = 0;
 #pragma unroll
       for (int j = 0; j < R; ++j) {
-        st[j] = 1ull << P.tile_pos[P.rounds[nrounds - 1].reg_pos[j]];
+        st[j] = 1ull << P.out_pos[P.rounds[nrounds - 1].reg_pos[j]];
         fx |= ((f >> j) & 1u) ? st[j] : 0ull;
       }
+      // out of place: tile number t is block t of the destination (its qubits now sit on the low bits)
+      uint64_t obase = base;
+      if (P.oop) {  // block address: the tile number's bits, group by group, at their new places
+        obase = 0;
+        uint64_t t = tile_id - stride;
+        const uint32_t nor = P.onruns;
+        for (uint32_t k = 0; k < nor; ++k) {
+          const uint32_t len = P.orun_len[k];
+          obase |= (t & ((1ull << len) - 1ull)) << P.orun_shift[k];
+          t >>= len;
+        }
+      }
       if (st[0] == 1ull) {  // register bit 0 is physical bit 0: 32-byte stores of register pairs
-        const uint64_t at = (base + goff_tab[NT + tid]) ^ (fx & ~1ull);
+        const uint64_t at = (obase + goff_tab[NT + tid]) ^ (fx & ~1ull);
         const bool sw = (f & 1u) != 0;  // pending flip on that bit: the pair goes out in reverse order
 #pragma unroll
         for (int i = 0; i < NR; i += 2) {
@@ -590,7 +607,7 @@ __global__ void __launch_bounds__(1 << (T - R), MINB)
                      sw ? im[i] : im[i + 1]);
         }
       } else {
-        const uint64_t at = (base + goff_tab[NT + tid]) ^ fx;
+        const uint64_t at = (obase + goff_tab[NT + tid]) ^ fx;
 #pragma unroll
         for (int i = 0; i < NR; ++i) {
           uint64_t off = 0;
@@ -1259,6 +1276,53 @@ __global__ void __launch_bounds__(256) k_tensor_sharded(double2 *__restrict__ ou
     const double2 x = a[i >> nb], y = b_shards[j >> Lb][j & lmask];
     out[i] = make_double2(x.x * y.x - x.y * y.y, x.x * y.y + x.y * y.x);
   }
+}
+
+// ---- qubit layouts other than the identity (global<->local swaps, out-of-place passes) -------------
+// Bit b of an index goes to bit pos[b]: applied to logical indices this is "where does amplitude x
+// live", applied to old physical indices it is a change of layout.
+struct BitMap {
+  uint8_t pos[64];
+  int nbits;
+};
+__device__ __forceinline__ uint64_t map_bits(const BitMap &m, uint64_t x) {
+  uint64_t o = 0;
+  for (int b = 0; b < m.nbits; ++b) o |= ((x >> b) & 1ull) << m.pos[b];
+  return o;
+}
+// out[i] = amps[where(first + i)]: amplitudes [first, first + count) in INDEX order (Show, :dump, parity)
+__global__ void __launch_bounds__(256) k_gather_logical(double2 *__restrict__ out, const double2 *__restrict__ amps,
+                                                        uint64_t first, uint64_t count, const __grid_constant__ BitMap m) {
+  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < count; i += uint64_t(gridDim.x) * blockDim.x)
+    out[i] = amps[map_bits(m, first + i)];
+}
+// dst[move(i)] = src[i] for every local index i: a whole change of layout in one sweep
+__global__ void __launch_bounds__(256) k_permute_bits(double2 *__restrict__ dst, const double2 *__restrict__ src, uint64_t n,
+                                                      const __grid_constant__ BitMap m) {
+  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x)
+    dst[map_bits(m, i)] = src[i];
+}
+
+cudaError_t launch_gather_logical(double2 *out, const double2 *amps, uint64_t first, uint64_t count, const int *pos, int nbits,
+                                  int sm_count, cudaStream_t stream) {
+  if (nbits > 64) return cudaErrorInvalidValue;
+  if (count == 0) return cudaSuccess;
+  BitMap m{};
+  m.nbits = nbits;
+  for (int b = 0; b < nbits; ++b) m.pos[b] = (uint8_t)pos[b];
+  k_gather_logical<<<grid_for(count, 256, sm_count, 8), 256, 0, stream>>>(out, amps, first, count, m);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_permute_bits(double2 *dst, const double2 *src, int local_bits, const int *newpos, int sm_count,
+                                cudaStream_t stream) {
+  if (local_bits > 64) return cudaErrorInvalidValue;
+  BitMap m{};
+  m.nbits = local_bits;
+  for (int b = 0; b < local_bits; ++b) m.pos[b] = (uint8_t)newpos[b];
+  const uint64_t n = 1ull << local_bits;
+  k_permute_bits<<<grid_for(n, 256, sm_count, 8), 256, 0, stream>>>(dst, src, n, m);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_axpy(double2 *y, const double2 *x, uint64_t n, const double z[2], int sm_count,

@@ -56,5 +56,12 @@ cudaError_t launch_swap_bits(double2 *amps, int local_bits, int b1, int b2, int 
 cudaError_t launch_tensor_sharded(double2 *out, const double2 *a, double2 *const *b_shards_dev, int a_local_bits, int bbits,
                                   int b_local_bits, int sm_count, cudaStream_t stream);
 cudaError_t launch_set_amp(double2 *amps, uint64_t idx, double re, double im, cudaStream_t stream);
+// out[i] = amps[index whose bit pos[b] is bit b of (first + i)], i < count: a range of amplitudes in index order from a
+// shard whose qubit layout is not the identity (pos = logical bit -> physical bit, nbits of them)
+cudaError_t launch_gather_logical(double2 *out, const double2 *amps, uint64_t first, uint64_t count, const int *pos, int nbits,
+                                  int sm_count, cudaStream_t stream);
+// dst[index with bit b moved to newpos[b]] = src[index]: a change of layout in one out-of-place sweep
+cudaError_t launch_permute_bits(double2 *dst, const double2 *src, int local_bits, const int *newpos, int sm_count,
+                                cudaStream_t stream);
 
 }  // namespace qb

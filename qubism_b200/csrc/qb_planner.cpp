@@ -68,6 +68,12 @@ bool set_opt(PlanOptions &o, const std::string &name, int64_t v) {
   } else if (name == "tma") {
     if (v < 0 || v > 3) return false;
     o.tma = (int)v;
+  } else if (name == "oop_low_bits") {
+    if (v < kLaneFixedBits || v > 10) return false;
+    o.oop_low_bits = (int)v;
+  } else if (name == "oop") {
+    if (v < 0 || v > 2) return false;  // 1: every qubit re-sorted by next use, 2: only the tile's
+    o.oop = (int)v;
   } else if (name == "jit") {
     if (v < 0 || v > 1000000) return false;
     o.jit = (int)v;
@@ -116,6 +122,8 @@ int64_t get_opt(const PlanOptions &o, const std::string &name) {
   if (name == "jit") return o.jit;
   if (name == "jit_pf_last") return o.jit_pf_last;
   if (name == "tma") return o.tma;
+  if (name == "oop") return o.oop;
+  if (name == "oop_low_bits") return o.oop_low_bits;
   if (name == "jit_minb") return o.jit_minb;
   if (name == "jit_mem") return o.jit_mem;
   if (name == "jit_group") return o.jit_group;
@@ -536,7 +544,7 @@ int tile_local_index(const std::vector<int> &tile_bits, int phys) {
 }  // namespace
 
 static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &done, int L, int rank,
-                          const PlanOptions &opt, PassPlan &out) {
+                          const PlanOptions &opt, PassPlan &out, const std::vector<int> &label) {
   const int T = opt.tile_bits, R = opt.reg_bits;
   const int C = std::min(std::max(opt.low_bits, kLaneFixedBits), T);
   const int max_rounds = std::max(1, std::min(opt.max_rounds, kMaxRounds));
@@ -817,6 +825,7 @@ static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &don
   }
 
   uint32_t gcount = 0;
+  std::vector<int> last_order;  // thread-bit order of the last round (tile-local bits, lanes first)
   for (int r = 0; r < nrounds; ++r) {
     DevRound &RD = P->rounds[r];
     const bool edge = (r == 0) || (r == nrounds - 1);
@@ -846,6 +855,7 @@ static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &don
     // slots this warp itself read in the last transpose of this tile.  If not, the kernel must
     // take a CTA barrier after the last transpose's loads even when the next transpose is local.
     RD.warp_local = (r > 0 ? warp_bits[r] == warp_bits[r - 1] : warp_bits[0] == warp_bits[nrounds - 1]) ? 1u : 0u;
+    if (r == nrounds - 1) last_order = order;
     for (int j = 0; j < T - R; ++j) RD.tid_pos[j] = (uint8_t)order[j];
     for (int j = 0; j < R; ++j) {
       RD.reg_pos[j] = (uint8_t)regs[j];
@@ -916,6 +926,103 @@ static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &don
     out.round_regmask.push_back(rounds[r].regmask);
   }
   out.gates.assign(G, G + gcount);
+  // ---- where the tile is stored.  In place: where it came from.  Out of place (every tile live):
+  // as one contiguous block, tile number = block number; WHICH tile qubit lands on which of the T
+  // low bits is free.  Bits 0..2 (one 128-byte line) go to three LANE bits of the last round, so
+  // that a quarter warp stores whole lines; among them, and for every other position, the qubits
+  // the remaining ops target soonest come first: the next pass always holds the lowest bits in
+  // its tile (its loads gather chunks of at least one line), and the longer the run of low bits it
+  // really needs, the longer those chunks are.
+  for (int i = 0; i < T; ++i) P->out_pos[i] = P->tile_pos[i];
+  P->oop = 0;
+  P->onruns = 0;
+  if (opt.oop && kmask == 0) {
+    std::vector<char> picked(ops.size(), 0);
+    for (auto &pr : chosen) picked[pr.first] = 1;
+    const long never = 1L << 40;
+    std::vector<long> next_phys(L, never);  // next use of the qubit on each local bit as a non-diagonal target
+    for (size_t i = 0; i < ops.size(); ++i) {
+      if (done[i] || picked[i]) continue;
+      const PhysOp &op = ops[i];
+      if (op.type == G_DIAG || op.target >= L) continue;
+      if (next_phys[op.target] == never) next_phys[op.target] = (long)i;
+    }
+    // soonest first; qubits nothing waits for in a layout-independent order (their labels)
+    auto before = [&](int pa, int pb) {
+      if (next_phys[pa] != next_phys[pb]) return next_phys[pa] < next_phys[pb];
+      return label[pa] < label[pb];
+    };
+    const int nlanes = std::min(5, T - R);
+    std::vector<int> lanes(last_order.begin(), last_order.begin() + nlanes);
+    std::sort(lanes.begin(), lanes.end(), [&](int a, int b) { return before(tile_bits[a], tile_bits[b]); });
+    std::vector<int> seq(lanes.begin(), lanes.begin() + std::min(3, nlanes));
+    std::vector<int> rest;
+    for (int i = 0; i < T; ++i)
+      if (std::find(seq.begin(), seq.end(), i) == seq.end()) rest.push_back(i);
+    std::sort(rest.begin(), rest.end(), [&](int a, int b) { return before(tile_bits[a], tile_bits[b]); });
+    seq.insert(seq.end(), rest.begin(), rest.end());
+    for (int p = 0; p < T; ++p) P->out_pos[seq[p]] = (uint8_t)p;
+    P->oop = 1;
+    out.newpos.assign(L, -1);
+    for (int i = 0; i < T; ++i) out.newpos[tile_bits[i]] = P->out_pos[i];
+    // the qubits outside the tile: sorted the same way above bit T (oop = 1), or left in their order
+    std::vector<int> outside;
+    for (int b = 0; b < L; ++b)
+      if (out.newpos[b] < 0) outside.push_back(b);
+    std::vector<int> sorted_out = outside;
+    if (opt.oop == 1) std::sort(sorted_out.begin(), sorted_out.end(), before);
+    for (size_t k = 0; k < sorted_out.size(); ++k) out.newpos[sorted_out[k]] = T + (int)k;
+    // ---- the ORDER in which the tile number enumerates the qubits outside the tile.  The CTAs of the
+    // persistent grid work on consecutive tile numbers at any one time, so the low bits of the tile
+    // number decide which addresses are in flight together -- on the load side through the bit each
+    // qubit comes from, on the store side through the bit it goes to.  Bits above the DRAM channel
+    // hash (address bit 27 = index bit 23 on B200, measured: scripts/copy_ubench2.cu) map to the same
+    // channel: if they vary among concurrent tiles, the whole grid queues on a few channels.  Fast
+    // tile-number bits therefore go to qubits that sit LOW on both sides.
+    std::vector<int> order = outside;
+    std::stable_sort(order.begin(), order.end(),
+                     [&](int a, int b) { return std::max(a, out.newpos[a]) < std::max(b, out.newpos[b]); });
+    for (int attempt = 0; attempt < 3; ++attempt) {
+      // attempt 0: that order; 1: ascending source bits (the in-place enumeration); 2: also the qubits
+      // outside the tile keep their order (always fits: one run on the store side)
+      if (attempt >= 1) order = outside;
+      if (attempt == 2)
+        for (size_t k = 0; k < outside.size(); ++k) out.newpos[outside[k]] = T + (int)k;
+      uint32_t nin = 0, nout = 0;
+      bool fits = true;
+      uint32_t in_shift[kMaxRuns], in_len[kMaxRuns];
+      for (size_t j = 0; j < order.size() && fits;) {  // load side: runs of consecutive source bits
+        size_t e = j + 1;
+        while (e < order.size() && order[e] == order[e - 1] + 1) ++e;
+        if (nin >= (uint32_t)kMaxRuns) fits = false;
+        else {
+          in_shift[nin] = (uint32_t)order[j];
+          in_len[nin] = (uint32_t)(e - j);
+          ++nin;
+        }
+        j = e;
+      }
+      for (size_t j = 0; j < order.size() && fits;) {  // store side: runs of consecutive destination bits
+        size_t e = j + 1;
+        while (e < order.size() && out.newpos[order[e]] == out.newpos[order[e - 1]] + 1) ++e;
+        if (nout >= (uint32_t)kMaxOutRuns) fits = false;
+        else {
+          P->orun_len[nout] = (uint8_t)(e - j);
+          P->orun_shift[nout] = (uint8_t)out.newpos[order[j]];
+          ++nout;
+        }
+        j = e;
+      }
+      if (!fits) continue;
+      P->onruns = nout;
+      P->nruns = nin;
+      for (uint32_t k = 0; k < nin; ++k) {
+        P->run_shift[k] = in_shift[k];
+        P->run_len[k] = in_len[k];
+      }
+      break;
+    }
+  }
   {
     bool lite = opt.lite != 0;
     for (uint32_t gi = 0; gi < gcount && lite; ++gi) {
@@ -1018,17 +1125,58 @@ static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &don
   return true;
 }
 
-PlanResult plan_passes(const std::vector<PhysOp> &ops, int local_bits, int rank, const PlanOptions &opt_in,
-                       const double *gscale) {
+PlanResult plan_passes(const std::vector<PhysOp> &ops_in, int local_bits, int rank, const PlanOptions &opt_in,
+                       const double *gscale, const std::vector<int> *labels) {
   PlanResult res;
+  std::vector<int> label(local_bits);
+  for (int b = 0; b < local_bits; ++b) label[b] = (labels && b < (int)labels->size()) ? (*labels)[b] : b;
   PlanOptions opt = opt_in;  // known_mask / known_val evolve pass by pass
   if (gscale && !(std::isfinite(gscale[0]) && std::isfinite(gscale[1]))) opt.known_mask = 0;
+  std::vector<PhysOp> ops = ops_in;  // (an out-of-place pass moves qubits: the ops after it are relabelled)
   std::vector<char> done(ops.size(), 0);
   size_t ndone = 0;
+  auto relabel_mask = [&](uint64_t m, const std::vector<int> &np) {
+    uint64_t o = 0;
+    for (uint64_t b = m; b; b &= b - 1) {
+      const int bit = __builtin_ctzll(b);
+      o |= 1ull << (bit < local_bits ? np[bit] : bit);
+    }
+    return o;
+  };
   while (ndone < ops.size()) {
     PassPlan p;
-    if (!plan_one_pass(ops, done, local_bits, rank, opt, p)) break;
+    if (!plan_one_pass(ops, done, local_bits, rank, opt, p, label)) break;
     ndone += p.op_index.size();
+    if (!p.newpos.empty()) {
+      // (the support bookkeeping below still reads this pass's ops with their OLD positions)
+      for (int oi : p.op_index) {
+        const PhysOp &op = ops[oi];
+        if (op.type != G_DIAG) opt.known_mask &= ~(1ull << op.target);
+        for (int k = 0; k < 8; ++k)
+          if (!std::isfinite(op.m[k])) opt.known_mask = 0;
+      }
+      opt.known_val &= opt.known_mask;
+      const std::vector<int> &np = p.newpos;
+      for (size_t i = 0; i < ops.size(); ++i) {
+        if (done[i]) continue;
+        if (ops[i].target < local_bits) ops[i].target = np[ops[i].target];
+        ops[i].ctrl = relabel_mask(ops[i].ctrl, np);
+      }
+      opt.known_val = relabel_mask(opt.known_val, np);
+      opt.known_mask = relabel_mask(opt.known_mask, np);
+      if (res.final_pos.empty()) {
+        res.final_pos.resize(local_bits);
+        for (int b = 0; b < local_bits; ++b) res.final_pos[b] = b;
+      }
+      for (int b = 0; b < local_bits; ++b) res.final_pos[b] = np[res.final_pos[b]];
+      {
+        std::vector<int> nl(local_bits);
+        for (int b = 0; b < local_bits; ++b) nl[np[b]] = label[b];
+        label.swap(nl);
+      }
+      res.passes.push_back(std::move(p));
+      continue;
+    }
     // a non-diagonal gate forgets its target; a non-finite matrix forgets everything
     for (int oi : p.op_index) {
       const PhysOp &op = ops[oi];
@@ -1062,6 +1210,11 @@ std::string describe_plan(const PlanResult &r) {
     for (int b = 0; b < p.tile_bits; ++b) os << (b ? "," : "") << (int)P->tile_pos[b];
     os << "] rounds=" << p.nrounds << " gates=" << p.ngates << " gscale=" << P->has_gscale << " lite=" << P->lite
        << " steps=" << P->nsteps;
+    if (P->oop) {
+      os << " out=[";
+      for (int b = 0; b < p.tile_bits; ++b) os << (b ? "," : "") << (int)P->out_pos[b];
+      os << "]";
+    }
     {
       const DevGate *G = p.gates.data();
       int kinds[8] = {0};

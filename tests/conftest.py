@@ -25,7 +25,7 @@ def ctx():
 @pytest.fixture()
 def default_opts(ctx):
     """Restore planner options after a test that changes them."""
-    names = ["tile_bits", "reg_bits", "low_bits", "max_rounds", "peephole", "fuse", "max_pass_gates", "rot", "lite", "lane_fixed", "jit", "tma", "linear"]
+    names = ["tile_bits", "reg_bits", "low_bits", "max_rounds", "peephole", "fuse", "max_pass_gates", "rot", "lite", "lane_fixed", "jit", "tma", "linear", "oop", "oop_low_bits", "l2_prefetch"]
     saved = {k: ctx.get_option(k) for k in names}
     yield ctx
     for k, v in saved.items():

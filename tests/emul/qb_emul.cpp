@@ -193,13 +193,17 @@ void run_pass(const PassPlan &pp, int L, std::vector<double> &amps, EmuStats &st
       st.max_bank_conflict = std::max<int64_t>(st.max_bank_conflict, conflict_degree(P.rounds[r - 1], T, R, i));
       st.max_bank_conflict = std::max<int64_t>(st.max_bank_conflict, conflict_degree(P.rounds[r], T, R, i));
     }
-  auto goff = [&](const DevRound &rd, uint32_t tid, int i) {
+  auto goff = [&](const DevRound &rd, uint32_t tid, int i, const uint8_t *pos) {
     uint64_t o = 0;
-    for (int j = 0; j < T - R; ++j) o |= uint64_t((tid >> j) & 1u) << P.tile_pos[rd.tid_pos[j]];
+    for (int j = 0; j < T - R; ++j) o |= uint64_t((tid >> j) & 1u) << pos[rd.tid_pos[j]];
     for (int j = 0; j < R; ++j)
-      if ((i >> j) & 1) o += 1ull << P.tile_pos[rd.reg_pos[j]];
+      if ((i >> j) & 1) o += 1ull << pos[rd.reg_pos[j]];
     return o;
   };
+  // out of place: tile number t becomes block t of a second array, its bits permuted (out_pos)
+  std::vector<double> other;
+  if (P.oop) other.assign(amps.size(), NAN);
+  std::vector<double> &dst = P.oop ? other : amps;
   for (uint64_t tile_id = 0; tile_id < pp.ntiles; ++tile_id) {
     uint64_t base = 0, t = tile_id;
     for (uint32_t k = 0; k < P.nruns; ++k) {
@@ -207,10 +211,19 @@ void run_pass(const PassPlan &pp, int L, std::vector<double> &amps, EmuStats &st
       t >>= P.run_len[k];
     }
     base |= P.base_fixed;
+    uint64_t obase = base;
+    if (P.oop) {
+      obase = 0;
+      uint64_t tt = tile_id;
+      for (uint32_t k = 0; k < P.onruns; ++k) {
+        obase |= (tt & ((1ull << P.orun_len[k]) - 1)) << P.orun_shift[k];
+        tt >>= P.orun_len[k];
+      }
+    }
     const uint64_t basefull = base | P.rank_bits;
     for (int tid = 0; tid < NT; ++tid)
       for (int i = 0; i < NR; ++i) {
-        const uint64_t a = base + goff(P.rounds[0], tid, i);
+        const uint64_t a = base + goff(P.rounds[0], tid, i, P.tile_pos);
         re[tid][i] = amps[2 * a];
         im[tid][i] = amps[2 * a + 1];
       }
@@ -266,11 +279,12 @@ void run_pass(const PassPlan &pp, int L, std::vector<double> &amps, EmuStats &st
           xi = P.gscale[0] * xi + P.gscale[1] * xr;
           xr = yr;
         }
-        const uint64_t a = base + goff(P.rounds[P.nrounds - 1], tid, i);
-        amps[2 * a] = xr;
-        amps[2 * a + 1] = xi;
+        const uint64_t a = obase + goff(P.rounds[P.nrounds - 1], tid, i, P.out_pos);
+        dst[2 * a] = xr;
+        dst[2 * a + 1] = xi;
       }
   }
+  if (P.oop) amps.swap(other);
   st.passes++;
   st.rounds += P.nrounds;
   for (uint32_t r = 1; r < P.nrounds; ++r) {
@@ -278,6 +292,21 @@ void run_pass(const PassPlan &pp, int L, std::vector<double> &amps, EmuStats &st
     st.local_transposes += P.rounds[r].warp_local ? 1 : 0;
   }
   (void)L;
+}
+
+// Out-of-place passes leave the amplitudes in a new qubit layout (PlanResult::final_pos): put them
+// back in index order, as the library's layout-aware read does.
+void undo_layout(const PlanResult &plan, int nlocal, std::vector<double> &a) {
+  if (plan.final_pos.empty()) return;
+  std::vector<double> b(a.size());
+  for (uint64_t x = 0; x < (1ull << nlocal); ++x) {
+    uint64_t phys = 0;
+    for (int bit = 0; bit < nlocal; ++bit)
+      if ((x >> bit) & 1) phys |= 1ull << plan.final_pos[bit];
+    b[2 * x] = a[2 * phys];
+    b[2 * x + 1] = a[2 * phys + 1];
+  }
+  a.swap(b);
 }
 
 }  // namespace
@@ -318,6 +347,7 @@ int qbe_run(int nlocal, const qb_op *ops, int64_t nops, const char *options, dou
   opt.tile_bits = T;
   opt.reg_bits = R;
   if (!opt.fuse) opt.max_pass_gates = 1;
+  if (opt.oop && opt.low_bits < opt.oop_low_bits) opt.low_bits = std::min(opt.oop_low_bits, T);
   std::vector<PhysOp> pops;
   for (const auto &h : q.ops) {
     if (h.dead) continue;
@@ -333,6 +363,7 @@ int qbe_run(int nlocal, const qb_op *ops, int64_t nops, const char *options, dou
   std::vector<double> a(amps, amps + (size_t(2) << nlocal));
   EmuStats st;
   for (const auto &p : plan.passes) run_pass(p, nlocal, a, st);
+  undo_layout(plan, nlocal, a);
   if (plan.passes.empty() && !(q.gscale[0] == 1.0 && q.gscale[1] == 0.0)) {
     for (size_t i = 0; i < (size_t(1) << nlocal); ++i) {
       const double xr = a[2 * i], xi = a[2 * i + 1];
@@ -390,6 +421,7 @@ int qbe_run_jit(int nlocal, const qb_op *ops, int64_t nops, const char *options,
   if (T == 0) return -2;
   opt.tile_bits = T;
   opt.reg_bits = R;
+  if (opt.oop && opt.low_bits < opt.oop_low_bits) opt.low_bits = std::min(opt.oop_low_bits, T);
   std::vector<PhysOp> pops;
   for (const auto &h : q.ops) {
     if (h.dead) continue;
@@ -468,12 +500,19 @@ int qbe_run_jit(int nlocal, const qb_op *ops, int64_t nops, const char *options,
     }
     const double one[2] = {1.0, 0.0};
     const std::vector<uint8_t> args = jit_pack_args(kp, P.has_gscale ? P.gscale : one, P.rank_bits, P.base_fixed);
-    typedef int (*host_fn)(double *, uint64_t, const void *, uint64_t);
-    if (reinterpret_cast<host_fn>(fn)(a.data(), p.ntiles, args.data(), (uint64_t)args.size()) != 0) return -13;
+    typedef int (*host_fn)(double *, const double *, uint64_t, const void *, uint64_t);
+    if (P.oop) {
+      std::vector<double> other(a.size(), NAN);
+      if (reinterpret_cast<host_fn>(fn)(other.data(), a.data(), p.ntiles, args.data(), (uint64_t)args.size()) != 0) return -13;
+      a.swap(other);
+    } else if (reinterpret_cast<host_fn>(fn)(a.data(), a.data(), p.ntiles, args.data(), (uint64_t)args.size()) != 0) {
+      return -13;
+    }
     pending *= kp.left_out;
     ++njit;
     st.passes++;
   }
+  undo_layout(plan, nlocal, a);
   const bool qg = plan.passes.empty() && !(q.gscale[0] == 1.0 && q.gscale[1] == 0.0);
   for (size_t i = 0; i < (size_t(1) << nlocal); ++i) {
     double xr = a[2 * i] * pending, xi = a[2 * i + 1] * pending;
@@ -529,6 +568,7 @@ int qbe_jit_dump(int nlocal, const qb_op *ops, int64_t nops, const char *options
   if (T == 0) return -2;
   opt.tile_bits = T;
   opt.reg_bits = R;
+  if (opt.oop && opt.low_bits < opt.oop_low_bits) opt.low_bits = std::min(opt.oop_low_bits, T);
   std::vector<PhysOp> pops;
   for (const auto &h : q.ops) {
     if (h.dead) continue;
@@ -617,6 +657,8 @@ int qbe_layout_trace(int n, int nranks, const qb_op *ops, int64_t nops, const ch
   if (T == 0) return -2;
   opt.tile_bits = T;
   opt.reg_bits = R;
+  if (nranks > 1) opt.oop = 0;  // (sharded states run in place, as in qb_api.cpp)
+  if (opt.oop && opt.low_bits < opt.oop_low_bits) opt.low_bits = std::min(opt.oop_low_bits, T);
   std::vector<int> perm(n);
   for (int i = 0; i < n; ++i) perm[i] = i;
   std::vector<std::string> seen_keys;
@@ -647,7 +689,10 @@ int qbe_layout_trace(int n, int nranks, const qb_op *ops, int64_t nops, const ch
         pops[i].ctrl = cm;
         std::memcpy(pops[i].m, h.m, sizeof(h.m));
       }
-      PlanResult plan = plan_passes(pops, L, 0, opt, nullptr);
+      std::vector<int> labels(L, 0);  // the logical bit on each local physical bit
+      for (int qq = 0; qq < n; ++qq)
+        if (perm[qq] < L) labels[perm[qq]] = qq;
+      PlanResult plan = plan_passes(pops, L, 0, opt, nullptr, &labels);
       for (const auto &p : plan.passes) {
         ++npass;
         JitProgram kp;
@@ -671,6 +716,9 @@ int qbe_layout_trace(int n, int nranks, const qb_op *ops, int64_t nops, const ch
           step_keys.push_back(kp.key);
         }
       }
+      if (!plan.final_pos.empty())  // out-of-place passes moved the local qubits
+        for (int &x : perm)
+          if (x < L) x = plan.final_pos[x];
       if (plan.consumed == seg.size()) break;
       std::vector<const HostOp *> rest;
       for (size_t i = 0; i < seg.size(); ++i)
@@ -734,6 +782,7 @@ int qbe_run_rank(int n, int nranks, int rank, const qb_op *ops, int64_t nops, co
     q.push_1q(n - 1 - o.target, cm, o.kind == 1 ? X : reinterpret_cast<const double *>(o.m));
   }
   int T, R;
+  opt.oop = 0;  // (sharded states run in place, as in qb_api.cpp)
   effective_tile(opt, L, T, R);
   if (T == 0) return -2;
   opt.tile_bits = T;

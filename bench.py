@@ -305,9 +305,9 @@ def run_ours(args):
     # pass structures that came back during the warm-up are being compiled into specialised
     # kernels on background threads: let that finish, and give the next sighting (which loads
     # the modules) its own untimed steps -- the timed region measures the steady state
-    # (sharded: the layout of the state cycles with a period of a few steps, a structure has to come
-    #  round twice before it is compiled)
-    for _ in range(2 if world == 1 else 6):
+    # (the qubit layout of the state cycles with a period of a few steps -- 2 on one GPU, where every
+    #  pass re-sorts it; 2-3 sharded -- and a structure has to come round twice before it is compiled)
+    for _ in range(6):
         ctx.jit_wait()
         step()
     barrier()
@@ -489,12 +489,12 @@ def run_ours(args):
         "config": {"workload": workload_name(n, args.workload), "qubits": n, "local_qubits": L, "primitive_ops_per_step": nops,
                    "state_bytes_per_gpu": 16 << L, "l2_policy": "inputs larger than L2 (state >= 16 GiB >> 126 MB)",
                    "parallelism": f"shard{world}" if world > 1 else "single",
-                   "planner": {k: ctx.get_option(k) for k in ("tile_bits", "reg_bits", "low_bits", "lane_fixed", "max_rounds", "peephole", "rot", "lite", "jit", "tma")},
+                   "planner": {k: ctx.get_option(k) for k in ("tile_bits", "reg_bits", "low_bits", "lane_fixed", "max_rounds", "peephole", "rot", "lite", "jit", "tma", "oop", "oop_low_bits", "l2_prefetch")},
                    "specialised_kernels": {"compiled": st["jit_compiled"], "compile_ms_total": st["jit_compile_ms"],
                                            "launches_in_timed_region": st["jit_launches"],
                                            "toolchain": lib.qb_jit_toolchain().decode(),
                                            "note": "pass structures seen twice are compiled with NVRTC on background threads during "
-                                                   "the warm-up steps (W + 2 untimed steps); the timed steps hit the cache"},
+                                                   "the warm-up steps (W + 6 untimed steps: the qubit layout cycles with period 2); the timed steps hit the cache"},
                    "ops_executed_per_step": ops_exec, "ops_folded_per_step": ops_fold,
                    "passes_per_step": passes, "rounds_per_step": st["rounds"] / args.steps,
                    "exchanges_per_step": st["exchanges"] / args.steps,

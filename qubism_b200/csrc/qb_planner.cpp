@@ -544,13 +544,20 @@ int tile_local_index(const std::vector<int> &tile_bits, int phys) {
 }  // namespace
 
 static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &done, int L, int rank,
-                          const PlanOptions &opt, PassPlan &out, const std::vector<int> &label) {
+                          const PlanOptions &opt, PassPlan &out, const std::vector<int> &label, bool layout_unknown) {
   const int T = opt.tile_bits, R = opt.reg_bits;
   const int C = std::min(std::max(opt.low_bits, kLaneFixedBits), T);
   const int max_rounds = std::max(1, std::min(opt.max_rounds, kMaxRounds));
   const int max_gates = std::max(1, std::min(opt.max_pass_gates, kMaxPassGates));
   uint64_t tile_mask = (1ull << C) - 1;
   int ntile = C;
+  // Out-of-place passes re-sort the qubit layout after every pass, and that layout must depend on the
+  // op stream only (an iterated circuit then finds its pass structures again).  Every decision below
+  // is therefore taken by qubit LABEL where it used to be taken by position, and the first pass of a
+  // plan -- which meets whatever layout history left -- picks its gates as if the low bits were empty:
+  // the qubits sitting there are passengers (T - C targets at most, whoever they are).
+  const bool by_label = opt.oop != 0;
+  const bool passengers = by_label && layout_unknown;
   uint64_t hot_mask = 0;  // bits that carry a non-diagonal gate in this pass
   const int max_hot = (opt.hot_bits > 0 && opt.hot_bits < T) ? opt.hot_bits : 0;
   uint64_t blocked = 0;
@@ -587,6 +594,10 @@ static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &don
       }
       const bool in_tile = (tile_mask & tb) != 0;
       if (!in_tile && ntile >= T) {
+        blocked |= qmask;
+        continue;
+      }
+      if (passengers && !(hot_mask & tb) && popc(hot_mask) >= T - C) {
         blocked |= qmask;
         continue;
       }
@@ -643,17 +654,48 @@ static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &don
   if (rounds.back().regmask & lowfixed) rounds.emplace_back();
   if (rounds[0].regmask & lowfixed) return false;  // cannot happen (edge rule), defensive
 
-  // fill the tile with the lowest unused local bits -- bits whose value is KNOWN for every
-  // non-zero amplitude last: outside the tile each of them halves the number of live tiles
-  for (int pass2 = 0; pass2 < 2; ++pass2)
-    for (int b = 0; b < L && ntile < T; ++b)
-      if (!(tile_mask & (1ull << b)) && (pass2 == 1 || !(opt.known_mask & (1ull << b)))) {
-        tile_mask |= 1ull << b;
-        ++ntile;
-      }
+  // what the remaining ops want next: first use of the qubit on each local bit as a non-diagonal target
+  const long never = 1L << 40;
+  std::vector<long> next_phys(L, never);
+  {
+    std::vector<char> picked(ops.size(), 0);
+    for (auto &pr : chosen) picked[pr.first] = 1;
+    for (size_t i = 0; i < ops.size(); ++i) {
+      if (done[i] || picked[i]) continue;
+      const PhysOp &op = ops[i];
+      if (op.type == G_DIAG || op.target >= L) continue;
+      if (next_phys[op.target] == never) next_phys[op.target] = (long)i;
+    }
+  }
+  // soonest first; qubits nothing waits for in a layout-independent order (their labels)
+  auto before = [&](int pa, int pb) {
+    if (next_phys[pa] != next_phys[pb]) return next_phys[pa] < next_phys[pb];
+    return label[pa] < label[pb];
+  };
+  // fill the tile -- bits whose value is KNOWN for every non-zero amplitude last: outside the tile
+  // each of them halves the number of live tiles.  In place: the lowest unused local bits.  Out of
+  // place: the qubits needed soonest, wherever they sit (they arrive in the block one pass early).
+  {
+    std::vector<int> cand;
+    for (int b = 0; b < L; ++b)
+      if (!(tile_mask & (1ull << b))) cand.push_back(b);
+    if (by_label) std::sort(cand.begin(), cand.end(), before);
+    for (int pass2 = 0; pass2 < 2; ++pass2)
+      for (int b : cand)
+        if (ntile < T && !(tile_mask & (1ull << b)) && (pass2 == 1 || !(opt.known_mask & (1ull << b)))) {
+          tile_mask |= 1ull << b;
+          ++ntile;
+        }
+  }
+  // tile-local bit order: ascending position -- or, by label, the low C bits (the contiguous chunk)
+  // followed by the other members in label order: everything the rounds below decide then depends
+  // on WHO is in the tile, not on where history put them
   std::vector<int> tile_bits;
   for (int b = 0; b < L; ++b)
     if (tile_mask & (1ull << b)) tile_bits.push_back(b);
+  if (by_label)
+    std::sort(tile_bits.begin() + std::min<size_t>(C, tile_bits.size()), tile_bits.end(),
+              [&](int a, int b) { return label[a] < label[b]; });
 
   const int nrounds = (int)rounds.size();
   // ---- layout of every round: which tile bits sit in registers / lanes / warp-id bits.
@@ -937,29 +979,21 @@ static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &don
   P->oop = 0;
   P->onruns = 0;
   if (opt.oop && kmask == 0) {
-    std::vector<char> picked(ops.size(), 0);
-    for (auto &pr : chosen) picked[pr.first] = 1;
-    const long never = 1L << 40;
-    std::vector<long> next_phys(L, never);  // next use of the qubit on each local bit as a non-diagonal target
-    for (size_t i = 0; i < ops.size(); ++i) {
-      if (done[i] || picked[i]) continue;
-      const PhysOp &op = ops[i];
-      if (op.type == G_DIAG || op.target >= L) continue;
-      if (next_phys[op.target] == never) next_phys[op.target] = (long)i;
-    }
-    // soonest first; qubits nothing waits for in a layout-independent order (their labels)
-    auto before = [&](int pa, int pb) {
-      if (next_phys[pa] != next_phys[pb]) return next_phys[pa] < next_phys[pb];
-      return label[pa] < label[pb];
+    // a passenger of the first pass that no gate of it touched goes behind the pass's own qubits
+    auto plain_passenger = [&](int pb) { return passengers && pb < C && !(hot_mask & (1ull << pb)); };
+    auto before_out = [&](int pa, int pb) {
+      const bool xa = plain_passenger(pa), xb = plain_passenger(pb);
+      if (xa != xb) return xb;
+      return before(pa, pb);
     };
     const int nlanes = std::min(5, T - R);
     std::vector<int> lanes(last_order.begin(), last_order.begin() + nlanes);
-    std::sort(lanes.begin(), lanes.end(), [&](int a, int b) { return before(tile_bits[a], tile_bits[b]); });
+    std::sort(lanes.begin(), lanes.end(), [&](int a, int b) { return before_out(tile_bits[a], tile_bits[b]); });
     std::vector<int> seq(lanes.begin(), lanes.begin() + std::min(3, nlanes));
     std::vector<int> rest;
     for (int i = 0; i < T; ++i)
       if (std::find(seq.begin(), seq.end(), i) == seq.end()) rest.push_back(i);
-    std::sort(rest.begin(), rest.end(), [&](int a, int b) { return before(tile_bits[a], tile_bits[b]); });
+    std::sort(rest.begin(), rest.end(), [&](int a, int b) { return before_out(tile_bits[a], tile_bits[b]); });
     seq.insert(seq.end(), rest.begin(), rest.end());
     for (int p = 0; p < T; ++p) P->out_pos[seq[p]] = (uint8_t)p;
     P->oop = 1;
@@ -1145,7 +1179,7 @@ PlanResult plan_passes(const std::vector<PhysOp> &ops_in, int local_bits, int ra
   };
   while (ndone < ops.size()) {
     PassPlan p;
-    if (!plan_one_pass(ops, done, local_bits, rank, opt, p, label)) break;
+    if (!plan_one_pass(ops, done, local_bits, rank, opt, p, label, res.final_pos.empty())) break;
     ndone += p.op_index.size();
     if (!p.newpos.empty()) {
       // (the support bookkeeping below still reads this pass's ops with their OLD positions)

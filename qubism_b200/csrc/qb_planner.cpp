@@ -740,7 +740,10 @@ static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &don
         if (have_qw) busy |= (1u << qw[0]) | (1u << qw[1]) | (1u << qw[2]);
         // candidates: free bits >= 3, furthest next use as a register first (Belady)
         std::vector<std::pair<int, int>> cand;
-        for (int i = kLaneFixedBits; i < T; ++i) {
+        // (out of place: the whole contiguous chunk -- tile-local bits < C -- stays on lanes, so that a
+        //  warp's load covers 2^C contiguous amplitudes: measured 6.3 -> 6.0 ms per memory-only pass)
+        const int first_warp_cand = (by_label && T - C >= nw + R + 0) ? C : kLaneFixedBits;
+        for (int i = first_warp_cand; i < T; ++i) {
           if (busy & (1u << i)) continue;
           int next = 1000;
           for (int r2 = r + 1; r2 < nrounds; ++r2)
@@ -989,6 +992,9 @@ static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &don
     const int nlanes = std::min(5, T - R);
     std::vector<int> lanes(last_order.begin(), last_order.begin() + nlanes);
     std::sort(lanes.begin(), lanes.end(), [&](int a, int b) { return before_out(tile_bits[a], tile_bits[b]); });
+    // (only three: all five lanes on the five lowest bits would make a warp's store 512 contiguous
+    //  bytes, but the qubits needed next are the last round's REGISTER bits more often than not, and
+    //  keeping them off the low bits costs 5 passes in 31)
     std::vector<int> seq(lanes.begin(), lanes.begin() + std::min(3, nlanes));
     std::vector<int> rest;
     for (int i = 0; i < T; ++i)

@@ -212,6 +212,8 @@ struct PlanOptions {
                           // the run right above the block: 512-byte chunks inside a few 2 MB pages, and the
                           // layout depends on the op stream only, so the structures of an iterated circuit come
                           // back); 2: only the tile's qubits move.  Single-GPU states with room for a second shard.
+  int chunk_lanes = 0;    // out of place: the chunk bits are never warp-id bits (a warp's load covers the whole
+                          // chunk), at the price of fewer warp-local transposes
   int oop_low_bits = 5;   // low_bits while passes run out of place: the low bits hold the qubits needed next, so
                           // a longer contiguous chunk costs no extra passes there (measured 30-31 passes either way)
 };

@@ -68,6 +68,8 @@ bool set_opt(PlanOptions &o, const std::string &name, int64_t v) {
   } else if (name == "tma") {
     if (v < 0 || v > 3) return false;
     o.tma = (int)v;
+  } else if (name == "chunk_lanes") {
+    o.chunk_lanes = v ? 1 : 0;
   } else if (name == "oop_low_bits") {
     if (v < kLaneFixedBits || v > 10) return false;
     o.oop_low_bits = (int)v;
@@ -124,6 +126,7 @@ int64_t get_opt(const PlanOptions &o, const std::string &name) {
   if (name == "tma") return o.tma;
   if (name == "oop") return o.oop;
   if (name == "oop_low_bits") return o.oop_low_bits;
+  if (name == "chunk_lanes") return o.chunk_lanes;
   if (name == "jit_minb") return o.jit_minb;
   if (name == "jit_mem") return o.jit_mem;
   if (name == "jit_group") return o.jit_group;
@@ -742,7 +745,7 @@ static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &don
         std::vector<std::pair<int, int>> cand;
         // (out of place: the whole contiguous chunk -- tile-local bits < C -- stays on lanes, so that a
         //  warp's load covers 2^C contiguous amplitudes: measured 6.3 -> 6.0 ms per memory-only pass)
-        const int first_warp_cand = (by_label && T - C >= nw + R + 0) ? C : kLaneFixedBits;
+        const int first_warp_cand = (by_label && opt.chunk_lanes && T - C >= nw + R) ? C : kLaneFixedBits;
         for (int i = first_warp_cand; i < T; ++i) {
           if (busy & (1u << i)) continue;
           int next = 1000;

@@ -61,7 +61,10 @@ def test_product_does_not_import_oracle():
 OPTION_SETS = ["", "reg_bits=5", "reg_bits=3", "tile_bits=11,reg_bits=4", "tile_bits=10,reg_bits=3", "peephole=0",
                "fuse=0", "max_rounds=3", "low_bits=3", "low_bits=7", "max_pass_gates=5",
                "tile_bits=13,reg_bits=5,low_bits=7", "tile_bits=13,reg_bits=4", "lane_fixed=1", "lane_fixed=2,reg_bits=5",
-               "lane_fixed=1,tile_bits=11,reg_bits=3", "lane_fixed=0", "lane_fixed=0,reg_bits=5"]
+               "lane_fixed=1,tile_bits=11,reg_bits=3", "lane_fixed=0", "lane_fixed=0,reg_bits=5",
+               # out-of-place passes are the default (oop = 1); the in-place schedule and the other flavours:
+               "oop=0", "oop=0,reg_bits=5", "oop=0,lane_fixed=1", "oop=2", "oop=1,chunk_lanes=1", "oop=1,oop_low_bits=3",
+               "oop=1,oop_low_bits=7"]
 
 
 def extras(n):
@@ -187,6 +190,36 @@ def test_emulated_random_circuits_random_knobs(emul, seed):
     ref = S.run_ops(n, ops, v)
     out, st = emul(n, ops, v, opts)
     assert np.abs(out - ref).max() < 1e-12, opts
+
+
+def test_out_of_place_layouts_depend_on_the_op_stream_only():
+    """Every out-of-place pass re-sorts the qubit layout by next use, with ties broken by qubit label,
+    and the first pass of a plan treats the qubits on the low bits as passengers: the layout a flush
+    leaves behind is a function of its ops, so an iterated circuit (the benchmark's steps, a
+    variational loop) plans the same pass structures again after a short transient -- which is what
+    lets the structure-specialised kernels (qb_jit.cpp) find their cubins."""
+    import ctypes as C
+    import os
+    import subprocess
+    from qubism_b200.circuits import qft_ops
+    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emul")
+    subprocess.check_call(["make", "-C", d, "libqb_emul.so"], stdout=subprocess.DEVNULL)
+    E = C.CDLL(os.path.join(d, "libqb_emul.so"))
+    E.qbe_layout_trace.argtypes = [C.c_int, C.c_int, C.POINTER(capi.QbOp), C.c_int64, C.c_char_p, C.c_int, C.c_int,
+                                   C.POINTER(C.c_int), C.POINTER(C.c_int64)]
+    for n, ops, opts in ((30, qft_ops(30) + random_layers(30, 20, seed=1000), b""),
+                         (30, qft_ops(30) + random_layers(30, 20, seed=1000), b"oop_low_bits=6"),
+                         (30, qft_ops(30) + random_layers(30, 20, seed=1000), b"oop_low_bits=3"),
+                         (26, random_layers(26, 12, seed=5), b""), (22, qft_ops(22), b"tile_bits=11")):
+        nsteps = 10
+        packed = capi.pack_ops(ops)
+        perm = (C.c_int * (nsteps * n))()
+        cnt = (C.c_int64 * (nsteps * 3))()
+        assert E.qbe_layout_trace(n, 1, packed, len(packed), opts, nsteps, 0, perm, cnt) == 0
+        layouts = [tuple(perm[s * n:(s + 1) * n]) for s in range(nsteps)]
+        assert any(all(layouts[s] == layouts[s - p] for s in range(6, nsteps)) for p in (1, 2, 3, 4)), "the layout does not cycle"
+        assert all(cnt[3 * s + 2] == 0 for s in range(6, nsteps)), "new pass structures keep appearing"
+        assert max(cnt[3 * s] for s in range(nsteps)) <= 1.15 * min(cnt[3 * s] for s in range(nsteps)) + 1
 
 
 def capi_variant_ok(opts: str, n: int) -> bool:

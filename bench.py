@@ -307,7 +307,7 @@ def run_ours(args):
     # the modules) its own untimed steps -- the timed region measures the steady state
     # (the qubit layout of the state cycles with a period of a few steps -- 2 on one GPU, where every
     #  pass re-sorts it; 2-3 sharded -- and a structure has to come round twice before it is compiled)
-    for _ in range(6):
+    for _ in range(6 if world == 1 else 20):
         ctx.jit_wait()
         step()
     barrier()

@@ -109,6 +109,9 @@ struct Buffer {
   double2 *alt = nullptr;        // second shard of the same size (allocated on first use): out-of-place passes
                                  // read `amps`, write `alt`, and the two trade places (option "oop")
   std::vector<double2 *> peers;  // distributed: every rank's shard (IPC / same process); empty: NCCL swaps
+  std::vector<double2 *> peers_alt;  // ... and every rank's SECOND shard (the two tables trade places with the shards)
+  bool alt_zero = false;         // the second shard holds only zeros (a rank whose shard is all zero skips its
+                                 // passes; the out-of-place ones must still trade two all-zero shards)
   const double2 *cow_src = nullptr;  // copy-on-write in progress: the first full pass reads its tiles here
   std::vector<int> perm;  // logical bit -> physical bit (bits >= L are rank bits)
   // SUPPORT of the amplitudes on the device: every non-zero amplitude has
@@ -163,7 +166,7 @@ int init_common(qb_ctx *c) {
   QB_CUDA(cudaMallocHost(&c->red_host, sizeof(double) * 4));
   QB_CUDA(cudaMalloc(&c->kq_bits_dev, sizeof(int) * 2 * QB_MAX_KQ));
   QB_CUDA(cudaMalloc(&c->kq_mat_dev, sizeof(double2) << (2 * QB_MAX_KQ)));
-  for (const char *name : {"tile_bits", "reg_bits", "low_bits", "max_rounds", "peephole", "fuse", "max_pass_gates", "l2_prefetch", "avoid_regswap", "hot_bits", "rot", "lite", "dbg_skip", "lane_fixed", "skip_dead", "support", "jit", "jit_group", "jit_pf_last", "jit_minb", "jit_mem", "tma", "oop", "oop_low_bits", "chunk_lanes"}) {
+  for (const char *name : {"tile_bits", "reg_bits", "low_bits", "max_rounds", "peephole", "fuse", "max_pass_gates", "l2_prefetch", "avoid_regswap", "hot_bits", "rot", "lite", "dbg_skip", "lane_fixed", "skip_dead", "support", "jit", "jit_group", "jit_pf_last", "jit_minb", "jit_mem", "tma", "oop", "oop_low_bits", "chunk_lanes", "oop_dist"}) {
     std::string env = "QB_";
     for (const char *p = name; *p; ++p) env.push_back((char)toupper(*p));
     const char *v = getenv(env.c_str());
@@ -186,6 +189,34 @@ void free_buffer_memory(Buffer *b) {
 bool ensure_alt(Buffer *b) {
   if (b->alt) return true;
   qb_ctx *c = b->ctx;
+  if (c->nranks > 1) {
+    // sharded: every rank allocates, all agree on the outcome (one rank out of memory keeps every
+    // rank in place), the peers map the new shard like the first one.  Collective: every rank runs
+    // the same flush.
+    bool ok = cudaMalloc(&b->alt, sizeof(double2) << b->L) == cudaSuccess;
+    if (!ok) {
+      (void)cudaGetLastError();
+      b->alt = nullptr;
+    }
+    double bad = ok ? 0.0 : 1.0;
+    if (dist_allreduce_sum(c->dist, &bad, 1, c->stream) != QB_OK) bad = 1.0;
+    if (bad == 0.0) {
+      ok = cudaMemsetAsync(b->alt, 0, sizeof(double2) << b->L, c->stream) == cudaSuccess;
+      if (dist_register(c->dist, b->alt, b->peers_alt, c->stream) != QB_OK) ok = false;
+      if (b->peers_alt.size() != b->peers.size()) ok = false;  // (one shard peer-mapped, the other not: stay in place)
+      bad = ok ? 0.0 : 1.0;
+      if (dist_allreduce_sum(c->dist, &bad, 1, c->stream) != QB_OK) bad = 1.0;
+      if (bad != 0.0 && !b->peers_alt.empty()) dist_unregister(c->dist, b->peers_alt, c->stream);
+    }
+    if (bad != 0.0) {
+      if (b->alt) cudaFree(b->alt);
+      b->alt = nullptr;
+      b->peers_alt.clear();
+      return false;
+    }
+    b->alt_zero = true;
+    return true;
+  }
   for (size_t i = 0; i < c->pool.size(); ++i)  // a spare shard of the right size is as good as a new one
     if (c->pool[i]->L == b->L && c->pool[i]->peers.empty()) {
       Buffer *p = c->pool[i];
@@ -235,6 +266,12 @@ int drain_graveyard(qb_ctx *c) {
   bool any_free = false;
   for (Buffer *b : gone) {
     c->graveyard.erase(std::find(c->graveyard.begin(), c->graveyard.end(), b));
+    if (b->alt) {  // the second shard is never pooled (same `gone` and same shards on every rank: collective)
+      if (!b->peers_alt.empty()) dist_unregister(c->dist, b->peers_alt, c->stream);
+      cudaFree(b->alt);
+      b->alt = nullptr;
+      b->peers_alt.clear();
+    }
     if ((int)c->pool.size() < c->pool_max) {
       c->pool.push_back(b);  // stays mapped by the peers: reuse needs no collective
     } else {
@@ -323,7 +360,7 @@ void release_buffer(Buffer *b) {
   qb_ctx *c = b->ctx;
   b->log.clear();
   b->released = true;
-  if (b->alt) {  // (single-GPU contexts only: nothing collective about it) -> the spare pool, if there is room
+  if (b->alt && c->nranks == 1) {  // (nothing collective about it) -> the spare pool, if there is room
     if ((int)c->pool.size() + 1 < c->pool_max) {
       Buffer *p = new Buffer();
       p->ctx = c;
@@ -553,7 +590,7 @@ int run_fused_segment(Buffer *s, std::vector<const HostOp *> seg, const double *
   if (!opt.fuse) opt.max_pass_gates = 1;
   // out-of-place passes (tiles written as contiguous blocks, qubits relabelled): single-GPU states
   // with room for a second shard
-  opt.oop = (c->opt.oop && c->nranks == 1 && T > 0 && ensure_alt(s)) ? c->opt.oop : 0;
+  opt.oop = (c->opt.oop && (c->nranks == 1 || c->opt.oop_dist) && T > 0 && ensure_alt(s)) ? c->opt.oop : 0;
   if (opt.oop && opt.low_bits < c->opt.oop_low_bits) opt.low_bits = std::min(c->opt.oop_low_bits, T);
   while (!seg.empty()) {
     std::vector<PhysOp> pops(seg.size());
@@ -700,7 +737,11 @@ int run_fused_segment(Buffer *s, std::vector<const HostOp *> seg, const double *
       const bool oop_pass = reinterpret_cast<const DevPass *>(p.blob.data())->oop != 0;
       double2 *dst = s->amps;
       if (oop_pass && !src) {
-        if (rank_dead || !s->alt) return fail(QB_ERR_STATE, "internal: out-of-place pass without a second shard");
+        if (!s->alt) return fail(QB_ERR_STATE, "internal: out-of-place pass without a second shard");
+        if (rank_dead && !s->alt_zero) {  // this rank's shard is all zero and stays so: the other one must be, too
+          QB_CUDA(cudaMemsetAsync(s->alt, 0, sizeof(double2) << s->L, c->stream));
+          s->alt_zero = true;
+        }
         dst = s->alt;
         src = s->amps;
       }
@@ -718,7 +759,11 @@ int run_fused_segment(Buffer *s, std::vector<const HostOp *> seg, const double *
                                     c->sm_count, c->stream, nullptr));
         }
       }
-      if (dst != s->amps) std::swap(s->amps, s->alt);
+      if (dst != s->amps) {
+        std::swap(s->amps, s->alt);
+        std::swap(s->peers, s->peers_alt);
+        if (!rank_dead) s->alt_zero = false;  // (the shard just read holds amplitudes)
+      }
       c->stats.tiles += rank_dead ? 0 : p.ntiles;
       if (e0) {
         QB_CUDA(cudaEventRecord(e1, c->stream));
@@ -728,9 +773,11 @@ int run_fused_segment(Buffer *s, std::vector<const HostOp *> seg, const double *
       c->stats.rounds += p.nrounds;
       c->stats.ops_executed += p.ngates;
     }
-    if (!plan.final_pos.empty())  // the out-of-place passes moved the local qubits
+    if (!plan.final_pos.empty()) {  // the out-of-place passes moved the local qubits
       for (int &x : s->perm)
         if (x < s->L) x = plan.final_pos[x];
+      opt.layout_known = 1;  // (a replan after the swap below starts from a layout this flush produced)
+    }
     for (size_t i = 0; i < seg.size(); ++i) {  // the scheduled ops now shape the support
       if (!plan.done[i]) continue;
       const HostOp &h = *seg[i];
@@ -1770,17 +1817,18 @@ int qb_tensor(qb_state *a, qb_state *b, qb_state **out) {
   QB_TRY(flush_locked(b));
   QB_TRY(flush_locked(a));
   Buffer *ab = a->b, *bb = b->b;
-  if (c->nranks > 1) {
-    // sharded: a's qubits are the high ones (StateVec.hs:98-100), so with both operands in the
-    // identity layout rank r's shard of the product is (r's shard of a) x (ALL of b): b is read
-    // through the peers' mapped shards, a local fill otherwise
+  {
+    // both operands in the identity layout (global<->local swaps and out-of-place passes move qubits).
+    // Sharded: a's qubits are the high ones (StateVec.hs:98-100), so rank r's shard of the product is
+    // (r's shard of a) x (ALL of b): b is read through the peers' mapped shards, a local fill
+    // otherwise
     std::vector<int> ident(ab->n);
     for (int i = 0; i < ab->n; ++i) ident[i] = i;
     if (ab->perm != ident) QB_TRY(relayout(ab, ident));
     ident.resize(bb->n);
     for (int i = 0; i < bb->n; ++i) ident[i] = i;
     if (bb->perm != ident) QB_TRY(relayout(bb, ident));
-    if ((int)bb->peers.size() != c->nranks)
+    if (c->nranks > 1 && (int)bb->peers.size() != c->nranks)
       return fail(QB_ERR_UNSUPPORTED, "tensor of distributed states needs peer-mapped shards (CUDA IPC or a rank group)");
   }
   Buffer *s = nullptr;

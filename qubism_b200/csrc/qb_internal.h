@@ -212,6 +212,10 @@ struct PlanOptions {
                           // the run right above the block: 512-byte chunks inside a few 2 MB pages, and the
                           // layout depends on the op stream only, so the structures of an iterated circuit come
                           // back); 2: only the tile's qubits move.  Single-GPU states with room for a second shard.
+  int layout_known = 0;   // (set by the caller per plan) the layout this plan starts from was produced by
+                          // out-of-place passes of the same flush (a replan after a global<->local swap): its
+                          // first pass need not treat the low bits as passengers
+  int oop_dist = 1;       // sharded states run out of place too (second shard peer-mapped like the first)
   int chunk_lanes = 0;    // out of place: the chunk bits are never warp-id bits (a warp's load covers the whole
                           // chunk), at the price of fewer warp-local transposes
   int oop_low_bits = 5;   // low_bits while passes run out of place: the low bits hold the qubits needed next, so

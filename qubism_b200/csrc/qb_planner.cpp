@@ -68,6 +68,8 @@ bool set_opt(PlanOptions &o, const std::string &name, int64_t v) {
   } else if (name == "tma") {
     if (v < 0 || v > 3) return false;
     o.tma = (int)v;
+  } else if (name == "oop_dist") {
+    o.oop_dist = v ? 1 : 0;
   } else if (name == "chunk_lanes") {
     o.chunk_lanes = v ? 1 : 0;
   } else if (name == "oop_low_bits") {
@@ -127,6 +129,7 @@ int64_t get_opt(const PlanOptions &o, const std::string &name) {
   if (name == "oop") return o.oop;
   if (name == "oop_low_bits") return o.oop_low_bits;
   if (name == "chunk_lanes") return o.chunk_lanes;
+  if (name == "oop_dist") return o.oop_dist;
   if (name == "jit_minb") return o.jit_minb;
   if (name == "jit_mem") return o.jit_mem;
   if (name == "jit_group") return o.jit_group;
@@ -1188,7 +1191,7 @@ PlanResult plan_passes(const std::vector<PhysOp> &ops_in, int local_bits, int ra
   };
   while (ndone < ops.size()) {
     PassPlan p;
-    if (!plan_one_pass(ops, done, local_bits, rank, opt, p, label, res.final_pos.empty())) break;
+    if (!plan_one_pass(ops, done, local_bits, rank, opt, p, label, res.final_pos.empty() && !opt.layout_known)) break;
     ndone += p.op_index.size();
     if (!p.newpos.empty()) {
       // (the support bookkeeping below still reads this pass's ops with their OLD positions)

@@ -657,7 +657,7 @@ int qbe_layout_trace(int n, int nranks, const qb_op *ops, int64_t nops, const ch
   if (T == 0) return -2;
   opt.tile_bits = T;
   opt.reg_bits = R;
-  if (nranks > 1) opt.oop = 0;  // (sharded states run in place, as in qb_api.cpp)
+  if (nranks > 1 && !opt.oop_dist) opt.oop = 0;  // (as in qb_api.cpp)
   if (opt.oop && opt.low_bits < opt.oop_low_bits) opt.low_bits = std::min(opt.oop_low_bits, T);
   std::vector<int> perm(n);
   for (int i = 0; i < n; ++i) perm[i] = i;
@@ -676,6 +676,7 @@ int qbe_layout_trace(int n, int nranks, const qb_op *ops, int64_t nops, const ch
     std::vector<const HostOp *> seg;
     for (const auto &h : q.ops)
       if (!h.dead) seg.push_back(&h);
+    opt.layout_known = 0;
     int64_t npass = 0, nswap = 0, nnew = 0;
     std::vector<std::string> step_keys;
     while (!seg.empty()) {
@@ -716,9 +717,11 @@ int qbe_layout_trace(int n, int nranks, const qb_op *ops, int64_t nops, const ch
           step_keys.push_back(kp.key);
         }
       }
-      if (!plan.final_pos.empty())  // out-of-place passes moved the local qubits
+      if (!plan.final_pos.empty()) {  // out-of-place passes moved the local qubits
         for (int &x : perm)
           if (x < L) x = plan.final_pos[x];
+        opt.layout_known = 1;
+      }
       if (plan.consumed == seg.size()) break;
       std::vector<const HostOp *> rest;
       for (size_t i = 0; i < seg.size(); ++i)
@@ -782,11 +785,12 @@ int qbe_run_rank(int n, int nranks, int rank, const qb_op *ops, int64_t nops, co
     q.push_1q(n - 1 - o.target, cm, o.kind == 1 ? X : reinterpret_cast<const double *>(o.m));
   }
   int T, R;
-  opt.oop = 0;  // (sharded states run in place, as in qb_api.cpp)
+  if (!opt.oop_dist) opt.oop = 0;  // (as in qb_api.cpp)
   effective_tile(opt, L, T, R);
   if (T == 0) return -2;
   opt.tile_bits = T;
   opt.reg_bits = R;
+  if (opt.oop && opt.low_bits < opt.oop_low_bits) opt.low_bits = std::min(opt.oop_low_bits, T);
   std::vector<int> perm(perm_inout, perm_inout + n);
   std::vector<const HostOp *> seg;
   for (const auto &h : q.ops)
@@ -806,7 +810,10 @@ int qbe_run_rank(int n, int nranks, int rank, const qb_op *ops, int64_t nops, co
       pops[i].ctrl = cm;
       std::memcpy(pops[i].m, h.m, sizeof(h.m));
     }
-    PlanResult plan = plan_passes(pops, L, rank, opt, nullptr);
+    std::vector<int> labels(L, 0);
+    for (int qq = 0; qq < n; ++qq)
+      if (perm[qq] < L) labels[perm[qq]] = qq;
+    PlanResult plan = plan_passes(pops, L, rank, opt, nullptr, &labels);
     const bool all = plan.consumed == seg.size();
     if (all && !gdone && !plan.passes.empty()) {
       DevPass *P = reinterpret_cast<DevPass *>(plan.passes.back().blob.data());
@@ -816,6 +823,11 @@ int qbe_run_rank(int n, int nranks, int rank, const qb_op *ops, int64_t nops, co
       gdone = true;
     }
     for (const auto &p : plan.passes) run_pass(p, L, a, st);
+    if (!plan.final_pos.empty()) {
+      for (int &x : perm)
+        if (x < L) x = plan.final_pos[x];
+      opt.layout_known = 1;
+    }
     if (all) break;
     std::vector<const HostOp *> rest;
     for (size_t i = 0; i < seg.size(); ++i)

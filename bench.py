@@ -279,8 +279,13 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def mark(what):
+        if os.environ.get("QB_BENCH_TRACE"):
+            print(f"[bench rank {rank}] {what}", file=sys.stderr, flush=True)
+
     sv = Q.StateVec.create(n, True, ctx)
     ctx.set_option("time_kernels", 1)
+    mark("state created")
 
     # ---------------- device-resident throughput (`value`)
     def step():
@@ -300,6 +305,7 @@ def run_ours(args):
     f1.record(stream)
     barrier()
     first_step_ms = max_over_ranks(f0.elapsed_time(f1))
+    mark("first step done")
     for _ in range(max(0, args.warmup - 1)):
         step()
     # pass structures that came back during the warm-up are being compiled into specialised
@@ -311,6 +317,7 @@ def run_ours(args):
         ctx.jit_wait()
         step()
     barrier()
+    mark("warm-up done")
     ctx.reset_stats()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -322,6 +329,7 @@ def run_ours(args):
     barrier()
     elapsed = e0.elapsed_time(e1) / 1e3
     st = ctx.stats()
+    mark("timed steps done")
     if world == 1 and elapsed < 1.5:
         # nvidia-smi samples every 100 ms: keep the same load running (outside the timed region,
         # after the counters were read) until it has seen at least 1.5 s of it
@@ -354,6 +362,7 @@ def run_ours(args):
                       "what": "fresh |0...0> -> workload -> inverse workload, first 2^20 logical amplitudes + the norm"}
         rt.free()
         barrier()
+        mark("round trip done")
 
     # ---------------- end to end through the C ABI from host buffers (`e2e`)
     # every step: upload this rank's shard from pinned host memory, then drive the boundary the way
@@ -375,8 +384,9 @@ def run_ours(args):
         s0 = cur["sv"]
         for off in range(0, shard, chunk):
             s0.write_local((host.data_ptr(), chunk), first=off)
-        if rank == 0:
-            s0.write_local((one.data_ptr(), 1), first=0)
+        # (every rank makes the same calls: an upload into a state that was ever cloned agrees on its
+        #  handles across ranks, i.e. it is a collective)
+        s0.write_local((one.data_ptr() if rank == 0 else host.data_ptr(), 1), first=0)
         h = s0._h
         for ptr in op_ptrs:
             nh = C.c_void_p()
@@ -393,10 +403,13 @@ def run_ours(args):
         w = s1.local_to_host(0, win)
         return red, w
 
+    mark("e2e: buffers ready")
     e2e_step()
+    mark("e2e: first step done")
     ctx.jit_wait()
     e2e_step()
     barrier()
+    mark("e2e: warm-up done")
     ctx.reset_stats()
     t0 = time.perf_counter()
     e2e_steps = max(1, min(args.steps, 2))

@@ -439,7 +439,7 @@ def run_ours(args):
     alg_bytes = 32.0 * float(1 << L)  # 16 B read + 16 B written per local amplitude per pass
     achieved = alg_bytes / (fused_ms / 1e3) / 1e9 if fused_ms > 0 else None
     traffic, traffic_src = None, None
-    for tag in ("r02", "r01e", "r01d"):  # newest ncu --set full capture of the dominant kernel
+    for tag in ("r02c", "r02", "r01e", "r01d"):  # newest ncu --set full capture of the dominant kernel
         try:
             prof = json.load(open(os.path.join(ROOT, "profiles", f"{tag}_fused_pass_summary.json")))
             traffic = prof.get("dram_bytes_per_launch_scaled_to", {}).get(str(L))

@@ -550,7 +550,8 @@ int tile_local_index(const std::vector<int> &tile_bits, int phys) {
 }  // namespace
 
 static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &done, int L, int rank,
-                          const PlanOptions &opt, PassPlan &out, const std::vector<int> &label, bool layout_unknown) {
+                          const PlanOptions &opt, PassPlan &out, const std::vector<int> &label, bool layout_unknown,
+                          const std::vector<long> &again) {
   const int T = opt.tile_bits, R = opt.reg_bits;
   const int C = std::min(std::max(opt.low_bits, kLaneFixedBits), T);
   const int max_rounds = std::max(1, std::min(opt.max_rounds, kMaxRounds));
@@ -673,7 +674,13 @@ static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &don
       if (next_phys[op.target] == never) next_phys[op.target] = (long)i;
     }
   }
-  // soonest first; qubits nothing waits for in a layout-independent order (their labels)
+  // soonest first.  Qubits nothing waits for any more: as if the same op stream came again (an
+  // iterated circuit -- the layout a flush leaves behind is then the one its own first pass wants:
+  // low bits plus the run above the block instead of the top bits of the index, 7.3 instead of
+  // 10.5 ms for that pass); what the stream never targets, by label.  All of it layout-independent.
+  for (int b = 0; b < L; ++b)
+    if (next_phys[b] == never && label[b] >= 0 && label[b] < (int)again.size() && again[label[b]] < never)
+      next_phys[b] = (long)ops.size() + again[label[b]];
   auto before = [&](int pa, int pb) {
     if (next_phys[pa] != next_phys[pb]) return next_phys[pa] < next_phys[pb];
     return label[pa] < label[pb];
@@ -1179,6 +1186,19 @@ PlanResult plan_passes(const std::vector<PhysOp> &ops_in, int local_bits, int ra
   PlanOptions opt = opt_in;  // known_mask / known_val evolve pass by pass
   if (gscale && !(std::isfinite(gscale[0]) && std::isfinite(gscale[1]))) opt.known_mask = 0;
   std::vector<PhysOp> ops = ops_in;  // (an out-of-place pass moves qubits: the ops after it are relabelled)
+  // first use of every qubit (by label) in this op stream as a non-diagonal target
+  std::vector<long> again;
+  {
+    int maxl = -1;
+    for (int b = 0; b < local_bits; ++b) maxl = std::max(maxl, label[b]);
+    again.assign(maxl + 1, 1L << 40);
+    for (size_t i = 0; i < ops.size(); ++i) {
+      const PhysOp &op = ops[i];
+      if (op.type == G_DIAG || op.target >= local_bits) continue;
+      const int lb = label[op.target];
+      if (lb >= 0 && again[lb] == (1L << 40)) again[lb] = (long)i;
+    }
+  }
   std::vector<char> done(ops.size(), 0);
   size_t ndone = 0;
   auto relabel_mask = [&](uint64_t m, const std::vector<int> &np) {
@@ -1191,7 +1211,7 @@ PlanResult plan_passes(const std::vector<PhysOp> &ops_in, int local_bits, int ra
   };
   while (ndone < ops.size()) {
     PassPlan p;
-    if (!plan_one_pass(ops, done, local_bits, rank, opt, p, label, res.final_pos.empty() && !opt.layout_known)) break;
+    if (!plan_one_pass(ops, done, local_bits, rank, opt, p, label, res.final_pos.empty() && !opt.layout_known, again)) break;
     ndone += p.op_index.size();
     if (!p.newpos.empty()) {
       // (the support bookkeeping below still reads this pass's ops with their OLD positions)

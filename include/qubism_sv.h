@@ -124,7 +124,8 @@ uint64_t qb_state_local_len(const qb_state *s);
  * LOGICAL index space to the host.  Forces a flush.  Distributed: a collective -- every
  * rank calls it with the same range and receives the same data. */
 int qb_state_read(qb_state *s, uint64_t first, uint64_t count, qb_c64 *out);
-/* Copy this rank's raw shard (physical order) to the host: bench/e2e only. */
+/* Copy amplitudes of this rank's shard to the host: bench/e2e only.  Single GPU: the shard is the
+ * state, amplitudes in index order (as qb_state_read); sharded: the raw shard in physical order. */
 int qb_state_read_local(qb_state *s, uint64_t first, uint64_t count, qb_c64 *out);
 /* Overwrite amplitudes [first, first+count) of this rank's shard from a host buffer (pinned
  * memory makes the copy asynchronous to the host).  An upload STARTS at first = 0: queued gates,
@@ -218,7 +219,13 @@ void *qb_ctx_stream(qb_ctx *ctx);
  * seen k times is compiled with NVRTC into a straight-line kernel -- structure as literals, gate
  * coefficients still kernel parameters -- and cached; k = 1 compiles at first sight in the
  * calling thread, k >= 2 in background threads while the generic kernel keeps running;
- * 0 = generic kernels only), "linear" (see qb_state_clone), "pool" (spare shards kept for reuse).  Returns
+ * 0 = generic kernels only), "linear" (see qb_state_clone), "pool" (spare shards kept for reuse),
+ * "oop" (1, default: fused passes run OUT OF PLACE into a second shard of the same size, every tile
+ * stored as one contiguous block and the qubit layout re-sorted by next use after every pass --
+ * invisible through this ABI, which always speaks the reference's qubit numbers and index order;
+ * 2: only the tile's qubits move; 0: in place, half the memory), "oop_low_bits", "oop_dist" (sharded
+ * states run out of place too), "chunk_lanes", "tma" (tile loads as bulk copies), "l2_prefetch".
+ * A state that cannot get its second shard (36 qubits on 8 GPUs) stays in place.  Returns
  * QB_ERR_ARG for unknown names / bad values. */
 int qb_set_option(qb_ctx *ctx, const char *name, int64_t value);
 int64_t qb_get_option(const qb_ctx *ctx, const char *name);

@@ -136,7 +136,8 @@ struct DevPass {
   uint32_t onruns;                    // oop: the block address of tile number t.  Its bits are taken from the low
                                       // end in onruns groups of orun_len[k] bits, group k placed at bit
                                       // orun_shift[k] (>= T): the qubits outside the tile may be re-ordered too
-  uint32_t _pad_tma;
+  uint32_t pf_lines;                  // specialised kernels: lines per thread the L2 prefetch of the next tile covers
+                                      // (0 = the whole tile; 1 of 2 = half of it: fewer tiles in flight per SM)
   uint8_t out_pos[16];                // physical bit position tile-local bit i is STORED at
   uint8_t orun_len[kMaxOutRuns];
   uint8_t orun_shift[kMaxOutRuns];
@@ -215,6 +216,7 @@ struct PlanOptions {
   int layout_known = 0;   // (set by the caller per plan) the layout this plan starts from was produced by
                           // out-of-place passes of the same flush (a replan after a global<->local swap): its
                           // first pass need not treat the low bits as passengers
+  int pf_lines = 0;       // see DevPass::pf_lines
   int oop_dist = 1;       // sharded states run out of place too (second shard peer-mapped like the first)
   int chunk_lanes = 0;    // out of place: the chunk bits are never warp-id bits (a warp's load covers the whole
                           // chunk), at the price of fewer warp-local transposes

@@ -149,6 +149,8 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
   const bool has_gs = P.has_gscale != 0;
   g.dec(has_gs);
   const int LPT = 1 << (R - 3);
+  const int npf = (P.pf_lines > 0 && (int)P.pf_lines < LPT) ? (int)P.pf_lines : LPT;  // lines per thread the L2 prefetch covers
+  g.dec(npf);
   // ---- one shared-memory swizzle PER TRANSPOSE.  The slot of tile-local index u is
   // u ^ (XOR over the set bits p >= 3 of u of col[p]), col[p] in 1..7: a bijection for any choice.
   // A 128-bit access of a quarter warp is conflict-free iff the three lowest lane bits move the
@@ -738,7 +740,7 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
              "      if (next_id < ntiles32) {\n      u64 nb_;\n";
         deposit("nb_", "next_id");
         o << "      next_base = nb_;\n";
-        for (int k = 0; k < LPT; ++k)
+        for (int k = 0; k < npf; ++k)
           o << "      asm volatile(\"prefetch.global.L2 [%0];\" ::\"l\"(src + nb_ + ((u64)line_tab[" << k << " * QBJ_NT + tid] << 3)));\n";
         o << "      }\n    }\n";
       }
@@ -881,7 +883,7 @@ bool jit_quick(const PassPlan &pp, JitProgram &out, std::string *why) {
   for (int i = 0; i < T; ++i) mix(P.out_pos[i]);
   mix(P.onruns);
   for (uint32_t k = 0; k < P.onruns && k < (uint32_t)kMaxOutRuns; ++k) { mix(P.orun_len[k]); mix(P.orun_shift[k]); }
-  mix(P.jit_group); mix(P.jit_pf_last); mix(P.jit_minb); mix(P.jit_mem); mix(P.nsteps); mix(P.tma); mix(P.dbg_skip);
+  mix(P.jit_group); mix(P.jit_pf_last); mix(P.jit_minb); mix(P.jit_mem); mix(P.nsteps); mix(P.tma); mix(P.dbg_skip); mix(P.pf_lines);
   out.coefs.clear();
   double left = 1.0;
   bool bad = false;

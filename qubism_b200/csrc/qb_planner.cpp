@@ -68,6 +68,9 @@ bool set_opt(PlanOptions &o, const std::string &name, int64_t v) {
   } else if (name == "tma") {
     if (v < 0 || v > 3) return false;
     o.tma = (int)v;
+  } else if (name == "pf_lines") {
+    if (v < 0 || v > 4) return false;
+    o.pf_lines = (int)v;
   } else if (name == "oop_dist") {
     o.oop_dist = v ? 1 : 0;
   } else if (name == "chunk_lanes") {
@@ -130,6 +133,7 @@ int64_t get_opt(const PlanOptions &o, const std::string &name) {
   if (name == "oop_low_bits") return o.oop_low_bits;
   if (name == "chunk_lanes") return o.chunk_lanes;
   if (name == "oop_dist") return o.oop_dist;
+  if (name == "pf_lines") return o.pf_lines;
   if (name == "jit_minb") return o.jit_minb;
   if (name == "jit_mem") return o.jit_mem;
   if (name == "jit_group") return o.jit_group;
@@ -859,6 +863,7 @@ static bool plan_one_pass(const std::vector<PhysOp> &ops, std::vector<char> &don
   P->jit_minb = (uint32_t)opt.jit_minb;
   P->jit_mem = (uint32_t)opt.jit_mem;
   P->tma = (uint32_t)opt.tma;
+  P->pf_lines = (uint32_t)opt.pf_lines;
   P->dbg_skip = (uint32_t)opt.dbg_skip;
   P->sm_count = 148;
   for (int i = 0; i < T; ++i) P->tile_pos[i] = (uint8_t)tile_bits[i];

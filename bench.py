@@ -458,7 +458,11 @@ def run_ours(args):
                 "kernel_share_of_step": (st["fused_ms"] / 1e3) / elapsed if elapsed > 0 else None,
                 # what the ops that REACH a kernel would move one sweep per op: may exceed
                 # the HBM peak, which is the point of fusing.  Folded ops are not counted here.
-                "unfused_equivalent_gbs_executed_ops": ops_exec * float(1 << n) / (elapsed / args.steps) / world * 32.0 / 1e9}
+                "unfused_equivalent_gbs_executed_ops": ops_exec * float(1 << n) / (elapsed / args.steps) / world * 32.0 / 1e9,
+                "gates_per_launch": ops_exec / max(1.0, passes),
+                "note": "frac is per launch: a plan that packs the same gates into fewer, denser passes lowers it while the "
+                        "step gets faster (DESIGN.md section 6); the memory side of a pass alone (its loads, L2 prefetch and "
+                        "stores, no gates) takes 7.1-7.6 ms per 34 GB on this pool's boxes (profiles/r02z_density.txt)"}
     if world > 1:
         # T_roof(P) = passes x 32 B x 2^L / HBM  +  bytes sent per GPU / NVLink per direction
         nvl = 770.0  # GB/s per direction, measured peer copy on this pool (900 nominal)

@@ -207,6 +207,8 @@ typedef struct {
   uint64_t clones;          /* qb_state_clone calls (all lazy)                               */
   uint64_t cow_fused;       /* copy-on-write copies that rode on a fused pass (no extra traffic) */
   uint64_t cow_copies;      /* copy-on-write / fork copies done as a separate device copy     */
+  uint64_t exchanges_fused; /* of `exchanges`: swaps carried by the stores of a fused pass (no sweep of
+                               their own: the tiles go straight to their next owner over NVLink) */
 } qb_stats;
 int qb_get_stats(const qb_ctx *ctx, qb_stats *out);
 int qb_reset_stats(qb_ctx *ctx);
@@ -224,7 +226,9 @@ void *qb_ctx_stream(qb_ctx *ctx);
  * stored as one contiguous block and the qubit layout re-sorted by next use after every pass --
  * invisible through this ABI, which always speaks the reference's qubit numbers and index order;
  * 2: only the tile's qubits move; 0: in place, half the memory), "oop_low_bits", "oop_dist" (sharded
- * states run out of place too), "chunk_lanes", "tma" (tile loads as bulk copies), "l2_prefetch".
+ * states run out of place too), "chunk_lanes", "tma" (tile loads as bulk copies), "l2_prefetch", "fuse_exchange" (1, default: on
+ * sharded out-of-place states the pass before a global<->local swap stores every tile straight
+ * into the second shard of the rank that owns it after the swap; 0: store locally, then exchange).
  * A state that cannot get its second shard (36 qubits on 8 GPUs) stays in place.  Returns
  * QB_ERR_ARG for unknown names / bad values. */
 int qb_set_option(qb_ctx *ctx, const char *name, int64_t value);

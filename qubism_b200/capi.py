@@ -38,7 +38,8 @@ class QbStats(C.Structure):
                 ("reduce_launches", C.c_uint64), ("exchange_bytes", C.c_uint64), ("exchanges", C.c_uint64),
                 ("plan_ms", C.c_double), ("fused_ms", C.c_double), ("fused_timed", C.c_uint64), ("tiles", C.c_uint64),
                 ("jit_compiled", C.c_uint64), ("jit_launches", C.c_uint64), ("jit_compile_ms", C.c_double),
-                ("clones", C.c_uint64), ("cow_fused", C.c_uint64), ("cow_copies", C.c_uint64)]
+                ("clones", C.c_uint64), ("cow_fused", C.c_uint64), ("cow_copies", C.c_uint64),
+                ("exchanges_fused", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -166,7 +166,7 @@ int init_common(qb_ctx *c) {
   QB_CUDA(cudaMallocHost(&c->red_host, sizeof(double) * 4));
   QB_CUDA(cudaMalloc(&c->kq_bits_dev, sizeof(int) * 2 * QB_MAX_KQ));
   QB_CUDA(cudaMalloc(&c->kq_mat_dev, sizeof(double2) << (2 * QB_MAX_KQ)));
-  for (const char *name : {"tile_bits", "reg_bits", "low_bits", "max_rounds", "peephole", "fuse", "max_pass_gates", "l2_prefetch", "avoid_regswap", "hot_bits", "rot", "lite", "dbg_skip", "lane_fixed", "skip_dead", "support", "jit", "jit_group", "jit_pf_last", "jit_minb", "jit_mem", "tma", "oop", "oop_low_bits", "chunk_lanes", "oop_dist", "pf_lines"}) {
+  for (const char *name : {"tile_bits", "reg_bits", "low_bits", "max_rounds", "peephole", "fuse", "max_pass_gates", "l2_prefetch", "avoid_regswap", "hot_bits", "rot", "lite", "dbg_skip", "lane_fixed", "skip_dead", "support", "jit", "jit_group", "jit_pf_last", "jit_minb", "jit_mem", "tma", "oop", "oop_low_bits", "chunk_lanes", "oop_dist", "pf_lines", "fuse_exchange"}) {
     std::string env = "QB_";
     for (const char *p = name; *p; ++p) env.push_back((char)toupper(*p));
     const char *v = getenv(env.c_str());
@@ -626,6 +626,31 @@ int run_fused_segment(Buffer *s, std::vector<const HostOp *> seg, const double *
       if (s->perm[q] < s->L) labels[s->perm[q]] = q;
     PlanResult plan = plan_passes(pops, s->L, c->rank, opt, nullptr, &labels);
     const bool all = plan.consumed == seg.size();
+    // ---- a global<->local swap follows this plan (something is left that targets a global qubit):
+    // fuse it into the stores of the plan's last pass -- that pass writes every tile straight into
+    // the second shard of the rank that owns it after the swap, over NVLink peer memory, instead of
+    // a local store plus a separate exchange sweep (XchGeom, qb_internal.h).  Needs: an out-of-place
+    // last pass, both shards peer-mapped on every rank, no rank whose shard is known to be all zero
+    // (it would skip the pass), no pending copy-on-write, and every victim outside that pass's block.
+    std::vector<SwapPair> xsw;
+    if (!all && c->nranks > 1 && c->opt.fuse_exchange && !plan.passes.empty() && !plan.final_pos.empty() && s->zmask == 0 &&
+        !s->cow_src && s->alt && c->nranks <= kMaxXchRanks && dist_has_peers(c->dist, s->peers) &&
+        dist_has_peers(c->dist, s->peers_alt)) {
+      DevPass *LP = reinterpret_cast<DevPass *>(plan.passes.back().blob.data());
+      if (LP->oop) {
+        std::vector<int> perm2 = s->perm;  // the layout after this plan
+        for (int &x : perm2)
+          if (x < s->L) x = plan.final_pos[x];
+        std::vector<const HostOp *> rest0, future;
+        for (size_t i = 0; i < seg.size(); ++i)
+          if (!plan.done[i]) rest0.push_back(seg[i]);
+        for (const auto &op : s->q.ops)
+          if (!op.dead && op.kind == 0) future.push_back(&op);
+        std::vector<SwapPair> sw = choose_swaps(s->n, s->L, perm2, rest0, true, &future);  // (what make_local would choose)
+        // (the destination pointers are filled in at launch: the two shards trade places with every pass before it)
+        if (fused_exchange_geometry(*LP, s->L, c->rank, c->nranks, sw, &LP->xch)) xsw.swap(sw);
+      }
+    }
     c->stats.plan_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     // ---- which passes run as structure-specialised kernels (qb_jit.cpp).  Every rank takes the
     // same decisions (same plans, same sighting counts): the factors those kernels leave out
@@ -713,9 +738,16 @@ int run_fused_segment(Buffer *s, std::vector<const HostOp *> seg, const double *
       }
     }
     for (size_t i = 0; i < npass; ++i) {
-      const PassPlan &p = plan.passes[i];
+      PassPlan &p = plan.passes[i];
+      const bool xpass = !xsw.empty() && i + 1 == npass;  // this pass's stores carry the swap
+      if (xpass) {  // every rank's second shard as of NOW; nobody still reads the shard the peers are about to write
+        XchGeom &X = reinterpret_cast<DevPass *>(p.blob.data())->xch;
+        for (int r = 0; r < c->nranks; ++r) X.peer[r] = reinterpret_cast<uint64_t>(s->peers_alt[r]);
+        int rc = dist_stream_barrier(c->dist, c->stream);
+        if (rc != QB_OK) return fail(rc, "barrier before the fused swap failed: %s", dist_last_error());
+      }
       cudaEvent_t e0 = nullptr, e1 = nullptr;
-      if (c->opt.time_kernels) {
+      if (c->opt.time_kernels && !xpass) {  // (its duration is NVLink's, not the pass's: not part of fused_ms)
         QB_TRY(get_event(c, &e0));
         QB_TRY(get_event(c, &e1));
         QB_CUDA(cudaEventRecord(e0, c->stream));
@@ -751,13 +783,20 @@ int run_fused_segment(Buffer *s, std::vector<const HostOp *> seg, const double *
           double gs[2] = {P->gscale[0], P->gscale[1]};
           if (!P->has_gscale) gs[0] = 1.0, gs[1] = 0.0;
           std::string err;
-          const std::vector<uint8_t> args = jit_pack_args(jit_prog[i], gs, P->rank_bits, P->base_fixed);
+          const std::vector<uint8_t> args = jit_pack_args(jit_prog[i], gs, P->rank_bits, P->base_fixed, P->xch.n ? &P->xch : nullptr);
           if (jit_launch(jit_handle[i], dst, src, p.ntiles, args, c->sm_count, c->stream, &err) != 0)
             return fail(QB_ERR_CUDA, "%s", err.c_str());
         } else {
           QB_CUDA(launch_fused_pass(dst, src, p.blob.data(), (uint32_t)p.blob.size(), p.tile_bits, p.reg_bits, p.ntiles,
                                     c->sm_count, c->stream, nullptr));
         }
+      }
+      if (xpass) {  // every rank's tiles have landed before anybody reads its new shard
+        int rc = dist_stream_barrier(c->dist, c->stream);
+        if (rc != QB_OK) return fail(rc, "barrier after the fused swap failed: %s", dist_last_error());
+        c->stats.exchanges++;
+        c->stats.exchanges_fused++;
+        c->stats.exchange_bytes += ((sizeof(double2) << s->L) >> xsw.size()) * ((1ull << xsw.size()) - 1ull);
       }
       if (dst != s->amps) {
         std::swap(s->amps, s->alt);
@@ -778,6 +817,7 @@ int run_fused_segment(Buffer *s, std::vector<const HostOp *> seg, const double *
         if (x < s->L) x = plan.final_pos[x];
       opt.layout_known = 1;  // (a replan after the swap below starts from a layout this flush produced)
     }
+    if (!xsw.empty()) apply_swaps_to_perm(s->perm, xsw);  // (the last pass's stores carried it)
     for (size_t i = 0; i < seg.size(); ++i) {  // the scheduled ops now shape the support
       if (!plan.done[i]) continue;
       const HostOp &h = *seg[i];
@@ -789,7 +829,7 @@ int run_fused_segment(Buffer *s, std::vector<const HostOp *> seg, const double *
     std::vector<const HostOp *> rest;
     for (size_t i = 0; i < seg.size(); ++i)
       if (!plan.done[i]) rest.push_back(seg[i]);
-    if (plan.passes.empty() || true) {
+    if (xsw.empty()) {
       // whatever is left starts with gates on global qubits: remap them into the shard
       QB_TRY(make_local(s, rest));
     }

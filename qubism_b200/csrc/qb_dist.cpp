@@ -271,7 +271,9 @@ int dist_allreduce_sum(DistState *d, double *vals, int n, cudaStream_t stream) {
 
 // stream-ordered barrier over all ranks: every rank's earlier work on its stream is complete
 // before anything enqueued after it starts on any rank
-static int stream_barrier(DistState *d, cudaStream_t stream) {
+int dist_stream_barrier(DistState *d, cudaStream_t stream);
+static int stream_barrier(DistState *d, cudaStream_t stream) { return dist_stream_barrier(d, stream); }
+int dist_stream_barrier(DistState *d, cudaStream_t stream) {
   if (d->grp) {
     QB_DCUDA(cudaStreamSynchronize(stream));
     QB_GROUP_BARRIER(d);

@@ -44,6 +44,9 @@ int dist_make_local(DistState *d, double2 *amps, const std::vector<double2 *> &p
 int dist_swap_pairs(DistState *d, double2 *amps, const std::vector<double2 *> &peers, int L, std::vector<int> &perm,
                     const std::vector<SwapPair> &sw, int sm_count, cudaStream_t stream, qb_stats *stats);
 bool dist_has_peers(const DistState *d, const std::vector<double2 *> &peers);
+// stream-ordered barrier over all ranks: every rank's earlier work on its stream is complete before
+// anything enqueued after it starts on any rank
+int dist_stream_barrier(DistState *d, cudaStream_t stream);
 
 // Collective read of logical amplitudes [first, first + count) into `out` on every rank.
 int dist_read_logical(DistState *d, const double2 *amps, int n, int L, const std::vector<int> &perm, uint64_t first,

@@ -94,6 +94,23 @@ struct alignas(16) DevStep {
 };
 static_assert(sizeof(DevStep) == 416, "DevStep layout");
 
+// A global<->local swap FUSED into the store of an out-of-place pass (sharded states): the pass
+// that precedes the swap writes every tile straight to the rank that owns it afterwards -- into
+// that rank's second shard, over NVLink peer memory -- instead of writing locally and exchanging
+// in a second sweep.  The k victim qubits sit on bits lbit[i] >= 1 of an amplitude's address in the new
+// layout: destination rank = rbase | (their values, on rank bits rbit[i]), destination address =
+// the address with those bits replaced by this rank's old rank-bit values.  Worked out store by
+// store (the victims are usually the qubits the pass has just finished with: bits INSIDE its block).
+constexpr int kMaxXchRanks = 16;
+struct XchGeom {
+  uint64_t peer[kMaxXchRanks];  // every rank's destination shard as mapped into this process (0 = unused)
+  uint64_t vmask, vconst;       // the victims' bits of the block address / what replaces them
+  uint32_t n, rbase;            // swapped pairs (0 = plain pass) / this rank with the swapped rank bits cleared
+  uint32_t lbit[4], rbit[4];
+  uint32_t _pad[2];
+};
+static_assert(sizeof(XchGeom) == 192, "XchGeom layout (mirrored by the generated QbjXch)");
+
 struct DevRound {
   uint32_t gate_begin, gate_end;
   uint32_t nthr_bits;                 // T - R
@@ -141,6 +158,7 @@ struct DevPass {
   uint8_t out_pos[16];                // physical bit position tile-local bit i is STORED at
   uint8_t orun_len[kMaxOutRuns];
   uint8_t orun_shift[kMaxOutRuns];
+  XchGeom xch;                        // n != 0: this pass's stores carry a global<->local swap (see XchGeom)
   DevRound rounds[kMaxRounds];
   // followed in memory by ngates DevGate records (lite: by nsteps DevStep records)
 };
@@ -216,6 +234,8 @@ struct PlanOptions {
   int layout_known = 0;   // (set by the caller per plan) the layout this plan starts from was produced by
                           // out-of-place passes of the same flush (a replan after a global<->local swap): its
                           // first pass need not treat the low bits as passengers
+  int fuse_exchange = 1;  // sharded, out of place: the pass before a global<->local swap stores its tiles straight
+                          // into the second shard of the rank that owns them after the swap (XchGeom)
   int pf_lines = 0;       // see DevPass::pf_lines
   int oop_dist = 1;       // sharded states run out of place too (second shard peer-mapped like the first)
   int chunk_lanes = 0;    // out of place: the chunk bits are never warp-id bits (a warp's load covers the whole
@@ -327,6 +347,12 @@ std::vector<SwapStep> swap_schedule(int rank, int L, const std::vector<SwapPair>
 void apply_swaps_to_perm(std::vector<int> &perm, const std::vector<SwapPair> &pairs);
 // scatter the k-bit selector into the local-bit positions of `pairs`
 uint64_t place_sel(uint32_t sel, const std::vector<SwapPair> &pairs);
+// Can the stores of out-of-place pass `last` (the last pass of a plan; layout after it = the one
+// `sw` was chosen on) carry the swap `sw`?  Any victim but bit 0 will do (the destination is worked
+// out store by store; 32-byte stores of register pairs must stay whole) as long as the pair count
+// fits XchGeom.  On success fills everything of *out except the peer pointers (the caller knows
+// where every rank's second shard is mapped).
+bool fused_exchange_geometry(const DevPass &last, int L, int rank, int nranks, const std::vector<SwapPair> &sw, XchGeom *out);
 
 // classification of a caller-supplied 2x2 (value-based)
 struct Classified {

@@ -126,6 +126,7 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
   if (tma) group = 1;
   const bool oop = P.oop != 0;  // tiles are stored as contiguous blocks of the destination, bits permuted (out_pos)
   if (oop) group = 1;
+  const bool xch = oop && P.xch.n != 0;  // the stores carry a global<->local swap: every tile goes to the rank that owns it next
   const size_t tables_bytes = size_t(std::max(1, 2 * (nrounds - 1))) * NT * sizeof(uint16_t) + size_t(2) * NT * sizeof(uint64_t) +
                               (size_t(group) << (T - 3)) * sizeof(uint32_t) + (tma ? NT * sizeof(uint16_t) + 16 : 0);
   // tma = 2: ONE CTA per SM holds TWO groups of 2^(T-R) threads, each working on its own tile with a
@@ -244,6 +245,7 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
   g.dec(tma);
   g.dec(dual);
   g.dec(oop);
+  g.dec(xch);
   const std::string sPFK = g.dec((group > 1 && P.jit_pf_last) ? group - 1 : 0);  // prefetch while this tile of the group computes
 
   // ---------------------------------------------------------------- fragments shared by both modes
@@ -554,7 +556,21 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
     g.cur = &g.o;
     const std::string rounds_txt = side.str();
     const size_t nc = std::max<size_t>(1, g.coefs.size());
-    o << "struct QbjArgs { double gs[2]; u64 rank_bits; u64 base_fixed; double c[" << nc << "]; };\n";
+    o << "struct QbjXch { u64 peer[" << kMaxXchRanks << "]; u64 vmask, vconst; u32 n, rbase; u32 lbit[4], rbit[4]; u32 pad_[2]; };\n"
+         "struct QbjArgs { double gs[2]; u64 rank_bits; u64 base_fixed; QbjXch x; double c[" << nc << "]; };\n";
+    if (xch) {
+      // the stores carry a global<->local swap: amplitude address a of the new layout -> the rank that owns
+      // it after the swap (the victims' bits of a pick it) and its address there (those bits take this
+      // rank's old rank-bit values); peer[] = every rank's second shard as mapped here (XchGeom)
+      g.tag("xch");
+      o << (g.host ? "static inline double *" : "__device__ __forceinline__ double2 *")
+        << "qbj_xch_dst(const QbjXch &X, u64 a) {\n"
+           "  u32 rr_ = X.rbase;\n"
+           "  for (u32 k_ = 0; k_ < X.n; ++k_) rr_ |= (u32)((a >> X.lbit[k_]) & 1ull) << X.rbit[k_];\n"
+        << (g.host ? "  return reinterpret_cast<double *>(X.peer[rr_]) + 2 * ((a & ~X.vmask) | X.vconst);\n"
+                   : "  return reinterpret_cast<double2 *>(X.peer[rr_]) + ((a & ~X.vmask) | X.vconst);\n")
+        << "}\n";
+    }
     // Coefficients are loop-invariant kernel parameters.  Up to ~30 of them the compiler keeps them
     // in uniform registers across the tile loop; beyond that it hoists them into ordinary
     // registers and spills those (the general-class passes of the benchmark: 200-300 bytes per
@@ -567,11 +583,12 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
     if (!g.host) {
       o << "#define QBJ_LD2(p, i) qbj_ld256(src + (p), re[i], im[i], re[(i) + 1], im[(i) + 1])\n"
            "#define QBJ_LD1(p, i) qbj_ld128(src + (p), re[i], im[i])\n"
-           "#define QBJ_ST2(p, a0, a1, b0, b1) qbj_st256(amps + (p), a0, a1, b0, b1)\n"
-           "#define QBJ_ST1(p, xr, xi) qbj_st128(amps + (p), xr, xi)\n"
+           "#define QBJ_ST2(p, a0, a1, b0, b1) qbj_st256(QBJ_DST(p), a0, a1, b0, b1)\n"
+           "#define QBJ_ST1(p, xr, xi) qbj_st128(QBJ_DST(p), xr, xi)\n"
            "#define QBJ_STS(off, xr, xi) *reinterpret_cast<double2 *>(sm_ + (off)) = make_double2(xr, xi)\n"
            "#define QBJ_LDS(off, i) { const double2 a_ = *reinterpret_cast<const double2 *>(sm_ + (off)); re[i] = a_.x; im[i] = a_.y; }\n"
            "#define QBJ_LDSI(off, i) { const double2 a_ = *reinterpret_cast<const double2 *>(in_ + (off)); re[i] = a_.x; im[i] = a_.y; }\n";
+      o << (xch ? "#define QBJ_DST(p) qbj_xch_dst(A.x, (p))\n" : "#define QBJ_DST(p) (amps + (p))\n");
       if (dual)
         o << "#define QBJ_BAR() asm volatile(\"bar.sync %0, %1;\" ::\"r\"(grp_ + 1u), \"r\"((u32)QBJ_NT) : \"memory\")\n";
       else
@@ -798,8 +815,9 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
     } else {
       o << "#define QBJ_LD2(p, i) { re[i] = amps[2 * (p)]; im[i] = amps[2 * (p) + 1]; re[(i) + 1] = amps[2 * (p) + 2]; im[(i) + 1] = amps[2 * (p) + 3]; }\n"
            "#define QBJ_LD1(p, i) { re[i] = amps[2 * (p)]; im[i] = amps[2 * (p) + 1]; }\n"
-           "#define QBJ_ST2(p, a0, a1, b0, b1) { dst[2 * (p)] = a0; dst[2 * (p) + 1] = a1; dst[2 * (p) + 2] = b0; dst[2 * (p) + 3] = b1; }\n"
-           "#define QBJ_ST1(p, xr, xi) { dst[2 * (p)] = xr; dst[2 * (p) + 1] = xi; }\n"
+           "#define QBJ_ST2(p, a0, a1, b0, b1) { double *d_ = QBJ_DST(p); d_[0] = a0; d_[1] = a1; d_[2] = b0; d_[3] = b1; }\n"
+           "#define QBJ_ST1(p, xr, xi) { double *d_ = QBJ_DST(p); d_[0] = xr; d_[1] = xi; }\n"
+        << (xch ? "#define QBJ_DST(p) qbj_xch_dst(A.x, (p))\n" : "#define QBJ_DST(p) (dst + 2 * (p))\n") <<
            "#define QBJ_STS(off, xr, xi) { SM[2 * ((off) >> 4)] = xr; SM[2 * ((off) >> 4) + 1] = xi; }\n"
            "#define QBJ_LDS(off, i) { re[i] = SM[2 * ((off) >> 4)]; im[i] = SM[2 * ((off) >> 4) + 1]; }\n"
            "#define QBJ_LDSI(off, i) QBJ_LDS(off, i)\n"
@@ -880,6 +898,7 @@ bool jit_quick(const PassPlan &pp, JitProgram &out, std::string *why) {
   for (uint32_t k = 0; k < P.nruns && k < (uint32_t)kMaxRuns; ++k) { mix(P.run_shift[k]); mix(P.run_len[k]); }
   for (int i = 0; i < T; ++i) mix(P.tile_pos[i]);
   mix(P.oop);
+  mix(P.oop != 0 && P.xch.n != 0);
   for (int i = 0; i < T; ++i) mix(P.out_pos[i]);
   mix(P.onruns);
   for (uint32_t k = 0; k < P.onruns && k < (uint32_t)kMaxOutRuns; ++k) { mix(P.orun_len[k]); mix(P.orun_shift[k]); }
@@ -958,9 +977,12 @@ bool jit_quick(const PassPlan &pp, JitProgram &out, std::string *why) {
   return true;
 }
 
-std::vector<uint8_t> jit_pack_args(const JitProgram &p, const double gs[2], uint64_t rank_bits, uint64_t base_fixed) {
+std::vector<uint8_t> jit_pack_args(const JitProgram &p, const double gs[2], uint64_t rank_bits, uint64_t base_fixed,
+                                   const XchGeom *xch) {
   std::vector<uint8_t> a(p.args_bytes, 0);
   JitArgsHead h;
+  std::memset(&h, 0, sizeof h);
+  if (xch) h.xch = *xch;
   h.gs[0] = gs[0];
   h.gs[1] = gs[1];
   h.rank_bits = rank_bits;

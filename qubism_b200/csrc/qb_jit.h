@@ -46,8 +46,10 @@ struct JitArgsHead {
   double gs[2];
   uint64_t rank_bits;
   uint64_t base_fixed;
+  XchGeom xch;  // run-time geometry of a swap fused into the stores (peer pointers differ from process to process)
 };
-std::vector<uint8_t> jit_pack_args(const JitProgram &p, const double gs[2], uint64_t rank_bits, uint64_t base_fixed);
+std::vector<uint8_t> jit_pack_args(const JitProgram &p, const double gs[2], uint64_t rank_bits, uint64_t base_fixed,
+                                   const XchGeom *xch = nullptr);
 
 #ifndef QB_JIT_NO_RUNTIME
 struct JitStats {

@@ -594,6 +594,15 @@ __global__ void __launch_bounds__(1 << (T - R), MINB)
           t >>= len;
         }
       }
+      // the stores carry a global<->local swap: every amplitude goes to the rank that owns it after it,
+      // over NVLink (the victims' bits of its address pick the rank and take this rank's old values)
+      const bool xch = P.oop && P.xch.n != 0;
+      auto dst_of = [&](uint64_t a) -> double2 * {
+        if (!xch) return amps + a;
+        uint32_t rr = P.xch.rbase;
+        for (uint32_t k = 0; k < P.xch.n; ++k) rr |= uint32_t((a >> P.xch.lbit[k]) & 1ull) << P.xch.rbit[k];
+        return reinterpret_cast<double2 *>(P.xch.peer[rr]) + ((a & ~P.xch.vmask) | P.xch.vconst);
+      };
       if (st[0] == 1ull) {  // register bit 0 is physical bit 0: 32-byte stores of register pairs
         const uint64_t at = (obase + goff_tab[NT + tid]) ^ (fx & ~1ull);
         const bool sw = (f & 1u) != 0;  // pending flip on that bit: the pair goes out in reverse order
@@ -603,7 +612,7 @@ __global__ void __launch_bounds__(1 << (T - R), MINB)
 #pragma unroll
           for (int j = 1; j < R; ++j)
             if ((i >> j) & 1) off |= st[j];
-          st_pair256(amps + (at ^ off), sw ? re[i + 1] : re[i], sw ? im[i + 1] : im[i], sw ? re[i] : re[i + 1],
+          st_pair256(dst_of(at ^ off), sw ? re[i + 1] : re[i], sw ? im[i + 1] : im[i], sw ? re[i] : re[i + 1],
                      sw ? im[i] : im[i + 1]);
         }
       } else {
@@ -614,7 +623,7 @@ __global__ void __launch_bounds__(1 << (T - R), MINB)
 #pragma unroll
           for (int j = 0; j < R; ++j)
             if ((i >> j) & 1) off |= st[j];
-          __stcs(amps + (at ^ off), make_double2(re[i], im[i]));
+          __stcs(dst_of(at ^ off), make_double2(re[i], im[i]));
         }
       }
     }

@@ -68,6 +68,8 @@ bool set_opt(PlanOptions &o, const std::string &name, int64_t v) {
   } else if (name == "tma") {
     if (v < 0 || v > 3) return false;
     o.tma = (int)v;
+  } else if (name == "fuse_exchange") {
+    o.fuse_exchange = v ? 1 : 0;
   } else if (name == "pf_lines") {
     if (v < 0 || v > 4) return false;
     o.pf_lines = (int)v;
@@ -134,6 +136,7 @@ int64_t get_opt(const PlanOptions &o, const std::string &name) {
   if (name == "chunk_lanes") return o.chunk_lanes;
   if (name == "oop_dist") return o.oop_dist;
   if (name == "pf_lines") return o.pf_lines;
+  if (name == "fuse_exchange") return o.fuse_exchange;
   if (name == "jit_minb") return o.jit_minb;
   if (name == "jit_mem") return o.jit_mem;
   if (name == "jit_group") return o.jit_group;
@@ -516,6 +519,26 @@ std::vector<SwapStep> swap_schedule(int rank, int L, const std::vector<SwapPair>
     out.push_back({r, sel, mine});
   }
   return out;
+}
+
+bool fused_exchange_geometry(const DevPass &last, int L, int rank, int nranks, const std::vector<SwapPair> &sw, XchGeom *out) {
+  if (!last.oop || sw.empty() || sw.size() > 4 || nranks > kMaxXchRanks) return false;
+  for (const SwapPair &sp : sw)
+    if (sp.lbit < 1 || sp.lbit >= L || sp.gbit < L) return false;  // (bit 0: a 32-byte store of a register pair stays whole)
+  XchGeom X;
+  memset(&X, 0, sizeof X);
+  X.n = (uint32_t)sw.size();
+  X.rbase = (uint32_t)rank;
+  for (size_t i = 0; i < sw.size(); ++i) {
+    const uint32_t rb = (uint32_t)(sw[i].gbit - L);
+    X.lbit[i] = (uint32_t)sw[i].lbit;
+    X.rbit[i] = rb;
+    X.vmask |= 1ull << sw[i].lbit;
+    X.vconst |= uint64_t((rank >> rb) & 1) << sw[i].lbit;
+    X.rbase &= ~(1u << rb);
+  }
+  *out = X;
+  return true;
 }
 
 uint64_t place_sel(uint32_t sel, const std::vector<SwapPair> &pairs) {

@@ -180,7 +180,11 @@ int conflict_degree(const DevRound &rd, int T, int R, int i) {
   return worst;
 }
 
-void run_pass(const PassPlan &pp, int L, std::vector<double> &amps, EmuStats &st) {
+// xdst != nullptr and P.xch.n != 0: the stores carry a global<->local swap (XchGeom) -- tile by tile
+// they go to (*xdst)[destination rank] exactly as the kernels address their peers' second shards;
+// `amps` is left alone and the caller moves the buffers between the ranks.
+void run_pass(const PassPlan &pp, int L, std::vector<double> &amps, EmuStats &st,
+              std::vector<std::vector<double>> *xdst = nullptr) {
   const DevPass &P = *reinterpret_cast<const DevPass *>(pp.blob.data());
   const DevGate *G = pp.gates.data();
   const DevStep *S = reinterpret_cast<const DevStep *>(pp.blob.data() + sizeof(DevPass));
@@ -279,12 +283,19 @@ void run_pass(const PassPlan &pp, int L, std::vector<double> &amps, EmuStats &st
           xi = P.gscale[0] * xi + P.gscale[1] * xr;
           xr = yr;
         }
-        const uint64_t a = obase + goff(P.rounds[P.nrounds - 1], tid, i, P.out_pos);
-        dst[2 * a] = xr;
-        dst[2 * a + 1] = xi;
+        uint64_t a = obase + goff(P.rounds[P.nrounds - 1], tid, i, P.out_pos);
+        std::vector<double> *dstp = &dst;
+        if (P.oop && P.xch.n) {  // (as k_fused_pass / the generated kernels compute it, store by store)
+          uint32_t rr = P.xch.rbase;
+          for (uint32_t k = 0; k < P.xch.n; ++k) rr |= uint32_t((a >> P.xch.lbit[k]) & 1ull) << P.xch.rbit[k];
+          a = (a & ~P.xch.vmask) | P.xch.vconst;
+          dstp = &(*xdst)[rr];
+        }
+        (*dstp)[2 * a] = xr;
+        (*dstp)[2 * a + 1] = xi;
       }
   }
-  if (P.oop) amps.swap(other);
+  if (P.oop && !P.xch.n) amps.swap(other);
   st.passes++;
   st.rounds += P.nrounds;
   for (uint32_t r = 1; r < P.nrounds; ++r) {
@@ -310,6 +321,38 @@ void undo_layout(const PlanResult &plan, int nlocal, std::vector<double> &a) {
 }
 
 }  // namespace
+
+// structural key -> host function of the generated code (g++ on the host flavour of the source),
+// PROCESS-WIDE: if two different structures ever shared a key, a later circuit would run the wrong
+// code here and fail its parity check -- the tests thereby also check that the key captures
+// everything that shapes the generated source
+typedef int (*host_fn)(double *, const double *, uint64_t, const void *, uint64_t);
+static std::vector<std::pair<std::string, void *>> g_host_libs;
+int host_code_for(const PassPlan &p, const JitProgram &kp, const char *workdir, host_fn *out) {
+  static int nlibs = 0;  // (file names must never repeat inside a process: dlopen caches by path)
+  void *fn = nullptr;
+  for (auto &pr : g_host_libs)
+    if (pr.first == kp.key) fn = pr.second;
+  if (!fn) {
+    JitProgram hp;
+    std::string why;
+    if (!jit_generate(p, JIT_HOST_SRC, hp, &why)) return -6;
+    const std::string base = std::string(workdir) + "/qbj_" + std::to_string((long)getpid()) + "_" + std::to_string(nlibs++);
+    FILE *f = std::fopen((base + ".cpp").c_str(), "w");
+    if (!f) return -9;
+    std::fwrite(hp.src.data(), 1, hp.src.size(), f);
+    std::fclose(f);
+    const std::string cmd = "g++ -std=c++17 -O1 -fPIC -shared -Wno-unknown-pragmas -o " + base + ".so " + base + ".cpp 2> " + base + ".log";
+    if (std::system(cmd.c_str()) != 0) return -10;
+    void *lib = dlopen((base + ".so").c_str(), RTLD_NOW | RTLD_LOCAL);
+    if (!lib) return -11;
+    fn = dlsym(lib, "qb_jit_pass_host");
+    if (!fn) return -12;
+    g_host_libs.emplace_back(kp.key, fn);
+  }
+  *out = reinterpret_cast<host_fn>(fn);
+  return 0;
+}
 
 extern "C" {
 
@@ -438,11 +481,7 @@ int qbe_run_jit(int nlocal, const qb_op *ops, int64_t nops, const char *options,
   EmuStats st;
   double pending = 1.0;
   int njit = 0;
-  static int nlibs = 0;  // (file names must never repeat inside a process: dlopen caches by path)
-  // structural key -> host function, PROCESS-WIDE: if two different structures ever shared a key,
-  // a later circuit would run the wrong code here and fail its parity check -- the tests thereby
-  // also check that the key captures everything that shapes the generated source
-  static std::vector<std::pair<std::string, void *>> libs;
+  auto &libs = g_host_libs;
   const size_t libs_before = libs.size();
   int nguard = 0;
   for (auto &p : plan.passes) {
@@ -479,33 +518,15 @@ int qbe_run_jit(int nlocal, const qb_op *ops, int64_t nops, const char *options,
       std::memcpy(dev_src_out, dp.src.c_str(), dp.src.size() + 1);
       if (dp.key.size() == 0 || dp.coefs != kp.coefs) return -8;
     }
-    void *fn = nullptr;
-    for (auto &pr : libs)
-      if (pr.first == kp.key) fn = pr.second;
-    if (!fn) {
-      JitProgram hp;
-      if (!jit_generate(p, JIT_HOST_SRC, hp, &why)) return -6;
-      const std::string base = std::string(workdir) + "/qbj_" + std::to_string((long)getpid()) + "_" + std::to_string(nlibs++);
-      FILE *f = std::fopen((base + ".cpp").c_str(), "w");
-      if (!f) return -9;
-      std::fwrite(hp.src.data(), 1, hp.src.size(), f);
-      std::fclose(f);
-      const std::string cmd = "g++ -std=c++17 -O1 -fPIC -shared -Wno-unknown-pragmas -o " + base + ".so " + base + ".cpp 2> " + base + ".log";
-      if (std::system(cmd.c_str()) != 0) return -10;
-      void *lib = dlopen((base + ".so").c_str(), RTLD_NOW | RTLD_LOCAL);
-      if (!lib) return -11;
-      fn = dlsym(lib, "qb_jit_pass_host");
-      if (!fn) return -12;
-      libs.emplace_back(kp.key, fn);
-    }
+    host_fn fn = nullptr;
+    if (int rc = host_code_for(p, kp, workdir, &fn)) return rc;
     const double one[2] = {1.0, 0.0};
     const std::vector<uint8_t> args = jit_pack_args(kp, P.has_gscale ? P.gscale : one, P.rank_bits, P.base_fixed);
-    typedef int (*host_fn)(double *, const double *, uint64_t, const void *, uint64_t);
     if (P.oop) {
       std::vector<double> other(a.size(), NAN);
-      if (reinterpret_cast<host_fn>(fn)(other.data(), a.data(), p.ntiles, args.data(), (uint64_t)args.size()) != 0) return -13;
+      if (fn(other.data(), a.data(), p.ntiles, args.data(), (uint64_t)args.size()) != 0) return -13;
       a.swap(other);
-    } else if (reinterpret_cast<host_fn>(fn)(a.data(), a.data(), p.ntiles, args.data(), (uint64_t)args.size()) != 0) {
+    } else if (fn(a.data(), a.data(), p.ntiles, args.data(), (uint64_t)args.size()) != 0) {
       return -13;
     }
     pending *= kp.left_out;
@@ -633,6 +654,8 @@ int qbe_jit_dump(int nlocal, const qb_op *ops, int64_t nops, const char *options
 // and choose swaps exactly as a flush would, `nsteps` times in a row; out_perm receives the
 // logical->physical map after every step (nsteps x n ints), out_counts per step
 // (passes, swaps, structures not seen in any earlier step).
+static int64_t g_trace_fused = 0;  // swaps of the last qbe_layout_trace call that a pass's stores could carry
+int64_t qbe_trace_fused() { return g_trace_fused; }
 int qbe_layout_trace(int n, int nranks, const qb_op *ops, int64_t nops, const char *options, int nsteps, int any_local,
                      int *out_perm, int64_t *out_counts) {
   PlanOptions opt;
@@ -663,6 +686,7 @@ int qbe_layout_trace(int n, int nranks, const qb_op *ops, int64_t nops, const ch
   for (int i = 0; i < n; ++i) perm[i] = i;
   std::vector<std::string> seen_keys;
   static const double X[8] = {0, 0, 1, 0, 1, 0, 0, 0};
+  g_trace_fused = 0;
   for (int step = 0; step < nsteps; ++step) {
     OpQueue q;
     q.reset(n, opt.peephole != 0, opt.rot != 0);
@@ -731,6 +755,18 @@ int qbe_layout_trace(int n, int nranks, const qb_op *ops, int64_t nops, const ch
         if (!h.dead) all.push_back(&h);
       std::vector<SwapPair> sw = choose_swaps(n, L, perm, rest, (any_local & 1) != 0, (any_local & 2) ? &all : nullptr);
       if (sw.empty()) return -4;
+      if (!plan.passes.empty() && !plan.final_pos.empty()) {  // would the last pass's stores carry this swap? (option fuse_exchange)
+        XchGeom X;
+        const DevPass &LP = *reinterpret_cast<const DevPass *>(plan.passes.back().blob.data());
+        if (fused_exchange_geometry(LP, L, 0, nranks, sw, &X)) ++g_trace_fused;
+        else if (getenv("QBE_TRACE_WHY")) {
+          std::fprintf(stderr, "step %d: not fusable: oop=%d T=%d pairs", step, (int)LP.oop, (int)LP.tile_bits);
+          for (const SwapPair &sp : sw) std::fprintf(stderr, " (g%d,l%d)", sp.gbit, sp.lbit);
+          std::fprintf(stderr, "\n");
+        }
+      } else if (getenv("QBE_TRACE_WHY")) {
+        std::fprintf(stderr, "step %d: no pass before the swap (passes %zu, final_pos %zu)\n", step, plan.passes.size(), plan.final_pos.size());
+      }
       apply_swaps_to_perm(perm, sw);
       ++nswap;
       seg.swap(rest);
@@ -798,6 +834,7 @@ int qbe_run_rank(int n, int nranks, int rank, const qb_op *ops, int64_t nops, co
   std::vector<double> a(amps, amps + (size_t(2) << L));
   EmuStats st;
   int nswaps = 0;
+  int64_t nfused = 0, njit_fused = 0;
   bool gdone = (q.gscale[0] == 1.0 && q.gscale[1] == 0.0);
   while (!seg.empty()) {
     std::vector<PhysOp> pops(seg.size());
@@ -822,23 +859,117 @@ int qbe_run_rank(int n, int nranks, int rank, const qb_op *ops, int64_t nops, co
       P->has_gscale = 1;
       gdone = true;
     }
-    for (const auto &p : plan.passes) run_pass(p, L, a, st);
+    std::vector<const HostOp *> rest;
+    for (size_t i = 0; i < seg.size(); ++i)
+      if (!plan.done[i]) rest.push_back(seg[i]);
+    // any_local: bit 0 = Belady over any local bit (peer-memory path), bit 1 = cyclic tie-break
+    // (the flush's own op stream as the future, as qb_api.cpp's make_local passes it), bit 2 = the
+    // swap rides on the stores of the plan's last pass where it can (option fuse_exchange)
+    std::vector<const HostOp *> all_ops;
+    for (const auto &h : q.ops)
+      if (!h.dead) all_ops.push_back(&h);
+    std::vector<SwapPair> sw;
+    bool fused = false;
+    if (!all) {
+      std::vector<int> perm2 = perm;  // the layout after this plan: what the swap is chosen on
+      if (!plan.final_pos.empty())
+        for (int &x : perm2)
+          if (x < L) x = plan.final_pos[x];
+      sw = choose_swaps(n, L, perm2, rest, (any_local & 1) != 0, (any_local & 2) ? &all_ops : nullptr);
+      if (sw.empty()) return -4;
+      if ((any_local & 4) && !plan.passes.empty() && !plan.final_pos.empty()) {
+        DevPass *LP = reinterpret_cast<DevPass *>(plan.passes.back().blob.data());
+        fused = fused_exchange_geometry(*LP, L, rank, nranks, sw, &LP->xch);
+      }
+    }
+    for (size_t pi = 0; pi < plan.passes.size(); ++pi) {
+      if (!fused || pi + 1 < plan.passes.size()) {
+        run_pass(plan.passes[pi], L, a, st);
+        continue;
+      }
+      // the last pass stores into one buffer per destination rank; gloo then stands in for NVLink:
+      // what I wrote for `peer` goes there, what `peer` wrote for me fills the places whose victim
+      // bits carry the peer's old rank-bit values
+      const DevPass &LP = *reinterpret_cast<const DevPass *>(plan.passes[pi].blob.data());
+      std::vector<std::vector<double>> xdst(nranks);
+      for (uint32_t sel = 0; sel < (1u << LP.xch.n); ++sel) {
+        uint32_t rr = LP.xch.rbase;
+        for (uint32_t j = 0; j < LP.xch.n; ++j) rr |= ((sel >> j) & 1u) << LP.xch.rbit[j];
+        xdst[rr].assign(a.size(), NAN);
+      }
+      JitProgram kp;
+      if ((any_local & 8) && jit_quick(plan.passes[pi], kp, nullptr)) {
+        // the same pass as GENERATED code (host flavour; the peer table holds the per-rank buffers):
+        // what it leaves out is applied right away
+        DevPass &XP = *reinterpret_cast<DevPass *>(plan.passes[pi].blob.data());
+        for (int r = 0; r < nranks; ++r) XP.xch.peer[r] = reinterpret_cast<uint64_t>(xdst[r].data());
+        host_fn fn = nullptr;
+        const char *wd = getenv("QBE_WORKDIR");
+        if (int rc = host_code_for(plan.passes[pi], kp, wd ? wd : "/tmp", &fn)) return rc;
+        const double one[2] = {1.0, 0.0};
+        const std::vector<uint8_t> args = jit_pack_args(kp, XP.has_gscale ? XP.gscale : one, XP.rank_bits, XP.base_fixed, &XP.xch);
+        if (fn(nullptr, a.data(), plan.passes[pi].ntiles, args.data(), (uint64_t)args.size()) != 0) return -13;
+        for (auto &v : xdst)
+          for (double &x : v) x *= kp.left_out;  // (NaN stays NaN)
+        st.passes++;
+        ++njit_fused;
+      } else {
+        run_pass(plan.passes[pi], L, a, st, &xdst);
+      }
+      const int k = (int)sw.size();
+      const uint64_t block = 1ull << (L - k);
+      auto deposit = [&](uint64_t t) {
+        uint64_t idx = 0;
+        int src = 0;
+        for (int b2 = 0; b2 < L; ++b2)
+          if (!(LP.xch.vmask & (1ull << b2))) {
+            idx |= ((t >> src) & 1ull) << b2;
+            ++src;
+          }
+        return idx;
+      };
+      auto vbits_of = [&](int r) {  // rank r's values on the swapped rank bits, placed on the victims' positions
+        uint64_t v = 0;
+        for (uint32_t j = 0; j < LP.xch.n; ++j) v |= uint64_t((r >> LP.xch.rbit[j]) & 1) << LP.xch.lbit[j];
+        return v;
+      };
+      std::vector<double> b(a.size(), NAN), send(2 * block), recv(2 * block);
+      for (uint32_t sel = 0; sel < (1u << LP.xch.n); ++sel) {
+        int peer = rank;
+        for (uint32_t j = 0; j < LP.xch.n; ++j) peer ^= int((sel >> j) & 1u) << LP.xch.rbit[j];
+        for (uint64_t t = 0; t < block; ++t) {
+          const uint64_t i = deposit(t) | LP.xch.vconst;
+          send[2 * t] = xdst[peer][2 * i];
+          send[2 * t + 1] = xdst[peer][2 * i + 1];
+        }
+        if (peer == rank) recv = send;
+        else if (xchg(peer, send.data(), recv.data(), (int64_t)(2 * block)) != 0) return -5;
+        const uint64_t at = vbits_of(peer);
+        for (uint64_t t = 0; t < block; ++t) {
+          const uint64_t i = deposit(t) | at;
+          b[2 * i] = recv[2 * t];
+          b[2 * i + 1] = recv[2 * t + 1];
+        }
+      }
+      // nothing else may have been written: every other place of the per-rank buffers is still NaN
+      for (int r = 0; r < nranks; ++r)
+        for (size_t i = 0; i < xdst[r].size() / 2; ++i)
+          if ((i & LP.xch.vmask) != LP.xch.vconst && !std::isnan(xdst[r][2 * i])) return -6;
+      a.swap(b);
+      ++nfused;
+    }
     if (!plan.final_pos.empty()) {
       for (int &x : perm)
         if (x < L) x = plan.final_pos[x];
       opt.layout_known = 1;
     }
     if (all) break;
-    std::vector<const HostOp *> rest;
-    for (size_t i = 0; i < seg.size(); ++i)
-      if (!plan.done[i]) rest.push_back(seg[i]);
-    // any_local: bit 0 = Belady over any local bit (peer-memory path), bit 1 = cyclic tie-break
-    // (the flush's own op stream as the future, as qb_api.cpp's make_local passes it)
-    std::vector<const HostOp *> all_ops;
-    for (const auto &h : q.ops)
-      if (!h.dead) all_ops.push_back(&h);
-    std::vector<SwapPair> sw = choose_swaps(n, L, perm, rest, (any_local & 1) != 0, (any_local & 2) ? &all_ops : nullptr);
-    if (sw.empty()) return -4;
+    if (fused) {
+      apply_swaps_to_perm(perm, sw);
+      ++nswaps;
+      seg.swap(rest);
+      continue;
+    }
     const int k = (int)sw.size();
     const uint64_t block = 1ull << (L - k);
     uint64_t swapped = 0;
@@ -887,6 +1018,8 @@ int qbe_run_rank(int n, int nranks, int rank, const qb_op *ops, int64_t nops, co
     stats_out[1] = st.rounds;
     stats_out[2] = st.gates;
     stats_out[3] = st.max_bank_conflict;
+    stats_out[4] = nfused;
+    stats_out[5] = njit_fused;
   }
   return nswaps;
 }

@@ -24,7 +24,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, n, seed, out_dir, any_local):
+def _worker(rank, world, port, n, seed, out_dir, any_local, options=b"", nsteps=1):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -62,10 +62,15 @@ def _worker(rank, world, port, n, seed, out_dir, any_local):
     shard = np.ascontiguousarray(full[rank << L:(rank + 1) << L]).copy()
     perm = (C.c_int * n)(*range(n))
     arr = capi.pack_ops(ops)
-    st = (C.c_int64 * 4)()
+    st = (C.c_int64 * 6)()
     cb = XCHG(xchg)
-    nsw = E.qbe_run_rank(n, world, rank, arr, len(arr), b"", shard.ctypes.data_as(C.c_void_p), perm, cb, st, any_local)
-    assert nsw >= 1, f"expected at least one global<->local swap, rc={nsw}"
+    nsw = nfused = njit = 0
+    for _ in range(nsteps):  # (an iterated circuit: the later steps start from the layout the earlier ones left)
+        rc = E.qbe_run_rank(n, world, rank, arr, len(arr), options, shard.ctypes.data_as(C.c_void_p), perm, cb, st, any_local)
+        assert rc >= 1, f"expected at least one global<->local swap, rc={rc}"
+        nsw += rc
+        nfused += st[4]
+        njit += st[5]
     # every rank must have made the same layout decisions
     perms = [None] * world
     dist.all_gather_object(perms, list(perm))
@@ -79,10 +84,12 @@ def _worker(rank, world, port, n, seed, out_dir, any_local):
         for q in range(n):
             pidx |= ((idx >> q) & 1) << perms[0][q]
         got = phys[pidx]
-        ref = S.run_ops(n, ops, full)
+        ref = full
+        for _ in range(nsteps):
+            ref = S.run_ops(n, ops, ref)
         err = float(np.abs(got - ref).max())
         with open(os.path.join(out_dir, "result.txt"), "w") as f:
-            f.write(f"{err} {nsw} {nbytes[0]} {L}")
+            f.write(f"{err} {nsw} {nbytes[0]} {L} {nfused} {njit}")
     dist.barrier()
     dist.destroy_process_group()
 
@@ -96,9 +103,34 @@ def test_sharded_exchange_over_gloo(tmp_path, emul, world, n, any_local):
     import torch.multiprocessing as mp
     port = _free_port()
     mp.spawn(_worker, args=(world, port, n, 77 + world, str(tmp_path), any_local), nprocs=world, join=True)
-    err, nsw, nbytes, L = open(tmp_path / "result.txt").read().split()
+    err, nsw, nbytes, L, _, _ = open(tmp_path / "result.txt").read().split()
     assert float(err) < 1e-13
     # volume per swap of k bits is (1 - 2^-k) of the shard each way
+    assert int(nbytes) <= int(nsw) * 16 * (1 << int(L))
+
+
+@pytest.mark.parametrize("world,n,options,nsteps,how", [(2, 13, b"tile_bits=10,reg_bits=3", 2, 7), (4, 14, b"tile_bits=10,reg_bits=3", 2, 15),
+                                                        (8, 16, b"tile_bits=10,reg_bits=3", 2, 7), (8, 15, b"", 3, 15),
+                                                        (2, 18, b"", 4, 15)],
+                         ids=lambda v: str(v))
+def test_swap_carried_by_the_stores_of_the_last_pass(tmp_path, emul, world, n, options, nsteps, how):
+    """Option fuse_exchange: the out-of-place pass before a global<->local swap stores every tile
+    straight into the shard of the rank that owns it afterwards.  The emulator runs the planner's
+    geometry (fused_exchange_geometry -> XchGeom) and the kernels' destination arithmetic per tile,
+    with one buffer per destination rank and gloo in NVLink's place; nothing lands outside the
+    places a rank owns in its peers' shards, and several steps in a row (each starts from the
+    layout the one before left) reassemble to the oracle's state.  how = 7: the emulated generic
+    kernel; 15: the GENERATED code of that pass (host flavour of the specialised kernel's source,
+    its peer table aimed at the per-rank buffers)."""
+    os.environ["QBE_WORKDIR"] = str(tmp_path)
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, n, 31 + world, str(tmp_path), how, options, nsteps), nprocs=world,
+             join=True)
+    err, nsw, nbytes, L, nfused, njit = open(tmp_path / "result.txt").read().split()
+    assert float(err) < 1e-13
+    assert int(nfused) >= 1, "no swap was carried by a pass"
+    assert how != 15 or int(njit) >= 1, "the generated code never ran"
     assert int(nbytes) <= int(nsw) * 16 * (1 << int(L))
 
 

@@ -221,3 +221,46 @@ def test_read_beyond_two_to_the_22(groups):
     for got in run_group(ctxs, rank_fn):
         assert np.array_equal(got, full)
         assert np.signbit(got[5].real)
+
+
+@pytest.mark.parametrize("P,n", [(2, 16), (4, 18), (8, 20)])
+def test_swap_carried_by_the_stores_of_a_fused_pass(groups, P, n):
+    """Option fuse_exchange (default on): the pass before a global<->local swap writes every tile
+    straight into the second shard of the rank that owns it after the swap (XchGeom, qb_internal.h)
+    instead of a local store plus an exchange sweep.  Same amplitudes, bit for bit, as the two-step
+    path; generic and specialised kernels; the layouts that follow are the same too."""
+    import qubism_b200 as Q
+    from oracle import structured as S
+    from qubism_b200.circuits import random_layers, qft_ops
+    ctxs = groups(P)
+    L = n - (P.bit_length() - 1)
+    ops = random_layers(n, 4, seed=3 + n, lam0=False) + qft_ops(n)
+    full = S.gen_state(n, np.random.default_rng(77 + P))
+    ref = S.run_ops(n, ops, S.run_ops(n, ops, full))
+
+    def rank_fn(r, ctx):
+        outs = {}
+        for fuse, jit in ((1, 0), (0, 0), (1, 1)):
+            ctx.set_option("fuse_exchange", fuse)
+            ctx.set_option("jit", jit)
+            ctx.reset_stats()
+            sv = Q.StateVec.from_host(full[r << L:(r + 1) << L], n=n, ctx=ctx)
+            for _ in range(2):
+                sv.submit(ops)
+                sv.flush()
+            outs[(fuse, jit)] = (sv.to_host(), ctx.stats())
+        ctx.set_option("fuse_exchange", 1)
+        ctx.set_option("jit", 2)
+        return outs
+
+    for outs in run_group(ctxs, rank_fn):
+        a, sa = outs[(1, 0)]
+        b, sb = outs[(0, 0)]
+        c, sc = outs[(1, 1)]
+        assert np.abs(a - ref).max() < TOL and np.abs(b - ref).max() < TOL and np.abs(c - ref).max() < TOL
+        assert np.array_equal(a, b)
+        assert sb["exchanges_fused"] == 0 and sb["exchanges"] >= 2
+        assert sa["exchanges"] == sb["exchanges"] and sa["exchange_bytes"] == sb["exchange_bytes"]
+        assert sa["exchanges_fused"] >= 1 and sc["exchanges_fused"] == sa["exchanges_fused"]
+        assert sa["passes"] == sb["passes"]
+        assert sc["jit_launches"] >= 1

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     assert C.sizeof(capi.QbC64) == 16
     assert C.sizeof(capi.QbOp) == 4 * 8 + 64
-    assert C.sizeof(capi.QbStats) == 9 * 8 + 8 + 16 + 8 + 24 + 24
+    assert C.sizeof(capi.QbStats) == 9 * 8 + 8 + 16 + 8 + 24 + 24 + 8
 
 
 def test_no_cpu_fallback_without_gpu():

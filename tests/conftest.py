@@ -14,6 +14,26 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+_MAX_ERR = {}
+
+
+def note_error(err, tol):
+    """Parity tests report every |GPU - oracle| maximum they compare; the session writes the largest
+    per test (and its tolerance) to gpurun_out/parity_max_err.json when that directory exists."""
+    name = os.environ.get("PYTEST_CURRENT_TEST", "?").split(" ")[0]
+    old = _MAX_ERR.get(name, (0.0, tol))
+    _MAX_ERR[name] = (max(old[0], err), tol)
+
+
+def pytest_sessionfinish(session, exitstatus):
+    out = os.path.join(ROOT, "gpurun_out")
+    if _MAX_ERR and os.path.isdir(out):
+        import json
+        worst = max(v[0] for v in _MAX_ERR.values())
+        with open(os.path.join(out, "parity_max_err.json"), "w") as f:
+            json.dump({"worst": worst, "tests": {k: {"max_abs_err": v[0], "tol": v[1]} for k, v in sorted(_MAX_ERR.items())}}, f, indent=1)
+
+
 @pytest.fixture(scope="session")
 def ctx():
     """The process-wide device context.  Fails loudly (no fallback) if the CUDA library or a

@@ -86,7 +86,7 @@ def test_algebra_between_states_with_different_layouts(ctx, default_opts):
     a.submit(oa)
     b.submit(ob)
     ra, rb = S.run_ops(n, oa, va), S.run_ops(n, ob, vb)
-    assert abs(a.inner(b) - np.vdot(ra, rb)) < 1e-11
+    assert abs(a.inner(b) - np.vdot(ra, rb)) < 1e-12
     c = a.clone()
     c.submit(ob)  # the older value `a` stays alive: copy-on-write
     assert np.abs(c.to_host() - S.run_ops(n, ob, ra)).max() < TOL
@@ -125,4 +125,4 @@ def test_an_iterated_circuit_finds_its_specialised_kernels_again(ctx, default_op
         ref = S.run_ops(n, ops, ref)
     assert st["jit_launches"] == st["passes"], f"{st['jit_launches']} of {st['passes']} passes specialised in step 8"
     got = sv.to_host()
-    assert np.abs(got - ref).max() < 1e-11 * max(1.0, float(np.abs(ref).max()))
+    assert np.abs(got - ref).max() < 1e-12 * max(1.0, float(np.abs(ref).max()))

@@ -25,7 +25,10 @@ def close(a, b, tol=TOL):
     a, b = np.asarray(a), np.asarray(b)
     if np.isnan(a).any() or np.isnan(b).any():
         return bool(np.isnan(a).any() and np.isnan(b).any())
-    return bool(np.abs(a - b).max() <= tol)
+    err = float(np.abs(a - b).max())
+    import conftest
+    conftest.note_error(err, tol)  # (the largest |difference| each test saw goes to gpurun_out/parity_max_err.json)
+    return err <= tol
 
 
 def cvec(v):
@@ -130,7 +133,7 @@ def test_fused_passes_planner_knobs(default_opts, opts):
     ops = random_layers(n, 2, seed=9, lam0=False) + extras(n) + qft_ops(n)
     sv = Q.StateVec.from_host(v)
     sv.submit([o for o in ops])  # batch path (qb_submit)
-    assert close(sv.to_host(), S.run_ops(n, ops, v), 1e-11 if opts.get("peephole") == 0 else TOL)
+    assert close(sv.to_host(), S.run_ops(n, ops, v))
 
 
 @pytest.mark.parametrize("lane_fixed", [3, 1, 0])
@@ -210,7 +213,7 @@ def test_specialised_kernels_random_mixes(default_opts, seed):
     ref = S.run_ops(n, ops, v, record=rec_ref)
     rec = sv.run_ops(ops)
     assert [(q, b) for q, b, _ in rec] == [(q, b) for q, b, _ in rec_ref]
-    assert close(sv.to_host(), ref, 1e-11)
+    assert close(sv.to_host(), ref)
 
 
 def test_specialised_kernels_second_sighting_default(default_opts):
@@ -269,7 +272,7 @@ def test_random_mixed_circuits_random_knobs(default_opts, seed):
     ref = S.run_ops(n, ops, v, record=rec_ref)
     rec = sv.run_ops(ops)
     assert [(q, b) for q, b, _ in rec] == [(q, b) for q, b, _ in rec_ref]
-    assert close(sv.to_host(), ref, 1e-11)
+    assert close(sv.to_host(), ref)
 
 
 @pytest.mark.parametrize("jit", [0, 1])
@@ -309,7 +312,8 @@ def test_dense_kq_blocks(ctx):
             for ctrls in ((), (free[0],)):
                 got = Q.StateVec.from_host(v).apply_1q(free[-1], D.hadamard()).apply_kq(qs, M, ctrls).to_host()
                 ref = S.apply_kq(n, qs, M, S.apply_1q(n, free[-1], D.hadamard(), v), ctrls)
-                assert close(got, ref, 1e-11)
+                # (M is not normalised: 1e-12 relative to the largest amplitude it produces)
+                assert close(got, ref, TOL * max(1.0, float(np.abs(ref).max())))
     # kronecker a b acts with a on the FIRST qubits (QGate.hs:142-144)
     a, b = D.unitary(1, 2, 3), D.unitary(.4, .5, .6)
     v = S.gen_state(2, rng)
@@ -374,7 +378,7 @@ def test_support_tracking_from_basis_state_measure_reset_and_observers(ctx):
     assert close(c.to_host(), v)
     w = S.gen_state(n, rng)
     other = Q.StateVec.from_host(w)
-    assert abs(sv.inner(other) - np.vdot(v, w)) < 1e-11
+    assert abs(sv.inner(other) - np.vdot(v, w)) < TOL
     assert close((sv + other).to_host(), v + w) and close((other - sv).to_host(), w - v)
     assert close((2j * sv).to_host(), 2j * v)
     sv.collapse_(3, 0)  # the dead value of a known bit: weight 0 -> NaN everywhere, as the reference
@@ -475,7 +479,7 @@ def test_symbolic_gates_through_the_abi(ctx):
     lin = (0.5 - 2j) * g + Q.kronecker(Q.onRange(2, 0, 1, Q.pauliY()), Q.cnot(2, 1, 0)) - Q.ident(n)
     own = Q.controlled(1, Q.onJust(n, 1, Q.pauliX()))  # literal M.P + I - P, not a controlled gate
     for gate in (g, lin, own):
-        assert close(Q.apply(gate, Q.StateVec.from_host(v)).to_host(), gate.dense() @ v, 1e-11)
+        assert close(Q.apply(gate, Q.StateVec.from_host(v)).to_host(), gate.dense() @ v)
 
 
 class GpuBackend:
@@ -572,7 +576,25 @@ def test_persistent_tile_loop_vs_oracle_22q(default_opts, jit):
         sv.submit(ops)
         assert close(sv.to_host(), ref)
         sv.submit(_inverse(ops))
-        assert close(sv.to_host(), v, 1e-11)
+        assert close(sv.to_host(), v)
+
+
+def test_qft_24_every_amplitude_against_the_c_port(ctx):
+    """BASELINE.json config C2 (QFT at 24 qubits), plus two random layers, from a random state:
+    all 2^24 amplitudes against the C/OpenMP restatement of the reference (oracle/csrc, itself held
+    to the literal-dense and structured oracles by tests/test_oracle.py), generic and specialised
+    kernels."""
+    from oracle import cport
+    n = 24
+    v = S.gen_state(n, np.random.default_rng(24))
+    ops = qft_ops(n) + random_layers(n, 2, seed=24)
+    ref = cport.run_ops(n, ops, v)
+    for jit in (0, 1):
+        ctx.set_option("jit", jit)
+        sv = Q.StateVec.from_host(v)
+        sv.submit(ops)
+        assert close(sv.to_host(), ref)
+    ctx.set_option("jit", 2)
 
 
 @pytest.mark.parametrize("n", [26, 30])
@@ -584,7 +606,7 @@ def test_full_size_round_trip_and_norm(ctx, n):
     ctx.set_option("jit", 1)  # specialised kernels at full size
     sv.submit(ops)
     tot = sv.norm2() ** 2
-    assert abs(tot - 1.0) < 1e-11
+    assert abs(tot - 1.0) < TOL
     for q in (0, n // 2, n - 1):
         s0, s1 = sv.sumsq(q)
         assert abs(s0 + s1 - tot) < 1e-12 and 0 < s1 < 1
@@ -592,8 +614,8 @@ def test_full_size_round_trip_and_norm(ctx, n):
     assert np.abs(window).max() < 1e-2  # spread out, nothing left of the basis state
     sv.submit(_inverse(ops))
     head = sv.to_host(0, 4096)
-    assert abs(head[0] - 1.0) < 1e-11 and np.abs(head[1:]).max() < 1e-12
-    assert abs(sv.norm2() - 1.0) < 1e-11
+    assert abs(head[0] - 1.0) < TOL and np.abs(head[1:]).max() < 1e-12
+    assert abs(sv.norm2() - 1.0) < TOL
     ctx.set_option("jit", 2)
 
 
@@ -622,5 +644,5 @@ def test_specialised_kernels_range_guard_on_a_long_flush(default_opts):
     ref = S.run_ops(n, ops, v)
     sv = Q.StateVec.from_host(v)
     sv.submit(ops)
-    assert close(sv.to_host(), ref, 1e-11)
-    assert abs(sv.norm2() - np.linalg.norm(ref)) < 1e-11
+    assert close(sv.to_host(), ref)
+    assert abs(sv.norm2() - np.linalg.norm(ref)) < TOL

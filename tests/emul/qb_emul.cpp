@@ -1024,4 +1024,70 @@ int qbe_run_rank(int n, int nranks, int rank, const qb_op *ops, int64_t nops, co
   return nswaps;
 }
 
+// Device source of a pass whose stores carry a global<->local swap (option fuse_exchange), for an
+// NVRTC compile check that needs no GPU: plan `ops` on an nlocal-qubit shard of rank 1 of 4, hand the
+// last out-of-place pass a swap of the two rank bits with local bits `lbit0`, `lbit1`, generate.
+int qbe_xch_source(int nlocal, const qb_op *ops, int64_t nops, const char *options, int lbit0, int lbit1, char *out, int64_t cap) {
+  PlanOptions opt;
+  if (options) {
+    std::string o(options);
+    size_t pos = 0;
+    while (pos < o.size()) {
+      size_t e = o.find(',', pos);
+      if (e == std::string::npos) e = o.size();
+      std::string kv = o.substr(pos, e - pos);
+      size_t eq = kv.find('=');
+      if (eq != std::string::npos && !set_opt(opt, kv.substr(0, eq), strtoll(kv.c_str() + eq + 1, nullptr, 10)))
+        return -1;
+      pos = e + 1;
+    }
+  }
+  OpQueue q;
+  q.reset(nlocal, opt.peephole != 0, opt.rot != 0);
+  static const double X[8] = {0, 0, 1, 0, 1, 0, 0, 0};
+  for (int64_t i = 0; i < nops; ++i) {
+    const qb_op &o = ops[i];
+    uint64_t cm = 0;
+    const int nc = o.kind == 1 ? 1 : o.nctrl;
+    for (int k = 0; k < nc; ++k) cm |= 1ull << (nlocal - 1 - o.ctrl[k]);
+    q.push_1q(nlocal - 1 - o.target, cm, o.kind == 1 ? X : reinterpret_cast<const double *>(o.m));
+  }
+  int T, R;
+  effective_tile(opt, nlocal, T, R);
+  if (T == 0) return -2;
+  opt.tile_bits = T;
+  opt.reg_bits = R;
+  if (opt.oop && opt.low_bits < opt.oop_low_bits) opt.low_bits = std::min(opt.oop_low_bits, T);
+  std::vector<PhysOp> pops;
+  for (const auto &h : q.ops) {
+    if (h.dead) continue;
+    PhysOp p;
+    p.type = h.type;
+    p.target = h.target;
+    p.ctrl = h.ctrl;
+    std::memcpy(p.m, h.m, sizeof(h.m));
+    pops.push_back(p);
+  }
+  PlanResult plan = plan_passes(pops, nlocal, 1, opt, nullptr);
+  if (plan.passes.empty()) return -3;
+  PassPlan &pp = plan.passes.back();
+  DevPass &LP = *reinterpret_cast<DevPass *>(pp.blob.data());
+  const std::vector<SwapPair> sw = {{nlocal, lbit0}, {nlocal + 1, lbit1}};
+  if (!fused_exchange_geometry(LP, nlocal, 1, 4, sw, &LP.xch)) return -4;
+  JitProgram dp, plain;
+  std::string why;
+  if (!jit_generate(pp, JIT_DEVICE_SRC, dp, &why)) return -6;
+  if ((int64_t)dp.src.size() + 1 > cap) return -7;
+  std::memcpy(out, dp.src.c_str(), dp.src.size() + 1);
+  // the structure key tells the two kinds of pass apart, and nothing of the geometry leaks into it
+  JitProgram k1, k2;
+  if (!jit_quick(pp, k1, nullptr)) return -8;
+  LP.xch.lbit[0] ^= 1u;
+  LP.xch.rbase ^= 2u;
+  if (!jit_quick(pp, k2, nullptr) || k1.key != k2.key) return -9;
+  LP.xch.n = 0;
+  if (!jit_quick(pp, plain, nullptr) || plain.key == k1.key) return -10;
+  return 0;
+}
+
 }  // extern "C"

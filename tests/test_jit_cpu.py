@@ -167,6 +167,28 @@ def test_device_source_compiles_with_nvrtc(jit_emul, opts):
     assert nbytes.value > 1000
 
 
+@pytest.mark.parametrize("opts,lbits", [("", (11, 10)), ("", (12, 3)), ("reg_bits=5", (9, 1)), ("tile_bits=10,reg_bits=3", (12, 11))])
+def test_swap_carrying_pass_compiles_with_nvrtc(jit_emul, opts, lbits):
+    """The generated kernel whose stores carry a global<->local swap (option fuse_exchange): peer table
+    and geometry are kernel arguments (QbjXch), the destination is worked out store by store
+    (qbj_xch_dst); one flag of the structure key tells it from the plain pass."""
+    n = 13
+    E = C.CDLL(os.path.join(ROOT, "tests", "emul", "libqb_emul.so"))
+    E.qbe_xch_source.argtypes = [C.c_int, C.POINTER(capi.QbOp), C.c_int64, C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_int64]
+    ops = capi.pack_ops(random_layers(n, 4, seed=5, lam0=True))
+    cap = 1 << 21
+    buf = C.create_string_buffer(cap)
+    assert E.qbe_xch_source(n, ops, len(ops), opts.encode(), lbits[0], lbits[1], buf, cap) == 0
+    src = buf.value.decode()
+    assert "qbj_xch_dst(A.x" in src and "#define QBJ_DST(p) qbj_xch_dst" in src
+    nbytes = C.c_int64(0)
+    rc = capi.lib().qb_jit_compile_check(src.encode(), C.byref(nbytes))
+    if rc == capi.QB_ERR_UNSUPPORTED:
+        pytest.skip("libnvrtc not available: " + capi.lib().qb_last_error().decode())
+    assert rc == 0, capi.lib().qb_last_error().decode()[:2000]
+    assert nbytes.value > 1000
+
+
 def test_range_guard_applies_the_running_factor_mid_flush(jit_emul):
     """~1,100 rotations near 90 degrees in one flush: the product of the factors their 2-FMA forms
     leave out drops below 2^-300, so a pass in the middle must apply the running factor (its

@@ -515,6 +515,9 @@ def run_ours(args):
                    "ops_executed_per_step": ops_exec, "ops_folded_per_step": ops_fold,
                    "passes_per_step": passes, "rounds_per_step": st["rounds"] / args.steps,
                    "exchanges_per_step": st["exchanges"] / args.steps,
+                   # of those: swaps carried by the stores of the pass before them (option fuse_exchange: that pass
+                   # writes over NVLink peer memory into the next owner's second shard; no exchange sweep)
+                   "exchanges_fused_per_step": st.get("exchanges_fused", 0) / args.steps,
                    "exchange_bytes_per_gpu_per_step": st["exchange_bytes"] / args.steps,
                    "plan_ms_per_step": st["plan_ms"] / args.steps},
         "clocks": clk,

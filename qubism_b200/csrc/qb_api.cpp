@@ -166,7 +166,7 @@ int init_common(qb_ctx *c) {
   QB_CUDA(cudaMallocHost(&c->red_host, sizeof(double) * 4));
   QB_CUDA(cudaMalloc(&c->kq_bits_dev, sizeof(int) * 2 * QB_MAX_KQ));
   QB_CUDA(cudaMalloc(&c->kq_mat_dev, sizeof(double2) << (2 * QB_MAX_KQ)));
-  for (const char *name : {"tile_bits", "reg_bits", "low_bits", "max_rounds", "peephole", "fuse", "max_pass_gates", "l2_prefetch", "avoid_regswap", "hot_bits", "rot", "lite", "dbg_skip", "lane_fixed", "skip_dead", "support", "jit", "jit_group", "jit_pf_last", "jit_minb", "jit_mem", "tma", "oop", "oop_low_bits", "chunk_lanes", "oop_dist", "pf_lines", "fuse_exchange"}) {
+  for (const char *name : {"tile_bits", "reg_bits", "low_bits", "max_rounds", "peephole", "fuse", "max_pass_gates", "l2_prefetch", "avoid_regswap", "hot_bits", "rot", "lite", "dbg_skip", "lane_fixed", "skip_dead", "support", "jit", "jit_group", "jit_pf_last", "jit_minb", "jit_mem", "tma", "oop", "oop_low_bits", "chunk_lanes", "oop_dist", "pf_lines", "fuse_exchange", "defer_tail"}) {
     std::string env = "QB_";
     for (const char *p = name; *p; ++p) env.push_back((char)toupper(*p));
     const char *v = getenv(env.c_str());
@@ -624,7 +624,7 @@ int run_fused_segment(Buffer *s, std::vector<const HostOp *> seg, const double *
     std::vector<int> labels(s->L, 0);  // the logical bit on each local physical bit (ties between qubits nothing
     for (int q = 0; q < s->n; ++q)     // waits for: the layouts out-of-place passes produce depend on the ops only)
       if (s->perm[q] < s->L) labels[s->perm[q]] = q;
-    PlanResult plan = plan_passes(pops, s->L, c->rank, opt, nullptr, &labels);
+    PlanResult plan = plan_passes_until_swap(pops, s->L, c->rank, opt, &labels);
     const bool all = plan.consumed == seg.size();
     // ---- a global<->local swap follows this plan (something is left that targets a global qubit):
     // fuse it into the stores of the plan's last pass -- that pass writes every tile straight into

@@ -234,6 +234,10 @@ struct PlanOptions {
   int layout_known = 0;   // (set by the caller per plan) the layout this plan starts from was produced by
                           // out-of-place passes of the same flush (a replan after a global<->local swap): its
                           // first pass need not treat the low bits as passengers
+  int defer_tail = 12;    // sharded: a plan that ends stuck on global qubits drops its LAST passes while they carry at most
+                          // this many gates each -- those gates wait for the plan after the swap, whose first passes
+                          // have room for them (a pass costs one sweep of the shard however few gates it carries)
+  int max_passes = 0;     // (set by plan_passes_until_swap) stop after this many passes (0 = no limit)
   int fuse_exchange = 1;  // sharded, out of place: the pass before a global<->local swap stores its tiles straight
                           // into the second shard of the rank that owns them after the swap (XchGeom)
   int pf_lines = 0;       // see DevPass::pf_lines
@@ -294,6 +298,11 @@ struct PlanResult {
 // bit); out-of-place passes break ties by it, so that the layouts they produce depend on the op stream only.
 PlanResult plan_passes(const std::vector<PhysOp> &ops, int local_bits, int rank, const PlanOptions &opt,
                        const double *gscale, const std::vector<int> *labels = nullptr);
+
+// plan_passes for one stretch of a flush: if the plan ends stuck (a global<->local swap follows) and
+// option defer_tail is set, the sparse passes at its end are dropped (see PlanOptions::defer_tail).
+PlanResult plan_passes_until_swap(const std::vector<PhysOp> &ops, int local_bits, int rank, const PlanOptions &opt,
+                                  const std::vector<int> *labels);
 
 std::string describe_plan(const PlanResult &r);
 

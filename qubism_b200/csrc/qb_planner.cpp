@@ -68,6 +68,9 @@ bool set_opt(PlanOptions &o, const std::string &name, int64_t v) {
   } else if (name == "tma") {
     if (v < 0 || v > 3) return false;
     o.tma = (int)v;
+  } else if (name == "defer_tail") {
+    if (v < 0 || v > kMaxPassGates) return false;
+    o.defer_tail = (int)v;
   } else if (name == "fuse_exchange") {
     o.fuse_exchange = v ? 1 : 0;
   } else if (name == "pf_lines") {
@@ -137,6 +140,7 @@ int64_t get_opt(const PlanOptions &o, const std::string &name) {
   if (name == "oop_dist") return o.oop_dist;
   if (name == "pf_lines") return o.pf_lines;
   if (name == "fuse_exchange") return o.fuse_exchange;
+  if (name == "defer_tail") return o.defer_tail;
   if (name == "jit_minb") return o.jit_minb;
   if (name == "jit_mem") return o.jit_mem;
   if (name == "jit_group") return o.jit_group;
@@ -1238,6 +1242,7 @@ PlanResult plan_passes(const std::vector<PhysOp> &ops_in, int local_bits, int ra
     return o;
   };
   while (ndone < ops.size()) {
+    if (opt.max_passes > 0 && (int)res.passes.size() >= opt.max_passes) break;
     PassPlan p;
     if (!plan_one_pass(ops, done, local_bits, rank, opt, p, label, res.final_pos.empty() && !opt.layout_known, again)) break;
     ndone += p.op_index.size();
@@ -1292,6 +1297,18 @@ PlanResult plan_passes(const std::vector<PhysOp> &ops_in, int local_bits, int ra
     P->has_gscale = 1;
   }
   return res;
+}
+
+PlanResult plan_passes_until_swap(const std::vector<PhysOp> &ops, int local_bits, int rank, const PlanOptions &opt,
+                                  const std::vector<int> *labels) {
+  PlanResult plan = plan_passes(ops, local_bits, rank, opt, nullptr, labels);
+  if (opt.defer_tail <= 0 || !opt.oop || plan.consumed == ops.size()) return plan;  // (in place: the schedule round 1 measured)
+  size_t keep = plan.passes.size();
+  while (keep > 1 && plan.passes[keep - 1].ngates <= opt.defer_tail) --keep;
+  if (keep == plan.passes.size()) return plan;
+  PlanOptions o2 = opt;  // (the passes are planned one after the other: the first `keep` come out the same)
+  o2.max_passes = (int)keep;
+  return plan_passes(ops, local_bits, rank, o2, nullptr, labels);
 }
 
 std::string describe_plan(const PlanResult &r) {

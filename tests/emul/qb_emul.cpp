@@ -717,7 +717,12 @@ int qbe_layout_trace(int n, int nranks, const qb_op *ops, int64_t nops, const ch
       std::vector<int> labels(L, 0);  // the logical bit on each local physical bit
       for (int qq = 0; qq < n; ++qq)
         if (perm[qq] < L) labels[perm[qq]] = qq;
-      PlanResult plan = plan_passes(pops, L, 0, opt, nullptr, &labels);
+      PlanResult plan = plan_passes_until_swap(pops, L, 0, opt, &labels);
+      if (getenv("QBE_TRACE_PLAN")) {
+        std::fprintf(stderr, "step %d: plan of %zu ops -> %zu passes, gates:", step, seg.size(), plan.passes.size());
+        for (const auto &p : plan.passes) std::fprintf(stderr, " %u/%ur", (unsigned)p.ngates, (unsigned)p.nrounds);
+        std::fprintf(stderr, " consumed %zu\n", plan.consumed);
+      }
       for (const auto &p : plan.passes) {
         ++npass;
         JitProgram kp;
@@ -850,7 +855,7 @@ int qbe_run_rank(int n, int nranks, int rank, const qb_op *ops, int64_t nops, co
     std::vector<int> labels(L, 0);
     for (int qq = 0; qq < n; ++qq)
       if (perm[qq] < L) labels[perm[qq]] = qq;
-    PlanResult plan = plan_passes(pops, L, rank, opt, nullptr, &labels);
+    PlanResult plan = plan_passes_until_swap(pops, L, rank, opt, &labels);
     const bool all = plan.consumed == seg.size();
     if (all && !gdone && !plan.passes.empty()) {
       DevPass *P = reinterpret_cast<DevPass *>(plan.passes.back().blob.data());

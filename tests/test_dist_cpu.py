@@ -111,7 +111,8 @@ def test_sharded_exchange_over_gloo(tmp_path, emul, world, n, any_local):
 
 @pytest.mark.parametrize("world,n,options,nsteps,how", [(2, 13, b"tile_bits=10,reg_bits=3", 2, 7), (4, 14, b"tile_bits=10,reg_bits=3", 2, 15),
                                                         (8, 16, b"tile_bits=10,reg_bits=3", 2, 7), (8, 15, b"", 3, 15),
-                                                        (2, 18, b"", 4, 15)],
+                                                        (2, 18, b"", 4, 15), (4, 15, b"defer_tail=0", 3, 7),
+                                                        (8, 16, b"defer_tail=20,tile_bits=10,reg_bits=3", 3, 7)],
                          ids=lambda v: str(v))
 def test_swap_carried_by_the_stores_of_the_last_pass(tmp_path, emul, world, n, options, nsteps, how):
     """Option fuse_exchange: the out-of-place pass before a global<->local swap stores every tile
@@ -161,6 +162,13 @@ def test_repeated_steps_settle_into_a_layout_cycle(world):
     period = next(p for p in range(1, 7) if all(layouts[s] == layouts[s - p] for s in range(13, nsteps)))
     assert period <= 6  # (1 at 2 ranks, 6 at 4, 3 at 8 on this circuit)
     assert all(cnt[3 * s + 2] == 0 for s in range(12, nsteps)), "new pass structures keep appearing"
+    # option defer_tail (default 12): sparse passes at the end of a stuck plan wait for the plan after the
+    # swap -- fewer sweeps per step than with every schedulable gate run as early as possible
+    steady = sum(cnt[3 * s] for s in range(14, nsteps))
+    swaps = sum(cnt[3 * s + 1] for s in range(14, nsteps))
+    assert E.qbe_layout_trace(n, world, ops, len(ops), b"defer_tail=0", nsteps, 3, perm, cnt) == 0
+    assert steady < sum(cnt[3 * s] for s in range(14, nsteps))
+    assert swaps <= sum(cnt[3 * s + 1] for s in range(14, nsteps)) + (nsteps - 14)  # (at most one more swap per step)
     # the in-place schedule (oop = 0) still cycles at 2 and 4 ranks
     if world <= 4:
         assert E.qbe_layout_trace(n, world, ops, len(ops), b"oop=0", 10, 3, perm, cnt) == 0

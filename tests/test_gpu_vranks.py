@@ -240,17 +240,19 @@ def test_swap_carried_by_the_stores_of_a_fused_pass(groups, P, n):
 
     def rank_fn(r, ctx):
         outs = {}
-        for fuse, jit in ((1, 0), (0, 0), (1, 1)):
+        for fuse, jit, tail in ((1, 0, 12), (0, 0, 12), (1, 1, 12), (1, 0, 0)):
             ctx.set_option("fuse_exchange", fuse)
             ctx.set_option("jit", jit)
+            ctx.set_option("defer_tail", tail)  # (0: sparse passes at the end of a stuck plan are not held back)
             ctx.reset_stats()
             sv = Q.StateVec.from_host(full[r << L:(r + 1) << L], n=n, ctx=ctx)
             for _ in range(2):
                 sv.submit(ops)
                 sv.flush()
-            outs[(fuse, jit)] = (sv.to_host(), ctx.stats())
+            outs[(fuse, jit) if tail else "tail0"] = (sv.to_host(), ctx.stats())
         ctx.set_option("fuse_exchange", 1)
         ctx.set_option("jit", 2)
+        ctx.set_option("defer_tail", 12)
         return outs
 
     for outs in run_group(ctxs, rank_fn):
@@ -264,3 +266,5 @@ def test_swap_carried_by_the_stores_of_a_fused_pass(groups, P, n):
         assert sa["exchanges_fused"] >= 1 and sc["exchanges_fused"] == sa["exchanges_fused"]
         assert sa["passes"] == sb["passes"]
         assert sc["jit_launches"] >= 1
+        d, sd = outs["tail0"]
+        assert np.abs(d - ref).max() < TOL and sd["passes"] >= sa["passes"]

@@ -228,7 +228,9 @@ void *qb_ctx_stream(qb_ctx *ctx);
  * 2: only the tile's qubits move; 0: in place, half the memory), "oop_low_bits", "oop_dist" (sharded
  * states run out of place too), "chunk_lanes", "tma" (tile loads as bulk copies), "l2_prefetch", "fuse_exchange" (1, default: on
  * sharded out-of-place states the pass before a global<->local swap stores every tile straight
- * into the second shard of the rank that owns it after the swap; 0: store locally, then exchange).
+ * into the second shard of the rank that owns it after the swap; 0: store locally, then exchange),
+ * "defer_tail" (12: the last passes of a plan that is stuck on global qubits are held back while they
+ * carry at most this many gates each; their gates run after the swap; 0: off).
  * A state that cannot get its second shard (36 qubits on 8 GPUs) stays in place.  Returns
  * QB_ERR_ARG for unknown names / bad values. */
 int qb_set_option(qb_ctx *ctx, const char *name, int64_t value);

@@ -1081,9 +1081,11 @@ int qbe_xch_source(int nlocal, const qb_op *ops, int64_t nops, const char *optio
   if (!fused_exchange_geometry(LP, nlocal, 1, 4, sw, &LP.xch)) return -4;
   JitProgram dp, plain;
   std::string why;
+  if (getenv("QBE_XCH_PLAIN")) LP.xch.n = 0;  // (the same pass without the swap, to compare the generated code)
   if (!jit_generate(pp, JIT_DEVICE_SRC, dp, &why)) return -6;
   if ((int64_t)dp.src.size() + 1 > cap) return -7;
   std::memcpy(out, dp.src.c_str(), dp.src.size() + 1);
+  if (LP.xch.n == 0) return 0;
   // the structure key tells the two kinds of pass apart, and nothing of the geometry leaks into it
   JitProgram k1, k2;
   if (!jit_quick(pp, k1, nullptr)) return -8;

@@ -107,9 +107,14 @@ struct XchGeom {
   uint64_t vmask, vconst;       // the victims' bits of the block address / what replaces them
   uint32_t n, rbase;            // swapped pairs (0 = plain pass) / this rank with the swapped rank bits cleared
   uint32_t lbit[4], rbit[4];
+  // dr[i]: what register index i of the pass's last round adds to the destination rank -- its store offset's
+  // bits on the victims' positions, moved to the rank bits.  With it a specialised kernel works out one
+  // destination per TILE (from the thread's base address) and one XOR per store instead of shifting
+  // run-time bit positions store by store.
+  uint8_t dr[32];
   uint32_t _pad[2];
 };
-static_assert(sizeof(XchGeom) == 192, "XchGeom layout (mirrored by the generated QbjXch)");
+static_assert(sizeof(XchGeom) == 224, "XchGeom layout (mirrored by the generated QbjXch)");
 
 struct DevRound {
   uint32_t gate_begin, gate_end;

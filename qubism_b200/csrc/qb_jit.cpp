@@ -349,21 +349,26 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
     if (ostride_of(RL, 0) == 1ull) {
       g.tag("p");
       g.line("  const u64 at_ = (" + sOB + " + goff_tab[QBJ_NT + tid]) ^ (fx_ & ~1ull);");
+      if (xch) g.line("  QBJ_XCH_TILE(at_)");
+      const std::string st2 = xch ? "  QBJ_ST2X(" : "  QBJ_ST2(at_ ^ ";
       const bool sw = (mf & 1u) != 0;
       if (sw) g.line("  const bool sw_ = (f & 1u) != 0;");
       for (int i = 0; i < NR; i += 2) {
         const std::string a = std::to_string(i), b = std::to_string(i + 1);
         const std::string off = reg_offset_expr(g, P.out_pos, RL, R, i, 1, "^");
+        const std::string head = xch ? st2 + a + ", " + off : st2 + off;
         if (sw)
-          g.line("  QBJ_ST2(at_ ^ " + off + ", sw_ ? re[" + b + "] : re[" + a + "], sw_ ? im[" + b + "] : im[" + a + "], sw_ ? re[" + a +
+          g.line(head + ", sw_ ? re[" + b + "] : re[" + a + "], sw_ ? im[" + b + "] : im[" + a + "], sw_ ? re[" + a +
                  "] : re[" + b + "], sw_ ? im[" + a + "] : im[" + b + "]);");
         else
-          g.line("  QBJ_ST2(at_ ^ " + off + ", re[" + a + "], im[" + a + "], re[" + b + "], im[" + b + "]);");
+          g.line(head + ", re[" + a + "], im[" + a + "], re[" + b + "], im[" + b + "]);");
       }
     } else {
       g.line("  const u64 at_ = (" + sOB + " + goff_tab[QBJ_NT + tid]) ^ fx_;");
+      if (xch) g.line("  QBJ_XCH_TILE(at_)");
       for (int i = 0; i < NR; ++i)
-        g.line("  QBJ_ST1(at_ ^ " + reg_offset_expr(g, P.out_pos, RL, R, i, 0, "^") + ", re[" + std::to_string(i) + "], im[" + std::to_string(i) + "]);");
+        g.line(std::string(xch ? "  QBJ_ST1X(" + std::to_string(i) + ", " : "  QBJ_ST1(at_ ^ ") + reg_offset_expr(g, P.out_pos, RL, R, i, 0, "^") +
+               ", re[" + std::to_string(i) + "], im[" + std::to_string(i) + "]);");
     }
     g.line("}");
   };
@@ -556,20 +561,22 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
     g.cur = &g.o;
     const std::string rounds_txt = side.str();
     const size_t nc = std::max<size_t>(1, g.coefs.size());
-    o << "struct QbjXch { u64 peer[" << kMaxXchRanks << "]; u64 vmask, vconst; u32 n, rbase; u32 lbit[4], rbit[4]; u32 pad_[2]; };\n"
+    o << "struct QbjXch { u64 peer[" << kMaxXchRanks << "]; u64 vmask, vconst; u32 n, rbase; u32 lbit[4], rbit[4]; unsigned char dr[32]; u32 pad_[2]; };\n"
          "struct QbjArgs { double gs[2]; u64 rank_bits; u64 base_fixed; QbjXch x; double c[" << nc << "]; };\n";
     if (xch) {
-      // the stores carry a global<->local swap: amplitude address a of the new layout -> the rank that owns
-      // it after the swap (the victims' bits of a pick it) and its address there (those bits take this
-      // rank's old rank-bit values); peer[] = every rank's second shard as mapped here (XchGeom)
+      // the stores carry a global<->local swap (XchGeom): amplitude address a of the new layout goes to the
+      // rank its victims' bits pick, at the address with those bits replaced by this rank's old rank-bit
+      // values.  Every store of a thread is its base address `at` XOR a literal offset, so the run-time bit
+      // positions are looked at ONCE per tile (rank and address of the base); a store then XORs what its
+      // register index adds to the rank (dr[i], worked out on the host) and its offset outside the victims.
       g.tag("xch");
-      o << (g.host ? "static inline double *" : "__device__ __forceinline__ double2 *")
-        << "qbj_xch_dst(const QbjXch &X, u64 a) {\n"
-           "  u32 rr_ = X.rbase;\n"
-           "  for (u32 k_ = 0; k_ < X.n; ++k_) rr_ |= (u32)((a >> X.lbit[k_]) & 1ull) << X.rbit[k_];\n"
-        << (g.host ? "  return reinterpret_cast<double *>(X.peer[rr_]) + 2 * ((a & ~X.vmask) | X.vconst);\n"
-                   : "  return reinterpret_cast<double2 *>(X.peer[rr_]) + ((a & ~X.vmask) | X.vconst);\n")
-        << "}\n";
+      o << "#define QBJ_XCH_TILE(at) u32 rrt_ = A.x.rbase; \\\n"
+           "  for (u32 k_ = 0; k_ < A.x.n; ++k_) rrt_ |= (u32)(((at) >> A.x.lbit[k_]) & 1ull) << A.x.rbit[k_]; \\\n"
+           "  const u64 nvm_ = ~A.x.vmask; const u64 bt_ = ((at) & nvm_) | A.x.vconst;\n";
+      if (g.host)
+        o << "#define QBJ_DSTX(i, off) (reinterpret_cast<double *>(A.x.peer[rrt_ ^ A.x.dr[i]]) + 2 * (bt_ ^ ((off) & nvm_)))\n";
+      else
+        o << "#define QBJ_DSTX(i, off) (reinterpret_cast<double2 *>(A.x.peer[rrt_ ^ A.x.dr[i]]) + (bt_ ^ ((off) & nvm_)))\n";
     }
     // Coefficients are loop-invariant kernel parameters.  Up to ~30 of them the compiler keeps them
     // in uniform registers across the tile loop; beyond that it hoists them into ordinary
@@ -588,7 +595,10 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
            "#define QBJ_STS(off, xr, xi) *reinterpret_cast<double2 *>(sm_ + (off)) = make_double2(xr, xi)\n"
            "#define QBJ_LDS(off, i) { const double2 a_ = *reinterpret_cast<const double2 *>(sm_ + (off)); re[i] = a_.x; im[i] = a_.y; }\n"
            "#define QBJ_LDSI(off, i) { const double2 a_ = *reinterpret_cast<const double2 *>(in_ + (off)); re[i] = a_.x; im[i] = a_.y; }\n";
-      o << (xch ? "#define QBJ_DST(p) qbj_xch_dst(A.x, (p))\n" : "#define QBJ_DST(p) (amps + (p))\n");
+      o << "#define QBJ_DST(p) (amps + (p))\n";
+      if (xch)
+        o << "#define QBJ_ST2X(i, off, a0, a1, b0, b1) qbj_st256(QBJ_DSTX(i, off), a0, a1, b0, b1)\n"
+             "#define QBJ_ST1X(i, off, xr, xi) qbj_st128(QBJ_DSTX(i, off), xr, xi)\n";
       if (dual)
         o << "#define QBJ_BAR() asm volatile(\"bar.sync %0, %1;\" ::\"r\"(grp_ + 1u), \"r\"((u32)QBJ_NT) : \"memory\")\n";
       else
@@ -817,7 +827,9 @@ bool jit_generate(const PassPlan &pp, JitEmit emit, JitProgram &out, std::string
            "#define QBJ_LD1(p, i) { re[i] = amps[2 * (p)]; im[i] = amps[2 * (p) + 1]; }\n"
            "#define QBJ_ST2(p, a0, a1, b0, b1) { double *d_ = QBJ_DST(p); d_[0] = a0; d_[1] = a1; d_[2] = b0; d_[3] = b1; }\n"
            "#define QBJ_ST1(p, xr, xi) { double *d_ = QBJ_DST(p); d_[0] = xr; d_[1] = xi; }\n"
-        << (xch ? "#define QBJ_DST(p) qbj_xch_dst(A.x, (p))\n" : "#define QBJ_DST(p) (dst + 2 * (p))\n") <<
+           "#define QBJ_DST(p) (dst + 2 * (p))\n"
+           "#define QBJ_ST2X(i, off, a0, a1, b0, b1) { double *d_ = QBJ_DSTX(i, off); d_[0] = a0; d_[1] = a1; d_[2] = b0; d_[3] = b1; }\n"
+           "#define QBJ_ST1X(i, off, xr, xi) { double *d_ = QBJ_DSTX(i, off); d_[0] = xr; d_[1] = xi; }\n"
            "#define QBJ_STS(off, xr, xi) { SM[2 * ((off) >> 4)] = xr; SM[2 * ((off) >> 4) + 1] = xi; }\n"
            "#define QBJ_LDS(off, i) { re[i] = SM[2 * ((off) >> 4)]; im[i] = SM[2 * ((off) >> 4) + 1]; }\n"
            "#define QBJ_LDSI(off, i) QBJ_LDS(off, i)\n"

@@ -541,6 +541,17 @@ bool fused_exchange_geometry(const DevPass &last, int L, int rank, int nranks, c
     X.vconst |= uint64_t((rank >> rb) & 1) << sw[i].lbit;
     X.rbase &= ~(1u << rb);
   }
+  // per register index of the last round: its store offset (as the kernels form it, out_pos of the round's
+  // register bits) seen through the victims' positions
+  const DevRound &RL = last.rounds[last.nrounds - 1];
+  for (uint32_t i = 0; i < (1u << last.reg_bits) && i < 32u; ++i) {
+    uint64_t off = 0;
+    for (uint32_t j = 0; j < last.reg_bits; ++j)
+      if ((i >> j) & 1u) off |= 1ull << last.out_pos[RL.reg_pos[j]];
+    uint32_t d = 0;
+    for (uint32_t k = 0; k < X.n; ++k) d |= uint32_t((off >> X.lbit[k]) & 1ull) << X.rbit[k];
+    X.dr[i] = (uint8_t)d;
+  }
   *out = X;
   return true;
 }

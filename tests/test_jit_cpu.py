@@ -170,8 +170,9 @@ def test_device_source_compiles_with_nvrtc(jit_emul, opts):
 @pytest.mark.parametrize("opts,lbits", [("", (11, 10)), ("", (12, 3)), ("reg_bits=5", (9, 1)), ("tile_bits=10,reg_bits=3", (12, 11))])
 def test_swap_carrying_pass_compiles_with_nvrtc(jit_emul, opts, lbits):
     """The generated kernel whose stores carry a global<->local swap (option fuse_exchange): peer table
-    and geometry are kernel arguments (QbjXch), the destination is worked out store by store
-    (qbj_xch_dst); one flag of the structure key tells it from the plain pass."""
+    and geometry are kernel arguments (QbjXch); the run-time bit positions are looked at once per tile
+    (QBJ_XCH_TILE), a store XORs its register index's share of the rank (dr[i]) and its offset outside
+    the victims (QBJ_DSTX); one flag of the structure key tells it from the plain pass."""
     n = 13
     E = C.CDLL(os.path.join(ROOT, "tests", "emul", "libqb_emul.so"))
     E.qbe_xch_source.argtypes = [C.c_int, C.POINTER(capi.QbOp), C.c_int64, C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_int64]
@@ -180,7 +181,9 @@ def test_swap_carrying_pass_compiles_with_nvrtc(jit_emul, opts, lbits):
     buf = C.create_string_buffer(cap)
     assert E.qbe_xch_source(n, ops, len(ops), opts.encode(), lbits[0], lbits[1], buf, cap) == 0
     src = buf.value.decode()
-    assert "qbj_xch_dst(A.x" in src and "#define QBJ_DST(p) qbj_xch_dst" in src
+    body = src.split("qb_jit_pass(")[1]
+    assert "QBJ_XCH_TILE(at_)" in body and ("QBJ_ST2X(" in body or "QBJ_ST1X(" in body)
+    assert "QBJ_ST2(" not in body and "QBJ_ST1(" not in body  # (no store bypasses the destination arithmetic)
     nbytes = C.c_int64(0)
     rc = capi.lib().qb_jit_compile_check(src.encode(), C.byref(nbytes))
     if rc == capi.QB_ERR_UNSUPPORTED:
